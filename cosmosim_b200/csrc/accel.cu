@@ -1,0 +1,434 @@
+// Stage A: all-pairs 2-D gravitational acceleration with the semi-implicit Euler update
+// fused into the same pass.  Replaces acc_blas (reference cosmosim/util/blas.py:4-41, call
+// site cosmosim/core/universe_old.py:174) and the integrator (universe_old.py:177-178).
+//
+// Shape of the computation (both precisions):
+//   grid = (target blocks, source splits).  A CTA owns BLOCK*IB target planets held in
+//   registers (IB per thread) and streams its share of the source planets through shared
+//   memory in tiles staged by the TMA engine's 1-D bulk copy (cp.async.bulk -> SASS UBLKCP)
+//   into a 2-deep mbarrier ring; every lane of a warp reads the same source element
+//   (shared-memory broadcast), so the inner loop is pure register math.  Partial sums of the
+//   source splits meet in `partial`; the last CTA to arrive for a target block (threadfence
+//   + arrival counter) reduces them in split order -- deterministic -- and integrates.
+//
+// FP64 parity flavour: reproduces the reference's rounding sequence of d^2 exactly (the
+// reference forms |p_i|^2 + |p_j|^2 - 2 p_i.p_j through zhpr/dspr2 and loses ~9 digits to
+// cancellation at AU scale; a direct dx^2+dy^2 kernel is 1e-9 away from it).  Every product
+// and sum of that chain is an explicit __dmul_rn/__dadd_rn so nothing is contracted.
+// 20 FP64-pipe instructions per interaction + 1 MUFU.RSQ64H.
+//
+// FP32 fast flavour: positions/masses rescaled by powers of two (exact) and packed to
+// float once per frame; inner loop on packed FFMA2/FMUL2/FADD2 (two sources per
+// instruction) -- 9 FMA-pipe instructions per TWO interactions + 2 MUFU.RSQ; per-tile FP32
+// sums are folded into FP64 accumulators; the integrator stays FP64.
+#include <math.h>
+
+#include "cosmo_device.cuh"
+#include "cosmo_internal.h"
+
+namespace cosmo {
+
+// ---------------------------------------------------------------------------------------
+// k_prep: per-frame O(N) preparation over ALL active slots (replicated on every rank).
+//   h[k]      half diagonal of the reference's d^2 chain (blas.py:23,27)
+//   pk_*      FP32 j-stage: x, y, m scaled by exact powers of two
+//   rinf      radii inflated for the stage-B candidate filter
+//   alive=1, escaped = |pos| > r_max on START-of-frame positions (universe_old.py:75-76,87)
+//   thread 0 resets the per-frame counters.
+// Slots in [n, n rounded up to COSMO_PAD) are zero-filled so tail tiles read benign data.
+// ---------------------------------------------------------------------------------------
+__global__ void k_prep(cosmo_state st, cosmo_scratch sc, double r_max, int pos_exp, int mass_exp,
+                       int do_f32) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int n_pad = min(st.cap, (n + COSMO_PAD - 1) / COSMO_PAD * COSMO_PAD);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st.status[COSMO_ST_N_PAIRS] = 0;
+        st.status[COSMO_ST_N_DEAD] = 0;
+        st.status[COSMO_ST_N_CAND] = 0;
+    }
+    const double2 *pos = reinterpret_cast<const double2 *>(st.pos);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_pad; k += gridDim.x * blockDim.x) {
+        if (k < n) {
+            double2 p = pos[k];
+            // c(k,k) = fl(fl(fl(fl(-2x*x) - 2) + fl(fl(-2y*y) - 2)) + 6)
+            double rx = __dadd_rn(__dmul_rn(-2.0 * p.x, p.x), -2.0);
+            double ry = __dadd_rn(__dmul_rn(-2.0 * p.y, p.y), -2.0);
+            double c = __dadd_rn(__dadd_rn(rx, ry), 6.0);
+            sc.h[k] = 0.5 * c;
+            double r = st.radius[k];
+            sc.rinf[k] = __dmul_rn(r, 1.0 + 9.313225746154785e-10);  // 1 + 2^-30
+            double nrm = sqrt(__dadd_rn(__dmul_rn(p.x, p.x), __dmul_rn(p.y, p.y)));
+            sc.escaped[k] = nrm > r_max ? 1 : 0;
+            sc.alive[k] = 1;
+            if (do_f32) {
+                sc.pk_x[k] = (float)scalbn(p.x, -pos_exp);
+                sc.pk_y[k] = (float)scalbn(p.y, -pos_exp);
+                sc.pk_m[k] = (float)scalbn(st.mass[k], -mass_exp);
+            }
+        } else {
+            sc.h[k] = 0.0;
+            sc.rinf[k] = 0.0;
+            sc.escaped[k] = 0;
+            sc.alive[k] = 0;
+            if (do_f32) {
+                sc.pk_x[k] = 0.f;
+                sc.pk_y[k] = 0.f;
+                sc.pk_m[k] = 0.f;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// epilogue shared by both flavours: a = G*S, v = v0 + a dt, p = p0 + v dt (two roundings per
+// update like numpy, universe_old.py:177-178), squared row norm of p for stage B
+// (sklearn row_norms: fl(fl(x^2) + fl(y^2))).  Immobile planets are integrated as well --
+// the reference uses their drifted rows for the collision test but never stores them
+// (universe_old.py:199-201).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void integrate_store(const cosmo_state &st, const cosmo_scratch &sc, int i,
+                                                double sx, double sy, double G, double dt,
+                                                bool store_acc) {
+    const double2 *pos = reinterpret_cast<const double2 *>(st.pos);
+    const double2 *vel = reinterpret_cast<const double2 *>(st.vel);
+    double ax = __dmul_rn(G, sx), ay = __dmul_rn(G, sy);
+    double2 p0 = pos[i], v0 = vel[i];
+    double vx = __dadd_rn(v0.x, __dmul_rn(ax, dt));
+    double vy = __dadd_rn(v0.y, __dmul_rn(ay, dt));
+    double px = __dadd_rn(p0.x, __dmul_rn(vx, dt));
+    double py = __dadd_rn(p0.y, __dmul_rn(vy, dt));
+    reinterpret_cast<double2 *>(sc.vel_new)[i] = make_double2(vx, vy);
+    reinterpret_cast<double2 *>(sc.pos_new)[i] = make_double2(px, py);
+    sc.xx_new[i] = __dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py));
+    if (store_acc) reinterpret_cast<double2 *>(sc.acc)[i] = make_double2(ax, ay);
+    if (!(isfinite(ax) && isfinite(ay)))
+        atomicOr(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_ERROR]),
+                 (unsigned long long)COSMO_ERR_NAN);
+}
+
+// Cross-split reduction: every CTA of a target block publishes its partial sums; the last
+// one to arrive adds them in split order and integrates.
+template <int BLOCK, int IB>
+__device__ __forceinline__ void reduce_and_integrate(const cosmo_state &st, const cosmo_scratch &sc,
+                                                     int base, int i_hi, const double (&sx)[IB],
+                                                     const double (&sy)[IB], int jsplit, double G,
+                                                     double dt, bool store_acc) {
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    if (jsplit == 1) {
+#pragma unroll
+        for (int k = 0; k < IB; ++k) {
+            int i = base + k * BLOCK + tid;
+            if (i < i_hi) integrate_store(st, sc, i, sx[k], sy[k], G, dt, store_acc);
+        }
+        return;
+    }
+    double2 *partial = reinterpret_cast<double2 *>(sc.partial);
+    const size_t cap = (size_t)st.cap;
+#pragma unroll
+    for (int k = 0; k < IB; ++k) {
+        int i = base + k * BLOCK + tid;
+        if (i < i_hi) __stcg(&partial[blockIdx.y * cap + i], make_double2(sx[k], sy[k]));
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        int old = atomicAdd(&sc.tile_ctr[blockIdx.x], 1);
+        s_last = (old == jsplit - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < IB; ++k) {
+        int i = base + k * BLOCK + tid;
+        if (i < i_hi) {
+            double ax = 0.0, ay = 0.0;
+            for (int s = 0; s < jsplit; ++s) {
+                double2 v = __ldcg(&partial[s * cap + i]);
+                ax += v.x;
+                ay += v.y;
+            }
+            integrate_store(st, sc, i, ax, ay, G, dt, store_acc);
+        }
+    }
+    if (tid == 0) sc.tile_ctr[blockIdx.x] = 0;  // re-armed for the next frame
+}
+
+// ---------------------------------------------------------------------------------------
+// FP64 parity kernel
+// ---------------------------------------------------------------------------------------
+// One interaction i <- j following blas.py:9-41 (see oracle/cosmo_oracle.c for the same
+// chain on the CPU):
+//   R_k = fl(fl(q_ik p_jk) - 2), q = -2 p_i        (zhpr real part)
+//   c   = fl(fl(R_x + R_y) + 6)                     (trck.real.sum(0) + 6)
+//   d2  = fl(fl(c - h_hi) - h_lo), hi/lo = max/min(i,j)   (dspr2: column axpy, then row)
+//   term = (p_j - p_i) * m_j / (d2 sqrt(d2)) if d2 != 0 else (p_j - p_i) * m_j
+// Only the d2 chain needs the reference's exact roundings (it is the ill-conditioned part);
+// 1/(d2 sqrt d2) is formed as y^3 with y = rsqrt(d2) refined from the MUFU seed by one
+// third-order step (relative error ~2e-16), instead of sqrt + divide.
+__device__ __forceinline__ void pair_f64(double xi, double yi, double qix, double qiy, double hi,
+                                         int i, double xj, double yj, double hj, double mj, int j,
+                                         double &ax, double &ay) {
+    double rx = __dadd_rn(__dmul_rn(qix, xj), -2.0);
+    double ry = __dadd_rn(__dmul_rn(qiy, yj), -2.0);
+    double c = __dadd_rn(__dadd_rn(rx, ry), 6.0);
+    const bool ge = j >= i;
+    double a1 = ge ? hj : hi;
+    double a2 = ge ? hi : hj;
+    double d2 = __dadd_rn(__dadd_rn(c, -a1), -a2);
+    double dx = xj - xi, dy = yj - yi;
+    double y = rsqrt_approx_f64(d2);
+    double t = d2 * y;
+    double e = __fma_rn(-t, y, 1.0);       // 1 - d2 y^2
+    double p = __fma_rn(e, 0.375, 0.5);    // 1/2 + 3e/8
+    double ye = y * e;
+    y = __fma_rn(ye, p, y);                // y (1 + e/2 + 3 e^2/8)
+    double s = (mj * y) * (y * y);
+    // where= mask of blas.py:31: entries with d2 == 0 keep the undivided difference
+    s = ((__double2hiint(d2) << 1) | __double2loint(d2)) == 0 ? mj : s;
+    ax = __fma_rn(dx, s, ax);
+    ay = __fma_rn(dy, s, ay);
+}
+
+template <int BLOCK, int IB, int TJ>
+__global__ void __launch_bounds__(BLOCK)
+k_accel_f64(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit, double G, double dt,
+            int store_acc) {
+    __shared__ __align__(16) double2 s_xy[2][TJ];
+    __shared__ __align__(16) double s_h[2][TJ];
+    __shared__ __align__(16) double s_m[2][TJ];
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int i_hi = min(i_end, n);
+    const int base = i_begin + blockIdx.x * (BLOCK * IB);
+    if (base >= i_hi) return;
+    const int tid = threadIdx.x;
+
+    const double2 *pos = reinterpret_cast<const double2 *>(st.pos);
+    double xi[IB], yi[IB], qix[IB], qiy[IB], hi[IB], ax[IB], ay[IB];
+    int ii[IB];
+#pragma unroll
+    for (int k = 0; k < IB; ++k) {
+        int i = base + k * BLOCK + tid;
+        ii[k] = i;
+        int ic = min(i, i_hi - 1);
+        double2 p = pos[ic];
+        xi[k] = p.x; yi[k] = p.y;
+        qix[k] = -2.0 * p.x; qiy[k] = -2.0 * p.y;
+        hi[k] = sc.h[ic];
+        ax[k] = 0.0; ay[k] = 0.0;
+    }
+
+    const int tiles = (n + TJ - 1) / TJ;
+    const int t0 = (int)(((long long)blockIdx.y * tiles) / jsplit);
+    const int t1 = (int)(((long long)(blockIdx.y + 1) * tiles) / jsplit);
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    constexpr uint32_t kTileBytes = TJ * (sizeof(double2) + 2 * sizeof(double));
+    auto issue = [&](int t, int b) {
+        const size_t j0 = (size_t)t * TJ;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar[b], kTileBytes);
+        bulk_g2s(&s_xy[b][0], pos + j0, TJ * sizeof(double2), &s_bar[b]);
+        bulk_g2s(&s_h[b][0], sc.h + j0, TJ * sizeof(double), &s_bar[b]);
+        bulk_g2s(&s_m[b][0], st.mass + j0, TJ * sizeof(double), &s_bar[b]);
+    };
+    if (tid == 0 && t0 < t1) issue(t0, 0);
+
+    for (int t = t0; t < t1; ++t) {
+        const int it = t - t0;
+        const int b = it & 1;
+        if (tid == 0 && t + 1 < t1) issue(t + 1, b ^ 1);
+        mbar_wait(&s_bar[b], (it >> 1) & 1);
+        const int j0 = t * TJ;
+        const int cnt = min(TJ, n - j0);
+#pragma unroll 2
+        for (int jj = 0; jj < cnt; ++jj) {
+            const double2 pj = s_xy[b][jj];
+            const double hj = s_h[b][jj];
+            const double mj = s_m[b][jj];
+#pragma unroll
+            for (int k = 0; k < IB; ++k)
+                pair_f64(xi[k], yi[k], qix[k], qiy[k], hi[k], ii[k], pj.x, pj.y, hj, mj, j0 + jj,
+                         ax[k], ay[k]);
+        }
+        __syncthreads();  // everyone is done with buffer b before it is refilled
+    }
+    reduce_and_integrate<BLOCK, IB>(st, sc, base, i_hi, ax, ay, jsplit, G, dt, store_acc != 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// FP32 fast kernel
+// ---------------------------------------------------------------------------------------
+#define COSMO_F32_TINY 8.673617379884035e-19f /* 2^-60: keeps rsqrt finite for r2 == 0 */
+
+template <int BLOCK, int IB, int TJ, bool PACKED>
+__global__ void __launch_bounds__(BLOCK)
+k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit, double G, double dt,
+            double unscale, int store_acc) {
+    __shared__ __align__(16) float s_x[2][TJ];
+    __shared__ __align__(16) float s_y[2][TJ];
+    __shared__ __align__(16) float s_m[2][TJ];
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int i_hi = min(i_end, n);
+    const int base = i_begin + blockIdx.x * (BLOCK * IB);
+    if (base >= i_hi) return;
+    const int tid = threadIdx.x;
+
+    float xi[IB], yi[IB];
+    double axd[IB], ayd[IB];
+#pragma unroll
+    for (int k = 0; k < IB; ++k) {
+        int ic = min(base + k * BLOCK + tid, i_hi - 1);
+        xi[k] = sc.pk_x[ic];
+        yi[k] = sc.pk_y[ic];
+        axd[k] = 0.0; ayd[k] = 0.0;
+    }
+
+    const int tiles = (n + TJ - 1) / TJ;
+    const int t0 = (int)(((long long)blockIdx.y * tiles) / jsplit);
+    const int t1 = (int)(((long long)(blockIdx.y + 1) * tiles) / jsplit);
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    constexpr uint32_t kTileBytes = TJ * 3 * sizeof(float);
+    auto issue = [&](int t, int b) {
+        const size_t j0 = (size_t)t * TJ;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar[b], kTileBytes);
+        bulk_g2s(&s_x[b][0], sc.pk_x + j0, TJ * sizeof(float), &s_bar[b]);
+        bulk_g2s(&s_y[b][0], sc.pk_y + j0, TJ * sizeof(float), &s_bar[b]);
+        bulk_g2s(&s_m[b][0], sc.pk_m + j0, TJ * sizeof(float), &s_bar[b]);
+    };
+    if (tid == 0 && t0 < t1) issue(t0, 0);
+
+    for (int t = t0; t < t1; ++t) {
+        const int it = t - t0;
+        const int b = it & 1;
+        if (tid == 0 && t + 1 < t1) issue(t + 1, b ^ 1);
+        mbar_wait(&s_bar[b], (it >> 1) & 1);
+        // Slots past n inside the tile hold zero mass (k_prep), so full tiles are always
+        // processed: no tail bound in the hot loop.
+        if (PACKED) {
+            uint64_t xi2[IB], yi2[IB], ax2[IB], ay2[IB];
+#pragma unroll
+            for (int k = 0; k < IB; ++k) {
+                xi2[k] = pack2(xi[k], xi[k]);
+                yi2[k] = pack2(yi[k], yi[k]);
+                ax2[k] = 0ull; ay2[k] = 0ull;
+            }
+            const uint64_t *px = reinterpret_cast<const uint64_t *>(&s_x[b][0]);
+            const uint64_t *py = reinterpret_cast<const uint64_t *>(&s_y[b][0]);
+            const uint64_t *pm = reinterpret_cast<const uint64_t *>(&s_m[b][0]);
+#pragma unroll 4
+            for (int jj = 0; jj < TJ / 2; ++jj) {
+                const uint64_t xj2 = px[jj], yj2 = py[jj], mj2 = pm[jj];
+#pragma unroll
+                for (int k = 0; k < IB; ++k) {
+                    uint64_t dx = sub2(xj2, xi2[k]);
+                    uint64_t dy = sub2(yj2, yi2[k]);
+                    uint64_t r2 = fma2(dy, dy, mul2(dx, dx));
+                    float r2a, r2b;
+                    unpack2(r2, r2a, r2b);
+                    float ia = rsqrt_approx_f32(fmaxf(r2a, COSMO_F32_TINY));
+                    float ib = rsqrt_approx_f32(fmaxf(r2b, COSMO_F32_TINY));
+                    uint64_t rinv = pack2(ia, ib);
+                    uint64_t s = mul2(mul2(mj2, rinv), mul2(rinv, rinv));
+                    ax2[k] = fma2(dx, s, ax2[k]);
+                    ay2[k] = fma2(dy, s, ay2[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < IB; ++k) {
+                float a, c;
+                unpack2(ax2[k], a, c);
+                axd[k] += (double)a + (double)c;
+                unpack2(ay2[k], a, c);
+                ayd[k] += (double)a + (double)c;
+            }
+        } else {
+            float ax[IB], ay[IB];
+#pragma unroll
+            for (int k = 0; k < IB; ++k) { ax[k] = 0.f; ay[k] = 0.f; }
+#pragma unroll 8
+            for (int jj = 0; jj < TJ; ++jj) {
+                const float xj = s_x[b][jj], yj = s_y[b][jj], mj = s_m[b][jj];
+#pragma unroll
+                for (int k = 0; k < IB; ++k) {
+                    float dx = xj - xi[k], dy = yj - yi[k];
+                    float r2 = fmaf(dy, dy, dx * dx);
+                    float rinv = rsqrt_approx_f32(fmaxf(r2, COSMO_F32_TINY));
+                    float s = (mj * rinv) * (rinv * rinv);
+                    ax[k] = fmaf(dx, s, ax[k]);
+                    ay[k] = fmaf(dy, s, ay[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < IB; ++k) { axd[k] += (double)ax[k]; ayd[k] += (double)ay[k]; }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < IB; ++k) { axd[k] *= unscale; ayd[k] *= unscale; }
+    reduce_and_integrate<BLOCK, IB>(st, sc, base, i_hi, axd, ayd, jsplit, G, dt, store_acc != 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+constexpr int F64_BLOCK = 128, F64_IB = 2, F64_TJ = 256;
+constexpr int F32_BLOCK = 256, F32_IB = 4, F32_TJ = 512;
+static_assert(COSMO_PAD % F64_TJ == 0 && COSMO_PAD % F32_TJ == 0, "tiles must divide the slot padding");
+
+int launch_prep(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                cudaStream_t s) {
+    int n_pad = (p.n_upper + COSMO_PAD - 1) / COSMO_PAD * COSMO_PAD;
+    if (n_pad > st.cap) n_pad = st.cap;
+    int blocks = (n_pad + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_prep<<<blocks, 256, 0, s>>>(st, sc, p.r_max, p.pos_exp, p.mass_exp, (p.opts & COSMO_OPT_FP32) ? 1 : 0);
+    return COSMO_LAUNCH_CHECK("k_prep");
+}
+
+int launch_accel(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                 cudaStream_t s) {
+    const int rows = p.i_end - p.i_begin;
+    if (rows <= 0) return COSMO_OK;
+    int jsplit = p.jsplit < 1 ? 1 : p.jsplit;
+    if (jsplit > sc.jsplit_max) jsplit = sc.jsplit_max;
+    const int store_acc = (p.opts & COSMO_OPT_STORE_ACC) ? 1 : 0;
+    if (p.opts & COSMO_OPT_FP32) {
+        const int per = F32_BLOCK * F32_IB;
+        dim3 grid((rows + per - 1) / per, jsplit);
+        // S = S_scaled * 2^(mass_exp - 2 pos_exp)
+        const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
+        if (p.opts & COSMO_OPT_F32_SCALAR)
+            k_accel_f32<F32_BLOCK, F32_IB, F32_TJ, false><<<grid, F32_BLOCK, 0, s>>>(
+                st, sc, p.i_begin, p.i_end, jsplit, p.G, p.dt, unscale, store_acc);
+        else
+            k_accel_f32<F32_BLOCK, F32_IB, F32_TJ, true><<<grid, F32_BLOCK, 0, s>>>(
+                st, sc, p.i_begin, p.i_end, jsplit, p.G, p.dt, unscale, store_acc);
+        return COSMO_LAUNCH_CHECK("k_accel_f32");
+    }
+    const int per = F64_BLOCK * F64_IB;
+    dim3 grid((rows + per - 1) / per, jsplit);
+    k_accel_f64<F64_BLOCK, F64_IB, F64_TJ><<<grid, F64_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit,
+                                                                     p.G, p.dt, store_acc);
+    return COSMO_LAUNCH_CHECK("k_accel_f64");
+}
+
+}  // namespace cosmo

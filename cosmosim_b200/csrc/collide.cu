@@ -1,0 +1,462 @@
+// Stage B (collision-pair detection) and stage C (ordered merge resolver, commit, stable
+// compaction).  Replaces pairwise_distances + collision_matrix (reference
+// cosmosim/core/universe_old.py:180,192-193), the Python merge loop (:196-210),
+// Planet.absorb/destroy (cosmosim/core/planet.py:74-91) and destroy_escaped_planets
+// (universe_old.py:78-80,349-350).
+#include <math.h>
+
+#include "cosmo_device.cuh"
+#include "cosmo_internal.h"
+
+namespace cosmo {
+
+// ---------------------------------------------------------------------------------------
+// Exact predicate of the reference on the NEW positions (sklearn euclidean_distances):
+//   XX   = fl(fl(x^2) + fl(y^2))                 (xx_new, written by stage A)
+//   dot  = fma(y_i, y_j, fl(x_i x_j))            (dgemm, K = 2)
+//   d2   = fl(fl(-2 dot + XX_i) + XX_j)          (row norm first => not symmetric in i,j)
+//   flag = max(sqrt(max(d2, 0)), 1) <= fl(r_i + r_j)
+// q = -2 p_i is exact, so fma(q_y, y_j, fl(q_x x_j)) == -2 dot bit-for-bit.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double pred_d2(double qxi, double qyi, double xxi, double xj, double yj,
+                                          double xxj) {
+    double m2dot = __fma_rn(qyi, yj, __dmul_rn(qxi, xj));
+    return __dadd_rn(__dadd_rn(m2dot, xxi), xxj);
+}
+
+__device__ __forceinline__ bool pred_exact(double d2, double ri, double rj) {
+    double d = sqrt(fmax(d2, 0.0));  // IEEE sqrt
+    d = fmax(d, 1.0);                // np.clip(d, 1, None)
+    return d <= __dadd_rn(ri, rj);
+}
+
+__device__ __forceinline__ void emit_pair(const cosmo_state &st, const cosmo_scratch &sc, int i, int j) {
+    unsigned long long idx =
+        atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_PAIRS]), 1ull);
+    if ((long long)idx < sc.pair_cap)
+        sc.pairs[idx] = ((uint64_t)(uint32_t)i << 32) | (uint32_t)j;
+    else
+        atomicOr(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_ERROR]),
+                 (unsigned long long)COSMO_ERR_PAIR_OVERFLOW);
+}
+
+// All-pairs detection: same tiling as stage A (targets in registers, sources through a
+// bulk-copy/mbarrier ring).  7 FP64-pipe instructions per ordered pair for the candidate
+// filter d2 <= (r'_i + r'_j)^2 with radii inflated by 2^-30 (a superset of the flagged
+// pairs); the rare candidates go through the exact predicate with the true radii.
+template <int BLOCK, int IB, int TJ>
+__global__ void __launch_bounds__(BLOCK)
+k_detect_allpairs(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit) {
+    __shared__ __align__(16) double2 s_xy[2][TJ];
+    __shared__ __align__(16) double s_xx[2][TJ];
+    __shared__ __align__(16) double s_r[2][TJ];
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int i_hi = min(i_end, n);
+    const int base = i_begin + blockIdx.x * (BLOCK * IB);
+    if (base >= i_hi) return;
+    const int tid = threadIdx.x;
+    const double2 *pn = reinterpret_cast<const double2 *>(sc.pos_new);
+
+    double qx[IB], qy[IB], xxi[IB], ri[IB];
+    int ii[IB];
+#pragma unroll
+    for (int k = 0; k < IB; ++k) {
+        int i = base + k * BLOCK + tid;
+        ii[k] = i < i_hi ? i : -1;
+        int ic = min(i, i_hi - 1);
+        double2 p = pn[ic];
+        qx[k] = -2.0 * p.x; qy[k] = -2.0 * p.y;
+        xxi[k] = sc.xx_new[ic];
+        ri[k] = sc.rinf[ic];
+    }
+
+    const int tiles = (n + TJ - 1) / TJ;
+    const int t0 = (int)(((long long)blockIdx.y * tiles) / jsplit);
+    const int t1 = (int)(((long long)(blockIdx.y + 1) * tiles) / jsplit);
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    constexpr uint32_t kTileBytes = TJ * (sizeof(double2) + 2 * sizeof(double));
+    auto issue = [&](int t, int b) {
+        const size_t j0 = (size_t)t * TJ;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar[b], kTileBytes);
+        bulk_g2s(&s_xy[b][0], pn + j0, TJ * sizeof(double2), &s_bar[b]);
+        bulk_g2s(&s_xx[b][0], sc.xx_new + j0, TJ * sizeof(double), &s_bar[b]);
+        bulk_g2s(&s_r[b][0], sc.rinf + j0, TJ * sizeof(double), &s_bar[b]);
+    };
+    if (tid == 0 && t0 < t1) issue(t0, 0);
+
+    for (int t = t0; t < t1; ++t) {
+        const int it = t - t0;
+        const int b = it & 1;
+        if (tid == 0 && t + 1 < t1) issue(t + 1, b ^ 1);
+        mbar_wait(&s_bar[b], (it >> 1) & 1);
+        const int j0 = t * TJ;
+        const int cnt = min(TJ, n - j0);
+#pragma unroll 4
+        for (int jj = 0; jj < cnt; ++jj) {
+            const double2 pj = s_xy[b][jj];
+            const double xxj = s_xx[b][jj];
+            const double rj = s_r[b][jj];
+#pragma unroll
+            for (int k = 0; k < IB; ++k) {
+                double d2 = pred_d2(qx[k], qy[k], xxi[k], pj.x, pj.y, xxj);
+                double rs = ri[k] + rj;
+                if (d2 <= rs * rs) {
+                    const int i = ii[k], j = j0 + jj;
+                    if (i >= 0 && i != j && pred_exact(d2, st.radius[i], st.radius[j]))
+                        emit_pair(st, sc, i, j);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Pair list utilities
+// ---------------------------------------------------------------------------------------
+__global__ void k_append_pairs(cosmo_state st, cosmo_scratch sc, const uint64_t *src,
+                               const int64_t *count_ptr) {
+    const long long cnt = *count_ptr;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < cnt;
+         k += (long long)gridDim.x * blockDim.x) {
+        uint64_t key = src[k];
+        emit_pair(st, sc, (int)(key >> 32), (int)(key & 0xffffffffu));
+    }
+}
+
+// Rank sort of the (unique) keys i<<32|j: row-major order = the order in which the
+// reference's double loop meets the flags.  O(M^2) compares spread over the grid; M is
+// normally a handful.
+__global__ void __launch_bounds__(256) k_sort_pairs(cosmo_state st, cosmo_scratch sc) {
+    __shared__ uint64_t s_keys[256];
+    long long M = st.status[COSMO_ST_N_PAIRS];
+    if (M > sc.pair_cap) M = sc.pair_cap;
+    if (M == 0) return;
+    const long long span = (long long)gridDim.x * blockDim.x;
+    const long long rounds = (M + span - 1) / span;
+    for (long long r = 0; r < rounds; ++r) {
+        const long long k = r * span + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        const uint64_t key = k < M ? sc.pairs[k] : ~0ull;
+        long long rank = 0;
+        for (long long b0 = 0; b0 < M; b0 += 256) {
+            __syncthreads();
+            s_keys[threadIdx.x] = b0 + threadIdx.x < M ? sc.pairs[b0 + threadIdx.x] : ~0ull;
+            __syncthreads();
+            const int lim = (int)min(256ll, M - b0);
+            for (int q = 0; q < lim; ++q) rank += s_keys[q] < key;
+        }
+        if (k < M) sc.pairs_sorted[rank] = key;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Ordered merge resolver.  Single thread: the reference's loop is inherently sequential
+// (live masses, stale positions) and the pair list is tiny.
+//
+// The reference walks i = 0..n-1 ("row"), first storing p_new[i], v_new[i] into planet i if
+// it is alive and mobile, then absorbing along the flagged j of that row.  Equivalent
+// lazy evaluation for the planets that occur in flagged pairs -- value of planet k when
+// row i is being processed:
+//     immobile k           : the stored (old) state, never modified
+//     k <= i (visited)     : merged value if k was modified at a row >= k, else p_new[k]
+//     k >  i (not visited) : merged value if modified at all (stale otherwise: old state)
+// A modification made before a mobile planet's own row is discarded when the row reaches
+// it (universe_old.py:199-201 overwrite) -- only mass/volume/radius/planets_eaten persist.
+// ---------------------------------------------------------------------------------------
+struct PV {
+    double2 p, v;
+};
+
+__device__ PV current_value(const cosmo_state &st, const cosmo_scratch &sc, int k, int row, int stamp) {
+    PV out;
+    const double2 *pos = reinterpret_cast<const double2 *>(st.pos);
+    const double2 *vel = reinterpret_cast<const double2 *>(st.vel);
+    if (st.flags[k] & COSMO_F_IMMOBILE) {
+        out.p = pos[k];
+        out.v = vel[k];
+        return out;
+    }
+    const bool mod = sc.mod_step[k] == stamp;
+    bool use_cur;
+    if (k <= row) use_cur = mod && sc.mod_row[k] >= k;
+    else use_cur = mod;
+    if (use_cur) {
+        out.p = reinterpret_cast<const double2 *>(sc.cur_pos)[k];
+        out.v = reinterpret_cast<const double2 *>(sc.cur_vel)[k];
+    } else if (k <= row) {
+        out.p = reinterpret_cast<const double2 *>(sc.pos_new)[k];
+        out.v = reinterpret_cast<const double2 *>(sc.vel_new)[k];
+    } else {
+        out.p = pos[k];
+        out.v = vel[k];
+    }
+    return out;
+}
+
+__device__ __forceinline__ double merge1(double ma, double a, double mo, double o, double msum) {
+    // ((m_s * x_s) + (m_o * x_o)) / (m_s + m_o), numpy elementwise, no contraction
+    return __ddiv_rn(__dadd_rn(__dmul_rn(ma, a), __dmul_rn(mo, o)), msum);
+}
+
+__global__ void k_resolve(cosmo_state st, cosmo_scratch sc) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    long long M = st.status[COSMO_ST_N_PAIRS];
+    if (M > sc.pair_cap) M = sc.pair_cap;
+    if (M == 0) return;
+    const int stamp = (int)st.status[COSMO_ST_STEP];
+    long long nev = st.status[COSMO_ST_N_EVENTS];
+    double2 *cur_pos = reinterpret_cast<double2 *>(sc.cur_pos);
+    double2 *cur_vel = reinterpret_cast<double2 *>(sc.cur_vel);
+    for (long long q = 0; q < M; ++q) {
+        const uint64_t key = sc.pairs_sorted[q];
+        const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
+        if (!sc.alive[i] || !sc.alive[j]) continue;  // absorb() guard, planet.py:75
+        const bool i_int = st.flags[i] & COSMO_F_MASS_INT, j_int = st.flags[j] & COSMO_F_MASS_INT;
+        const u128 mi = (((u128)st.mass_hi[i]) << 64) | st.mass_lo[i];
+        const u128 mj = (((u128)st.mass_hi[j]) << 64) | st.mass_lo[j];
+        // universe_old.py:206: `planet.mass >= other_planet.mass` -- row planet wins ties
+        const bool i_wins = mass_ge(i_int, mi, st.mass[i], j_int, mj, st.mass[j]);
+        const int W = i_wins ? i : j, L = i_wins ? j : i;
+        const double mW = st.mass[W], mL = st.mass[L];
+        double msum;
+        const bool both_int = i_int && j_int;
+        u128 isum = 0;
+        if (both_int) {
+            isum = mi + mj;
+            msum = u128_to_double(isum);
+        } else {
+            msum = __dadd_rn(mW, mL);
+        }
+        if (!(st.flags[W] & COSMO_F_IMMOBILE)) {  // planet.py:76-79
+            PV w = current_value(st, sc, W, i, stamp);
+            PV l = current_value(st, sc, L, i, stamp);
+            cur_pos[W] = make_double2(merge1(mW, w.p.x, mL, l.p.x, msum), merge1(mW, w.p.y, mL, l.p.y, msum));
+            cur_vel[W] = make_double2(merge1(mW, w.v.x, mL, l.v.x, msum), merge1(mW, w.v.y, mL, l.v.y, msum));
+            sc.mod_row[W] = i;
+            sc.mod_step[W] = stamp;
+        }
+        st.mass[W] = msum;  // planet.py:80
+        if (both_int) {
+            st.mass_hi[W] = (uint64_t)(isum >> 64);
+            st.mass_lo[W] = (uint64_t)isum;
+        } else {
+            st.flags[W] &= ~COSMO_F_MASS_INT;
+        }
+        const double vol = __dadd_rn(st.volume[W], st.volume[L]);  // planet.py:81
+        st.volume[W] = vol;
+        st.radius[W] = pow_third(__ddiv_rn(__dmul_rn(3.0, vol), 4.0 * 3.141592653589793));  // :82
+        st.eaten[W] += 1 + st.eaten[L];  // planet.py:84
+        sc.alive[L] = 0;                 // planet.py:83,86-91
+        if (nev < st.event_cap) {
+            st.events[3 * nev + 0] = stamp;
+            st.events[3 * nev + 1] = st.id[W];
+            st.events[3 * nev + 2] = st.id[L];
+        } else {
+            st.status[COSMO_ST_ERROR] |= COSMO_ERR_EVENT_OVERFLOW;
+        }
+        ++nev;
+    }
+    st.status[COSMO_ST_N_EVENTS] = nev;
+}
+
+// ---------------------------------------------------------------------------------------
+// Commit + stable compaction.  1024 slots per CTA (256 threads x 4 consecutive... slots
+// are taken strided so loads coalesce).
+// ---------------------------------------------------------------------------------------
+constexpr int CHUNK = 1024;
+
+__global__ void __launch_bounds__(256) k_commit(cosmo_state st, cosmo_scratch sc, int bounded) {
+    __shared__ int s_cnt[8];
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int c0 = blockIdx.x * CHUNK;
+    if (c0 >= n) return;
+    const int stamp = (int)st.status[COSMO_ST_STEP];
+    double2 *pos = reinterpret_cast<double2 *>(st.pos);
+    double2 *vel = reinterpret_cast<double2 *>(st.vel);
+    int survivors = 0, escaped_now = 0;
+    for (int q = 0; q < CHUNK / 256; ++q) {
+        const int k = c0 + q * 256 + threadIdx.x;
+        if (k >= n) break;
+        const bool alive = sc.alive[k] != 0;
+        const uint8_t fl = st.flags[k];
+        if (alive && !(fl & COSMO_F_IMMOBILE)) {
+            const bool use_cur = sc.mod_step[k] == stamp && sc.mod_row[k] >= k;
+            pos[k] = use_cur ? reinterpret_cast<const double2 *>(sc.cur_pos)[k]
+                             : reinterpret_cast<const double2 *>(sc.pos_new)[k];
+            vel[k] = use_cur ? reinterpret_cast<const double2 *>(sc.cur_vel)[k]
+                             : reinterpret_cast<const double2 *>(sc.vel_new)[k];
+        }
+        const bool esc = bounded && sc.escaped[k];  // flagged BEFORE interact, universe_old.py:345-350
+        const bool live = alive && !esc;
+        if (alive && esc) ++escaped_now;
+        if (!live) {
+            const int id = st.id[k];
+            st.rec_mass[id] = st.mass[k];
+            st.rec_mass_hi[id] = st.mass_hi[k];
+            st.rec_mass_lo[id] = st.mass_lo[k];
+            st.rec_radius[id] = st.radius[k];
+            st.rec_volume[id] = st.volume[k];
+            st.rec_eaten[id] = st.eaten[k];
+            st.rec_flags[id] = fl;
+            st.rec_death[id] = stamp;
+        }
+        sc.alive[k] = live ? 1 : 0;
+        survivors += live;
+    }
+    // block reduction of the survivor / escape counts
+    int packed = survivors | (escaped_now << 16);
+    for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xffffffffu, packed, o);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = packed;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) tot += s_cnt[w];
+        const int surv = tot & 0xffff, esc = tot >> 16;
+        sc.chunk_alive[blockIdx.x] = surv;
+        const int len = min(CHUNK, n - c0);
+        if (len != surv)
+            atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_DEAD]),
+                      (unsigned long long)(len - surv));
+        if (esc)
+            atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_ESCAPED]),
+                      (unsigned long long)esc);
+    }
+}
+
+// survivors of chunk c move to [sum(chunk_alive[0..c)) + rank within chunk): stable.
+__global__ void __launch_bounds__(256) k_compact_scatter(cosmo_state st, cosmo_scratch sc) {
+    if (st.status[COSMO_ST_N_DEAD] == 0) return;
+    __shared__ int s_red[8];
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int c0 = blockIdx.x * CHUNK;
+    if (c0 >= n) return;
+    // exclusive prefix of the chunk counts (redundant per CTA; chunk counts are few)
+    int part = 0;
+    for (int c = threadIdx.x; c < (int)blockIdx.x; c += 256) part += sc.chunk_alive[c];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        s_base = t;
+    }
+    __syncthreads();
+    int running = s_base;
+    const double2 *pos = reinterpret_cast<const double2 *>(st.pos);
+    const double2 *vel = reinterpret_cast<const double2 *>(st.vel);
+    for (int q = 0; q < CHUNK / 256; ++q) {
+        const int k = c0 + q * 256 + threadIdx.x;
+        const int live = (k < n && sc.alive[k]) ? 1 : 0;
+        // block-wide exclusive scan of `live` over 256 threads
+        const unsigned ballot = __ballot_sync(0xffffffffu, live);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const int in_warp = __popc(ballot & ((1u << lane) - 1));
+        __syncthreads();
+        if (lane == 0) s_warp[w] = __popc(ballot);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int x = 0; x < 8; ++x) {
+            const int c = s_warp[x];
+            before += x < w ? c : 0;
+            total += c;
+        }
+        if (live) {
+            const int d = running + before + in_warp;
+            reinterpret_cast<double2 *>(sc.t_pos)[d] = pos[k];
+            reinterpret_cast<double2 *>(sc.t_vel)[d] = vel[k];
+            sc.t_mass[d] = st.mass[k];
+            sc.t_mass_hi[d] = st.mass_hi[k];
+            sc.t_mass_lo[d] = st.mass_lo[k];
+            sc.t_radius[d] = st.radius[k];
+            sc.t_volume[d] = st.volume[k];
+            sc.t_eaten[d] = st.eaten[k];
+            sc.t_id[d] = st.id[k];
+            sc.t_flags[d] = st.flags[k];
+        }
+        running += total;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_compact_copyback(cosmo_state st, cosmo_scratch sc) {
+    const long long dead = st.status[COSMO_ST_N_DEAD];
+    if (dead == 0) return;
+    const int n_new = (int)(st.status[COSMO_ST_N_ACTIVE] - dead);
+    double2 *pos = reinterpret_cast<double2 *>(st.pos);
+    double2 *vel = reinterpret_cast<double2 *>(st.vel);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_new; k += gridDim.x * blockDim.x) {
+        pos[k] = reinterpret_cast<const double2 *>(sc.t_pos)[k];
+        vel[k] = reinterpret_cast<const double2 *>(sc.t_vel)[k];
+        st.mass[k] = sc.t_mass[k];
+        st.mass_hi[k] = sc.t_mass_hi[k];
+        st.mass_lo[k] = sc.t_mass_lo[k];
+        st.radius[k] = sc.t_radius[k];
+        st.volume[k] = sc.t_volume[k];
+        st.eaten[k] = sc.t_eaten[k];
+        st.id[k] = sc.t_id[k];
+        st.flags[k] = sc.t_flags[k];
+    }
+}
+
+__global__ void k_end_frame(cosmo_state st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        st.status[COSMO_ST_N_ACTIVE] -= st.status[COSMO_ST_N_DEAD];
+        st.status[COSMO_ST_STEP] += 1;  // universe_old.py:361
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+constexpr int DET_BLOCK = 128, DET_IB = 2, DET_TJ = 256;
+
+int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                  cudaStream_t s) {
+    if (!(p.opts & COSMO_OPT_COLLISIONS)) return COSMO_OK;
+    const int rows = p.i_end - p.i_begin;
+    if (rows <= 0) return COSMO_OK;
+    int jsplit = p.jsplit < 1 ? 1 : p.jsplit;
+    const int per = DET_BLOCK * DET_IB;
+    dim3 grid((rows + per - 1) / per, jsplit);
+    k_detect_allpairs<DET_BLOCK, DET_IB, DET_TJ><<<grid, DET_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit);
+    return COSMO_LAUNCH_CHECK("k_detect_allpairs");
+}
+
+int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const uint64_t *src,
+                        const int64_t *count_ptr, cudaStream_t s) {
+    k_append_pairs<<<32, 256, 0, s>>>(st, sc, src, count_ptr);
+    return COSMO_LAUNCH_CHECK("k_append_pairs");
+}
+
+int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                          cudaStream_t s) {
+    const int chunks = (p.n_upper + CHUNK - 1) / CHUNK > 0 ? (p.n_upper + CHUNK - 1) / CHUNK : 1;
+    if (p.opts & COSMO_OPT_COLLISIONS) {
+        k_sort_pairs<<<64, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_sort_pairs"));
+        k_resolve<<<1, 32, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_resolve"));
+    }
+    k_commit<<<chunks, 256, 0, s>>>(st, sc, (p.opts & COSMO_OPT_BOUNDED) ? 1 : 0);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k_commit"));
+    k_compact_scatter<<<chunks, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k_compact_scatter"));
+    int cb = chunks * 4;
+    if (cb > 148 * 8) cb = 148 * 8;
+    k_compact_copyback<<<cb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k_compact_copyback"));
+    k_end_frame<<<1, 32, 0, s>>>(st);
+    return COSMO_LAUNCH_CHECK("k_end_frame");
+}
+
+}  // namespace cosmo

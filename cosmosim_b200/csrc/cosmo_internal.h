@@ -1,0 +1,39 @@
+// Internal declarations shared by the translation units of libcosmosim_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cosmosim_b200.h"
+
+namespace cosmo {
+
+// error plumbing (abi.cu)
+void set_error(const char *fmt, ...);
+int check_cuda(cudaError_t e, const char *what);
+
+#define COSMO_TRY(expr)                                  \
+    do {                                                 \
+        int _rc = (expr);                                \
+        if (_rc != COSMO_OK) return _rc;                 \
+    } while (0)
+#define COSMO_LAUNCH_CHECK(what) ::cosmo::check_cuda(cudaGetLastError(), what)
+
+// accel.cu
+int launch_prep(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                cudaStream_t s);
+int launch_accel(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                 cudaStream_t s);
+
+// collide.cu
+int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                  cudaStream_t s);
+int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc,
+                          const cosmo_step_params &p, cudaStream_t s);
+int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const uint64_t *src,
+                        const int64_t *count_ptr, cudaStream_t s);
+
+// microbench.cu
+int launch_microbench(int kind, int blocks, int threads, int iters, double *out,
+                      int64_t *ops_per_thread, cudaStream_t s);
+
+}  // namespace cosmo

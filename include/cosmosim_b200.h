@@ -1,0 +1,253 @@
+/*
+ * cosmosim_b200.h -- C ABI of the B200-native per-timestep physics update of cosmosim.
+ *
+ * The reference has no FFI: its seam is two Python call sites inside
+ * Universe.interact() (reference cosmosim/core/universe_old.py:166-212):
+ *     acc_blas(p0, m, G)                  universe_old.py:174  (cosmosim/util/blas.py:4-41)
+ *     pairwise_distances(p, n_jobs=-1)    universe_old.py:180
+ * plus the numpy integrator (:177-178) and the Python merge loop (:196-210) with
+ * Planet.absorb/destroy (cosmosim/core/planet.py:74-91).  Each entry point below names
+ * the reference lines it replaces.  INTEGRATION.md shows the ctypes stub a maintainer of
+ * the reference would add at those call sites.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every array argument is a DEVICE pointer owned by
+ *     the caller (the Python host keeps them alive as torch tensors) unless the name ends
+ *     in _host; `stream` is a cudaStream_t passed as void*;
+ *   - every function returns 0 on success, a negative COSMO_E_* code otherwise, never
+ *     throws and never allocates device memory; cosmo_last_error() returns a
+ *     thread-local description of the last failure;
+ *   - launches are asynchronous on `stream`; nothing synchronises unless documented.
+ *
+ * Data layout in HBM (SoA, one slot per ACTIVE planet, slots ordered by insertion order of
+ * the planets that are still alive -- the order of Universe.active_planets,
+ * universe_old.py:63-64,83):
+ *     pos, vel            double[cap][2]   (16-byte aligned, loaded as double2)
+ *     mass                double[cap]      float(mass)
+ *     mass_hi, mass_lo    uint64[cap]      128-bit integer mass when COSMO_F_MASS_INT
+ *     radius, volume      double[cap]
+ *     eaten               int64[cap]       Planet.planets_eaten
+ *     id                  int32[cap]       insertion index in Universe.planets
+ *     flags               uint8[cap]       COSMO_F_* bits
+ * `cap` must be a multiple of COSMO_PAD and all arrays hold `cap` elements.
+ */
+#ifndef COSMOSIM_B200_H
+#define COSMOSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COSMO_ABI_VERSION 1
+#define COSMO_PAD 512 /* slot capacity granularity (tile size of the all-pairs kernels) */
+
+/* error codes */
+#define COSMO_OK 0
+#define COSMO_E_ARG (-1)       /* bad argument */
+#define COSMO_E_CUDA (-2)      /* a CUDA runtime call failed, see cosmo_last_error() */
+#define COSMO_E_NO_DEVICE (-3) /* no sm_100 device */
+
+/* per-planet flag bits */
+#define COSMO_F_IMMOBILE 1u /* Planet.immobile (planet.py:32) */
+#define COSMO_F_MASS_INT 2u /* mass is a Python int held exactly in mass_hi:mass_lo */
+
+/* step option bits */
+#define COSMO_OPT_COLLISIONS 1u  /* simulate(collisions=True), universe_old.py:191,202 */
+#define COSMO_OPT_BOUNDED 2u     /* Universe(bounded=True), universe_old.py:349 */
+#define COSMO_OPT_FP32 4u        /* FP32 fast path for the all-pairs sum (state stays FP64) */
+#define COSMO_OPT_STORE_ACC 8u   /* also write the accelerations to scratch.acc */
+#define COSMO_OPT_F32_SCALAR 16u /* FP32 path: scalar FFMA inner loop instead of packed f32x2 */
+
+/* indices into the device-side int64 status block (cosmo_state.status, COSMO_STATUS_LEN) */
+#define COSMO_ST_N_ACTIVE 0    /* active planets = slots [0, n) */
+#define COSMO_ST_STEP 1        /* frames executed (Universe.iterations, universe_old.py:361) */
+#define COSMO_ST_N_EVENTS 2    /* merge events logged so far (cumulative) */
+#define COSMO_ST_N_PAIRS 3     /* flagged ordered pairs of the last frame */
+#define COSMO_ST_N_DEAD 4      /* planets that died in the last frame (absorbed + escaped) */
+#define COSMO_ST_ERROR 5       /* sticky COSMO_ERR_* bits */
+#define COSMO_ST_N_ESCAPED 6   /* escaped planets destroyed so far (cumulative) */
+#define COSMO_ST_N_CAND 7      /* broad-phase candidates of the last frame (diagnostic) */
+#define COSMO_STATUS_LEN 16
+
+#define COSMO_ERR_PAIR_OVERFLOW 1  /* more flagged pairs than pair_cap */
+#define COSMO_ERR_EVENT_OVERFLOW 2 /* event log full */
+#define COSMO_ERR_NAN 4            /* non-finite d^2 met in the acceleration pass */
+
+/* Persistent state.  All pointers are device pointers. */
+typedef struct cosmo_state {
+    int32_t cap;      /* slots allocated (multiple of COSMO_PAD) */
+    int32_t n_total;  /* planets ever inserted = length of the rec_* arrays */
+    double *pos;      /* [cap][2] */
+    double *vel;      /* [cap][2] */
+    double *mass;     /* [cap] */
+    uint64_t *mass_hi;
+    uint64_t *mass_lo;
+    double *radius;
+    double *volume;
+    int64_t *eaten;
+    int32_t *id;
+    uint8_t *flags;
+    int64_t *status;  /* [COSMO_STATUS_LEN] */
+    /* records of dead planets, indexed by insertion id (Planet keeps mass/radius after
+       destroy(), planet.py:86-91) */
+    double *rec_mass;      /* [n_total] */
+    uint64_t *rec_mass_hi; /* [n_total] */
+    uint64_t *rec_mass_lo; /* [n_total] */
+    double *rec_radius;    /* [n_total] */
+    double *rec_volume;    /* [n_total] */
+    int64_t *rec_eaten;    /* [n_total] */
+    int32_t *rec_death;    /* [n_total] frame of death, -1 while alive */
+    uint8_t *rec_flags;    /* [n_total] */
+    /* merge stream: (frame, absorber id, absorbed id) triples in visitation order */
+    int64_t *events; /* [event_cap][3] */
+    int64_t event_cap;
+} cosmo_state;
+
+/* Per-step scratch (device).  Contents are undefined between calls except where noted. */
+typedef struct cosmo_scratch {
+    double *h;         /* [cap]      half diagonal of the d^2 chain */
+    float *pk_x;       /* [cap]      FP32 j-stage (scaled x, y, mass) */
+    float *pk_y;       /* [cap] */
+    float *pk_m;       /* [cap] */
+    double *acc;       /* [cap][2]   accelerations of the last frame (COSMO_OPT_STORE_ACC) */
+    double *pos_new;   /* [cap][2]   integrated positions of ALL active planets (A2) */
+    double *vel_new;   /* [cap][2] */
+    double *xx_new;    /* [cap]      squared row norms of pos_new (A3) */
+    double *rinf;      /* [cap]      radii inflated by 2^-30 (candidate filter of stage B) */
+    double *partial;   /* [jsplit_max][cap][2] partial sums of the all-pairs pass */
+    int32_t jsplit_max;
+    int32_t *tile_ctr; /* [cap / COSMO_PAD * 4 + 4] arrival counters, must start zeroed */
+    uint8_t *alive;    /* [cap]      1 while the slot's planet is alive in this frame */
+    uint8_t *escaped;  /* [cap]      start-of-frame escape flags (A6) */
+    uint64_t *pairs;   /* [pair_cap] flagged ordered pairs (i << 32 | j), unsorted */
+    uint64_t *pairs_sorted; /* [pair_cap] */
+    int64_t pair_cap;
+    double *cur_pos;   /* [cap][2]   resolver: merged position/velocity of touched planets */
+    double *cur_vel;   /* [cap][2] */
+    int32_t *mod_row;  /* [cap]      resolver: row of last modification */
+    int32_t *mod_step; /* [cap]      resolver: frame stamp of mod_row, must start at -1 */
+    int32_t *chunk_alive; /* [cap / 1024 + 1] survivors per 1024-slot chunk */
+    /* compaction staging: one array per persistent field */
+    double *t_pos; double *t_vel; double *t_mass; uint64_t *t_mass_hi; uint64_t *t_mass_lo;
+    double *t_radius; double *t_volume; int64_t *t_eaten; int32_t *t_id; uint8_t *t_flags;
+    /* broad phase (uniform grid) */
+    int32_t *cell_of;    /* [cap] */
+    int32_t *cell_count; /* [grid_cells + 1] */
+    int32_t *cell_start; /* [grid_cells + 1] */
+    int32_t *cell_items; /* [cap] */
+    int32_t *giants;     /* [giant_cap] */
+    int32_t grid_cells;  /* capacity of the cell arrays */
+    int32_t giant_cap;
+} cosmo_scratch;
+
+/* Parameters of one frame. */
+typedef struct cosmo_step_params {
+    double G;        /* Universe.G (universe_old.py:24-25) */
+    double dt;       /* Universe.dt = speed/fps (universe_old.py:318-319) */
+    double r_max;    /* Universe.r_max */
+    uint32_t opts;   /* COSMO_OPT_* */
+    int32_t n_upper; /* host-side upper bound of the active count (sizes the grids) */
+    int32_t i_begin; /* target-row shard [i_begin, i_end) of this rank; 0, n_upper if single */
+    int32_t i_end;
+    int32_t pos_exp;  /* FP32 path: positions are scaled by 2^-pos_exp, masses by 2^-mass_exp */
+    int32_t mass_exp;
+    int32_t jsplit;   /* source-range splits of the all-pairs pass (>=1, <= jsplit_max) */
+    int32_t detect_mode; /* 0 = all-pairs predicate, 1 = uniform-grid broad phase */
+    double cell_size;    /* detect_mode 1 */
+    double grid_origin;  /* detect_mode 1: grid covers [origin, origin + cells_per_side*cell_size)^2 */
+    int32_t cells_per_side;
+    int32_t reserved;
+    double giant_radius; /* detect_mode 1: planets with radius above this are brute-forced */
+} cosmo_step_params;
+
+int cosmo_abi_version(void);
+const char *cosmo_last_error(void);
+/* Number of SMs / compute capability of the current device (host query). */
+int cosmo_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/*
+ * Stage A -- replaces acc_blas (blas.py:4-41; call site universe_old.py:174) and the
+ * integrator (universe_old.py:177-178).  Reads state.{pos,vel,mass,flags} of slots
+ * [0, n) as sources and integrates target rows [i_begin, i_end):
+ *     scratch.pos_new/vel_new/xx_new[i] (and scratch.acc[i] with COSMO_OPT_STORE_ACC).
+ * Also evaluates the start-of-frame escape flags (universe_old.py:75-76) and resets
+ * scratch.alive.  FP64 path reproduces the reference's rounding sequence of d^2.
+ */
+int cosmo_accel_integrate(const cosmo_state *st, const cosmo_scratch *sc,
+                          const cosmo_step_params *p, void *stream);
+
+/*
+ * Stage B -- replaces pairwise_distances + the collision matrix (universe_old.py:180,
+ * 192-193): appends every flagged ordered pair (i, j), i in [i_begin, i_end), j in [0, n),
+ * i != j, to scratch.pairs and counts them in status[COSMO_ST_N_PAIRS] (which the caller
+ * resets through cosmo_begin_frame).  Needs pos_new/xx_new of ALL slots (all-gathered by
+ * the caller when sharded).
+ */
+int cosmo_detect_pairs(const cosmo_state *st, const cosmo_scratch *sc,
+                       const cosmo_step_params *p, void *stream);
+
+/*
+ * Stage C -- replaces the ordered merge loop (universe_old.py:196-210) and
+ * Planet.absorb/destroy (planet.py:74-91): sorts the flagged pairs row-major, replays the
+ * reference's visitation order, logs (frame, absorber id, absorbed id), commits positions
+ * and velocities, destroys escaped planets when bounded (universe_old.py:349-350), then
+ * stably compacts the survivors and bumps status[COSMO_ST_STEP].
+ */
+int cosmo_resolve_commit(const cosmo_state *st, const cosmo_scratch *sc,
+                         const cosmo_step_params *p, void *stream);
+
+/* Zeroes the per-frame counters (N_PAIRS, N_DEAD, N_CAND).  First launch of a frame. */
+int cosmo_begin_frame(const cosmo_state *st, const cosmo_scratch *sc,
+                      const cosmo_step_params *p, void *stream);
+
+/* Suggested source-range split for `rows` target rows against n sources on this device. */
+int cosmo_suggest_jsplit(int32_t rows, int32_t n, int fp32, int32_t jsplit_max);
+
+/* Convenience: begin_frame + A + B + C on one device (no sharding). */
+int cosmo_step(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p,
+               void *stream);
+
+/* Appends `count_ptr[0]` pairs from `src` (another rank's list) to scratch.pairs. */
+int cosmo_append_pairs(const cosmo_state *st, const cosmo_scratch *sc, const uint64_t *src,
+                       const int64_t *count_ptr, void *stream);
+
+/*
+ * Function-level seam for callers that only want the reference's acc_blas replaced:
+ * accelerations [n][2] from positions [n][2] and masses [n] (device pointers), FP64 parity
+ * path or FP32 fast path (fp32 != 0; pos_exp/mass_exp as above).  workspace: at least
+ * cosmo_accel_workspace_bytes(n) bytes of device memory, zero-initialised once.
+ */
+int64_t cosmo_accel_workspace_bytes(int32_t n);
+int cosmo_accel(const double *pos, const double *mass, int32_t n, double G, int fp32,
+                int32_t pos_exp, int32_t mass_exp, double *acc_out, void *workspace,
+                void *stream);
+
+/* Host-buffer variant (the e2e call): copies pos/mass in, runs cosmo_accel, copies acc out
+   and synchronises the stream.  *_host pointers are host memory (pinned for full speed). */
+int cosmo_accel_host(const double *pos_host, const double *mass_host, int32_t n, double G,
+                     int fp32, int32_t pos_exp, int32_t mass_exp, double *acc_out_host,
+                     void *dev_workspace, int64_t dev_workspace_bytes, void *stream);
+
+/*
+ * Pipe micro-benchmarks (the roofline denominators must be measured).
+ * kind: 0 FFMA, 1 FFMA2 (fma.rn.f32x2), 2 DFMA, 3 MUFU.RSQ, 4 DADD, 5 DMUL, 6 FMUL, 7 FADD.
+ * Runs `iters` iterations of 8 independent chains per thread on `blocks` x `threads`;
+ * out (device, >= blocks*threads doubles) receives a value so nothing is optimised away.
+ * ops_per_thread receives the instruction count per thread.
+ */
+int cosmo_microbench(int kind, int blocks, int threads, int iters, double *out,
+                     int64_t *ops_per_thread, void *stream);
+
+/* Host-side copies of the resolver's exact scalar helpers (no GPU needed): float(int) with
+   round-half-even, Python's exact int/float `>=`, and pow(x, 1/3) as planet.py:82 rounds it. */
+double cosmo_host_pow_third(double x);
+double cosmo_host_u128_to_double(uint64_t hi, uint64_t lo);
+int cosmo_host_mass_ge(int a_int, uint64_t a_hi, uint64_t a_lo, double a_f, int b_int, uint64_t b_hi,
+                       uint64_t b_lo, double b_f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSMOSIM_B200_H */
