@@ -1,0 +1,113 @@
+"""ctypes binding of include/cosmosim_b200.h.  No fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+ABI_VERSION = 1
+PAD = 512
+STATUS_LEN = 16
+
+# flag / option / status constants (mirror the header)
+F_IMMOBILE, F_MASS_INT = 1, 2
+OPT_COLLISIONS, OPT_BOUNDED, OPT_FP32, OPT_STORE_ACC, OPT_F32_SCALAR = 1, 2, 4, 8, 16
+ST_N_ACTIVE, ST_STEP, ST_N_EVENTS, ST_N_PAIRS, ST_N_DEAD, ST_ERROR, ST_N_ESCAPED, ST_N_CAND = range(8)
+ERR_PAIR_OVERFLOW, ERR_EVENT_OVERFLOW, ERR_NAN = 1, 2, 4
+
+_vp = C.c_void_p
+
+
+class State(C.Structure):
+    _fields_ = [("cap", C.c_int32), ("n_total", C.c_int32),
+                ("pos", _vp), ("vel", _vp), ("mass", _vp), ("mass_hi", _vp), ("mass_lo", _vp),
+                ("radius", _vp), ("volume", _vp), ("eaten", _vp), ("id", _vp), ("flags", _vp),
+                ("status", _vp),
+                ("rec_mass", _vp), ("rec_mass_hi", _vp), ("rec_mass_lo", _vp), ("rec_radius", _vp),
+                ("rec_volume", _vp), ("rec_eaten", _vp), ("rec_death", _vp), ("rec_flags", _vp),
+                ("events", _vp), ("event_cap", C.c_int64)]
+
+
+class Scratch(C.Structure):
+    _fields_ = [("h", _vp), ("pk_x", _vp), ("pk_y", _vp), ("pk_m", _vp), ("acc", _vp),
+                ("pos_new", _vp), ("vel_new", _vp), ("xx_new", _vp), ("rinf", _vp),
+                ("partial", _vp), ("jsplit_max", C.c_int32), ("tile_ctr", _vp),
+                ("alive", _vp), ("escaped", _vp), ("pairs", _vp), ("pairs_sorted", _vp),
+                ("pair_cap", C.c_int64), ("cur_pos", _vp), ("cur_vel", _vp), ("mod_row", _vp),
+                ("mod_step", _vp), ("chunk_alive", _vp),
+                ("t_pos", _vp), ("t_vel", _vp), ("t_mass", _vp), ("t_mass_hi", _vp),
+                ("t_mass_lo", _vp), ("t_radius", _vp), ("t_volume", _vp), ("t_eaten", _vp),
+                ("t_id", _vp), ("t_flags", _vp),
+                ("cell_of", _vp), ("cell_count", _vp), ("cell_start", _vp), ("cell_items", _vp),
+                ("giants", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32)]
+
+
+class StepParams(C.Structure):
+    _fields_ = [("G", C.c_double), ("dt", C.c_double), ("r_max", C.c_double),
+                ("opts", C.c_uint32), ("n_upper", C.c_int32), ("i_begin", C.c_int32),
+                ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
+                ("jsplit", C.c_int32), ("detect_mode", C.c_int32), ("cell_size", C.c_double),
+                ("grid_origin", C.c_double), ("cells_per_side", C.c_int32), ("reserved", C.c_int32),
+                ("giant_radius", C.c_double)]
+
+
+# name -> (restype, argtypes); every symbol include/cosmosim_b200.h declares
+SYMBOLS = {
+    "cosmo_abi_version": (C.c_int, []),
+    "cosmo_last_error": (C.c_char_p, []),
+    "cosmo_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "cosmo_suggest_jsplit": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int32]),
+    "cosmo_begin_frame": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
+    "cosmo_accel_integrate": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
+    "cosmo_detect_pairs": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
+    "cosmo_resolve_commit": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
+    "cosmo_step": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
+    "cosmo_append_pairs": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), _vp, _vp, _vp]),
+    "cosmo_accel_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "cosmo_accel": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp, _vp, _vp]),
+    "cosmo_accel_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp,
+                                   _vp, C.c_int64, _vp]),
+    "cosmo_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_int64), _vp]),
+    "cosmo_host_pow_third": (C.c_double, [C.c_double]),
+    "cosmo_host_u128_to_double": (C.c_double, [C.c_uint64, C.c_uint64]),
+    "cosmo_host_mass_ge": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_double,
+                                     C.c_int, C.c_uint64, C.c_uint64, C.c_double]),
+}
+
+_lib = None
+
+
+class CosmoError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libcosmosim_b200.so (building it in-tree if the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if _build.is_stale():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box and no prebuilt library
+            if not os.path.exists(path):
+                raise CosmoError(
+                    "libcosmosim_b200.so is missing and cannot be built (%s); there is no "
+                    "CPU or PyTorch fallback for the physics update" % e)
+    L = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(L, name)  # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if L.cosmo_abi_version() != ABI_VERSION:
+        raise CosmoError("ABI version mismatch: library %d, binding %d" % (L.cosmo_abi_version(), ABI_VERSION))
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().cosmo_last_error().decode("utf-8", "replace")
+        raise CosmoError("%s failed (%d): %s" % (what or "cosmosim_b200 call", rc, msg))

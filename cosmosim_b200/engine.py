@@ -1,0 +1,263 @@
+"""Device-resident SoA planet state and the per-frame launch sequence.
+
+PyTorch is used for exactly two things here: owning the device buffers (torch tensors whose
+``data_ptr()`` goes through the C ABI) and, in the sharded mode, ``torch.distributed``
+collectives.  All arithmetic happens in libcosmosim_b200.so.
+
+Replaces the body of ``Universe.interact`` (reference cosmosim/core/universe_old.py:166-212):
+the reference rebuilds numpy arrays from its Planet list every frame (:170-172,192); here the
+SoA buffers are the source of truth while stepping and the Planet objects are refreshed
+lazily.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import (F_IMMOBILE, F_MASS_INT, OPT_BOUNDED, OPT_COLLISIONS, OPT_F32_SCALAR, OPT_FP32,
+                   OPT_STORE_ACC, PAD, ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_ESCAPED, ST_N_EVENTS,
+                   ST_N_PAIRS, ST_STEP, STATUS_LEN)
+
+_MASK64 = (1 << 64) - 1
+MAX_INT_MASS = 1 << 127
+
+
+def split_mass(mass):
+    """Python mass -> (float(mass), is_int, hi, lo) following Python numeric semantics."""
+    if isinstance(mass, (int, np.integer)) and not isinstance(mass, (bool, np.bool_)):
+        m = int(mass)
+        if 0 <= m < MAX_INT_MASS:
+            return float(m), True, (m >> 64) & _MASK64, m & _MASK64
+        return float(m), False, 0, 0
+    return float(mass), False, 0, 0
+
+
+def _round_up(n, q):
+    return (int(n) + q - 1) // q * q
+
+
+class Engine:
+    """One GPU's replica of the world (optionally responsible for a shard of target rows)."""
+
+    JSPLIT_MAX = 16
+
+    def __init__(self, n_total, device=None, pair_cap=None, event_cap=None, group=None):
+        if not torch.cuda.is_available():
+            raise _abi.CosmoError("cosmosim_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _abi.lib()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.cosmo_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), "cosmo_device_info")
+        self.sm_count = sm.value
+        self.n_total = int(n_total)
+        self.cap = max(PAD, _round_up(self.n_total, PAD))
+        self.pair_cap = int(pair_cap or max(1 << 16, 4 * self.cap))
+        self.event_cap = int(event_cap or max(1 << 16, 2 * self.n_total))
+        self.group = group
+        self.rank, self.world = 0, 1
+        if group is not None:
+            import torch.distributed as dist
+            from . import sharded
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+            self.cap = sharded.required_capacity(self.n_total, self.world)
+        self._alloc()
+        self.n_upper = 0
+        self.pos_exp = 0
+        self.mass_exp = 0
+        self.frames = 0
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self):
+        dev, cap, nt = self.device, self.cap, max(1, self.n_total)
+        f64, i64, i32, u8, f32 = torch.float64, torch.int64, torch.int32, torch.uint8, torch.float32
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+        self.t = t = {}
+        # persistent state
+        t["pos"] = z(cap, 2, dtype=f64); t["vel"] = z(cap, 2, dtype=f64)
+        t["mass"] = z(cap, dtype=f64); t["mass_hi"] = z(cap, dtype=i64); t["mass_lo"] = z(cap, dtype=i64)
+        t["radius"] = z(cap, dtype=f64); t["volume"] = z(cap, dtype=f64)
+        t["eaten"] = z(cap, dtype=i64); t["id"] = z(cap, dtype=i32); t["flags"] = z(cap, dtype=u8)
+        t["status"] = z(STATUS_LEN, dtype=i64)
+        t["rec_mass"] = z(nt, dtype=f64); t["rec_mass_hi"] = z(nt, dtype=i64); t["rec_mass_lo"] = z(nt, dtype=i64)
+        t["rec_radius"] = z(nt, dtype=f64); t["rec_volume"] = z(nt, dtype=f64); t["rec_eaten"] = z(nt, dtype=i64)
+        t["rec_death"] = torch.full((nt,), -1, dtype=i32, device=dev); t["rec_flags"] = z(nt, dtype=u8)
+        t["events"] = z(self.event_cap, 3, dtype=i64)
+        # scratch
+        t["h"] = z(cap, dtype=f64)
+        t["pk_x"] = z(cap, dtype=f32); t["pk_y"] = z(cap, dtype=f32); t["pk_m"] = z(cap, dtype=f32)
+        t["acc"] = z(cap, 2, dtype=f64)
+        # pos_new | vel_new | xx_new live in one allocation so the sharded mode gathers once
+        t["new"] = z(cap, 5, dtype=f64)
+        t["rinf"] = z(cap, dtype=f64)
+        t["partial"] = z(self.JSPLIT_MAX, cap, 2, dtype=f64)
+        t["tile_ctr"] = z(cap // PAD * 4 + 4, dtype=i32)
+        t["alive"] = z(cap, dtype=u8); t["escaped"] = z(cap, dtype=u8)
+        t["pairs"] = z(self.pair_cap, dtype=i64); t["pairs_sorted"] = z(self.pair_cap, dtype=i64)
+        t["cur_pos"] = z(cap, 2, dtype=f64); t["cur_vel"] = z(cap, 2, dtype=f64)
+        t["mod_row"] = z(cap, dtype=i32); t["mod_step"] = torch.full((cap,), -1, dtype=i32, device=dev)
+        t["chunk_alive"] = z(cap // 1024 + 2, dtype=i32)
+        for k, dt_ in (("pos", f64), ("vel", f64)):
+            t["t_" + k] = z(cap, 2, dtype=dt_)
+        for k, dt_ in (("mass", f64), ("mass_hi", i64), ("mass_lo", i64), ("radius", f64), ("volume", f64),
+                       ("eaten", i64), ("id", i32), ("flags", u8)):
+            t["t_" + k] = z(cap, dtype=dt_)
+        # the three per-frame outputs of stage A are SoA planes of t["new"]
+        new = t["new"].view(-1)
+        self._pos_new = new[: 2 * cap]
+        self._vel_new = new[2 * cap: 4 * cap]
+        self._xx_new = new[4 * cap: 5 * cap]
+
+        p = lambda k: C.c_void_p(t[k].data_ptr())  # noqa: E731
+        st = _abi.State()
+        st.cap, st.n_total = cap, self.n_total
+        for k in ("pos", "vel", "mass", "mass_hi", "mass_lo", "radius", "volume", "eaten", "id", "flags",
+                  "status", "rec_mass", "rec_mass_hi", "rec_mass_lo", "rec_radius", "rec_volume",
+                  "rec_eaten", "rec_death", "rec_flags", "events"):
+            setattr(st, k, p(k))
+        st.event_cap = self.event_cap
+        sc = _abi.Scratch()
+        for k in ("h", "pk_x", "pk_y", "pk_m", "acc", "rinf", "partial", "tile_ctr", "alive", "escaped",
+                  "pairs", "pairs_sorted", "cur_pos", "cur_vel", "mod_row", "mod_step", "chunk_alive",
+                  "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_radius", "t_volume",
+                  "t_eaten", "t_id", "t_flags"):
+            setattr(sc, k, p(k))
+        sc.pos_new = C.c_void_p(self._pos_new.data_ptr())
+        sc.vel_new = C.c_void_p(self._vel_new.data_ptr())
+        sc.xx_new = C.c_void_p(self._xx_new.data_ptr())
+        sc.jsplit_max = self.JSPLIT_MAX
+        sc.pair_cap = self.pair_cap
+        sc.grid_cells = 0
+        sc.giant_cap = 0
+        self.st, self.sc = st, sc
+
+    # ------------------------------------------------------------------ host <-> device
+    def upload(self, arrays, frame=0):
+        """Load the ACTIVE planets (insertion order) from host numpy arrays.
+
+        arrays: pos[n,2], vel[n,2], mass_f64[n], mass_hi[n], mass_lo[n] (uint64), flags[n] (uint8),
+        radius[n], volume[n], eaten[n], id[n].  Pinned staging keeps the copy asynchronous.
+        """
+        n = int(arrays["radius"].shape[0])
+        if n > self.cap:
+            raise ValueError("upload of %d planets exceeds capacity %d" % (n, self.cap))
+        t = self.t
+
+        def put(key, src, dtype):
+            a = np.ascontiguousarray(src, dtype=dtype)
+            h = torch.from_numpy(a)
+            if a.dtype == np.uint64:
+                h = torch.from_numpy(a.view(np.int64))
+            dst = t[key]
+            dst[:n].copy_(h.reshape(dst[:n].shape), non_blocking=False)
+
+        put("pos", arrays["pos"], np.float64); put("vel", arrays["vel"], np.float64)
+        put("mass", arrays["mass_f64"], np.float64)
+        put("mass_hi", arrays["mass_hi"], np.uint64); put("mass_lo", arrays["mass_lo"], np.uint64)
+        put("radius", arrays["radius"], np.float64); put("volume", arrays["volume"], np.float64)
+        put("eaten", arrays["eaten"], np.int64); put("id", arrays["id"], np.int32)
+        put("flags", arrays["flags"], np.uint8)
+        status = torch.zeros(STATUS_LEN, dtype=torch.int64)
+        status[ST_N_ACTIVE] = n
+        status[ST_STEP] = int(frame)
+        keep = t["status"].cpu()
+        status[ST_N_EVENTS] = keep[ST_N_EVENTS]
+        status[ST_N_ESCAPED] = keep[ST_N_ESCAPED]
+        t["status"].copy_(status)
+        t["mod_step"].fill_(-1)
+        self.n_upper = n
+        self.frames = int(frame)
+        self._choose_scales(np.asarray(arrays["pos"], dtype=np.float64), np.asarray(arrays["mass_f64"], dtype=np.float64))
+
+    def _choose_scales(self, pos, mass):
+        # exact power-of-two rescaling for the FP32 path: max |coord| -> [32, 64), max mass -> [2^19, 2^20)
+        pmax = float(np.max(np.abs(pos))) if pos.size else 1.0
+        mmax = float(np.max(np.abs(mass))) if mass.size else 1.0
+        self.pos_exp = (math.frexp(pmax)[1] - 6) if pmax > 0 and math.isfinite(pmax) else 0
+        self.mass_exp = (math.frexp(mmax)[1] - 20) if mmax > 0 and math.isfinite(mmax) else 0
+
+    def status(self):
+        """Synchronising read of the device status block."""
+        s = self.t["status"].cpu().numpy()
+        self.n_upper = int(s[ST_N_ACTIVE])
+        return {"n_active": int(s[ST_N_ACTIVE]), "frame": int(s[ST_STEP]), "n_events": int(s[ST_N_EVENTS]),
+                "n_pairs": int(s[ST_N_PAIRS]), "n_dead": int(s[ST_N_DEAD]), "error": int(s[ST_ERROR]),
+                "n_escaped": int(s[ST_N_ESCAPED])}
+
+    def check_errors(self):
+        st = self.status()
+        err = st["error"]
+        if err:
+            what = [name for bit, name in ((1, "flagged-pair buffer overflow"), (2, "event log overflow"),
+                                           (4, "non-finite acceleration (d^2 < 0 or NaN input)")) if err & bit]
+            raise _abi.CosmoError("device reported: " + ", ".join(what))
+        return st
+
+    def download(self):
+        """Active planets (slot order == insertion order of survivors) + records of the dead."""
+        st = self.status()
+        n = st["n_active"]
+        t = self.t
+        out = {k: t[k][:n].cpu().numpy() for k in ("pos", "vel", "mass", "radius", "volume", "eaten", "id", "flags")}
+        out["mass_hi"] = t["mass_hi"][:n].cpu().numpy().view(np.uint64)
+        out["mass_lo"] = t["mass_lo"][:n].cpu().numpy().view(np.uint64)
+        for k in ("rec_mass", "rec_radius", "rec_volume", "rec_eaten", "rec_death", "rec_flags"):
+            out[k] = t[k].cpu().numpy()
+        out["rec_mass_hi"] = t["rec_mass_hi"].cpu().numpy().view(np.uint64)
+        out["rec_mass_lo"] = t["rec_mass_lo"].cpu().numpy().view(np.uint64)
+        out["status"] = st
+        return out
+
+    def events(self, start=0):
+        """Merge stream rows (frame, absorber id, absorbed id) from `start` on."""
+        n = min(self.status()["n_events"], self.event_cap)
+        return self.t["events"][start:n].cpu().numpy()
+
+    def last_frame_tensors(self):
+        """acc / pos_new / vel_new of the last frame in the slot order the frame STARTED with."""
+        cap = self.cap
+        return {"acc": self.t["acc"], "pos_new": self._pos_new.view(cap, 2), "vel_new": self._vel_new.view(cap, 2)}
+
+    # ------------------------------------------------------------------ stepping
+    def params(self, dt, G, r_max, collisions=True, bounded=True, fp32=False, store_acc=False,
+               f32_scalar=False, jsplit=None):
+        p = _abi.StepParams()
+        p.G, p.dt, p.r_max = float(G), float(dt), float(r_max)
+        p.opts = ((OPT_COLLISIONS if collisions else 0) | (OPT_BOUNDED if bounded else 0) |
+                  (OPT_FP32 if fp32 else 0) | (OPT_STORE_ACC if store_acc else 0) |
+                  (OPT_F32_SCALAR if f32_scalar else 0))
+        n = self.n_upper
+        p.n_upper = n
+        if self.world > 1:
+            from . import sharded
+            p.i_begin, p.i_end, _ = sharded.shard_rows(n, self.world, self.rank)
+        else:
+            p.i_begin, p.i_end = 0, n
+        p.pos_exp, p.mass_exp = self.pos_exp, self.mass_exp
+        rows = max(1, p.i_end - p.i_begin)
+        p.jsplit = int(jsplit) if jsplit else self.lib.cosmo_suggest_jsplit(rows, max(1, n), int(bool(fp32)), self.JSPLIT_MAX)
+        p.detect_mode = 0
+        return p
+
+    def step(self, n_frames, dt, G, r_max, **kw):
+        """Enqueue n_frames frames on the current stream; never synchronises (single GPU)."""
+        if self.n_upper <= 0 or n_frames <= 0:
+            return
+        p = self.params(dt, G, r_max, **kw)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        st, sc, pp = C.byref(self.st), C.byref(self.sc), C.byref(p)
+        if self.world == 1:
+            for _ in range(int(n_frames)):
+                _abi.check(self.lib.cosmo_step(st, sc, pp, stream), "cosmo_step")
+        else:
+            for _ in range(int(n_frames)):
+                self._step_sharded(p, stream)
+        self.frames += int(n_frames)
+
+    def _step_sharded(self, p, stream):
+        from . import sharded
+        sharded.frame(self, p, stream)

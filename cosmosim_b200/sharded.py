@@ -1,0 +1,71 @@
+"""Multi-GPU frame: target rows sharded over the ranks of one node, state replicated.
+
+One process per GPU (torch.distributed, NCCL over NVLink 5 / NVSwitch).  Per frame:
+  stage A on this rank's rows            -> pos_new / vel_new / xx_new of the shard
+  all-gather of the three planes         (the collision test needs everyone's NEW position,
+                                          reference universe_old.py:178-180)
+  stage B on this rank's rows            -> flagged ordered pairs (i, j) of the shard
+  all-gather of the per-rank pair lists  -> identical pair set on every rank
+  stage C replicated                     -> identical state on every rank, no further traffic
+The partition helpers are pure functions of (n, world) so the gloo/CPU tests can drive the
+exchange protocol without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _abi
+from ._abi import PAD, ST_N_PAIRS
+
+
+def shard_rows(n: int, world: int, rank: int):
+    """Contiguous, tile-aligned row shard [begin, end) of rank; every rank's `per` is equal."""
+    per = (-(-n // world) + PAD - 1) // PAD * PAD if n > 0 else PAD
+    return min(n, rank * per), min(n, (rank + 1) * per), per
+
+
+def required_capacity(n_total: int, world: int) -> int:
+    """Slots needed so that world equal shards of whole tiles fit."""
+    return shard_rows(max(1, n_total), world, 0)[2] * world
+
+
+def gather_planes(planes, per: int, rank: int, world: int, group=None):
+    """In-place all-gather of [cap*w] planes whose rows [rank*per, (rank+1)*per) are local."""
+    for plane, width in planes:
+        full = plane[: world * per * width]
+        mine = plane[rank * per * width: (rank + 1) * per * width]
+        dist.all_gather_into_tensor(full, mine, group=group)
+
+
+def exchange_pairs(local_pairs: torch.Tensor, local_count: torch.Tensor, xchg: torch.Tensor,
+                   rank: int, world: int, group=None):
+    """All-gather (count | pairs[:xcap]) rows.  xchg: int64 [world, 1 + xcap], updated in place."""
+    xcap = xchg.shape[1] - 1
+    xchg[rank, 0] = local_count.reshape(())
+    xchg[rank, 1:] = local_pairs[:xcap]
+    dist.all_gather_into_tensor(xchg.view(-1), xchg[rank], group=group)
+    return xchg
+
+
+def frame(eng, p, stream):
+    """One frame on engine `eng` (params p already hold this rank's row shard)."""
+    lib = eng.lib
+    st, sc, pp = C.byref(eng.st), C.byref(eng.sc), C.byref(p)
+    n = p.n_upper
+    _, _, per = shard_rows(n, eng.world, eng.rank)
+    _abi.check(lib.cosmo_begin_frame(st, sc, pp, stream), "cosmo_begin_frame")
+    _abi.check(lib.cosmo_accel_integrate(st, sc, pp, stream), "cosmo_accel_integrate")
+    gather_planes(((eng._pos_new, 2), (eng._vel_new, 2), (eng._xx_new, 1)), per, eng.rank, eng.world, eng.group)
+    _abi.check(lib.cosmo_detect_pairs(st, sc, pp, stream), "cosmo_detect_pairs")
+    status = eng.t["status"]
+    if not hasattr(eng, "_xchg"):
+        eng._xchg = torch.zeros(eng.world, 1 + eng.pair_cap, dtype=torch.int64, device=eng.device)
+    xchg = exchange_pairs(eng.t["pairs"], status[ST_N_PAIRS], eng._xchg, eng.rank, eng.world, eng.group)
+    status[ST_N_PAIRS] = 0
+    for r in range(eng.world):
+        _abi.check(lib.cosmo_append_pairs(st, sc, C.c_void_p(xchg[r, 1:].data_ptr()),
+                                          C.c_void_p(xchg[r, :1].data_ptr()), stream), "cosmo_append_pairs")
+    _abi.check(lib.cosmo_resolve_commit(st, sc, pp, stream), "cosmo_resolve_commit")

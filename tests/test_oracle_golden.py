@@ -1,0 +1,82 @@
+"""The CPU oracle (oracle/cosmo_oracle.c) against fixtures PRODUCED BY THE REFERENCE
+(oracle/gen_golden.py ran the unmodified reference; nothing here imports /root/reference)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, relerr_rows, snap_from
+from oracle import oracle as orc
+
+SCENES = ("star_with_disk", "cloud")
+
+
+def test_accel_matches_acc_blas_fixture():
+    g = load_golden("accel_n4001.npz")
+    a = orc.accel(g["pos"], g["mass"], float(g["G"]))
+    assert relerr_rows(a, g["acc"]).max() < 1e-13
+
+
+def test_accel_row_shards_concatenate():
+    g = load_golden("accel_n4001.npz")
+    n = g["mass"].shape[0]
+    full = orc.accel(g["pos"], g["mass"], float(g["G"]))
+    parts = [orc.accel(g["pos"], g["mass"], float(g["G"]), b, min(n, b + 1500)) for b in range(0, n, 1500)]
+    assert np.array_equal(np.concatenate(parts), full)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_single_steps_match_reference(scene):
+    st = load_golden(f"scene_{scene}_steps.npz")
+    G, dt = float(st["G"]), float(st["dt"])
+    for s in st["steps"]:
+        ou = orc.OracleUniverse(snap_from(st, f"s{s}_pre_"), G=G)
+        out = ou.frame(dt, record=True)
+        assert np.array_equal(out["active_idx"], st[f"s{s}_active_idx"])
+        assert relerr_rows(out["acc"], st[f"s{s}_acc"]).max() < 1e-13
+        assert np.abs(out["p_new"] - st[f"s{s}_p_new"]).max() <= 1e-13 * np.abs(st[f"s{s}_p_new"]).max()
+        assert np.array_equal(out["flag_pairs"], st[f"s{s}_flag_pairs"])      # bit-exact predicate
+        assert np.array_equal(out["events"], st[f"s{s}_events"])              # bit-exact merge order
+        post = ou.snapshot()
+        ref = snap_from(st, f"s{s}_post_")
+        al = ref["alive"]
+        assert np.array_equal(post["alive"], al)
+        for k in ("mass_f64", "radius", "volume", "eaten", "mass_int_hi", "mass_int_lo", "mass_is_int"):
+            assert np.array_equal(post[k], ref[k]), k                          # merge arithmetic exact
+        for k in ("pos", "vel"):
+            scale = np.abs(ref[k][al]).max()
+            assert np.abs(post[k][al] - ref[k][al]).max() <= 1e-12 * scale, k
+
+
+def test_micro_merges_bit_exact():
+    g = load_golden("micro_merges.npz")
+    for name in g["names"]:
+        ou = orc.OracleUniverse(snap_from(g, f"{name}_pre_"), G=1.0)
+        ev = []
+        for step, tag in ((0, "post1_"), (1, "post2_")):
+            out = ou.frame(1.0, record=(step == 0))
+            ev += [(step, int(a), int(b)) for a, b in out["events"]]
+            if step == 0:
+                assert np.abs(out["acc"] - g[f"{name}_acc0"]).max() <= 1e-13 * max(1e-300, np.abs(g[f"{name}_acc0"]).max())
+            post, ref = ou.snapshot(), snap_from(g, f"{name}_{tag}")
+            assert np.array_equal(post["alive"], ref["alive"]), name
+            al = ref["alive"]
+            for k in ("mass_f64", "radius", "volume", "eaten"):
+                assert np.array_equal(post[k], ref[k]), (name, k)
+            for k in ("pos", "vel"):
+                assert np.allclose(post[k][al], ref[k][al], rtol=1e-13, atol=0), (name, k)
+        assert ev == [tuple(int(x) for x in r) for r in g[f"{name}_events"]], name
+
+
+@pytest.mark.parametrize("scene,prefix_steps", [("star_with_disk", 51), ("cloud", 1000)])
+def test_free_run_merge_stream(scene, prefix_steps):
+    """Free-running the oracle reproduces the reference's merge stream for as long as chaos
+    allows (the only arithmetic difference is the summation order inside OpenBLAS zhpmv):
+    the whole 1000 frames for the cloud, the first 51 frames (20 merges) for the disk."""
+    init, run = load_golden(f"scene_{scene}_init.npz"), load_golden(f"scene_{scene}_run.npz")
+    ou = orc.OracleUniverse(snap_from(init, ""), G=float(init["G"]), bounded=bool(init["bounded"]),
+                            r_max=float(init["r_max"]))
+    ev = []
+    for s in range(prefix_steps):
+        ev += [(s, int(a), int(b)) for a, b in ou.frame(float(run["dt"]))["events"]]
+    ref = [tuple(int(x) for x in r) for r in run["events"] if r[0] < prefix_steps]
+    assert ev == ref
+    assert len(ref) >= 8
