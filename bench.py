@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Contract benchmark of the per-timestep physics update (BASELINE.json north_star).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+A "step" is one frame of the hot path (all-pairs acceleration + fused integrator + collision
+detection + ordered merges + compaction) over one synthetic scene.  Default workload is the
+configuration the metric is quoted on: star+disk, N = 1,048,576, FP32 fast path, merges on
+(BASELINE.json configs[4]); with N > 1 GPUs the target rows are sharded (strong scaling,
+same scene).  Prints ONE JSON line (rank 0).
+
+Metric: ordered pairwise interactions per second = N_active^2 * K / time (the reference's
+acc_blas also evaluates all N^2 ordered pairs).  `value` is timed with inputs resident in
+HBM; `e2e` repeats the measurement through the host-buffer path (state H2D from pinned
+memory + frame + results D2H every step).  `roofline` is for the dominant kernel (stage A),
+timed with CUDA events on the launching stream inside the timed region, against the FMA-pipe
+peak measured by the in-process micro-benchmark (MEASURED_PEAKS.json has no CUDA-core peak;
+its HBM figure is used for the hbm sub-object).  `cpu_baseline` times the CPU oracle (a C port
+of the reference's algorithm, all host threads) on a bounded row sample of the same scene.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+AU = 1.496e11
+DT = 1e6 / 33
+G = 6.674e-11
+R_MAX = 100 * AU
+
+WORKLOADS = {
+    # name: (builder, n, precision, collisions)
+    "star_disk_1m_fp32": ("star_disk", 1 << 20, "fp32", True),
+    "star_disk_64k_fp64": ("star_disk", 1 << 16, "fp64", True),
+    "cloud_256k_fp32": ("cloud", 1 << 18, "fp32", True),
+    "star_disk_1001_fp64": ("star_disk", 1001, "fp64", True),
+}
+# FMA-pipe instructions per ordered interaction of the dominant kernel
+INSTR_PER_INTERACTION = {"fp32": 9, "fp64": 20}
+
+
+def build_arrays(kind, n, seed=0):
+    from cosmosim_b200 import scenes
+    return scenes.star_disk_arrays(n, seed=seed) if kind == "star_disk" else scenes.cloud_arrays(n, seed=seed)
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------ CPU legs
+def cpu_oracle_leg(arrays, prec_n, seconds_target=12.0, steps=1, warmup=0):
+    """Time the CPU oracle (port of the reference's acc_blas + integrator + collision predicate)
+    on a bounded sample of target rows of the same scene, all host threads."""
+    from oracle import oracle as orc
+    n = arrays["radius"].shape[0]
+    pos, vel, mass, rad = arrays["pos"], arrays["vel"], arrays["mass_f64"], arrays["radius"]
+    cores = orc.num_threads()
+
+    def sample(rows):
+        t0 = time.perf_counter()
+        a = orc.accel(pos, mass, G, 0, rows)
+        p, v = orc.integrate(pos[:rows], vel[:rows], a, DT)
+        pn = pos.copy()
+        pn[:rows] = p
+        orc.flags(pn, rad, 0, rows)
+        return time.perf_counter() - t0
+
+    rows = min(n, max(cores, 8))
+    sample(rows)                                       # warms the library and the thread pool
+    for _ in range(4):                                 # grow the sample towards the time target
+        t = sample(rows)
+        want = int(min(n, max(rows, seconds_target * rows / max(t, 1e-9))))
+        if want <= rows * 1.25 or t >= 0.5 * seconds_target:
+            break
+        rows = min(want, rows * 16)
+    times = []
+    for _ in range(warmup):
+        sample(rows)
+    for _ in range(max(1, steps)):
+        times.append(sample(rows))
+    t = float(np.mean(times))
+    return {"value": rows * n / t, "unit": "interactions/s", "cores": cores, "kind": "port",
+            "sample": "oracle/cosmo_oracle.c accel+integrate+collision predicate on target rows [0,%d) of the "
+                      "N=%d scene (%d x %d ordered pairs, %.1f s per step, OpenMP %d threads)"
+                      % (rows, n, rows, n, t, cores),
+            "ms_per_step_sample": t * 1e3, "rows": rows}
+
+
+# ------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="star_disk_1m_fp32", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override the body count (development)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--f32-scalar", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    a = ap.parse_args()
+
+    kind, n, prec, collisions = WORKLOADS[a.workload]
+    if a.n:
+        n = a.n
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(3, a.warmup) if a.impl == "b200" else max(0, a.warmup)
+    K = max(1, a.steps)
+    config = {"workload": a.workload, "scene": kind, "n_bodies": n, "precision": prec, "collisions": collisions,
+              "dt": DT, "parallelism": "rows%d" % world if world > 1 else "single",
+              "l2": "256 MiB memset between steps (inside the timed region)"}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        arrays = build_arrays(kind, n)
+        leg = cpu_oracle_leg(arrays, n, seconds_target=min(a.cpu_seconds, 100.0 / (K + W)), steps=K, warmup=W)
+        line = {"impl": "reference", "metric": "pairwise_interactions_per_s", "value": leg["value"],
+                "unit": "interactions/s", "n_gpus": 0, "steps": K, "warmup": W,
+                "ms_per_step": leg["ms_per_step_sample"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": leg["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "steps_per_s_extrapolated": leg["value"] / (float(n) * n)}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    from cosmosim_b200 import _abi
+    from cosmosim_b200.engine import Engine
+
+    torch.cuda.set_device(local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        group = dist.group.WORLD
+    arrays = build_arrays(kind, n)
+    eng = Engine(n, device="cuda:%d" % local_rank, group=group)
+    eng.upload(arrays)
+    kw = dict(collisions=collisions, bounded=True, fp32=(prec == "fp32"), f32_scalar=a.f32_scalar)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # pipe peaks for the roofline denominator (tiny, before the timed region)
+    peaks = measure_pipe_peaks(eng, prec) if rank == 0 else {}
+
+    for _ in range(W):
+        eng.step(1, DT, G, R_MAX, **kw)
+        flush.zero_()
+    barrier()
+    n_active_start = eng.status()["n_active"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    stage_events = [] if world == 1 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        eng.step(1, DT, G, R_MAX, stage_events=stage_events, **kw)
+        flush.zero_()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    st = eng.check_errors()
+    # interactions actually evaluated: the active count shrinks as planets merge
+    n_eff = 0.5 * (n_active_start + st["n_active"])
+    interactions = n_eff * n_eff * K
+    value = interactions / (ms * 1e-3)
+
+    roofline = None
+    if stage_events:
+        accel_ms = float(np.mean([ev[1].elapsed_time(ev[2]) for ev in stage_events]))
+        detect_ms = float(np.mean([ev[2].elapsed_time(ev[3]) for ev in stage_events]))
+        resolve_ms = float(np.mean([ev[3].elapsed_time(ev[4]) for ev in stage_events]))
+        prep_ms = float(np.mean([ev[0].elapsed_time(ev[1]) for ev in stage_events]))
+        ipi = INSTR_PER_INTERACTION[prec]
+        achieved = n_eff * n_eff * ipi * 2 / (accel_ms * 1e-3) / 1e12      # FMA-equivalent TFLOP/s
+        peak_key = "ffma_tflops" if prec == "fp32" else "dfma_tflops"
+        peak = peaks.get(peak_key)
+        # algorithmic HBM bytes of stage A per launch: sources read once (L2-resident afterwards)
+        # + targets' state read + new state written
+        bytes_per_body = (12 + 8 + 16 + 16 + 40) if prec == "fp32" else (32 + 16 + 16 + 40)
+        hbm_gbs = n_eff * bytes_per_body / (accel_ms * 1e-3) / 1e9
+        mp = {}
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = mp.get("hbm_gbs", 6650.0)
+        roofline = {"bound": "fma_pipe_" + prec, "kernel": "k_accel_%s" % ("f32" if prec == "fp32" else "f64"),
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": (achieved / peak) if peak else None, "traffic": None,
+                    "peak_source": "in-process %s micro-benchmark (cosmo_microbench) on this GPU; "
+                                   "MEASURED_PEAKS.json holds no CUDA-core peak" % ("FFMA" if prec == "fp32" else "DFMA"),
+                    "instr_per_interaction": ipi, "kernel_ms": accel_ms,
+                    "interactions_per_s_kernel": n_eff * n_eff / (accel_ms * 1e-3),
+                    "stage_ms": {"prep": prep_ms, "accel_integrate": accel_ms, "detect": detect_ms,
+                                 "resolve_commit": resolve_ms},
+                    "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
+                            "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in mp else "fallback"},
+                    "mufu_rsq_per_s_peak": peaks.get("mufu_rsq_per_s")}
+
+    # ---------------------------------------------------------------- e2e (host buffers)
+    e2e = None
+    if not a.no_e2e:
+        eng.upload(arrays)
+        stg = eng.make_host_staging(arrays)
+        for _ in range(2):
+            eng.frame_from_host(stg, DT, G, R_MAX, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(K):
+            eng.frame_from_host(stg, DT, G, R_MAX, **kw)
+        f1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e_ms = max(f0.elapsed_time(f1), 0.0)
+        if world > 1:
+            tms = torch.tensor([e_ms], dtype=torch.float64, device=eng.device)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            e_ms = float(tms.item())
+        e2e = {"value": float(n) * n * K / (e_ms * 1e-3), "unit": "interactions/s",
+               "h2d_bytes_per_step": int(stg["h2d_bytes"]), "d2h_bytes_per_step": int(stg["d2h_bytes"]),
+               "ms_per_step": e_ms / K, "wall_ms_per_step": wall_ms / K,
+               "path": "Engine.frame_from_host: pinned host SoA -> H2D -> cosmo_step -> D2H, stream sync per step"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_oracle_leg(arrays, n, seconds_target=a.cpu_seconds)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "pairwise_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms / K, "steps_per_s": K / (ms * 1e-3),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32" if prec == "fp32" else "f64", "data": "synthetic", "config": config,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": K * (eng.LAUNCHES_PER_FRAME + (3 * world + 1 if world > 1 else 0)),
+                "roofline": roofline, "cpu_baseline": cpu,
+                "final_state": {"n_active": st["n_active"], "merges": st["n_events"], "escaped": st["n_escaped"]},
+                "jsplit": eng.params(DT, G, R_MAX, **kw).jsplit}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_pipe_peaks(eng, prec):
+    """FFMA / DFMA / MUFU peaks (thread-instructions per second) from the in-library
+    micro-benchmark: the measured denominators SURVEY.md section 8d asks for."""
+    import torch
+    from cosmosim_b200 import _abi
+    L = eng.lib
+    out = torch.zeros(eng.sm_count * 2 * 1024, dtype=torch.float64, device=eng.device)
+    stream = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
+
+    def rate(kind, iters):
+        best = 0.0
+        for threads, bps in ((512, 2), (1024, 1), (1024, 2)):
+            ops = C.c_int64()
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _abi.check(L.cosmo_microbench(kind, eng.sm_count * bps, threads, iters, C.c_void_p(out.data_ptr()),
+                                              C.byref(ops), stream), "cosmo_microbench")
+                e1.record()
+                torch.cuda.synchronize()
+                best = max(best, ops.value * eng.sm_count * bps * threads / (e0.elapsed_time(e1) * 1e-3))
+        return best
+
+    ffma, dfma, mufu = rate(0, 8000), rate(2, 3000), rate(3, 3000)
+    return {"ffma_per_s": ffma, "dfma_per_s": dfma, "mufu_rsq_per_s": mufu,
+            "ffma_tflops": 2 * ffma / 1e12, "dfma_tflops": 2 * dfma / 1e12}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

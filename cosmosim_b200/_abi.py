@@ -48,7 +48,7 @@ class StepParams(C.Structure):
                 ("opts", C.c_uint32), ("n_upper", C.c_int32), ("i_begin", C.c_int32),
                 ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
                 ("jsplit", C.c_int32), ("detect_mode", C.c_int32), ("cell_size", C.c_double),
-                ("grid_origin", C.c_double), ("cells_per_side", C.c_int32), ("reserved", C.c_int32),
+                ("grid_origin", C.c_double), ("cells_per_side", C.c_int32), ("jsplit_detect", C.c_int32),
                 ("giant_radius", C.c_double)]
 
 

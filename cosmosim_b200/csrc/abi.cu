@@ -54,7 +54,7 @@ static int suggest_jsplit(int rows, int n, int rows_per_cta, int tile, int slots
     for (int js = 1; js <= jmax && js <= tiles; ++js) {
         const long long waves = (iblocks * js + slots - 1) / slots;
         const long long per = (tiles + js - 1) / js;
-        const long long cost = waves * per * 64 + js;  // mild preference for fewer splits
+        const long long cost = waves * per * 1024 + js;  // mild preference for fewer splits
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best = js;
@@ -88,7 +88,7 @@ int cosmo_device_info(int *sm_count, int *cc_major, int *cc_minor) {
     return COSMO_OK;
 }
 
-int cosmo_suggest_jsplit(int32_t rows, int32_t n, int fp32, int32_t jsplit_max) {
+int cosmo_suggest_jsplit(int32_t rows, int32_t n, int kernel, int32_t jsplit_max) {
     int sms = 148;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) {
@@ -96,9 +96,11 @@ int cosmo_suggest_jsplit(int32_t rows, int32_t n, int fp32, int32_t jsplit_max) 
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
     }
     if (jsplit_max < 1) jsplit_max = 1;
-    // resident CTAs per SM: FP32 kernel 256 thr x 2, FP64 kernel 128 thr x 4 (register bound)
-    return fp32 ? suggest_jsplit(rows, n, 256 * 4, 512, sms * 2, jsplit_max)
-                : suggest_jsplit(rows, n, 128 * 2, 256, sms * 4, jsplit_max);
+    int rows_per_cta = 256, tile = 256, resident = 0;
+    if (kernel == 3) resident = detect_residency(&rows_per_cta, &tile);
+    else resident = accel_residency(kernel < 0 || kernel > 2 ? 0 : kernel, &rows_per_cta, &tile);
+    if (resident <= 0) resident = kernel == 1 || kernel == 2 ? 3 : 8;  // no device: documented defaults
+    return suggest_jsplit(rows, n, rows_per_cta, tile, sms * resident, jsplit_max);
 }
 
 int cosmo_begin_frame(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p,
@@ -223,7 +225,7 @@ int cosmo_accel(const double *pos, const double *mass, int32_t n, double G, int 
     p.i_end = n;
     p.pos_exp = pos_exp;
     p.mass_exp = mass_exp;
-    p.jsplit = cosmo_suggest_jsplit(n, n, fp32, kAccelJsplitMax);
+    p.jsplit = cosmo_suggest_jsplit(n, n, fp32 ? 1 : 0, kAccelJsplitMax);
     COSMO_TRY(launch_prep(w.st, w.sc, p, s));
     COSMO_TRY(launch_accel(w.st, w.sc, p, s));
     return check_cuda(cudaMemcpyAsync(acc_out, w.sc.acc, (size_t)n * 16, cudaMemcpyDeviceToDevice, s), "acc copy");

@@ -217,6 +217,8 @@ k_accel_f64(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
         double2 p = pos[ic];
         xi[k] = p.x; yi[k] = p.y;
         qix[k] = -2.0 * p.x; qiy[k] = -2.0 * p.y;
+        // keep q in registers: ptxas otherwise recomputes -2*p inside the loop on the FP64 pipe
+        asm volatile("" : "+d"(qix[k]), "+d"(qiy[k]));
         hi[k] = sc.h[ic];
         ax[k] = 0.0; ay[k] = 0.0;
     }
@@ -267,7 +269,11 @@ k_accel_f64(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
 // ---------------------------------------------------------------------------------------
 // FP32 fast kernel
 // ---------------------------------------------------------------------------------------
-#define COSMO_F32_TINY 8.673617379884035e-19f /* 2^-60: keeps rsqrt finite for r2 == 0 */
+// r2 is formed as dx*dx + dy*dy + 2^-60 (scaled units, i.e. a softening length of 2^-30 of
+// the position scale: ~2 m for the AU-scale scenes against radii >= 1e6 m).  It keeps
+// rsqrt finite for the self pair and for zero-mass padding without a compare/select in the
+// hot loop; the self term then contributes dx * s = 0 exactly.
+#define COSMO_F32_TINY 8.673617379884035e-19f
 
 template <int BLOCK, int IB, int TJ, bool PACKED>
 __global__ void __launch_bounds__(BLOCK)
@@ -324,6 +330,7 @@ k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
         // processed: no tail bound in the hot loop.
         if (PACKED) {
             uint64_t xi2[IB], yi2[IB], ax2[IB], ay2[IB];
+            const uint64_t eps2 = pack2(COSMO_F32_TINY, COSMO_F32_TINY);
 #pragma unroll
             for (int k = 0; k < IB; ++k) {
                 xi2[k] = pack2(xi[k], xi[k]);
@@ -340,11 +347,11 @@ k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
                 for (int k = 0; k < IB; ++k) {
                     uint64_t dx = sub2(xj2, xi2[k]);
                     uint64_t dy = sub2(yj2, yi2[k]);
-                    uint64_t r2 = fma2(dy, dy, mul2(dx, dx));
+                    uint64_t r2 = fma2(dy, dy, fma2(dx, dx, eps2));
                     float r2a, r2b;
                     unpack2(r2, r2a, r2b);
-                    float ia = rsqrt_approx_f32(fmaxf(r2a, COSMO_F32_TINY));
-                    float ib = rsqrt_approx_f32(fmaxf(r2b, COSMO_F32_TINY));
+                    float ia = rsqrt_approx_f32(r2a);
+                    float ib = rsqrt_approx_f32(r2b);
                     uint64_t rinv = pack2(ia, ib);
                     uint64_t s = mul2(mul2(mj2, rinv), mul2(rinv, rinv));
                     ax2[k] = fma2(dx, s, ax2[k]);
@@ -369,8 +376,8 @@ k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
 #pragma unroll
                 for (int k = 0; k < IB; ++k) {
                     float dx = xj - xi[k], dy = yj - yi[k];
-                    float r2 = fmaf(dy, dy, dx * dx);
-                    float rinv = rsqrt_approx_f32(fmaxf(r2, COSMO_F32_TINY));
+                    float r2 = fmaf(dy, dy, fmaf(dx, dx, COSMO_F32_TINY));
+                    float rinv = rsqrt_approx_f32(r2);
                     float s = (mj * rinv) * (rinv * rinv);
                     ax[k] = fmaf(dx, s, ax[k]);
                     ay[k] = fmaf(dy, s, ay[k]);
@@ -392,6 +399,24 @@ k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
 constexpr int F64_BLOCK = 128, F64_IB = 2, F64_TJ = 256;
 constexpr int F32_BLOCK = 256, F32_IB = 4, F32_TJ = 512;
 static_assert(COSMO_PAD % F64_TJ == 0 && COSMO_PAD % F32_TJ == 0, "tiles must divide the slot padding");
+
+// resident CTAs per SM of the all-pairs kernels (0: FP64, 1: FP32 packed, 2: FP32 scalar)
+int accel_residency(int which, int *rows_per_cta, int *tile) {
+    int nb = 0;
+    cudaError_t e;
+    if (which == 0) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accel_f64<F64_BLOCK, F64_IB, F64_TJ>, F64_BLOCK, 0);
+        *rows_per_cta = F64_BLOCK * F64_IB; *tile = F64_TJ;
+    } else if (which == 1) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accel_f32<F32_BLOCK, F32_IB, F32_TJ, true>, F32_BLOCK, 0);
+        *rows_per_cta = F32_BLOCK * F32_IB; *tile = F32_TJ;
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accel_f32<F32_BLOCK, F32_IB, F32_TJ, false>, F32_BLOCK, 0);
+        *rows_per_cta = F32_BLOCK * F32_IB; *tile = F32_TJ;
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nb;
+}
 
 int launch_prep(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                 cudaStream_t s) {

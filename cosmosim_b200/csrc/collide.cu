@@ -420,12 +420,22 @@ __global__ void k_end_frame(cosmo_state st) {
 // ---------------------------------------------------------------------------------------
 constexpr int DET_BLOCK = 128, DET_IB = 2, DET_TJ = 256;
 
+int detect_residency(int *rows_per_cta, int *tile) {
+    int nb = 0;
+    *rows_per_cta = DET_BLOCK * DET_IB; *tile = DET_TJ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_detect_allpairs<DET_BLOCK, DET_IB, DET_TJ>, DET_BLOCK, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return nb;
+}
+
 int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                   cudaStream_t s) {
     if (!(p.opts & COSMO_OPT_COLLISIONS)) return COSMO_OK;
     const int rows = p.i_end - p.i_begin;
     if (rows <= 0) return COSMO_OK;
-    int jsplit = p.jsplit < 1 ? 1 : p.jsplit;
+    int jsplit = p.jsplit_detect < 1 ? 1 : p.jsplit_detect;
     const int per = DET_BLOCK * DET_IB;
     dim3 grid((rows + per - 1) / per, jsplit);
     k_detect_allpairs<DET_BLOCK, DET_IB, DET_TJ><<<grid, DET_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit);

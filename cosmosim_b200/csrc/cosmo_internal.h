@@ -24,7 +24,10 @@ int launch_prep(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step
 int launch_accel(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                  cudaStream_t s);
 
+int accel_residency(int which, int *rows_per_cta, int *tile);
+
 // collide.cu
+int detect_residency(int *rows_per_cta, int *tile);
 int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                   cudaStream_t s);
 int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc,

@@ -43,7 +43,7 @@ def _round_up(n, q):
 class Engine:
     """One GPU's replica of the world (optionally responsible for a shard of target rows)."""
 
-    JSPLIT_MAX = 16
+    JSPLIT_MAX = 32
 
     def __init__(self, n_total, device=None, pair_cap=None, event_cap=None, group=None):
         if not torch.cuda.is_available():
@@ -239,25 +239,88 @@ class Engine:
             p.i_begin, p.i_end = 0, n
         p.pos_exp, p.mass_exp = self.pos_exp, self.mass_exp
         rows = max(1, p.i_end - p.i_begin)
-        p.jsplit = int(jsplit) if jsplit else self.lib.cosmo_suggest_jsplit(rows, max(1, n), int(bool(fp32)), self.JSPLIT_MAX)
+        kern = (2 if f32_scalar else 1) if fp32 else 0
+        with torch.cuda.device(self.device):
+            p.jsplit = int(jsplit) if jsplit else self.lib.cosmo_suggest_jsplit(rows, max(1, n), kern, self.JSPLIT_MAX)
+            p.jsplit_detect = int(jsplit) if jsplit else self.lib.cosmo_suggest_jsplit(rows, max(1, n), 3, self.JSPLIT_MAX)
         p.detect_mode = 0
         return p
 
-    def step(self, n_frames, dt, G, r_max, **kw):
-        """Enqueue n_frames frames on the current stream; never synchronises (single GPU)."""
+    def step(self, n_frames, dt, G, r_max, stage_events=None, **kw):
+        """Enqueue n_frames frames on the current stream; never synchronises.
+
+        stage_events: optional list; for every frame a tuple of four torch.cuda.Event
+        (start, after stage A, after stage B, after stage C) is appended -- bench.py uses them
+        to time the all-pairs kernel on the launching stream."""
         if self.n_upper <= 0 or n_frames <= 0:
             return
         p = self.params(dt, G, r_max, **kw)
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         st, sc, pp = C.byref(self.st), C.byref(self.sc), C.byref(p)
-        if self.world == 1:
-            for _ in range(int(n_frames)):
-                _abi.check(self.lib.cosmo_step(st, sc, pp, stream), "cosmo_step")
-        else:
-            for _ in range(int(n_frames)):
+        lib = self.lib
+        for _ in range(int(n_frames)):
+            if self.world > 1:
                 self._step_sharded(p, stream)
+            elif stage_events is None:
+                _abi.check(lib.cosmo_step(st, sc, pp, stream), "cosmo_step")
+            else:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                ev[0].record()
+                _abi.check(lib.cosmo_begin_frame(st, sc, pp, stream), "cosmo_begin_frame")
+                ev[1].record()
+                _abi.check(lib.cosmo_accel_integrate(st, sc, pp, stream), "cosmo_accel_integrate")
+                ev[2].record()
+                _abi.check(lib.cosmo_detect_pairs(st, sc, pp, stream), "cosmo_detect_pairs")
+                ev[3].record()
+                _abi.check(lib.cosmo_resolve_commit(st, sc, pp, stream), "cosmo_resolve_commit")
+                ev[4].record()
+                stage_events.append(ev)
         self.frames += int(n_frames)
+
+    LAUNCHES_PER_FRAME = 9  # prep, accel, detect, sort, resolve, commit, scatter, copyback, end
 
     def _step_sharded(self, p, stream):
         from . import sharded
         sharded.frame(self, p, stream)
+
+    # ------------------------------------------------------------------ host-buffer (e2e) path
+    E2E_IN = ("pos", "vel", "mass", "mass_hi", "mass_lo", "radius", "volume", "eaten", "id", "flags")
+    E2E_OUT = ("pos", "vel", "mass", "radius", "id")
+
+    def make_host_staging(self, arrays):
+        """Pinned host mirrors of the state (what a host-resident caller hands over per frame)."""
+        n = int(arrays["radius"].shape[0])
+        src = {"pos": arrays["pos"], "vel": arrays["vel"], "mass": arrays["mass_f64"],
+               "mass_hi": np.asarray(arrays["mass_hi"]).view(np.int64), "mass_lo": np.asarray(arrays["mass_lo"]).view(np.int64),
+               "radius": arrays["radius"], "volume": arrays["volume"], "eaten": arrays["eaten"],
+               "id": arrays["id"], "flags": arrays["flags"]}
+        stg = {"n": n, "in": {}, "out": {}}
+        for k in self.E2E_IN:
+            h = torch.from_numpy(np.ascontiguousarray(src[k])).pin_memory()
+            stg["in"][k] = h
+        for k in self.E2E_OUT:
+            stg["out"][k] = torch.empty_like(self.t[k][:n], device="cpu").pin_memory()
+        stg["status_in"] = torch.zeros(STATUS_LEN, dtype=torch.int64).pin_memory()
+        stg["status_out"] = torch.zeros(STATUS_LEN, dtype=torch.int64).pin_memory()
+        stg["h2d_bytes"] = sum(v.numel() * v.element_size() for v in stg["in"].values()) + STATUS_LEN * 8
+        stg["d2h_bytes"] = sum(v.numel() * v.element_size() for v in stg["out"].values()) + STATUS_LEN * 8
+        return stg
+
+    def frame_from_host(self, stg, dt, G, r_max, **kw):
+        """One frame the way a host-resident caller sees it: state H2D from pinned memory, the
+        frame, results D2H, stream synchronised.  Returns the device status block."""
+        n = stg["n"]
+        t = self.t
+        for k in self.E2E_IN:
+            t[k][:n].copy_(stg["in"][k].view(t[k][:n].shape), non_blocking=True)
+        stg["status_in"].zero_()
+        stg["status_in"][ST_N_ACTIVE] = n
+        stg["status_in"][ST_STEP] = self.frames
+        t["status"].copy_(stg["status_in"], non_blocking=True)
+        self.n_upper = n
+        self.step(1, dt, G, r_max, **kw)
+        for k in self.E2E_OUT:
+            stg["out"][k].copy_(t[k][:n], non_blocking=True)
+        stg["status_out"].copy_(t["status"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return stg["status_out"]

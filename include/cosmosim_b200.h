@@ -158,7 +158,7 @@ typedef struct cosmo_step_params {
     double cell_size;    /* detect_mode 1 */
     double grid_origin;  /* detect_mode 1: grid covers [origin, origin + cells_per_side*cell_size)^2 */
     int32_t cells_per_side;
-    int32_t reserved;
+    int32_t jsplit_detect; /* source-range splits of the stage-B all-pairs pass */
     double giant_radius; /* detect_mode 1: planets with radius above this are brute-forced */
 } cosmo_step_params;
 
@@ -202,8 +202,9 @@ int cosmo_resolve_commit(const cosmo_state *st, const cosmo_scratch *sc,
 int cosmo_begin_frame(const cosmo_state *st, const cosmo_scratch *sc,
                       const cosmo_step_params *p, void *stream);
 
-/* Suggested source-range split for `rows` target rows against n sources on this device. */
-int cosmo_suggest_jsplit(int32_t rows, int32_t n, int fp32, int32_t jsplit_max);
+/* Suggested source-range split for `rows` target rows against n sources on this device;
+   kernel: 0 FP64 accel, 1 FP32 packed accel, 2 FP32 scalar accel, 3 all-pairs detection. */
+int cosmo_suggest_jsplit(int32_t rows, int32_t n, int kernel, int32_t jsplit_max);
 
 /* Convenience: begin_frame + A + B + C on one device (no sharding). */
 int cosmo_step(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p,
