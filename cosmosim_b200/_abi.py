@@ -13,8 +13,9 @@ STATUS_LEN = 16
 # flag / option / status constants (mirror the header)
 F_IMMOBILE, F_MASS_INT = 1, 2
 OPT_COLLISIONS, OPT_BOUNDED, OPT_FP32, OPT_STORE_ACC, OPT_F32_SCALAR = 1, 2, 4, 8, 16
-ST_N_ACTIVE, ST_STEP, ST_N_EVENTS, ST_N_PAIRS, ST_N_DEAD, ST_ERROR, ST_N_ESCAPED, ST_N_CAND = range(8)
-ERR_PAIR_OVERFLOW, ERR_EVENT_OVERFLOW, ERR_NAN = 1, 2, 4
+ST_N_ACTIVE, ST_STEP, ST_N_EVENTS, ST_N_PAIRS, ST_N_DEAD, ST_ERROR, ST_N_ESCAPED, ST_N_CAND, ST_N_GIANTS, ST_PMAX2, ST_N_COMPLEX = range(11)
+SCAN_BLOCKS = 8192
+ERR_PAIR_OVERFLOW, ERR_EVENT_OVERFLOW, ERR_NAN, ERR_GIANT_OVERFLOW = 1, 2, 4, 8
 
 _vp = C.c_void_p
 
@@ -36,6 +37,8 @@ class Scratch(C.Structure):
                 ("alive", _vp), ("escaped", _vp), ("pairs", _vp), ("pairs_sorted", _vp),
                 ("pair_cap", C.c_int64), ("cur_pos", _vp), ("cur_vel", _vp), ("mod_row", _vp),
                 ("mod_step", _vp), ("chunk_alive", _vp),
+                ("row_count", _vp), ("row_start", _vp), ("pmin", _vp), ("pmax", _vp), ("scan_blk", _vp),
+                ("pair_flag", _vp), ("cplx_list", _vp), ("ev_tmp", _vp),
                 ("t_pos", _vp), ("t_vel", _vp), ("t_mass", _vp), ("t_mass_hi", _vp),
                 ("t_mass_lo", _vp), ("t_radius", _vp), ("t_volume", _vp), ("t_eaten", _vp),
                 ("t_id", _vp), ("t_flags", _vp),
@@ -47,8 +50,9 @@ class StepParams(C.Structure):
     _fields_ = [("G", C.c_double), ("dt", C.c_double), ("r_max", C.c_double),
                 ("opts", C.c_uint32), ("n_upper", C.c_int32), ("i_begin", C.c_int32),
                 ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
-                ("jsplit", C.c_int32), ("detect_mode", C.c_int32), ("cell_size", C.c_double),
-                ("grid_origin", C.c_double), ("cells_per_side", C.c_int32), ("jsplit_detect", C.c_int32),
+                ("jsplit", C.c_int32), ("detect_mode", C.c_int32), ("resolve_mode", C.c_int32),
+                ("small_tiles", C.c_int32), ("cell_size", C.c_double),
+                ("grid_origin_x", C.c_double), ("grid_origin_y", C.c_double), ("cells_per_side", C.c_int32), ("jsplit_detect", C.c_int32),
                 ("giant_radius", C.c_double)]
 
 

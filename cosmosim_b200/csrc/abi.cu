@@ -97,8 +97,13 @@ int cosmo_suggest_jsplit(int32_t rows, int32_t n, int kernel, int32_t jsplit_max
     }
     if (jsplit_max < 1) jsplit_max = 1;
     int rows_per_cta = 256, tile = 256, resident = 0;
-    if (kernel == 3) resident = detect_residency(&rows_per_cta, &tile);
-    else resident = accel_residency(kernel < 0 || kernel > 2 ? 0 : kernel, &rows_per_cta, &tile);
+    if (kernel == 3 || kernel == 5) resident = detect_residency(&rows_per_cta, &tile);
+    else resident = accel_residency(kernel < 0 || kernel > 4 ? 0 : kernel, &rows_per_cta, &tile);
+    if (kernel == 4 || kernel == 5) {  // small-N shapes: 64 rows x 64-source tiles per CTA
+        rows_per_cta = 64;
+        tile = 64;
+        resident = 16;
+    }
     if (resident <= 0) resident = kernel == 1 || kernel == 2 ? 3 : 8;  // no device: documented defaults
     return suggest_jsplit(rows, n, rows_per_cta, tile, sms * resident, jsplit_max);
 }
@@ -170,7 +175,7 @@ AccelWs carve(int32_t n, char *base) {
     w.st.cap = cap;
     w.st.n_total = cap;
     w.st.status = (int64_t *)take(COSMO_STATUS_LEN * 8);
-    w.sc.tile_ctr = (int32_t *)take((size_t)(cap / COSMO_PAD * 4 + 4) * 4);
+    w.sc.tile_ctr = (int32_t *)take((size_t)(cap / 64 + 4) * 4);
     w.st.pos = (double *)take((size_t)cap * 16);
     w.st.vel = (double *)take((size_t)cap * 16);
     w.st.mass = (double *)take((size_t)cap * 8);

@@ -45,6 +45,9 @@ __global__ void k_prep(cosmo_state st, cosmo_scratch sc, double r_max, int pos_e
         st.status[COSMO_ST_N_PAIRS] = 0;
         st.status[COSMO_ST_N_DEAD] = 0;
         st.status[COSMO_ST_N_CAND] = 0;
+        st.status[COSMO_ST_N_GIANTS] = 0;
+        st.status[COSMO_ST_PMAX2] = 0;
+        st.status[COSMO_ST_N_COMPLEX] = 0;
     }
     const double2 *pos = reinterpret_cast<const double2 *>(st.pos);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_pad; k += gridDim.x * blockDim.x) {
@@ -398,6 +401,7 @@ k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
 // ---------------------------------------------------------------------------------------
 constexpr int F64_BLOCK = 128, F64_IB = 2, F64_TJ = 256;
 constexpr int F32_BLOCK = 256, F32_IB = 4, F32_TJ = 512;
+constexpr int F64S_BLOCK = 64, F64S_IB = 1, F64S_TJ = 64;  // small-N shape: many short CTAs
 static_assert(COSMO_PAD % F64_TJ == 0 && COSMO_PAD % F32_TJ == 0, "tiles must divide the slot padding");
 
 // resident CTAs per SM of the all-pairs kernels (0: FP64, 1: FP32 packed, 2: FP32 scalar)
@@ -448,6 +452,13 @@ int launch_accel(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_ste
             k_accel_f32<F32_BLOCK, F32_IB, F32_TJ, true><<<grid, F32_BLOCK, 0, s>>>(
                 st, sc, p.i_begin, p.i_end, jsplit, p.G, p.dt, unscale, store_acc);
         return COSMO_LAUNCH_CHECK("k_accel_f32");
+    }
+    if (p.small_tiles) {
+        const int per = F64S_BLOCK * F64S_IB;
+        dim3 grid((rows + per - 1) / per, jsplit);
+        k_accel_f64<F64S_BLOCK, F64S_IB, F64S_TJ><<<grid, F64S_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit,
+                                                                            p.G, p.dt, store_acc);
+        return COSMO_LAUNCH_CHECK("k_accel_f64(small)");
     }
     const int per = F64_BLOCK * F64_IB;
     dim3 grid((rows + per - 1) / per, jsplit);

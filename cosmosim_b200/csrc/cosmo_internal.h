@@ -26,7 +26,7 @@ int launch_accel(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_ste
 
 int accel_residency(int which, int *rows_per_cta, int *tile);
 
-// collide.cu
+// detect.cu / resolve.cu
 int detect_residency(int *rows_per_cta, int *tile);
 int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                   cudaStream_t s);
@@ -34,6 +34,10 @@ int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc,
                           const cosmo_step_params &p, cudaStream_t s);
 int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const uint64_t *src,
                         const int64_t *count_ptr, cudaStream_t s);
+
+// scan.cu: out[k] = sum(in[0..k)), out[n] = total; n = min(*n_ptr + n_add, n_max) or n_max
+int launch_scan_exclusive(const int *in, int *out, int *blk, const int64_t *n_ptr, long long n_max,
+                          long long n_add, cudaStream_t s);
 
 // microbench.cu
 int launch_microbench(int kind, int blocks, int threads, int iters, double *out,

@@ -1,0 +1,289 @@
+// Stage B: collision-pair detection on the NEW positions.  Replaces pairwise_distances +
+// collision_matrix (reference cosmosim/core/universe_old.py:180,192-193).
+//
+// Two modes, same exact predicate (pred.cuh), same output (unsorted list of flagged ordered
+// pairs; stage C orders it):
+//   all-pairs   the reference's N x N test, tiled like stage A; used for small N;
+//   grid        uniform-grid broad phase: a counting sort of the planets into square cells no
+//               smaller than the largest possible flagged separation of two non-giant planets,
+//               so every flagged pair of non-giants sits in adjacent cells; "giants" (radius
+//               above giant_radius: the star) are tested against everybody.  The candidate
+//               set is a superset; every candidate goes through the exact predicate, so the
+//               flagged set is identical to the all-pairs one.
+#include <math.h>
+
+#include "pred.cuh"
+
+namespace cosmo {
+
+// All-pairs detection: same tiling as stage A (targets in registers, sources through a
+// bulk-copy/mbarrier ring).  7 FP64-pipe instructions per ordered pair for the candidate
+// filter d2 <= (r'_i + r'_j)^2 with radii inflated by 2^-30 (a superset of the flagged
+// pairs); the rare candidates go through the exact predicate with the true radii.
+template <int BLOCK, int IB, int TJ>
+__global__ void __launch_bounds__(BLOCK)
+k_detect_allpairs(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit) {
+    __shared__ __align__(16) double2 s_xy[2][TJ];
+    __shared__ __align__(16) double s_xx[2][TJ];
+    __shared__ __align__(16) double s_r[2][TJ];
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int i_hi = min(i_end, n);
+    const int base = i_begin + blockIdx.x * (BLOCK * IB);
+    if (base >= i_hi) return;
+    const int tid = threadIdx.x;
+    const double2 *pn = reinterpret_cast<const double2 *>(sc.pos_new);
+
+    double qx[IB], qy[IB], xxi[IB], ri[IB];
+    int ii[IB];
+#pragma unroll
+    for (int k = 0; k < IB; ++k) {
+        int i = base + k * BLOCK + tid;
+        ii[k] = i < i_hi ? i : -1;
+        int ic = min(i, i_hi - 1);
+        double2 p = pn[ic];
+        qx[k] = -2.0 * p.x; qy[k] = -2.0 * p.y;
+        xxi[k] = sc.xx_new[ic];
+        ri[k] = sc.rinf[ic];
+    }
+
+    const int tiles = (n + TJ - 1) / TJ;
+    const int t0 = (int)(((long long)blockIdx.y * tiles) / jsplit);
+    const int t1 = (int)(((long long)(blockIdx.y + 1) * tiles) / jsplit);
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    constexpr uint32_t kTileBytes = TJ * (sizeof(double2) + 2 * sizeof(double));
+    auto issue = [&](int t, int b) {
+        const size_t j0 = (size_t)t * TJ;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar[b], kTileBytes);
+        bulk_g2s(&s_xy[b][0], pn + j0, TJ * sizeof(double2), &s_bar[b]);
+        bulk_g2s(&s_xx[b][0], sc.xx_new + j0, TJ * sizeof(double), &s_bar[b]);
+        bulk_g2s(&s_r[b][0], sc.rinf + j0, TJ * sizeof(double), &s_bar[b]);
+    };
+    if (tid == 0 && t0 < t1) issue(t0, 0);
+
+    for (int t = t0; t < t1; ++t) {
+        const int it = t - t0;
+        const int b = it & 1;
+        if (tid == 0 && t + 1 < t1) issue(t + 1, b ^ 1);
+        mbar_wait(&s_bar[b], (it >> 1) & 1);
+        const int j0 = t * TJ;
+        const int cnt = min(TJ, n - j0);
+#pragma unroll 4
+        for (int jj = 0; jj < cnt; ++jj) {
+            const double2 pj = s_xy[b][jj];
+            const double xxj = s_xx[b][jj];
+            const double rj = s_r[b][jj];
+#pragma unroll
+            for (int k = 0; k < IB; ++k) {
+                double d2 = pred_d2(qx[k], qy[k], xxi[k], pj.x, pj.y, xxj);
+                double rs = ri[k] + rj;
+                if (d2 <= rs * rs) {
+                    const int i = ii[k], j = j0 + jj;
+                    if (i >= 0 && i != j && pred_exact(d2, st.radius[i], st.radius[j]))
+                        emit_pair(st, sc, i, j);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Uniform-grid broad phase
+// ---------------------------------------------------------------------------------------
+struct GridParams {
+    double h, ox, oy, rg;
+    int c;
+};
+
+// Cell edge actually used.  The reference compares the COMPUTED distance (expanded form,
+// absolute error E in d^2 of a few ulps of |p|^2) with r_i + r_j, so two non-giants (inflated
+// radius <= rg) can be flagged while truly sqrt(4 rg^2 + E) apart; the cell edge is never
+// smaller than that (plus slack for the rounding of the cell coordinate itself).
+__device__ __forceinline__ GridParams grid_params(const cosmo_state &st, double h, double ox, double oy,
+                                                  double rg, int c) {
+    GridParams g;
+    const double pmax2 = __longlong_as_double(st.status[COSMO_ST_PMAX2]);
+    const double e = 64.0 * 1.1102230246251565e-16 * pmax2;
+    const double hmin = sqrt(4.0 * rg * rg + e) * (1.0 + 1e-6);
+    g.h = fmax(h, hmin);
+    g.ox = ox; g.oy = oy; g.rg = rg; g.c = c;
+    return g;
+}
+
+__device__ __forceinline__ int cell_coord(double x, double o, double h, int c) {
+    double t = floor((x - o) / h);
+    t = fmin(fmax(t, 0.0), (double)(c - 1));  // outside the box: clamp (non-expansive)
+    return (int)t;
+}
+
+__global__ void __launch_bounds__(256) k_grid_max(cosmo_state st, cosmo_scratch sc) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    double m = 0.0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        m = fmax(m, sc.xx_new[k]);
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0)  // non-negative doubles order like their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_PMAX2]),
+                  (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void __launch_bounds__(256)
+k_grid_count(cosmo_state st, cosmo_scratch sc, double h, double ox, double oy, double rg, int c) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const GridParams g = grid_params(st, h, ox, oy, rg, c);
+    const double2 *pn = reinterpret_cast<const double2 *>(sc.pos_new);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        if (sc.rinf[k] > g.rg) {
+            unsigned long long idx =
+                atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_GIANTS]), 1ull);
+            if ((long long)idx < sc.giant_cap)
+                sc.giants[idx] = k;
+            else
+                atomicOr(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_ERROR]),
+                         (unsigned long long)COSMO_ERR_GIANT_OVERFLOW);
+            sc.cell_of[k] = -1;
+        } else {
+            const double2 p = pn[k];
+            const int cell = cell_coord(p.y, g.oy, g.h, g.c) * g.c + cell_coord(p.x, g.ox, g.h, g.c);
+            sc.cell_of[k] = cell;
+            atomicAdd(&sc.cell_count[cell], 1);
+        }
+    }
+}
+
+// counting-sort scatter; counts return to zero, so cell_count needs no per-frame memset
+__global__ void __launch_bounds__(256) k_grid_fill(cosmo_state st, cosmo_scratch sc) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int cell = sc.cell_of[k];
+        if (cell >= 0) {
+            const int slot = sc.cell_start[cell] + atomicSub(&sc.cell_count[cell], 1) - 1;
+            sc.cell_items[slot] = k;
+        }
+    }
+}
+
+__device__ __forceinline__ void test_and_emit(const cosmo_state &st, const cosmo_scratch &sc, int i, double qx,
+                                              double qy, double xxi, double ri, int j) {
+    const double2 pj = reinterpret_cast<const double2 *>(sc.pos_new)[j];
+    const double d2 = pred_d2(qx, qy, xxi, pj.x, pj.y, sc.xx_new[j]);
+    const double rs = ri + sc.rinf[j];
+    if (d2 <= rs * rs && pred_exact(d2, st.radius[i], st.radius[j])) emit_pair(st, sc, i, j);
+}
+
+// one thread per non-giant target row: 3 x 3 neighbourhood + the giants
+__global__ void __launch_bounds__(128)
+k_grid_detect(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int c) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int i_hi = min(i_end, n);
+    const int i = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i_hi) return;
+    const int cell = sc.cell_of[i];
+    if (cell < 0) return;
+    const double2 p = reinterpret_cast<const double2 *>(sc.pos_new)[i];
+    const double qx = -2.0 * p.x, qy = -2.0 * p.y, xxi = sc.xx_new[i], ri = sc.rinf[i];
+    const int cx = cell % c, cy = cell / c;
+    long long cand = 0;
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = cy + dy;
+        if (yy < 0 || yy >= c) continue;
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, c - 1);
+        // the three cells of a grid row are contiguous in the sorted item array
+        const int s0 = sc.cell_start[yy * c + x0], s1 = sc.cell_start[yy * c + x1 + 1];
+        for (int s = s0; s < s1; ++s) {
+            const int j = sc.cell_items[s];
+            if (j != i) test_and_emit(st, sc, i, qx, qy, xxi, ri, j);
+        }
+        cand += s1 - s0;
+    }
+    const int ng = (int)min((long long)st.status[COSMO_ST_N_GIANTS], (long long)sc.giant_cap);
+    for (int g = 0; g < ng; ++g) test_and_emit(st, sc, i, qx, qy, xxi, ri, sc.giants[g]);
+    // diagnostic only
+    if ((threadIdx.x & 31) == 0 && cand)
+        atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_CAND]), (unsigned long long)cand);
+}
+
+// rows of the giants: giant g against every planet (blockIdx.y strides over the giants)
+__global__ void __launch_bounds__(256)
+k_giant_rows(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int i_hi = min(i_end, n);
+    const int ng = (int)min((long long)st.status[COSMO_ST_N_GIANTS], (long long)sc.giant_cap);
+    for (int gi = blockIdx.y; gi < ng; gi += gridDim.y) {
+        const int g = sc.giants[gi];
+        if (g < i_begin || g >= i_hi) continue;
+        const double2 p = reinterpret_cast<const double2 *>(sc.pos_new)[g];
+        const double qx = -2.0 * p.x, qy = -2.0 * p.y, xxg = sc.xx_new[g], rg = sc.rinf[g];
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+            if (j != g) test_and_emit(st, sc, g, qx, qy, xxg, rg, j);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+constexpr int DET_BLOCK = 128, DET_IB = 2, DET_TJ = 256;
+constexpr int DETS_BLOCK = 64, DETS_IB = 1, DETS_TJ = 64;
+
+int detect_residency(int *rows_per_cta, int *tile) {
+    int nb = 0;
+    *rows_per_cta = DET_BLOCK * DET_IB; *tile = DET_TJ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_detect_allpairs<DET_BLOCK, DET_IB, DET_TJ>, DET_BLOCK, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return nb;
+}
+
+int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                  cudaStream_t s) {
+    if (!(p.opts & COSMO_OPT_COLLISIONS)) return COSMO_OK;
+    const int rows = p.i_end - p.i_begin;
+    if (rows <= 0 && p.detect_mode == 0) return COSMO_OK;
+    if (p.detect_mode == 1) {
+        const int c = p.cells_per_side;
+        if (c < 1 || (long long)c * c > sc.grid_cells || !sc.cell_count || !sc.giants) {
+            set_error("grid broad phase: cells_per_side=%d does not fit grid_cells=%d", c, sc.grid_cells);
+            return COSMO_E_ARG;
+        }
+        int nb = (p.n_upper + 255) / 256;
+        if (nb < 1) nb = 1;
+        if (nb > 148 * 8) nb = 148 * 8;
+        k_grid_max<<<nb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_max"));
+        k_grid_count<<<nb, 256, 0, s>>>(st, sc, p.cell_size, p.grid_origin_x, p.grid_origin_y, p.giant_radius, c);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_count"));
+        COSMO_TRY(launch_scan_exclusive(sc.cell_count, sc.cell_start, sc.scan_blk, nullptr, (long long)c * c, 0, s));
+        k_grid_fill<<<nb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_fill"));
+        if (rows > 0) {
+            k_grid_detect<<<(rows + 127) / 128, 128, 0, s>>>(st, sc, p.i_begin, p.i_end, c);
+            COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect"));
+            k_giant_rows<<<dim3(nb > 296 ? 296 : nb, 8), 256, 0, s>>>(st, sc, p.i_begin, p.i_end);
+            COSMO_TRY(COSMO_LAUNCH_CHECK("k_giant_rows"));
+        }
+        return COSMO_OK;
+    }
+    int jsplit = p.jsplit_detect < 1 ? 1 : p.jsplit_detect;
+    if (p.small_tiles) {
+        const int per = DETS_BLOCK * DETS_IB;
+        dim3 grid((rows + per - 1) / per, jsplit);
+        k_detect_allpairs<DETS_BLOCK, DETS_IB, DETS_TJ><<<grid, DETS_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit);
+    } else {
+        const int per = DET_BLOCK * DET_IB;
+        dim3 grid((rows + per - 1) / per, jsplit);
+        k_detect_allpairs<DET_BLOCK, DET_IB, DET_TJ><<<grid, DET_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit);
+    }
+    return COSMO_LAUNCH_CHECK("k_detect_allpairs");
+}
+
+}  // namespace cosmo

@@ -7,117 +7,9 @@
 
 #include "cosmo_device.cuh"
 #include "cosmo_internal.h"
+#include "pred.cuh"
 
 namespace cosmo {
-
-// ---------------------------------------------------------------------------------------
-// Exact predicate of the reference on the NEW positions (sklearn euclidean_distances):
-//   XX   = fl(fl(x^2) + fl(y^2))                 (xx_new, written by stage A)
-//   dot  = fma(y_i, y_j, fl(x_i x_j))            (dgemm, K = 2)
-//   d2   = fl(fl(-2 dot + XX_i) + XX_j)          (row norm first => not symmetric in i,j)
-//   flag = max(sqrt(max(d2, 0)), 1) <= fl(r_i + r_j)
-// q = -2 p_i is exact, so fma(q_y, y_j, fl(q_x x_j)) == -2 dot bit-for-bit.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double pred_d2(double qxi, double qyi, double xxi, double xj, double yj,
-                                          double xxj) {
-    double m2dot = __fma_rn(qyi, yj, __dmul_rn(qxi, xj));
-    return __dadd_rn(__dadd_rn(m2dot, xxi), xxj);
-}
-
-__device__ __forceinline__ bool pred_exact(double d2, double ri, double rj) {
-    double d = sqrt(fmax(d2, 0.0));  // IEEE sqrt
-    d = fmax(d, 1.0);                // np.clip(d, 1, None)
-    return d <= __dadd_rn(ri, rj);
-}
-
-__device__ __forceinline__ void emit_pair(const cosmo_state &st, const cosmo_scratch &sc, int i, int j) {
-    unsigned long long idx =
-        atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_PAIRS]), 1ull);
-    if ((long long)idx < sc.pair_cap)
-        sc.pairs[idx] = ((uint64_t)(uint32_t)i << 32) | (uint32_t)j;
-    else
-        atomicOr(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_ERROR]),
-                 (unsigned long long)COSMO_ERR_PAIR_OVERFLOW);
-}
-
-// All-pairs detection: same tiling as stage A (targets in registers, sources through a
-// bulk-copy/mbarrier ring).  7 FP64-pipe instructions per ordered pair for the candidate
-// filter d2 <= (r'_i + r'_j)^2 with radii inflated by 2^-30 (a superset of the flagged
-// pairs); the rare candidates go through the exact predicate with the true radii.
-template <int BLOCK, int IB, int TJ>
-__global__ void __launch_bounds__(BLOCK)
-k_detect_allpairs(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit) {
-    __shared__ __align__(16) double2 s_xy[2][TJ];
-    __shared__ __align__(16) double s_xx[2][TJ];
-    __shared__ __align__(16) double s_r[2][TJ];
-    __shared__ __align__(8) uint64_t s_bar[2];
-
-    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
-    const int i_hi = min(i_end, n);
-    const int base = i_begin + blockIdx.x * (BLOCK * IB);
-    if (base >= i_hi) return;
-    const int tid = threadIdx.x;
-    const double2 *pn = reinterpret_cast<const double2 *>(sc.pos_new);
-
-    double qx[IB], qy[IB], xxi[IB], ri[IB];
-    int ii[IB];
-#pragma unroll
-    for (int k = 0; k < IB; ++k) {
-        int i = base + k * BLOCK + tid;
-        ii[k] = i < i_hi ? i : -1;
-        int ic = min(i, i_hi - 1);
-        double2 p = pn[ic];
-        qx[k] = -2.0 * p.x; qy[k] = -2.0 * p.y;
-        xxi[k] = sc.xx_new[ic];
-        ri[k] = sc.rinf[ic];
-    }
-
-    const int tiles = (n + TJ - 1) / TJ;
-    const int t0 = (int)(((long long)blockIdx.y * tiles) / jsplit);
-    const int t1 = (int)(((long long)(blockIdx.y + 1) * tiles) / jsplit);
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    constexpr uint32_t kTileBytes = TJ * (sizeof(double2) + 2 * sizeof(double));
-    auto issue = [&](int t, int b) {
-        const size_t j0 = (size_t)t * TJ;
-        fence_proxy_async();
-        mbar_expect_tx(&s_bar[b], kTileBytes);
-        bulk_g2s(&s_xy[b][0], pn + j0, TJ * sizeof(double2), &s_bar[b]);
-        bulk_g2s(&s_xx[b][0], sc.xx_new + j0, TJ * sizeof(double), &s_bar[b]);
-        bulk_g2s(&s_r[b][0], sc.rinf + j0, TJ * sizeof(double), &s_bar[b]);
-    };
-    if (tid == 0 && t0 < t1) issue(t0, 0);
-
-    for (int t = t0; t < t1; ++t) {
-        const int it = t - t0;
-        const int b = it & 1;
-        if (tid == 0 && t + 1 < t1) issue(t + 1, b ^ 1);
-        mbar_wait(&s_bar[b], (it >> 1) & 1);
-        const int j0 = t * TJ;
-        const int cnt = min(TJ, n - j0);
-#pragma unroll 4
-        for (int jj = 0; jj < cnt; ++jj) {
-            const double2 pj = s_xy[b][jj];
-            const double xxj = s_xx[b][jj];
-            const double rj = s_r[b][jj];
-#pragma unroll
-            for (int k = 0; k < IB; ++k) {
-                double d2 = pred_d2(qx[k], qy[k], xxi[k], pj.x, pj.y, xxj);
-                double rs = ri[k] + rj;
-                if (d2 <= rs * rs) {
-                    const int i = ii[k], j = j0 + jj;
-                    if (i >= 0 && i != j && pred_exact(d2, st.radius[i], st.radius[j]))
-                        emit_pair(st, sc, i, j);
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
 
 // ---------------------------------------------------------------------------------------
 // Pair list utilities
@@ -206,6 +98,56 @@ __device__ __forceinline__ double merge1(double ma, double a, double mo, double 
     return __ddiv_rn(__dadd_rn(__dmul_rn(ma, a), __dmul_rn(mo, o)), msum);
 }
 
+// Replays ONE flagged pair (row i, partner j) exactly as planet.py:74-85 / universe_old.py:204-209
+// would at that point of the double loop.  Returns false when absorb()'s guard fails (one of
+// the two already dead).  On success writes the event ids to ev[0..1].
+__device__ bool replay_pair(const cosmo_state &st, const cosmo_scratch &sc, int i, int j, int stamp,
+                            int64_t *ev) {
+    if (!sc.alive[i] || !sc.alive[j]) return false;  // absorb() guard, planet.py:75
+    double2 *cur_pos = reinterpret_cast<double2 *>(sc.cur_pos);
+    double2 *cur_vel = reinterpret_cast<double2 *>(sc.cur_vel);
+    const bool i_int = st.flags[i] & COSMO_F_MASS_INT, j_int = st.flags[j] & COSMO_F_MASS_INT;
+    const u128 mi = (((u128)st.mass_hi[i]) << 64) | st.mass_lo[i];
+    const u128 mj = (((u128)st.mass_hi[j]) << 64) | st.mass_lo[j];
+    // universe_old.py:206: `planet.mass >= other_planet.mass` -- the row planet wins ties
+    const bool i_wins = mass_ge(i_int, mi, st.mass[i], j_int, mj, st.mass[j]);
+    const int W = i_wins ? i : j, L = i_wins ? j : i;
+    const double mW = st.mass[W], mL = st.mass[L];
+    double msum;
+    const bool both_int = i_int && j_int;
+    u128 isum = 0;
+    if (both_int) {
+        isum = mi + mj;
+        msum = u128_to_double(isum);
+    } else {
+        msum = __dadd_rn(mW, mL);
+    }
+    if (!(st.flags[W] & COSMO_F_IMMOBILE)) {  // planet.py:76-79
+        PV w = current_value(st, sc, W, i, stamp);
+        PV l = current_value(st, sc, L, i, stamp);
+        cur_pos[W] = make_double2(merge1(mW, w.p.x, mL, l.p.x, msum), merge1(mW, w.p.y, mL, l.p.y, msum));
+        cur_vel[W] = make_double2(merge1(mW, w.v.x, mL, l.v.x, msum), merge1(mW, w.v.y, mL, l.v.y, msum));
+        sc.mod_row[W] = i;
+        sc.mod_step[W] = stamp;
+    }
+    st.mass[W] = msum;  // planet.py:80
+    if (both_int) {
+        st.mass_hi[W] = (uint64_t)(isum >> 64);
+        st.mass_lo[W] = (uint64_t)isum;
+    } else {
+        st.flags[W] &= ~COSMO_F_MASS_INT;
+    }
+    const double vol = __dadd_rn(st.volume[W], st.volume[L]);  // planet.py:81
+    st.volume[W] = vol;
+    st.radius[W] = pow_third(__ddiv_rn(__dmul_rn(3.0, vol), 4.0 * 3.141592653589793));  // :82
+    st.eaten[W] += 1 + st.eaten[L];  // planet.py:84
+    sc.alive[L] = 0;                 // planet.py:83,86-91
+    ev[0] = st.id[W];
+    ev[1] = st.id[L];
+    return true;
+}
+
+// resolve_mode 0: one thread walks the rank-sorted pair list (few pairs, few launches)
 __global__ void k_resolve(cosmo_state st, cosmo_scratch sc) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     long long M = st.status[COSMO_ST_N_PAIRS];
@@ -213,58 +155,160 @@ __global__ void k_resolve(cosmo_state st, cosmo_scratch sc) {
     if (M == 0) return;
     const int stamp = (int)st.status[COSMO_ST_STEP];
     long long nev = st.status[COSMO_ST_N_EVENTS];
-    double2 *cur_pos = reinterpret_cast<double2 *>(sc.cur_pos);
-    double2 *cur_vel = reinterpret_cast<double2 *>(sc.cur_vel);
     for (long long q = 0; q < M; ++q) {
         const uint64_t key = sc.pairs_sorted[q];
-        const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
-        if (!sc.alive[i] || !sc.alive[j]) continue;  // absorb() guard, planet.py:75
-        const bool i_int = st.flags[i] & COSMO_F_MASS_INT, j_int = st.flags[j] & COSMO_F_MASS_INT;
-        const u128 mi = (((u128)st.mass_hi[i]) << 64) | st.mass_lo[i];
-        const u128 mj = (((u128)st.mass_hi[j]) << 64) | st.mass_lo[j];
-        // universe_old.py:206: `planet.mass >= other_planet.mass` -- row planet wins ties
-        const bool i_wins = mass_ge(i_int, mi, st.mass[i], j_int, mj, st.mass[j]);
-        const int W = i_wins ? i : j, L = i_wins ? j : i;
-        const double mW = st.mass[W], mL = st.mass[L];
-        double msum;
-        const bool both_int = i_int && j_int;
-        u128 isum = 0;
-        if (both_int) {
-            isum = mi + mj;
-            msum = u128_to_double(isum);
-        } else {
-            msum = __dadd_rn(mW, mL);
-        }
-        if (!(st.flags[W] & COSMO_F_IMMOBILE)) {  // planet.py:76-79
-            PV w = current_value(st, sc, W, i, stamp);
-            PV l = current_value(st, sc, L, i, stamp);
-            cur_pos[W] = make_double2(merge1(mW, w.p.x, mL, l.p.x, msum), merge1(mW, w.p.y, mL, l.p.y, msum));
-            cur_vel[W] = make_double2(merge1(mW, w.v.x, mL, l.v.x, msum), merge1(mW, w.v.y, mL, l.v.y, msum));
-            sc.mod_row[W] = i;
-            sc.mod_step[W] = stamp;
-        }
-        st.mass[W] = msum;  // planet.py:80
-        if (both_int) {
-            st.mass_hi[W] = (uint64_t)(isum >> 64);
-            st.mass_lo[W] = (uint64_t)isum;
-        } else {
-            st.flags[W] &= ~COSMO_F_MASS_INT;
-        }
-        const double vol = __dadd_rn(st.volume[W], st.volume[L]);  // planet.py:81
-        st.volume[W] = vol;
-        st.radius[W] = pow_third(__ddiv_rn(__dmul_rn(3.0, vol), 4.0 * 3.141592653589793));  // :82
-        st.eaten[W] += 1 + st.eaten[L];  // planet.py:84
-        sc.alive[L] = 0;                 // planet.py:83,86-91
+        int64_t ev[2];
+        if (!replay_pair(st, sc, (int)(key >> 32), (int)(key & 0xffffffffu), stamp, ev)) continue;
         if (nev < st.event_cap) {
             st.events[3 * nev + 0] = stamp;
-            st.events[3 * nev + 1] = st.id[W];
-            st.events[3 * nev + 2] = st.id[L];
+            st.events[3 * nev + 1] = ev[0];
+            st.events[3 * nev + 2] = ev[1];
         } else {
             st.status[COSMO_ST_ERROR] |= COSMO_ERR_EVENT_OVERFLOW;
         }
         ++nev;
     }
     st.status[COSMO_ST_N_EVENTS] = nev;
+    st.status[COSMO_ST_N_COMPLEX] = M;
+}
+
+// ---------------------------------------------------------------------------------------
+// resolve_mode 1: row-major (CSR) ordering of the flagged pairs by counting sort, then
+//   * "simple" pairs -- both planets have each other as their ONLY partner in the whole
+//     flagged set -- cannot interact with any other pair, so the sequential loop's outcome
+//     for them is independent of everything else: one thread each, in parallel;
+//   * everything else is replayed by one thread in sorted order (rare: chains and triples);
+//   * merge events land in a slot per sorted pair and are appended to the log in sorted
+//     order, which is the visitation order of the reference's double loop.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ long long pair_count(const cosmo_state &st, const cosmo_scratch &sc) {
+    long long M = st.status[COSMO_ST_N_PAIRS];
+    return M > sc.pair_cap ? sc.pair_cap : M;
+}
+
+__global__ void __launch_bounds__(256) k_csr_count(cosmo_state st, cosmo_scratch sc) {
+    const long long M = pair_count(st, sc);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const uint64_t key = sc.pairs[q];
+        const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
+        atomicAdd(&sc.row_count[i], 1);
+        atomicMin(&sc.pmin[i], j); atomicMax(&sc.pmax[i], j);
+        atomicMin(&sc.pmin[j], i); atomicMax(&sc.pmax[j], i);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_csr_fill(cosmo_state st, cosmo_scratch sc) {
+    const long long M = pair_count(st, sc);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const uint64_t key = sc.pairs[q];
+        const int i = (int)(key >> 32);
+        const int slot = sc.row_start[i] + atomicSub(&sc.row_count[i], 1) - 1;  // counts return to 0
+        sc.pairs_sorted[slot] = key;
+    }
+}
+
+// order every row by partner index (rows are short; the owner of the row's first slot sorts it)
+__global__ void __launch_bounds__(256) k_csr_sort_rows(cosmo_state st, cosmo_scratch sc) {
+    const long long M = pair_count(st, sc);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(sc.pairs_sorted[q] >> 32);
+        const int s0 = sc.row_start[i], s1 = sc.row_start[i + 1];
+        sc.pair_flag[q] = 0;
+        if (q != s0 || s1 - s0 < 2) continue;
+        for (int a = s0 + 1; a < s1; ++a) {
+            const uint64_t key = sc.pairs_sorted[a];
+            int b = a - 1;
+            while (b >= s0 && sc.pairs_sorted[b] > key) {
+                sc.pairs_sorted[b + 1] = sc.pairs_sorted[b];
+                --b;
+            }
+            sc.pairs_sorted[b + 1] = key;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_resolve_simple(cosmo_state st, cosmo_scratch sc) {
+    const long long M = pair_count(st, sc);
+    const int stamp = (int)st.status[COSMO_ST_STEP];
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const uint64_t key = sc.pairs_sorted[q];
+        const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
+        const bool simple = sc.pmin[i] == j && sc.pmax[i] == j && sc.pmin[j] == i && sc.pmax[j] == i;
+        if (!simple) {
+            sc.pair_flag[q] = 2;
+            continue;
+        }
+        // of the two orientations only the one the loop meets first can do anything
+        const bool first = i < j || sc.row_start[j + 1] == sc.row_start[j];
+        if (first && replay_pair(st, sc, i, j, stamp, &sc.ev_tmp[2 * q])) sc.pair_flag[q] = 1;
+    }
+}
+
+// One CTA: stable compaction of the indices q with (pair_flag[q] & bit) into cplx_list
+// (bit == 2) or of the merge events into the log (bit == 1).
+__global__ void __launch_bounds__(1024) k_ordered_compact(cosmo_state st, cosmo_scratch sc, int bit) {
+    __shared__ int s_w[32];
+    __shared__ long long s_base;
+    const long long M = pair_count(st, sc);
+    const int stamp = (int)st.status[COSMO_ST_STEP];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = bit == 1 ? st.status[COSMO_ST_N_EVENTS] : 0;
+    __syncthreads();
+    for (long long q0 = 0; q0 < M; q0 += 1024) {
+        const long long q = q0 + threadIdx.x;
+        const int f = (q < M && (sc.pair_flag[q] & bit)) ? 1 : 0;
+        const unsigned ballot = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_w[w] = __popc(ballot);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int x = 0; x < 32; ++x) {
+            const int c = s_w[x];
+            before += x < w ? c : 0;
+            total += c;
+        }
+        const long long pos = s_base + before + __popc(ballot & ((1u << lane) - 1));
+        if (f) {
+            if (bit == 2) {
+                sc.cplx_list[pos] = (int)q;
+            } else if (pos < st.event_cap) {
+                st.events[3 * pos + 0] = stamp;
+                st.events[3 * pos + 1] = sc.ev_tmp[2 * q];
+                st.events[3 * pos + 2] = sc.ev_tmp[2 * q + 1];
+            } else {
+                st.status[COSMO_ST_ERROR] |= COSMO_ERR_EVENT_OVERFLOW;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (bit == 2) st.status[COSMO_ST_N_COMPLEX] = s_base;
+        else st.status[COSMO_ST_N_EVENTS] = s_base;
+    }
+}
+
+__global__ void k_resolve_complex(cosmo_state st, cosmo_scratch sc) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const long long C = st.status[COSMO_ST_N_COMPLEX];
+    const int stamp = (int)st.status[COSMO_ST_STEP];
+    for (long long c = 0; c < C; ++c) {
+        const int q = sc.cplx_list[c];
+        const uint64_t key = sc.pairs_sorted[q];
+        if (replay_pair(st, sc, (int)(key >> 32), (int)(key & 0xffffffffu), stamp, &sc.ev_tmp[2 * q]))
+            sc.pair_flag[q] |= 1;
+    }
+}
+
+// re-arm the self-resetting partner arrays
+__global__ void __launch_bounds__(256) k_csr_cleanup(cosmo_state st, cosmo_scratch sc) {
+    const long long M = pair_count(st, sc);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const uint64_t key = sc.pairs[q];
+        const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
+        sc.pmin[i] = 0x7fffffff; sc.pmax[i] = -1;
+        sc.pmin[j] = 0x7fffffff; sc.pmax[j] = -1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -418,30 +462,6 @@ __global__ void k_end_frame(cosmo_state st) {
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
-constexpr int DET_BLOCK = 128, DET_IB = 2, DET_TJ = 256;
-
-int detect_residency(int *rows_per_cta, int *tile) {
-    int nb = 0;
-    *rows_per_cta = DET_BLOCK * DET_IB; *tile = DET_TJ;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_detect_allpairs<DET_BLOCK, DET_IB, DET_TJ>, DET_BLOCK, 0) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    return nb;
-}
-
-int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
-                  cudaStream_t s) {
-    if (!(p.opts & COSMO_OPT_COLLISIONS)) return COSMO_OK;
-    const int rows = p.i_end - p.i_begin;
-    if (rows <= 0) return COSMO_OK;
-    int jsplit = p.jsplit_detect < 1 ? 1 : p.jsplit_detect;
-    const int per = DET_BLOCK * DET_IB;
-    dim3 grid((rows + per - 1) / per, jsplit);
-    k_detect_allpairs<DET_BLOCK, DET_IB, DET_TJ><<<grid, DET_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit);
-    return COSMO_LAUNCH_CHECK("k_detect_allpairs");
-}
-
 int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const uint64_t *src,
                         const int64_t *count_ptr, cudaStream_t s) {
     k_append_pairs<<<32, 256, 0, s>>>(st, sc, src, count_ptr);
@@ -451,11 +471,31 @@ int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const ui
 int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                           cudaStream_t s) {
     const int chunks = (p.n_upper + CHUNK - 1) / CHUNK > 0 ? (p.n_upper + CHUNK - 1) / CHUNK : 1;
-    if (p.opts & COSMO_OPT_COLLISIONS) {
+    if ((p.opts & COSMO_OPT_COLLISIONS) && p.resolve_mode == 0) {
         k_sort_pairs<<<64, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_sort_pairs"));
         k_resolve<<<1, 32, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_resolve"));
+    } else if (p.opts & COSMO_OPT_COLLISIONS) {
+        const int pb = 296;
+        k_csr_count<<<pb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_csr_count"));
+        COSMO_TRY(launch_scan_exclusive(sc.row_count, sc.row_start, sc.scan_blk, &st.status[COSMO_ST_N_ACTIVE],
+                                        p.n_upper, 0, s));
+        k_csr_fill<<<pb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_csr_fill"));
+        k_csr_sort_rows<<<pb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_csr_sort_rows"));
+        k_resolve_simple<<<pb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_resolve_simple"));
+        k_ordered_compact<<<1, 1024, 0, s>>>(st, sc, 2);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_ordered_compact(complex)"));
+        k_resolve_complex<<<1, 32, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_resolve_complex"));
+        k_ordered_compact<<<1, 1024, 0, s>>>(st, sc, 1);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_ordered_compact(events)"));
+        k_csr_cleanup<<<pb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_csr_cleanup"));
     }
     k_commit<<<chunks, 256, 0, s>>>(st, sc, (p.opts & COSMO_OPT_BOUNDED) ? 1 : 0);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k_commit"));

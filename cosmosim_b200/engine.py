@@ -70,6 +70,11 @@ class Engine:
         self.pos_exp = 0
         self.mass_exp = 0
         self.frames = 0
+        self.grid = None            # (cell_size, origin_x, origin_y, cells_per_side, giant_radius)
+        self.grid_threshold = 8192  # planets from which the grid broad phase + parallel resolver pay off
+        self.small_threshold = 4096  # below: small-N kernel shape (more, shorter CTAs)
+        self.retune_every = 16      # frames between host-side refreshes of n_upper / grid tuning
+        self._since_tune = 0
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self):
@@ -95,12 +100,25 @@ class Engine:
         t["new"] = z(cap, 5, dtype=f64)
         t["rinf"] = z(cap, dtype=f64)
         t["partial"] = z(self.JSPLIT_MAX, cap, 2, dtype=f64)
-        t["tile_ctr"] = z(cap // PAD * 4 + 4, dtype=i32)
+        t["tile_ctr"] = z(cap // 64 + 4, dtype=i32)
         t["alive"] = z(cap, dtype=u8); t["escaped"] = z(cap, dtype=u8)
         t["pairs"] = z(self.pair_cap, dtype=i64); t["pairs_sorted"] = z(self.pair_cap, dtype=i64)
         t["cur_pos"] = z(cap, 2, dtype=f64); t["cur_vel"] = z(cap, 2, dtype=f64)
         t["mod_row"] = z(cap, dtype=i32); t["mod_step"] = torch.full((cap,), -1, dtype=i32, device=dev)
         t["chunk_alive"] = z(cap // 1024 + 2, dtype=i32)
+        # CSR of the flagged pairs + parallel resolver
+        t["row_count"] = z(cap + 1, dtype=i32); t["row_start"] = z(cap + 1, dtype=i32)
+        t["pmin"] = torch.full((cap,), 0x7fffffff, dtype=i32, device=dev)
+        t["pmax"] = torch.full((cap,), -1, dtype=i32, device=dev)
+        t["scan_blk"] = z(_abi.SCAN_BLOCKS + 1, dtype=i32)
+        t["pair_flag"] = z(self.pair_cap, dtype=i32); t["cplx_list"] = z(self.pair_cap, dtype=i32)
+        t["ev_tmp"] = z(self.pair_cap, 2, dtype=i64)
+        # uniform-grid broad phase
+        self.grid_cells = int(min(_abi.SCAN_BLOCKS * 4096 - 1, max(1 << 16, 8 * cap)))
+        self.giant_cap = 4096
+        t["cell_of"] = z(cap, dtype=i32); t["cell_items"] = z(cap, dtype=i32)
+        t["cell_count"] = z(self.grid_cells + 1, dtype=i32); t["cell_start"] = z(self.grid_cells + 1, dtype=i32)
+        t["giants"] = z(self.giant_cap, dtype=i32)
         for k, dt_ in (("pos", f64), ("vel", f64)):
             t["t_" + k] = z(cap, 2, dtype=dt_)
         for k, dt_ in (("mass", f64), ("mass_hi", i64), ("mass_lo", i64), ("radius", f64), ("volume", f64),
@@ -124,15 +142,17 @@ class Engine:
         for k in ("h", "pk_x", "pk_y", "pk_m", "acc", "rinf", "partial", "tile_ctr", "alive", "escaped",
                   "pairs", "pairs_sorted", "cur_pos", "cur_vel", "mod_row", "mod_step", "chunk_alive",
                   "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_radius", "t_volume",
-                  "t_eaten", "t_id", "t_flags"):
+                  "t_eaten", "t_id", "t_flags", "row_count", "row_start", "pmin", "pmax", "scan_blk",
+                  "pair_flag", "cplx_list", "ev_tmp", "cell_of", "cell_items", "cell_count", "cell_start",
+                  "giants"):
             setattr(sc, k, p(k))
         sc.pos_new = C.c_void_p(self._pos_new.data_ptr())
         sc.vel_new = C.c_void_p(self._vel_new.data_ptr())
         sc.xx_new = C.c_void_p(self._xx_new.data_ptr())
         sc.jsplit_max = self.JSPLIT_MAX
         sc.pair_cap = self.pair_cap
-        sc.grid_cells = 0
-        sc.giant_cap = 0
+        sc.grid_cells = self.grid_cells
+        sc.giant_cap = self.giant_cap
         self.st, self.sc = st, sc
 
     # ------------------------------------------------------------------ host <-> device
@@ -172,6 +192,42 @@ class Engine:
         self.n_upper = n
         self.frames = int(frame)
         self._choose_scales(np.asarray(arrays["pos"], dtype=np.float64), np.asarray(arrays["mass_f64"], dtype=np.float64))
+        self._tune_grid(np.asarray(arrays["pos"], dtype=np.float64), np.asarray(arrays["radius"], dtype=np.float64))
+        self._since_tune = 0
+
+    def _tune_grid(self, pos, radius):
+        """Pick the broad-phase grid from the current positions and radii (host side, O(N)).
+
+        giant_radius: planets with (inflated) radius above it are tested against everybody;
+        cell edge >= 2 * giant_radius so flagged non-giant pairs are always in adjacent cells
+        (the device enlarges the edge further by the rounding slack of the reference's d^2)."""
+        n = radius.shape[0]
+        if n < self.grid_threshold:
+            self.grid = None
+            return
+        r = radius * (1.0 + 2.0 ** -30)
+        rg = float(np.quantile(r, 0.999)) * 1.5
+        n_giant = int(np.count_nonzero(r > rg))
+        if n_giant > self.giant_cap // 4:               # heavy tail: let the largest decide
+            rg = float(np.sort(r)[-(self.giant_cap // 4)])
+        lo, hi = pos.min(axis=0), pos.max(axis=0)
+        span = float(max(hi[0] - lo[0], hi[1] - lo[1], 4.0 * rg)) * 1.1
+        cx, cy = 0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1])
+        cmax = int(math.isqrt(self.grid_cells))
+        h = max(2.0 * rg * 1.001, span / cmax, span / max(1.0, 2.0 * math.sqrt(n)))
+        c = max(1, min(cmax, int(math.ceil(span / h))))
+        self.grid = (h, cx - 0.5 * c * h, cy - 0.5 * c * h, c, rg)
+
+    def retune(self):
+        """Synchronising refresh of the host-side launch parameters (active count, grid)."""
+        st = self.status()
+        n = st["n_active"]
+        if n >= self.grid_threshold:
+            self._tune_grid(self.t["pos"][:n].cpu().numpy(), self.t["radius"][:n].cpu().numpy())
+        else:
+            self.grid = None
+        self._since_tune = 0
+        return st
 
     def _choose_scales(self, pos, mass):
         # exact power-of-two rescaling for the FP32 path: max |coord| -> [32, 64), max mass -> [2^19, 2^20)
@@ -243,7 +299,17 @@ class Engine:
         with torch.cuda.device(self.device):
             p.jsplit = int(jsplit) if jsplit else self.lib.cosmo_suggest_jsplit(rows, max(1, n), kern, self.JSPLIT_MAX)
             p.jsplit_detect = int(jsplit) if jsplit else self.lib.cosmo_suggest_jsplit(rows, max(1, n), 3, self.JSPLIT_MAX)
-        p.detect_mode = 0
+        if self.grid is not None and collisions:
+            p.detect_mode, p.resolve_mode = 1, 1
+            p.cell_size, p.grid_origin_x, p.grid_origin_y, p.cells_per_side, p.giant_radius = self.grid
+        else:
+            p.detect_mode, p.resolve_mode = 0, 0
+        p.small_tiles = 1 if n <= self.small_threshold else 0
+        if p.small_tiles and not jsplit:
+            with torch.cuda.device(self.device):
+                if not fp32:
+                    p.jsplit = self.lib.cosmo_suggest_jsplit(rows, max(1, n), 4, self.JSPLIT_MAX)
+                p.jsplit_detect = self.lib.cosmo_suggest_jsplit(rows, max(1, n), 5, self.JSPLIT_MAX)
         return p
 
     def step(self, n_frames, dt, G, r_max, stage_events=None, **kw):
@@ -259,6 +325,11 @@ class Engine:
         st, sc, pp = C.byref(self.st), C.byref(self.sc), C.byref(p)
         lib = self.lib
         for _ in range(int(n_frames)):
+            if self._since_tune >= self.retune_every and self.n_upper >= self.grid_threshold:
+                self.retune()                      # one small D2H every retune_every frames
+                p = self.params(dt, G, r_max, **kw)
+                pp = C.byref(p)
+            self._since_tune += 1
             if self.world > 1:
                 self._step_sharded(p, stream)
             elif stage_events is None:
@@ -277,7 +348,14 @@ class Engine:
                 stage_events.append(ev)
         self.frames += int(n_frames)
 
-    LAUNCHES_PER_FRAME = 9  # prep, accel, detect, sort, resolve, commit, scatter, copyback, end
+    def launches_per_frame(self, collisions=True):
+        """Kernels of this library launched per frame in the current mode (bench.py reports it)."""
+        base = 2 + 4                                   # prep, accel | commit, scatter, copyback, end
+        if not collisions:
+            return base
+        if self.grid is None:
+            return base + 1 + 2                        # all-pairs detect | rank sort, resolve
+        return base + (2 + 3 + 3) + (1 + 3 + 7)        # grid (max,count,scan x3,fill,detect,giants) | csr path
 
     def _step_sharded(self, p, stream):
         from . import sharded

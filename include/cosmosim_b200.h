@@ -42,6 +42,7 @@ extern "C" {
 
 #define COSMO_ABI_VERSION 1
 #define COSMO_PAD 512 /* slot capacity granularity (tile size of the all-pairs kernels) */
+#define COSMO_SCAN_BLOCKS 8192 /* device scans handle up to COSMO_SCAN_BLOCKS * 4096 items */
 
 /* error codes */
 #define COSMO_OK 0
@@ -69,11 +70,15 @@ extern "C" {
 #define COSMO_ST_ERROR 5       /* sticky COSMO_ERR_* bits */
 #define COSMO_ST_N_ESCAPED 6   /* escaped planets destroyed so far (cumulative) */
 #define COSMO_ST_N_CAND 7      /* broad-phase candidates of the last frame (diagnostic) */
+#define COSMO_ST_N_GIANTS 8    /* planets brute-forced by the broad phase in the last frame */
+#define COSMO_ST_PMAX2 9       /* bits of max |pos_new|^2 (double) of the last frame */
+#define COSMO_ST_N_COMPLEX 10  /* flagged pairs replayed sequentially in the last frame */
 #define COSMO_STATUS_LEN 16
 
 #define COSMO_ERR_PAIR_OVERFLOW 1  /* more flagged pairs than pair_cap */
 #define COSMO_ERR_EVENT_OVERFLOW 2 /* event log full */
 #define COSMO_ERR_NAN 4            /* non-finite d^2 met in the acceleration pass */
+#define COSMO_ERR_GIANT_OVERFLOW 8 /* more brute-forced planets than giant_cap */
 
 /* Persistent state.  All pointers are device pointers. */
 typedef struct cosmo_state {
@@ -118,7 +123,7 @@ typedef struct cosmo_scratch {
     double *rinf;      /* [cap]      radii inflated by 2^-30 (candidate filter of stage B) */
     double *partial;   /* [jsplit_max][cap][2] partial sums of the all-pairs pass */
     int32_t jsplit_max;
-    int32_t *tile_ctr; /* [cap / COSMO_PAD * 4 + 4] arrival counters, must start zeroed */
+    int32_t *tile_ctr; /* [cap / 64 + 4] arrival counters, must start zeroed */
     uint8_t *alive;    /* [cap]      1 while the slot's planet is alive in this frame */
     uint8_t *escaped;  /* [cap]      start-of-frame escape flags (A6) */
     uint64_t *pairs;   /* [pair_cap] flagged ordered pairs (i << 32 | j), unsorted */
@@ -129,12 +134,21 @@ typedef struct cosmo_scratch {
     int32_t *mod_row;  /* [cap]      resolver: row of last modification */
     int32_t *mod_step; /* [cap]      resolver: frame stamp of mod_row, must start at -1 */
     int32_t *chunk_alive; /* [cap / 1024 + 1] survivors per 1024-slot chunk */
+    /* row-major (CSR) form of the flagged pairs + parallel resolver */
+    int32_t *row_count;   /* [cap + 1] must start zeroed (self-resetting) */
+    int32_t *row_start;   /* [cap + 1] */
+    int32_t *pmin;        /* [cap] smallest partner, must start at INT32_MAX (self-resetting) */
+    int32_t *pmax;        /* [cap] largest partner, must start at -1 (self-resetting) */
+    int32_t *scan_blk;    /* [COSMO_SCAN_BLOCKS] block sums of the device scans */
+    int32_t *pair_flag;   /* [pair_cap] bit0: merge happened, bit1: needs sequential replay */
+    int32_t *cplx_list;   /* [pair_cap] sorted-pair indices replayed sequentially */
+    int64_t *ev_tmp;      /* [pair_cap][2] (absorber id, absorbed id) per sorted-pair slot */
     /* compaction staging: one array per persistent field */
     double *t_pos; double *t_vel; double *t_mass; uint64_t *t_mass_hi; uint64_t *t_mass_lo;
     double *t_radius; double *t_volume; int64_t *t_eaten; int32_t *t_id; uint8_t *t_flags;
     /* broad phase (uniform grid) */
     int32_t *cell_of;    /* [cap] */
-    int32_t *cell_count; /* [grid_cells + 1] */
+    int32_t *cell_count; /* [grid_cells + 1] must start zeroed (self-resetting) */
     int32_t *cell_start; /* [grid_cells + 1] */
     int32_t *cell_items; /* [cap] */
     int32_t *giants;     /* [giant_cap] */
@@ -155,8 +169,11 @@ typedef struct cosmo_step_params {
     int32_t mass_exp;
     int32_t jsplit;   /* source-range splits of the all-pairs pass (>=1, <= jsplit_max) */
     int32_t detect_mode; /* 0 = all-pairs predicate, 1 = uniform-grid broad phase */
+    int32_t resolve_mode; /* 0 = rank sort + sequential replay (few pairs), 1 = CSR + parallel */
+    int32_t small_tiles;  /* 1 = small-N kernel shape for stage A/B (more, shorter CTAs) */
     double cell_size;    /* detect_mode 1 */
-    double grid_origin;  /* detect_mode 1: grid covers [origin, origin + cells_per_side*cell_size)^2 */
+    double grid_origin_x; /* detect_mode 1: the grid covers [origin, origin + cells_per_side*cell_size) */
+    double grid_origin_y; /*                per axis; planets outside are clamped to the border cells */
     int32_t cells_per_side;
     int32_t jsplit_detect; /* source-range splits of the stage-B all-pairs pass */
     double giant_radius; /* detect_mode 1: planets with radius above this are brute-forced */
@@ -203,7 +220,8 @@ int cosmo_begin_frame(const cosmo_state *st, const cosmo_scratch *sc,
                       const cosmo_step_params *p, void *stream);
 
 /* Suggested source-range split for `rows` target rows against n sources on this device;
-   kernel: 0 FP64 accel, 1 FP32 packed accel, 2 FP32 scalar accel, 3 all-pairs detection. */
+   kernel: 0 FP64 accel, 1 FP32 packed accel, 2 FP32 scalar accel, 3 all-pairs detection,
+   4 / 5 the small-N shapes of the FP64 accel / detection kernels. */
 int cosmo_suggest_jsplit(int32_t rows, int32_t n, int kernel, int32_t jsplit_max);
 
 /* Convenience: begin_frame + A + B + C on one device (no sharding). */
