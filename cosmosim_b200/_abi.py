@@ -38,7 +38,7 @@ class Scratch(C.Structure):
                 ("pair_cap", C.c_int64), ("cur_pos", _vp), ("cur_vel", _vp), ("mod_row", _vp),
                 ("mod_step", _vp), ("chunk_alive", _vp),
                 ("row_count", _vp), ("row_start", _vp), ("pmin", _vp), ("pmax", _vp), ("scan_blk", _vp),
-                ("pair_flag", _vp), ("cplx_list", _vp), ("ev_tmp", _vp),
+                ("pair_flag", _vp), ("cplx_list", _vp), ("ev_tmp", _vp), ("label", _vp), ("comp_items", _vp),
                 ("t_pos", _vp), ("t_vel", _vp), ("t_mass", _vp), ("t_mass_hi", _vp),
                 ("t_mass_lo", _vp), ("t_radius", _vp), ("t_volume", _vp), ("t_eaten", _vp),
                 ("t_id", _vp), ("t_flags", _vp),
@@ -67,7 +67,7 @@ SYMBOLS = {
     "cosmo_detect_pairs": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_resolve_commit": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_step": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
-    "cosmo_append_pairs": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), _vp, _vp, _vp]),
+    "cosmo_append_pairs": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), _vp, _vp, C.c_int64, _vp]),
     "cosmo_accel_workspace_bytes": (C.c_int64, [C.c_int32]),
     "cosmo_accel": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "cosmo_accel_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp,

@@ -142,12 +142,12 @@ int cosmo_step(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_
 }
 
 int cosmo_append_pairs(const cosmo_state *st, const cosmo_scratch *sc, const uint64_t *src,
-                       const int64_t *count_ptr, void *stream) {
+                       const int64_t *count_ptr, int64_t max_count, void *stream) {
     if (!st || !sc || !src || !count_ptr) {
         set_error("cosmo_append_pairs: null argument");
         return COSMO_E_ARG;
     }
-    return launch_append_pairs(*st, *sc, src, count_ptr, (cudaStream_t)stream);
+    return launch_append_pairs(*st, *sc, src, count_ptr, max_count, (cudaStream_t)stream);
 }
 
 // ---- function-level seam: acc_blas replacement on raw arrays --------------------------

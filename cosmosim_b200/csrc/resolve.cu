@@ -15,8 +15,14 @@ namespace cosmo {
 // Pair list utilities
 // ---------------------------------------------------------------------------------------
 __global__ void k_append_pairs(cosmo_state st, cosmo_scratch sc, const uint64_t *src,
-                               const int64_t *count_ptr) {
-    const long long cnt = *count_ptr;
+                               const int64_t *count_ptr, long long max_count) {
+    long long cnt = *count_ptr;
+    if (cnt > max_count) {
+        cnt = max_count;
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            atomicOr(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_ERROR]),
+                     (unsigned long long)COSMO_ERR_PAIR_OVERFLOW);
+    }
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < cnt;
          k += (long long)gridDim.x * blockDim.x) {
         uint64_t key = src[k];
@@ -177,7 +183,8 @@ __global__ void k_resolve(cosmo_state st, cosmo_scratch sc) {
 //   * "simple" pairs -- both planets have each other as their ONLY partner in the whole
 //     flagged set -- cannot interact with any other pair, so the sequential loop's outcome
 //     for them is independent of everything else: one thread each, in parallel;
-//   * everything else is replayed by one thread in sorted order (rare: chains and triples);
+//   * everything else (chains, triples) is split into connected components, each replayed
+//     by one thread in sorted order;
 //   * merge events land in a slot per sorted pair and are appended to the log in sorted
 //     order, which is the visitation order of the reference's double loop.
 // ---------------------------------------------------------------------------------------
@@ -288,12 +295,73 @@ __global__ void __launch_bounds__(1024) k_ordered_compact(cosmo_state st, cosmo_
     }
 }
 
-__global__ void k_resolve_complex(cosmo_state st, cosmo_scratch sc) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// Pairs that are not simple form small clusters (chains, triples).  Clusters are disjoint
+// sets of planets, so they are independent of each other; inside a cluster the reference's
+// order matters.  One CTA labels the connected components by min-label propagation over the
+// cluster edges (iterating to the fixed point: __syncthreads_or), then a counting sort groups
+// the pairs by component and one thread per component replays its pairs in sorted order.
+__global__ void __launch_bounds__(1024) k_components(cosmo_state st, cosmo_scratch sc) {
     const long long C = st.status[COSMO_ST_N_COMPLEX];
-    const int stamp = (int)st.status[COSMO_ST_STEP];
-    for (long long c = 0; c < C; ++c) {
+    if (C == 0) return;
+    for (long long c = threadIdx.x; c < C; c += blockDim.x) {
+        const uint64_t key = sc.pairs_sorted[sc.cplx_list[c]];
+        const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
+        sc.label[i] = i;
+        sc.label[j] = j;
+    }
+    __syncthreads();
+    for (int iter = 0; iter < (1 << 20); ++iter) {
+        int changed = 0;
+        for (long long c = threadIdx.x; c < C; c += blockDim.x) {
+            const uint64_t key = sc.pairs_sorted[sc.cplx_list[c]];
+            const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
+            const int li = *(volatile int *)&sc.label[i], lj = *(volatile int *)&sc.label[j];
+            if (li != lj) {
+                const int m = min(li, lj);
+                atomicMin(&sc.label[i], m);
+                atomicMin(&sc.label[j], m);
+                changed = 1;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    for (long long c = threadIdx.x; c < C; c += blockDim.x) {
+        const int i = (int)(sc.pairs_sorted[sc.cplx_list[c]] >> 32);
+        atomicAdd(&sc.row_count[*(volatile int *)&sc.label[i]], 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_comp_fill(cosmo_state st, cosmo_scratch sc) {
+    const long long C = st.status[COSMO_ST_N_COMPLEX];
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
         const int q = sc.cplx_list[c];
+        const int root = sc.label[(int)(sc.pairs_sorted[q] >> 32)];
+        const int slot = sc.row_start[root] + atomicSub(&sc.row_count[root], 1) - 1;
+        sc.comp_items[slot] = q;
+    }
+}
+
+// one thread per component root: order the component's pairs (ascending sorted-pair index =
+// visitation order) and replay them
+__global__ void __launch_bounds__(128) k_comp_resolve(cosmo_state st, cosmo_scratch sc) {
+    if (st.status[COSMO_ST_N_COMPLEX] == 0) return;
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int s0 = sc.row_start[v], s1 = sc.row_start[v + 1];
+    if (s1 <= s0) return;
+    const int stamp = (int)st.status[COSMO_ST_STEP];
+    for (int a = s0 + 1; a < s1; ++a) {
+        const int q = sc.comp_items[a];
+        int b = a - 1;
+        while (b >= s0 && sc.comp_items[b] > q) {
+            sc.comp_items[b + 1] = sc.comp_items[b];
+            --b;
+        }
+        sc.comp_items[b + 1] = q;
+    }
+    for (int a = s0; a < s1; ++a) {
+        const int q = sc.comp_items[a];
         const uint64_t key = sc.pairs_sorted[q];
         if (replay_pair(st, sc, (int)(key >> 32), (int)(key & 0xffffffffu), stamp, &sc.ev_tmp[2 * q]))
             sc.pair_flag[q] |= 1;
@@ -463,8 +531,8 @@ __global__ void k_end_frame(cosmo_state st) {
 // launchers
 // ---------------------------------------------------------------------------------------
 int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const uint64_t *src,
-                        const int64_t *count_ptr, cudaStream_t s) {
-    k_append_pairs<<<32, 256, 0, s>>>(st, sc, src, count_ptr);
+                        const int64_t *count_ptr, int64_t max_count, cudaStream_t s) {
+    k_append_pairs<<<32, 256, 0, s>>>(st, sc, src, count_ptr, (long long)max_count);
     return COSMO_LAUNCH_CHECK("k_append_pairs");
 }
 
@@ -490,8 +558,14 @@ int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc, const 
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_resolve_simple"));
         k_ordered_compact<<<1, 1024, 0, s>>>(st, sc, 2);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_ordered_compact(complex)"));
-        k_resolve_complex<<<1, 32, 0, s>>>(st, sc);
-        COSMO_TRY(COSMO_LAUNCH_CHECK("k_resolve_complex"));
+        k_components<<<1, 1024, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_components"));
+        COSMO_TRY(launch_scan_exclusive(sc.row_count, sc.row_start, sc.scan_blk, &st.status[COSMO_ST_N_ACTIVE],
+                                        p.n_upper, 0, s));
+        k_comp_fill<<<pb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_comp_fill"));
+        k_comp_resolve<<<(p.n_upper + 127) / 128 > 0 ? (p.n_upper + 127) / 128 : 1, 128, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_comp_resolve"));
         k_ordered_compact<<<1, 1024, 0, s>>>(st, sc, 1);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_ordered_compact(events)"));
         k_csr_cleanup<<<pb, 256, 0, s>>>(st, sc);

@@ -113,9 +113,10 @@ class Engine:
         t["scan_blk"] = z(_abi.SCAN_BLOCKS + 1, dtype=i32)
         t["pair_flag"] = z(self.pair_cap, dtype=i32); t["cplx_list"] = z(self.pair_cap, dtype=i32)
         t["ev_tmp"] = z(self.pair_cap, 2, dtype=i64)
+        t["label"] = z(cap, dtype=i32); t["comp_items"] = z(self.pair_cap, dtype=i32)
         # uniform-grid broad phase
         self.grid_cells = int(min(_abi.SCAN_BLOCKS * 4096 - 1, max(1 << 16, 8 * cap)))
-        self.giant_cap = 4096
+        self.giant_cap = 1 << 16
         t["cell_of"] = z(cap, dtype=i32); t["cell_items"] = z(cap, dtype=i32)
         t["cell_count"] = z(self.grid_cells + 1, dtype=i32); t["cell_start"] = z(self.grid_cells + 1, dtype=i32)
         t["giants"] = z(self.giant_cap, dtype=i32)
@@ -143,7 +144,7 @@ class Engine:
                   "pairs", "pairs_sorted", "cur_pos", "cur_vel", "mod_row", "mod_step", "chunk_alive",
                   "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_radius", "t_volume",
                   "t_eaten", "t_id", "t_flags", "row_count", "row_start", "pmin", "pmax", "scan_blk",
-                  "pair_flag", "cplx_list", "ev_tmp", "cell_of", "cell_items", "cell_count", "cell_start",
+                  "pair_flag", "cplx_list", "ev_tmp", "label", "comp_items", "cell_of", "cell_items", "cell_count", "cell_start",
                   "giants"):
             setattr(sc, k, p(k))
         sc.pos_new = C.c_void_p(self._pos_new.data_ptr())
@@ -206,22 +207,36 @@ class Engine:
             self.grid = None
             return
         r = radius * (1.0 + 2.0 ** -30)
-        rg = float(np.quantile(r, 0.999)) * 1.5
-        n_giant = int(np.count_nonzero(r > rg))
-        if n_giant > self.giant_cap // 4:               # heavy tail: let the largest decide
-            rg = float(np.sort(r)[-(self.giant_cap // 4)])
         lo, hi = pos.min(axis=0), pos.max(axis=0)
-        span = float(max(hi[0] - lo[0], hi[1] - lo[1], 4.0 * rg)) * 1.1
         cx, cy = 0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1])
+        box = float(max(hi[0] - lo[0], hi[1] - lo[1]))
+        # cost model: g giants cost g*N exact tests, the rest 9 cells * (N / area) * h^2 each
+        top = min(n - 1, 1024)
+        biggest = np.sort(np.partition(r, n - 1 - top)[n - 1 - top:])[::-1]     # descending, top+1 values
+        area = max(box * box, 1.0)
+        best = None
+        for g in (0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
+            if g > top:
+                break
+            rg_g = float(biggest[g]) * 1.3                   # headroom: merged planets grow until the next retune
+            cost = g * n + n * 9.0 * (n / area) * (2.0 * rg_g) ** 2
+            if best is None or cost < best[0]:
+                best = (cost, rg_g)
+        rg = best[1]
+        span = max(box, 4.0 * rg) * 1.1
         cmax = int(math.isqrt(self.grid_cells))
         h = max(2.0 * rg * 1.001, span / cmax, span / max(1.0, 2.0 * math.sqrt(n)))
         c = max(1, min(cmax, int(math.ceil(span / h))))
+        rg = max(rg, h / (2.0 * 1.001))       # cells wider than 2*rg: admit larger planets for free
         self.grid = (h, cx - 0.5 * c * h, cy - 0.5 * c * h, c, rg)
 
     def retune(self):
         """Synchronising refresh of the host-side launch parameters (active count, grid)."""
+        before = self.n_upper
         st = self.status()
         n = st["n_active"]
+        # crowded scenes (many merges per frame) change the radius distribution quickly
+        self.retune_every = 4 if before > 0 and (before - n) > 0.02 * before else 16
         if n >= self.grid_threshold:
             self._tune_grid(self.t["pos"][:n].cpu().numpy(), self.t["radius"][:n].cpu().numpy())
         else:
@@ -249,7 +264,9 @@ class Engine:
         err = st["error"]
         if err:
             what = [name for bit, name in ((1, "flagged-pair buffer overflow"), (2, "event log overflow"),
-                                           (4, "non-finite acceleration (d^2 < 0 or NaN input)")) if err & bit]
+                                           (4, "non-finite acceleration (d^2 < 0 or NaN input)"),
+                                           (8, "broad-phase giant list overflow")) if err & bit]
+            what = what or ["error bits 0x%x" % err]
             raise _abi.CosmoError("device reported: " + ", ".join(what))
         return st
 
@@ -355,7 +372,7 @@ class Engine:
             return base
         if self.grid is None:
             return base + 1 + 2                        # all-pairs detect | rank sort, resolve
-        return base + (2 + 3 + 3) + (1 + 3 + 7)        # grid (max,count,scan x3,fill,detect,giants) | csr path
+        return base + (2 + 3 + 3) + (1 + 3 + 4 + 1 + 3 + 4)  # grid (max,count,scan x3,fill,detect,giants) | csr + components
 
     def _step_sharded(self, p, stream):
         from . import sharded

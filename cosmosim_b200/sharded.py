@@ -62,10 +62,13 @@ def frame(eng, p, stream):
     _abi.check(lib.cosmo_detect_pairs(st, sc, pp, stream), "cosmo_detect_pairs")
     status = eng.t["status"]
     if not hasattr(eng, "_xchg"):
-        eng._xchg = torch.zeros(eng.world, 1 + eng.pair_cap, dtype=torch.int64, device=eng.device)
+        # every rank may contribute up to its share of the pair buffer
+        eng._xchg = torch.zeros(eng.world, 1 + max(1024, eng.pair_cap // eng.world), dtype=torch.int64,
+                                device=eng.device)
     xchg = exchange_pairs(eng.t["pairs"], status[ST_N_PAIRS], eng._xchg, eng.rank, eng.world, eng.group)
     status[ST_N_PAIRS] = 0
     for r in range(eng.world):
         _abi.check(lib.cosmo_append_pairs(st, sc, C.c_void_p(xchg[r, 1:].data_ptr()),
-                                          C.c_void_p(xchg[r, :1].data_ptr()), stream), "cosmo_append_pairs")
+                                          C.c_void_p(xchg[r, :1].data_ptr()), xchg.shape[1] - 1, stream),
+                   "cosmo_append_pairs")
     _abi.check(lib.cosmo_resolve_commit(st, sc, pp, stream), "cosmo_resolve_commit")

@@ -143,6 +143,8 @@ typedef struct cosmo_scratch {
     int32_t *pair_flag;   /* [pair_cap] bit0: merge happened, bit1: needs sequential replay */
     int32_t *cplx_list;   /* [pair_cap] sorted-pair indices replayed sequentially */
     int64_t *ev_tmp;      /* [pair_cap][2] (absorber id, absorbed id) per sorted-pair slot */
+    int32_t *label;       /* [cap] connected-component label of clustered planets */
+    int32_t *comp_items;  /* [pair_cap] sorted-pair indices grouped by component */
     /* compaction staging: one array per persistent field */
     double *t_pos; double *t_vel; double *t_mass; uint64_t *t_mass_hi; uint64_t *t_mass_lo;
     double *t_radius; double *t_volume; int64_t *t_eaten; int32_t *t_id; uint8_t *t_flags;
@@ -228,9 +230,10 @@ int cosmo_suggest_jsplit(int32_t rows, int32_t n, int kernel, int32_t jsplit_max
 int cosmo_step(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p,
                void *stream);
 
-/* Appends `count_ptr[0]` pairs from `src` (another rank's list) to scratch.pairs. */
+/* Appends min(count_ptr[0], max_count) pairs from `src` (one rank's list) to scratch.pairs;
+   a count above max_count raises COSMO_ERR_PAIR_OVERFLOW in the status block. */
 int cosmo_append_pairs(const cosmo_state *st, const cosmo_scratch *sc, const uint64_t *src,
-                       const int64_t *count_ptr, void *stream);
+                       const int64_t *count_ptr, int64_t max_count, void *stream);
 
 /*
  * Function-level seam for callers that only want the reference's acc_blas replaced:
