@@ -225,7 +225,7 @@ class Engine:
         rg = best[1]
         span = max(box, 4.0 * rg) * 1.1
         cmax = int(math.isqrt(self.grid_cells))
-        h = max(2.0 * rg * 1.001, span / cmax, span / max(1.0, 2.0 * math.sqrt(n)))
+        h = max(2.0 * rg * 1.001, span / cmax, span * 4.0 / (3.0 * math.sqrt(n)))   # ~16 candidates per planet
         c = max(1, min(cmax, int(math.ceil(span / h))))
         rg = max(rg, h / (2.0 * 1.001))       # cells wider than 2*rg: admit larger planets for free
         self.grid = (h, cx - 0.5 * c * h, cy - 0.5 * c * h, c, rg)
