@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="star_disk_1m_fp32", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="override the body count (development)")
+    ap.add_argument("--bodies", dest="n", type=int, default=0, help="override the body count (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--f32-scalar", action="store_true")
