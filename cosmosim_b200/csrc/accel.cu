@@ -170,16 +170,31 @@ __device__ __forceinline__ void reduce_and_integrate(const cosmo_state &st, cons
 // Only the d2 chain needs the reference's exact roundings (it is the ill-conditioned part);
 // 1/(d2 sqrt d2) is formed as y^3 with y = rsqrt(d2) refined from the MUFU seed by one
 // third-order step (relative error ~2e-16), instead of sqrt + divide.
+// ORDER: 0 -- every source index j of the tile is below every target i of the CTA
+//             (d2 = (c - h_i) - h_j), 2 -- every j is above every i (d2 = (c - h_j) - h_i),
+//        1 -- mixed (diagonal tiles): per-pair select on j >= i.
+// CHECK0: honour the reference's where= mask for d2 == 0 (self pair, coincident planets).
+// Off-diagonal tiles run with CHECK0 = false -- no select / integer test in the hot loop, the
+// FP64 pipe's dispatch slots are the bottleneck -- and are re-run with the checked flavour
+// in the (practically never taken) case that an accumulator came out non-finite.
+template <int ORDER, bool CHECK0>
 __device__ __forceinline__ void pair_f64(double xi, double yi, double qix, double qiy, double hi,
                                          int i, double xj, double yj, double hj, double mj, int j,
                                          double &ax, double &ay) {
     double rx = __dadd_rn(__dmul_rn(qix, xj), -2.0);
     double ry = __dadd_rn(__dmul_rn(qiy, yj), -2.0);
     double c = __dadd_rn(__dadd_rn(rx, ry), 6.0);
-    const bool ge = j >= i;
-    double a1 = ge ? hj : hi;
-    double a2 = ge ? hi : hj;
-    double d2 = __dadd_rn(__dadd_rn(c, -a1), -a2);
+    double d2;
+    if (ORDER == 0) {
+        d2 = __dadd_rn(__dadd_rn(c, -hi), -hj);
+    } else if (ORDER == 2) {
+        d2 = __dadd_rn(__dadd_rn(c, -hj), -hi);
+    } else {
+        const bool ge = j >= i;
+        double a1 = ge ? hj : hi;
+        double a2 = ge ? hi : hj;
+        d2 = __dadd_rn(__dadd_rn(c, -a1), -a2);
+    }
     double dx = xj - xi, dy = yj - yi;
     double y = rsqrt_approx_f64(d2);
     double t = d2 * y;
@@ -189,9 +204,28 @@ __device__ __forceinline__ void pair_f64(double xi, double yi, double qix, doubl
     y = __fma_rn(ye, p, y);                // y (1 + e/2 + 3 e^2/8)
     double s = (mj * y) * (y * y);
     // where= mask of blas.py:31: entries with d2 == 0 keep the undivided difference
-    s = ((__double2hiint(d2) << 1) | __double2loint(d2)) == 0 ? mj : s;
+    if (CHECK0) s = ((__double2hiint(d2) << 1) | __double2loint(d2)) == 0 ? mj : s;
     ax = __fma_rn(dx, s, ax);
     ay = __fma_rn(dy, s, ay);
+}
+
+template <int IB, int ORDER, bool CHECK0>
+__device__ __forceinline__ void tile_f64(const double2 *__restrict__ sxy, const double *__restrict__ sh,
+                                         const double *__restrict__ sm, int cnt, int j0,
+                                         const double (&xi)[IB], const double (&yi)[IB],
+                                         const double (&qix)[IB], const double (&qiy)[IB],
+                                         const double (&hi)[IB], const int (&ii)[IB], double (&ax)[IB],
+                                         double (&ay)[IB]) {
+#pragma unroll 2
+    for (int jj = 0; jj < cnt; ++jj) {
+        const double2 pj = sxy[jj];
+        const double hj = sh[jj];
+        const double mj = sm[jj];
+#pragma unroll
+        for (int k = 0; k < IB; ++k)
+            pair_f64<ORDER, CHECK0>(xi[k], yi[k], qix[k], qiy[k], hi[k], ii[k], pj.x, pj.y, hj, mj, j0 + jj,
+                                    ax[k], ay[k]);
+    }
 }
 
 template <int BLOCK, int IB, int TJ>
@@ -254,15 +288,25 @@ k_accel_f64(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
         mbar_wait(&s_bar[b], (it >> 1) & 1);
         const int j0 = t * TJ;
         const int cnt = min(TJ, n - j0);
-#pragma unroll 2
-        for (int jj = 0; jj < cnt; ++jj) {
-            const double2 pj = s_xy[b][jj];
-            const double hj = s_h[b][jj];
-            const double mj = s_m[b][jj];
+        const int order = (j0 + TJ <= base) ? 0 : (j0 >= base + BLOCK * IB ? 2 : 1);
+        if (order == 1) {
+            tile_f64<IB, 1, true>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, ax, ay);
+        } else {
+            double sx[IB], sy[IB];
 #pragma unroll
-            for (int k = 0; k < IB; ++k)
-                pair_f64(xi[k], yi[k], qix[k], qiy[k], hi[k], ii[k], pj.x, pj.y, hj, mj, j0 + jj,
-                         ax[k], ay[k]);
+            for (int k = 0; k < IB; ++k) { sx[k] = ax[k]; sy[k] = ay[k]; }
+            if (order == 0)
+                tile_f64<IB, 0, false>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, ax, ay);
+            else
+                tile_f64<IB, 2, false>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, ax, ay);
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < IB; ++k) bad = bad || !(isfinite(ax[k]) && isfinite(ay[k]));
+            if (bad) {  // a d2 == 0 (or negative) entry off the diagonal: redo with the mask honoured
+#pragma unroll
+                for (int k = 0; k < IB; ++k) { ax[k] = sx[k]; ay[k] = sy[k]; }
+                tile_f64<IB, 1, true>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, ax, ay);
+            }
         }
         __syncthreads();  // everyone is done with buffer b before it is refilled
     }

@@ -66,6 +66,10 @@ class Engine:
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
             self.cap = sharded.required_capacity(self.n_total, self.world)
         self._alloc()
+        # last completed frame's status block, refreshed by an async D2H copy after every frame:
+        # the active count only shrinks, so a slightly stale value is a safe, tight upper bound
+        self._status_host = torch.zeros(STATUS_LEN, dtype=torch.int64).pin_memory()
+        self._status_epoch = 0       # frame counter at the last upload (guards against stale reads)
         self.n_upper = 0
         self.pos_exp = 0
         self.mass_exp = 0
@@ -73,7 +77,8 @@ class Engine:
         self.grid = None            # (cell_size, origin_x, origin_y, cells_per_side, giant_radius)
         self.grid_threshold = 8192  # planets from which the grid broad phase + parallel resolver pay off
         self.small_threshold = 4096  # below: small-N kernel shape (more, shorter CTAs)
-        self.retune_every = 16      # frames between host-side refreshes of n_upper / grid tuning
+        self.retune_every = 16      # frames between host-side refreshes of the grid tuning
+        self._manual_n = False
         self._since_tune = 0
 
     # ------------------------------------------------------------------ buffers
@@ -192,6 +197,9 @@ class Engine:
         t["mod_step"].fill_(-1)
         self.n_upper = n
         self.frames = int(frame)
+        torch.cuda.current_stream(self.device).synchronize()
+        self._status_host.copy_(status)
+        self._status_epoch = int(frame)
         self._choose_scales(np.asarray(arrays["pos"], dtype=np.float64), np.asarray(arrays["mass_f64"], dtype=np.float64))
         self._tune_grid(np.asarray(arrays["pos"], dtype=np.float64), np.asarray(arrays["radius"], dtype=np.float64))
         self._since_tune = 0
@@ -347,6 +355,13 @@ class Engine:
                 p = self.params(dt, G, r_max, **kw)
                 pp = C.byref(p)
             self._since_tune += 1
+            # non-blocking refresh of the launch bound from the newest COMPLETED frame
+            seen_n, seen_f = int(self._status_host[ST_N_ACTIVE]), int(self._status_host[ST_STEP])
+            if (self.world == 1 and self._status_epoch <= seen_f <= self.frames and 0 < seen_n < self.n_upper
+                    and not self._manual_n):   # sharded ranks must agree on the bound: they use retune() only
+                self.n_upper = seen_n
+                p = self.params(dt, G, r_max, **kw)
+                pp = C.byref(p)
             if self.world > 1:
                 self._step_sharded(p, stream)
             elif stage_events is None:
@@ -363,7 +378,8 @@ class Engine:
                 _abi.check(lib.cosmo_resolve_commit(st, sc, pp, stream), "cosmo_resolve_commit")
                 ev[4].record()
                 stage_events.append(ev)
-        self.frames += int(n_frames)
+            self.frames += 1
+            self._status_host.copy_(self.t["status"], non_blocking=True)
 
     def launches_per_frame(self, collisions=True):
         """Kernels of this library launched per frame in the current mode (bench.py reports it)."""
@@ -413,6 +429,7 @@ class Engine:
         stg["status_in"][ST_STEP] = self.frames
         t["status"].copy_(stg["status_in"], non_blocking=True)
         self.n_upper = n
+        self._status_epoch = self.frames + 1      # ignore status snapshots of earlier frames
         self.step(1, dt, G, r_max, **kw)
         for k in self.E2E_OUT:
             stg["out"][k].copy_(t[k][:n], non_blocking=True)

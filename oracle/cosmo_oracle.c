@@ -198,6 +198,11 @@ void oracle_integrate(int64_t n, const double *p0, const double *v0, const doubl
  *   d2    = fl(fl(-2 dot + XX_i) + XX_j)                 distances += XX; distances += YY
  *   d     = sqrt(max(d2, 0)); diagonal forced to 0       np.maximum / fill_diagonal
  *   flag  = max(d, 1) <= fl(r_i + r_j)                   np.clip(d,1,None) <= add.outer
+ * Known limit of "bit-exact" here: the dot's contraction is the one of OpenBLAS' main dgemm
+ * micro-kernel (verified bitwise on whole N x N matrices for N mod 8 < 4, incl. the fixture
+ * sizes 1000/1001).  For N mod 8 >= 4 OpenBLAS handles a 4-wide block of tail rows/columns with
+ * a kernel that does not fuse the K = 2 dot; those entries differ by a few ulps of |p|^2
+ * (<= 3e-12 relative in d).  The flag can only differ if d is within that distance of r_i + r_j.
  * Emits the flagged ordered pairs (i,j), i != j, row-major ascending -- exactly the set and
  * order in which the merge loop's `if c and i != j` fires (universe_old.py:203-204).
  * Returns the number of flagged pairs (may exceed cap; only the first cap are stored).
