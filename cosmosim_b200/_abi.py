@@ -7,12 +7,12 @@ import os
 from . import _build
 
 ABI_VERSION = 1
-PAD = 512
+PAD = 1024
 STATUS_LEN = 16
 
 # flag / option / status constants (mirror the header)
 F_IMMOBILE, F_MASS_INT = 1, 2
-OPT_COLLISIONS, OPT_BOUNDED, OPT_FP32, OPT_STORE_ACC, OPT_F32_SCALAR = 1, 2, 4, 8, 16
+OPT_COLLISIONS, OPT_BOUNDED, OPT_FP32, OPT_STORE_ACC, OPT_F32_SCALAR, OPT_F32_SYM, OPT_DEFER_INTEGRATE = 1, 2, 4, 8, 16, 32, 64
 ST_N_ACTIVE, ST_STEP, ST_N_EVENTS, ST_N_PAIRS, ST_N_DEAD, ST_ERROR, ST_N_ESCAPED, ST_N_CAND, ST_N_GIANTS, ST_PMAX2, ST_N_COMPLEX = range(11)
 SCAN_BLOCKS = 8192
 ERR_PAIR_OVERFLOW, ERR_EVENT_OVERFLOW, ERR_NAN, ERR_GIANT_OVERFLOW = 1, 2, 4, 8
@@ -33,7 +33,7 @@ class State(C.Structure):
 class Scratch(C.Structure):
     _fields_ = [("h", _vp), ("pk_x", _vp), ("pk_y", _vp), ("pk_m", _vp), ("acc", _vp),
                 ("pos_new", _vp), ("vel_new", _vp), ("xx_new", _vp), ("rinf", _vp),
-                ("partial", _vp), ("jsplit_max", C.c_int32), ("tile_ctr", _vp),
+                ("partial", _vp), ("jsplit_max", C.c_int32), ("colbuf", _vp), ("colbuf_rows", C.c_int64), ("tile_ctr", _vp),
                 ("alive", _vp), ("escaped", _vp), ("pairs", _vp), ("pairs_sorted", _vp),
                 ("pair_cap", C.c_int64), ("cur_pos", _vp), ("cur_vel", _vp), ("mod_row", _vp),
                 ("mod_step", _vp), ("chunk_alive", _vp),
@@ -51,7 +51,8 @@ class StepParams(C.Structure):
                 ("opts", C.c_uint32), ("n_upper", C.c_int32), ("i_begin", C.c_int32),
                 ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
                 ("jsplit", C.c_int32), ("detect_mode", C.c_int32), ("resolve_mode", C.c_int32),
-                ("small_tiles", C.c_int32), ("cell_size", C.c_double),
+                ("small_tiles", C.c_int32), ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("sym_chunk", C.c_int32), ("reserved0", C.c_int32),
+                ("cell_size", C.c_double),
                 ("grid_origin_x", C.c_double), ("grid_origin_y", C.c_double), ("cells_per_side", C.c_int32), ("jsplit_detect", C.c_int32),
                 ("giant_radius", C.c_double)]
 
@@ -64,6 +65,7 @@ SYMBOLS = {
     "cosmo_suggest_jsplit": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int32]),
     "cosmo_begin_frame": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_accel_integrate": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
+    "cosmo_integrate": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_detect_pairs": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_resolve_commit": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_step": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),

@@ -120,6 +120,11 @@ int cosmo_accel_integrate(const cosmo_state *st, const cosmo_scratch *sc, const 
     return launch_accel(*st, *sc, *p, (cudaStream_t)stream);
 }
 
+int cosmo_integrate(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p, void *stream) {
+    COSMO_TRY(check_args(st, sc, p));
+    return launch_sym_integrate(*st, *sc, *p, (cudaStream_t)stream);
+}
+
 int cosmo_detect_pairs(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p,
                        void *stream) {
     COSMO_TRY(check_args(st, sc, p));

@@ -1,0 +1,266 @@
+// Stage A, FP32 fast flavour, SYMMETRIC variant: every unordered pair {i, j} is evaluated once
+// and its (antisymmetric) force is accumulated on both planets -- 6 FMA-pipe instructions and
+// half a MUFU per ORDERED interaction instead of 9 and 1.  Same entry point / reference lines as
+// accel.cu (acc_blas, cosmosim/util/blas.py:4-41; integrator universe_old.py:177-178).
+//
+// Decomposition.  Planets are cut into blocks of 1024 (8 groups of 128).  A CTA of 8 warps owns
+// one ROW block I and walks a chunk of COLUMN blocks J >= I.  Warp w keeps group w of I in
+// registers (4 planets per lane: the "row" side, accumulated in packed FP32 registers).  For a
+// column block J, staged in shared memory by TMA bulk copies, the CTA runs 8 rounds; in round
+// `it` warp w works on column group g = (w + it) & 7, so no two warps touch the same column
+// group in the same round.  Inside a round the 128 column planets are dealt to the lanes in
+// chunks of 4 and ROTATE through the warp: at step s lane l reads chunk (l + s) & 31 from
+// shared memory and holds that chunk's partial column accumulators, which it then hands to
+// lane l-1 with 8 SHFLs -- after 32 steps every row planet of the warp has met every column
+// planet of the group and the accumulators are back in their home lane.  Per step and lane:
+// 4 x 4 pairs = 96 FFMA2-class instructions + 16 MUFU.RSQ + 3 LDS.128 + 8 SHFL.
+//
+// The column sums of a (I, J) pair go to colbuf[I][j] (float2); the row sums to partial[chunk][i]
+// (double2).  k_sym_reduce adds, for every planet, its row partials and the column partials of
+// all I < K in ascending order -- deterministic -- and runs the integrator epilogue.  The
+// diagonal pair (J == I) runs the same schedule without the column side, which evaluates each
+// of its ordered pairs exactly once.  HBM: colbuf is written and read once per frame
+// (8 B x N^2 / 2048: 4.3 GB at N = 2^20, ~1 ms of the 180 GB part's bandwidth).
+#include <math.h>
+
+#include "cosmo_device.cuh"
+#include "cosmo_internal.h"
+#include "integrate.cuh"
+
+namespace cosmo {
+
+constexpr int SYM_BLOCK = 1024;   // planets per block
+constexpr int SYM_GROUP = 128;    // planets per warp (4 per lane)
+constexpr int SYM_WARPS = 8;
+constexpr int SYM_THREADS = SYM_WARPS * 32;
+#define COSMO_F32_TINY_SYM 8.673617379884035e-19f /* 2^-60 softening, see accel.cu */
+
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src_lane) {
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    lo = __shfl_sync(0xffffffffu, lo, src_lane);
+    hi = __shfl_sync(0xffffffffu, hi, src_lane);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(SYM_THREADS, 2)
+k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int chunk) {
+    __shared__ __align__(16) float s_x[2][SYM_BLOCK];
+    __shared__ __align__(16) float s_y[2][SYM_BLOCK];
+    __shared__ __align__(16) float s_m[2][SYM_BLOCK];
+    __shared__ __align__(16) float s_cx[SYM_BLOCK];     // column accumulators of the current J
+    __shared__ __align__(16) float s_cy[SYM_BLOCK];
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int nblk = (n + SYM_BLOCK - 1) / SYM_BLOCK;
+    const int I = shard_index + blockIdx.x * shard_count;
+    if (I >= nblk) return;
+    const int J0 = I + blockIdx.y * chunk;
+    if (J0 >= nblk) return;
+    const int J1 = min(nblk, J0 + chunk);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+    // row side: 4 planets per lane, strided by 32 inside the warp's group (coalesced)
+    float xi[4], yi[4], nmi[4];
+    double rax[4], ray[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = I * SYM_BLOCK + w * SYM_GROUP + k * 32 + lane;
+        xi[k] = sc.pk_x[r];
+        yi[k] = sc.pk_y[r];
+        nmi[k] = -sc.pk_m[r];
+        rax[k] = 0.0; ray[k] = 0.0;
+    }
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    constexpr uint32_t kBytes = SYM_BLOCK * 3 * sizeof(float);
+    auto issue = [&](int J, int b) {
+        const size_t j0 = (size_t)J * SYM_BLOCK;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar[b], kBytes);
+        bulk_g2s(&s_x[b][0], sc.pk_x + j0, SYM_BLOCK * sizeof(float), &s_bar[b]);
+        bulk_g2s(&s_y[b][0], sc.pk_y + j0, SYM_BLOCK * sizeof(float), &s_bar[b]);
+        bulk_g2s(&s_m[b][0], sc.pk_m + j0, SYM_BLOCK * sizeof(float), &s_bar[b]);
+    };
+    if (tid == 0) issue(J0, 0);
+
+    const uint64_t eps2 = pack2(COSMO_F32_TINY_SYM, COSMO_F32_TINY_SYM);
+    float2 *colbuf = reinterpret_cast<float2 *>(sc.colbuf);
+    const size_t col_row = (size_t)blockIdx.x * (size_t)st.cap;   // local row-block index of this rank
+
+    for (int J = J0; J < J1; ++J) {
+        const int it_j = J - J0;
+        const int b = it_j & 1;
+        if (tid == 0 && J + 1 < J1) issue(J + 1, b ^ 1);
+        for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) { s_cx[q] = 0.f; s_cy[q] = 0.f; }
+        mbar_wait(&s_bar[b], (it_j >> 1) & 1);
+        __syncthreads();
+        const bool diag = (J == I);
+        uint64_t rx2[4], ry2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { rx2[k] = 0ull; ry2[k] = 0ull; }
+
+        for (int it = 0; it < SYM_WARPS; ++it) {
+            const int g = (w + it) & (SYM_WARPS - 1);
+            const float *gx = &s_x[b][g * SYM_GROUP];
+            const float *gy = &s_y[b][g * SYM_GROUP];
+            const float *gm = &s_m[b][g * SYM_GROUP];
+            uint64_t tx2[2] = {0ull, 0ull}, ty2[2] = {0ull, 0ull};   // travelling column sums
+#pragma unroll 1
+            for (int s = 0; s < 32; ++s) {
+                const int c = (lane + s) & 31;
+                const float4 X = *reinterpret_cast<const float4 *>(gx + 4 * c);
+                const float4 Y = *reinterpret_cast<const float4 *>(gy + 4 * c);
+                const float4 M = *reinterpret_cast<const float4 *>(gm + 4 * c);
+                const uint64_t xj2[2] = {pack2(X.x, X.y), pack2(X.z, X.w)};
+                const uint64_t yj2[2] = {pack2(Y.x, Y.y), pack2(Y.z, Y.w)};
+                const uint64_t mj2[2] = {pack2(M.x, M.y), pack2(M.z, M.w)};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t xik = pack2(xi[k], xi[k]), yik = pack2(yi[k], yi[k]);
+                    const uint64_t nmik = pack2(nmi[k], nmi[k]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint64_t dx = sub2(xj2[h], xik);
+                        const uint64_t dy = sub2(yj2[h], yik);
+                        const uint64_t r2 = fma2(dy, dy, fma2(dx, dx, eps2));
+                        float r2a, r2b;
+                        unpack2(r2, r2a, r2b);
+                        const uint64_t rinv = pack2(rsqrt_approx_f32(r2a), rsqrt_approx_f32(r2b));
+                        const uint64_t rinv3 = mul2(mul2(rinv, rinv), rinv);
+                        const uint64_t sj = mul2(mj2[h], rinv3);     // pull of the column planets on row k
+                        const uint64_t nsi = mul2(rinv3, nmik);      // minus the pull of row k on them
+                        rx2[k] = fma2(dx, sj, rx2[k]);
+                        ry2[k] = fma2(dy, sj, ry2[k]);
+                        tx2[h] = fma2(dx, nsi, tx2[h]);
+                        ty2[h] = fma2(dy, nsi, ty2[h]);
+                    }
+                }
+                // hand the chunk's column sums to the lane that meets this chunk next
+                const int src = (lane + 1) & 31;
+                tx2[0] = shfl64(tx2[0], src); tx2[1] = shfl64(tx2[1], src);
+                ty2[0] = shfl64(ty2[0], src); ty2[1] = shfl64(ty2[1], src);
+            }
+            if (!diag) {   // home again: lane l holds the sums of chunk l of group g
+                float4 cx = *reinterpret_cast<float4 *>(&s_cx[g * SYM_GROUP + 4 * lane]);
+                float4 cy = *reinterpret_cast<float4 *>(&s_cy[g * SYM_GROUP + 4 * lane]);
+                float a0, a1, a2, a3;
+                unpack2(tx2[0], a0, a1); unpack2(tx2[1], a2, a3);
+                cx.x += a0; cx.y += a1; cx.z += a2; cx.w += a3;
+                unpack2(ty2[0], a0, a1); unpack2(ty2[1], a2, a3);
+                cy.x += a0; cy.y += a1; cy.z += a2; cy.w += a3;
+                *reinterpret_cast<float4 *>(&s_cx[g * SYM_GROUP + 4 * lane]) = cx;
+                *reinterpret_cast<float4 *>(&s_cy[g * SYM_GROUP + 4 * lane]) = cy;
+            }
+            __syncthreads();   // the next round moves every warp to another column group
+        }
+        // fold this block's FP32 row sums into the FP64 accumulators
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float a, c2;
+            unpack2(rx2[k], a, c2);
+            rax[k] += (double)a + (double)c2;
+            unpack2(ry2[k], a, c2);
+            ray[k] += (double)a + (double)c2;
+        }
+        if (!diag) {
+            float2 *dst = colbuf + col_row + (size_t)J * SYM_BLOCK;
+            for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) dst[q] = make_float2(s_cx[q], s_cy[q]);
+        }
+        __syncthreads();   // column accumulators and buffer b are free again
+    }
+    double2 *partial = reinterpret_cast<double2 *>(sc.partial);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = I * SYM_BLOCK + w * SYM_GROUP + k * 32 + lane;
+        partial[(size_t)blockIdx.y * st.cap + r] = make_double2(rax[k], ray[k]);
+    }
+}
+
+// a_k = unscale * (sum of the row partials of block K + sum over I < K of colbuf[I][k]), then the
+// integrator epilogue (accel.cu).  With `defer` the per-rank sum goes to scratch.acc instead
+// (multi-GPU: all-reduced by the caller, then k_sym_integrate).
+__global__ void __launch_bounds__(256)
+k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int chunk, double unscale,
+             double G, double dt, int store_acc, int defer) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int nblk = (n + SYM_BLOCK - 1) / SYM_BLOCK;
+    const int K = k / SYM_BLOCK;
+    double ax = 0.0, ay = 0.0;
+    if (K % shard_count == shard_index) {
+        const double2 *partial = reinterpret_cast<const double2 *>(sc.partial);
+        const int nchunk = (nblk - K + chunk - 1) / chunk;
+        for (int c = 0; c < nchunk; ++c) {
+            const double2 v = partial[(size_t)c * st.cap + k];
+            ax += v.x;
+            ay += v.y;
+        }
+    }
+    const float2 *colbuf = reinterpret_cast<const float2 *>(sc.colbuf);
+    // row blocks I < K owned by this rank: I = shard_index + r * shard_count
+    int r = 0;
+    for (int I = shard_index; I < K; I += shard_count, ++r) {
+        const float2 v = __ldcs(&colbuf[(size_t)r * st.cap + k]);
+        ax += (double)v.x;
+        ay += (double)v.y;
+    }
+    ax *= unscale;
+    ay *= unscale;
+    if (defer) {
+        reinterpret_cast<double2 *>(sc.acc)[k] = make_double2(ax, ay);
+    } else {
+        integrate_store(st, sc, k, ax, ay, G, dt, store_acc != 0);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_sym_integrate(cosmo_state st, cosmo_scratch sc, double G, double dt) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double2 a = reinterpret_cast<const double2 *>(sc.acc)[k];
+    // sc.acc holds the all-reduced sums S; integrate_store multiplies by G and rewrites acc = G S
+    integrate_store(st, sc, k, a.x, a.y, G, dt, true);
+}
+
+int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                     cudaStream_t s) {
+    const int n = p.n_upper;
+    if (n <= 0) return COSMO_OK;
+    const int nblk = (n + SYM_BLOCK - 1) / SYM_BLOCK;
+    const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
+    const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
+    const int rows_local = (nblk - sh_i + sh_n - 1) / sh_n;
+    int chunk = p.sym_chunk > 0 ? p.sym_chunk : 32;
+    while ((nblk + chunk - 1) / chunk > sc.jsplit_max) ++chunk;
+    if (!sc.colbuf || (long long)rows_local > sc.colbuf_rows) {
+        set_error("symmetric accel: colbuf has %lld rows, %d needed", (long long)sc.colbuf_rows, rows_local);
+        return COSMO_E_ARG;
+    }
+    const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
+    if (rows_local > 0) {
+        dim3 grid(rows_local, (nblk + chunk - 1) / chunk);
+        k_accel_f32_sym<<<grid, SYM_THREADS, 0, s>>>(st, sc, sh_i, sh_n, chunk);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_accel_f32_sym"));
+    }
+    const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? 1 : 0;
+    k_sym_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, unscale, p.G, p.dt,
+                                                 (p.opts & COSMO_OPT_STORE_ACC) ? 1 : 0, defer);
+    return COSMO_LAUNCH_CHECK("k_sym_reduce");
+}
+
+int launch_sym_integrate(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                         cudaStream_t s) {
+    if (p.n_upper <= 0) return COSMO_OK;
+    k_sym_integrate<<<(p.n_upper + 255) / 256, 256, 0, s>>>(st, sc, p.G, p.dt);
+    return COSMO_LAUNCH_CHECK("k_sym_integrate");
+}
+
+}  // namespace cosmo

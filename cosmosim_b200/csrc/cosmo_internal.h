@@ -26,6 +26,12 @@ int launch_accel(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_ste
 
 int accel_residency(int which, int *rows_per_cta, int *tile);
 
+// accel_sym.cu
+int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                     cudaStream_t s);
+int launch_sym_integrate(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                         cudaStream_t s);
+
 // detect.cu / resolve.cu
 int detect_residency(int *rows_per_cta, int *tile);
 int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,

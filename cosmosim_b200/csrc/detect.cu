@@ -180,15 +180,20 @@ __device__ __forceinline__ void test_and_emit(const cosmo_state &st, const cosmo
     if (d2 <= rs * rs && pred_exact(d2, st.radius[i], st.radius[j])) emit_pair(st, sc, i, j);
 }
 
-// one thread per non-giant target row: 3 x 3 neighbourhood + the giants
+// One thread per non-giant target row, taken in CELL-SORTED order: the lanes of a warp then
+// work on planets of the same or neighbouring cells, so their candidate loops have similar trip
+// counts (the disk's surface density varies 20x between its inner and outer edge) and their
+// gathers hit the same lines.  Sharding splits the sorted order evenly; every row is still
+// produced exactly once.
 __global__ void __launch_bounds__(128)
-k_grid_detect(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int c) {
-    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
-    const int i_hi = min(i_end, n);
-    const int i = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= i_hi) return;
+k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int c) {
+    const int total = sc.cell_start[c * c];                       // non-giant planets
+    const int per = (total + shard_count - 1) / shard_count;
+    const int s_lo = shard_index * per, s_hi = min(total, s_lo + per);
+    const int slot = s_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= s_hi) return;
+    const int i = sc.cell_items[slot];
     const int cell = sc.cell_of[i];
-    if (cell < 0) return;
     const double2 p = reinterpret_cast<const double2 *>(sc.pos_new)[i];
     const double qx = -2.0 * p.x, qy = -2.0 * p.y, xxi = sc.xx_new[i], ri = sc.rinf[i];
     const int cx = cell % c, cy = cell / c;
@@ -208,8 +213,10 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int c) {
     const int ng = (int)min((long long)st.status[COSMO_ST_N_GIANTS], (long long)sc.giant_cap);
     for (int g = 0; g < ng; ++g) test_and_emit(st, sc, i, qx, qy, xxi, ri, sc.giants[g]);
     // diagnostic only
-    if ((threadIdx.x & 31) == 0 && cand)
-        atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_CAND]), (unsigned long long)cand);
+    const unsigned mask = __activemask();
+    const unsigned tot = __reduce_add_sync(mask, (unsigned)cand);
+    if ((threadIdx.x & 31) == __ffs(mask) - 1 && tot)
+        atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_CAND]), (unsigned long long)tot);
 }
 
 // rows of the giants: giant g against every planet (blockIdx.y strides over the giants)
@@ -265,9 +272,14 @@ int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_st
         COSMO_TRY(launch_scan_exclusive(sc.cell_count, sc.cell_start, sc.scan_blk, nullptr, (long long)c * c, 0, s));
         k_grid_fill<<<nb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_fill"));
-        if (rows > 0) {
-            k_grid_detect<<<(rows + 127) / 128, 128, 0, s>>>(st, sc, p.i_begin, p.i_end, c);
+        {
+            const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
+            const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
+            const int per = (p.n_upper + sh_n - 1) / sh_n;
+            k_grid_detect<<<(per + 127) / 128 > 0 ? (per + 127) / 128 : 1, 128, 0, s>>>(st, sc, sh_i, sh_n, c);
             COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect"));
+        }
+        if (rows > 0) {
             k_giant_rows<<<dim3(nb > 296 ? 296 : nb, 8), 256, 0, s>>>(st, sc, p.i_begin, p.i_end);
             COSMO_TRY(COSMO_LAUNCH_CHECK("k_giant_rows"));
         }

@@ -18,8 +18,8 @@ import numpy as np
 import torch
 
 from . import _abi
-from ._abi import (F_IMMOBILE, F_MASS_INT, OPT_BOUNDED, OPT_COLLISIONS, OPT_F32_SCALAR, OPT_FP32,
-                   OPT_STORE_ACC, PAD, ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_ESCAPED, ST_N_EVENTS,
+from ._abi import (F_IMMOBILE, F_MASS_INT, OPT_BOUNDED, OPT_COLLISIONS, OPT_DEFER_INTEGRATE, OPT_F32_SCALAR,
+                   OPT_F32_SYM, OPT_FP32, OPT_STORE_ACC, PAD, ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_ESCAPED, ST_N_EVENTS,
                    ST_N_PAIRS, ST_STEP, STATUS_LEN)
 
 _MASK64 = (1 << 64) - 1
@@ -77,6 +77,8 @@ class Engine:
         self.grid = None            # (cell_size, origin_x, origin_y, cells_per_side, giant_radius)
         self.grid_threshold = 8192  # planets from which the grid broad phase + parallel resolver pay off
         self.small_threshold = 4096  # below: small-N kernel shape (more, shorter CTAs)
+        self.sym_threshold = 32768   # FP32: from here on the symmetric kernel (each pair once) wins
+        self.sym_chunk = 0           # column blocks per CTA of the symmetric kernel (0 = library default)
         self.retune_every = 16      # frames between host-side refreshes of the grid tuning
         self._manual_n = False
         self._since_tune = 0
@@ -304,14 +306,29 @@ class Engine:
         return {"acc": self.t["acc"], "pos_new": self._pos_new.view(cap, 2), "vel_new": self._vel_new.view(cap, 2)}
 
     # ------------------------------------------------------------------ stepping
+    def _ensure_colbuf(self):
+        """Column-partial buffer of the symmetric FP32 kernel: one float2 row of `cap` per local row
+        block (8 B x N^2 / 1024 / ranks: 8.6 GB at N = 2^20 on one GPU -- HBM3e capacity is what makes
+        the deterministic, atomic-free reduction affordable)."""
+        rows = -(-(self.cap // PAD) // self.world)
+        if "colbuf" not in self.t or self.t["colbuf"].shape[0] < rows:
+            self.t["colbuf"] = torch.empty(rows, self.cap, 2, dtype=torch.float32, device=self.device)
+            self.sc.colbuf = C.c_void_p(self.t["colbuf"].data_ptr())
+            self.sc.colbuf_rows = rows
+
     def params(self, dt, G, r_max, collisions=True, bounded=True, fp32=False, store_acc=False,
-               f32_scalar=False, jsplit=None):
+               f32_scalar=False, jsplit=None, f32_sym=None):
         p = _abi.StepParams()
         p.G, p.dt, p.r_max = float(G), float(dt), float(r_max)
+        n = self.n_upper
+        sym = bool(fp32 and not f32_scalar and (f32_sym if f32_sym is not None else n >= self.sym_threshold))
+        if sym:
+            self._ensure_colbuf()
         p.opts = ((OPT_COLLISIONS if collisions else 0) | (OPT_BOUNDED if bounded else 0) |
                   (OPT_FP32 if fp32 else 0) | (OPT_STORE_ACC if store_acc else 0) |
-                  (OPT_F32_SCALAR if f32_scalar else 0))
-        n = self.n_upper
+                  (OPT_F32_SCALAR if f32_scalar else 0) | (OPT_F32_SYM if sym else 0) |
+                  (OPT_DEFER_INTEGRATE if (sym and self.world > 1) else 0))
+        p.sym_chunk = int(self.sym_chunk)
         p.n_upper = n
         if self.world > 1:
             from . import sharded
@@ -330,6 +347,7 @@ class Engine:
         else:
             p.detect_mode, p.resolve_mode = 0, 0
         p.small_tiles = 1 if n <= self.small_threshold else 0
+        p.shard_index, p.shard_count = self.rank, self.world
         if p.small_tiles and not jsplit:
             with torch.cuda.device(self.device):
                 if not fp32:

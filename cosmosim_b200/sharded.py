@@ -58,7 +58,13 @@ def frame(eng, p, stream):
     _, _, per = shard_rows(n, eng.world, eng.rank)
     _abi.check(lib.cosmo_begin_frame(st, sc, pp, stream), "cosmo_begin_frame")
     _abi.check(lib.cosmo_accel_integrate(st, sc, pp, stream), "cosmo_accel_integrate")
-    gather_planes(((eng._pos_new, 2), (eng._vel_new, 2), (eng._xx_new, 1)), per, eng.rank, eng.world, eng.group)
+    if p.opts & _abi.OPT_DEFER_INTEGRATE:
+        # symmetric FP32 kernel: every rank holds partial sums for ALL planets (its row blocks +
+        # the column sides of its pairs) -> all-reduce, then every rank integrates all rows
+        dist.all_reduce(eng.t["acc"][:n], op=dist.ReduceOp.SUM, group=eng.group)
+        _abi.check(lib.cosmo_integrate(st, sc, pp, stream), "cosmo_integrate")
+    else:
+        gather_planes(((eng._pos_new, 2), (eng._vel_new, 2), (eng._xx_new, 1)), per, eng.rank, eng.world, eng.group)
     _abi.check(lib.cosmo_detect_pairs(st, sc, pp, stream), "cosmo_detect_pairs")
     status = eng.t["status"]
     if not hasattr(eng, "_xchg"):

@@ -41,7 +41,7 @@ extern "C" {
 #endif
 
 #define COSMO_ABI_VERSION 1
-#define COSMO_PAD 512 /* slot capacity granularity (tile size of the all-pairs kernels) */
+#define COSMO_PAD 1024 /* slot capacity granularity (tile size of the all-pairs kernels) */
 #define COSMO_SCAN_BLOCKS 8192 /* device scans handle up to COSMO_SCAN_BLOCKS * 4096 items */
 
 /* error codes */
@@ -60,6 +60,9 @@ extern "C" {
 #define COSMO_OPT_FP32 4u        /* FP32 fast path for the all-pairs sum (state stays FP64) */
 #define COSMO_OPT_STORE_ACC 8u   /* also write the accelerations to scratch.acc */
 #define COSMO_OPT_F32_SCALAR 16u /* FP32 path: scalar FFMA inner loop instead of packed f32x2 */
+#define COSMO_OPT_F32_SYM 32u    /* FP32 path: symmetric kernel (each unordered pair once); needs colbuf */
+#define COSMO_OPT_DEFER_INTEGRATE 64u /* symmetric kernel, multi-GPU: leave this rank's partial sums in
+                                         scratch.acc (to be all-reduced), integrate with cosmo_integrate */
 
 /* indices into the device-side int64 status block (cosmo_state.status, COSMO_STATUS_LEN) */
 #define COSMO_ST_N_ACTIVE 0    /* active planets = slots [0, n) */
@@ -123,6 +126,8 @@ typedef struct cosmo_scratch {
     double *rinf;      /* [cap]      radii inflated by 2^-30 (candidate filter of stage B) */
     double *partial;   /* [jsplit_max][cap][2] partial sums of the all-pairs pass */
     int32_t jsplit_max;
+    float *colbuf;        /* [colbuf_rows][cap][2] column partial sums of the symmetric FP32 kernel */
+    int64_t colbuf_rows;  /* >= ceil(ceil(n / 1024) / ranks) */
     int32_t *tile_ctr; /* [cap / 64 + 4] arrival counters, must start zeroed */
     uint8_t *alive;    /* [cap]      1 while the slot's planet is alive in this frame */
     uint8_t *escaped;  /* [cap]      start-of-frame escape flags (A6) */
@@ -173,6 +178,10 @@ typedef struct cosmo_step_params {
     int32_t detect_mode; /* 0 = all-pairs predicate, 1 = uniform-grid broad phase */
     int32_t resolve_mode; /* 0 = rank sort + sequential replay (few pairs), 1 = CSR + parallel */
     int32_t small_tiles;  /* 1 = small-N kernel shape for stage A/B (more, shorter CTAs) */
+    int32_t shard_index;  /* this rank / number of ranks sharing the frame (0 / 1 if single): the */
+    int32_t shard_count;  /* grid broad phase splits its cell-sorted planet order evenly by these */
+    int32_t sym_chunk;    /* symmetric kernel: column blocks per CTA (0 = default) */
+    int32_t reserved0;
     double cell_size;    /* detect_mode 1 */
     double grid_origin_x; /* detect_mode 1: the grid covers [origin, origin + cells_per_side*cell_size) */
     double grid_origin_y; /*                per axis; planets outside are clamped to the border cells */
@@ -216,6 +225,11 @@ int cosmo_detect_pairs(const cosmo_state *st, const cosmo_scratch *sc,
  */
 int cosmo_resolve_commit(const cosmo_state *st, const cosmo_scratch *sc,
                          const cosmo_step_params *p, void *stream);
+
+/* Multi-GPU symmetric FP32 path: integrates ALL active rows from the all-reduced sums in
+   scratch.acc (see COSMO_OPT_DEFER_INTEGRATE). */
+int cosmo_integrate(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p,
+                    void *stream);
 
 /* Zeroes the per-frame counters (N_PAIRS, N_DEAD, N_CAND).  First launch of a frame. */
 int cosmo_begin_frame(const cosmo_state *st, const cosmo_scratch *sc,

@@ -84,7 +84,7 @@ def test_accel_seam_device_and_host_buffers():
     hp = torch.from_numpy(g["pos"]).pin_memory()
     hm = torch.from_numpy(g["mass"]).pin_memory()
     ho = torch.empty(n, 2, dtype=torch.float64).pin_memory()
-    cap = (n + 511) // 512 * 512
+    cap = (n + 1023) // 1024 * 1024
     ws2 = torch.zeros(L.cosmo_accel_workspace_bytes(n) + cap * 40, dtype=torch.uint8, device="cuda")
     _abi.check(L.cosmo_accel_host(p(hp), p(hm), n, float(g["G"]), 1, 31, 71, p(ho), p(ws2), ws2.numel(), stream),
                "cosmo_accel_host")
@@ -241,9 +241,9 @@ def test_fp32_fast_path_error_bound():
     for arr in (scenes.star_disk_arrays(20000, seed=1), scenes.cloud_arrays(20000, seed=2)):
         n = arr["radius"].shape[0]
         ref = orc.accel(arr["pos"], arr["mass_f64"], G)
-        for scalar in (False, True):
+        for scalar, sym in ((False, False), (True, False), (False, True)):
             eng = make_engine(arr)
-            eng.step(1, DT, G, 100 * AU, collisions=False, store_acc=True, fp32=True, f32_scalar=scalar)
+            eng.step(1, DT, G, 100 * AU, collisions=False, store_acc=True, fp32=True, f32_scalar=scalar, f32_sym=sym)
             acc = eng.last_frame_tensors()["acc"][:n].cpu().numpy()
             eng.check_errors()
             rel = relerr_rows(acc, ref)
@@ -353,3 +353,20 @@ def test_grid_and_allpairs_flag_the_same_pairs_at_65536():
     assert np.array_equal(res[0][1], res[1][1])
     for k in ("id", "mass", "pos", "vel", "radius"):
         assert np.array_equal(res[0][2][k], res[1][2][k]), k
+
+
+def test_fp32_symmetric_kernel_matches_plain_kernel():
+    """The symmetric kernel evaluates the same FP32 pair terms once per unordered pair; against
+    the one-sided kernel only the summation order differs (sizes that are / are not multiples of
+    the 1024-planet block, incl. a single block)."""
+    from cosmosim_b200 import scenes
+    for n in (700, 1024, 5000, 40000):
+        arr = scenes.star_disk_arrays(n, seed=n)
+        out = []
+        for sym in (False, True):
+            eng = make_engine(arr)
+            eng.step(1, DT, G, 100 * AU, collisions=False, store_acc=True, fp32=True, f32_sym=sym)
+            out.append(eng.last_frame_tensors()["acc"][:n].cpu().numpy())
+            eng.check_errors()
+        rel = relerr_rows(out[1], out[0])
+        assert np.median(rel) < 2e-6 and rel.max() < 2e-3, (n, np.median(rel), rel.max())

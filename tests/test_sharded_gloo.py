@@ -22,7 +22,7 @@ def test_shard_rows_partition():
         for world in (1, 2, 4, 8):
             spans = [shard_rows(n, world, r) for r in range(world)]
             per = spans[0][2]
-            assert per % 512 == 0 and all(s[2] == per for s in spans)
+            assert per % 1024 == 0 and all(s[2] == per for s in spans)
             assert spans[0][0] == 0 and spans[-1][1] == n
             for a, b in zip(spans, spans[1:]):
                 assert a[1] == b[0] or (a[1] == n and b[0] == n)
