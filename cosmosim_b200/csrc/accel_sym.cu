@@ -42,7 +42,8 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src_lane) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-__global__ void __launch_bounds__(SYM_THREADS, 2)
+template <int MINB, int SUNROLL>
+__global__ void __launch_bounds__(SYM_THREADS, MINB)
 k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int chunk) {
     __shared__ __align__(16) float s_x[2][SYM_BLOCK];
     __shared__ __align__(16) float s_y[2][SYM_BLOCK];
@@ -111,7 +112,7 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
             const float *gy = &s_y[b][g * SYM_GROUP];
             const float *gm = &s_m[b][g * SYM_GROUP];
             uint64_t tx2[2] = {0ull, 0ull}, ty2[2] = {0ull, 0ull};   // travelling column sums
-#pragma unroll 1
+#pragma unroll SUNROLL
             for (int s = 0; s < 32; ++s) {
                 const int c = (lane + s) & 31;
                 const float4 X = *reinterpret_cast<const float4 *>(gx + 4 * c);
@@ -247,7 +248,13 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
     const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
     if (rows_local > 0) {
         dim3 grid(rows_local, (nblk + chunk - 1) / chunk);
-        k_accel_f32_sym<<<grid, SYM_THREADS, 0, s>>>(st, sc, sh_i, sh_n, chunk);
+        switch (p.reserved0) {   // development variants; 0 is the shipped one
+            case 1: k_accel_f32_sym<1, 1><<<grid, SYM_THREADS, 0, s>>>(st, sc, sh_i, sh_n, chunk); break;
+            case 2: k_accel_f32_sym<1, 2><<<grid, SYM_THREADS, 0, s>>>(st, sc, sh_i, sh_n, chunk); break;
+            case 3: k_accel_f32_sym<3, 1><<<grid, SYM_THREADS, 0, s>>>(st, sc, sh_i, sh_n, chunk); break;
+            case 4: k_accel_f32_sym<2, 1><<<grid, SYM_THREADS, 0, s>>>(st, sc, sh_i, sh_n, chunk); break;
+            default: k_accel_f32_sym<2, 2><<<grid, SYM_THREADS, 0, s>>>(st, sc, sh_i, sh_n, chunk); break;
+        }
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_accel_f32_sym"));
     }
     const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? 1 : 0;

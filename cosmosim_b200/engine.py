@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -329,6 +330,7 @@ class Engine:
                   (OPT_F32_SCALAR if f32_scalar else 0) | (OPT_F32_SYM if sym else 0) |
                   (OPT_DEFER_INTEGRATE if (sym and self.world > 1) else 0))
         p.sym_chunk = int(self.sym_chunk)
+        p.reserved0 = int(os.environ.get("COSMO_SYM_VARIANT", "0"))
         p.n_upper = n
         if self.world > 1:
             from . import sharded
