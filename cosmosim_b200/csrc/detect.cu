@@ -180,18 +180,38 @@ __device__ __forceinline__ void test_and_emit(const cosmo_state &st, const cosmo
     if (d2 <= rs * rs && pred_exact(d2, st.radius[i], st.radius[j])) emit_pair(st, sc, i, j);
 }
 
+// This rank's share of the cell-sorted order, cut at CELL boundaries: the order of the planets
+// inside a cell comes from atomics and differs from rank to rank, the cell populations do not.
+// Rank r takes the cells whose first slot lies in [r * per, (r + 1) * per).
+__global__ void k_grid_ranges(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int c) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int ncell = c * c;
+    const int total = sc.cell_start[ncell];
+    const int per = (total + shard_count - 1) / shard_count;
+    int bound[2];
+    for (int e = 0; e < 2; ++e) {
+        const long long target = (long long)(shard_index + e) * per;
+        if (target >= total || shard_index + e >= shard_count) { bound[e] = total; continue; }
+        int lo = 0, hi = ncell;                    // smallest cell with cell_start[cell] >= target
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (sc.cell_start[mid] >= target) hi = mid; else lo = mid + 1;
+        }
+        bound[e] = sc.cell_start[lo];
+    }
+    st.status[COSMO_ST_SLOT_LO] = bound[0];
+    st.status[COSMO_ST_SLOT_HI] = bound[1];
+}
+
 // One thread per non-giant target row, taken in CELL-SORTED order: the lanes of a warp then
 // work on planets of the same or neighbouring cells, so their candidate loops have similar trip
 // counts (the disk's surface density varies 20x between its inner and outer edge) and their
-// gathers hit the same lines.  Sharding splits the sorted order evenly; every row is still
-// produced exactly once.
+// gathers hit the same lines.  Every row is produced by exactly one rank (k_grid_ranges).
 __global__ void __launch_bounds__(128)
-k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int c) {
-    const int total = sc.cell_start[c * c];                       // non-giant planets
-    const int per = (total + shard_count - 1) / shard_count;
-    const int s_lo = shard_index * per, s_hi = min(total, s_lo + per);
-    const int slot = s_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= s_hi) return;
+k_grid_detect(cosmo_state st, cosmo_scratch sc, int c) {
+    const int s_lo = (int)st.status[COSMO_ST_SLOT_LO], s_hi = (int)st.status[COSMO_ST_SLOT_HI];
+    unsigned cand_total = 0;
+  for (int slot = s_lo + blockIdx.x * blockDim.x + threadIdx.x; slot < s_hi; slot += gridDim.x * blockDim.x) {
     const int i = sc.cell_items[slot];
     const int cell = sc.cell_of[i];
     const double2 p = reinterpret_cast<const double2 *>(sc.pos_new)[i];
@@ -212,10 +232,11 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count
     }
     const int ng = (int)min((long long)st.status[COSMO_ST_N_GIANTS], (long long)sc.giant_cap);
     for (int g = 0; g < ng; ++g) test_and_emit(st, sc, i, qx, qy, xxi, ri, sc.giants[g]);
-    // diagnostic only
-    const unsigned mask = __activemask();
-    const unsigned tot = __reduce_add_sync(mask, (unsigned)cand);
-    if ((threadIdx.x & 31) == __ffs(mask) - 1 && tot)
+    cand_total += (unsigned)cand;
+  }
+    // diagnostic only (all lanes are back together after the loop)
+    const unsigned tot = __reduce_add_sync(0xffffffffu, cand_total);
+    if ((threadIdx.x & 31) == 0 && tot)
         atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_CAND]), (unsigned long long)tot);
 }
 
@@ -276,7 +297,9 @@ int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_st
             const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
             const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
             const int per = (p.n_upper + sh_n - 1) / sh_n;
-            k_grid_detect<<<(per + 127) / 128 > 0 ? (per + 127) / 128 : 1, 128, 0, s>>>(st, sc, sh_i, sh_n, c);
+            k_grid_ranges<<<1, 32, 0, s>>>(st, sc, sh_i, sh_n, c);
+            COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_ranges"));
+            k_grid_detect<<<(per + 127) / 128 > 0 ? (per + 127) / 128 : 1, 128, 0, s>>>(st, sc, c);
             COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect"));
         }
         if (rows > 0) {

@@ -76,6 +76,8 @@ extern "C" {
 #define COSMO_ST_N_GIANTS 8    /* planets brute-forced by the broad phase in the last frame */
 #define COSMO_ST_PMAX2 9       /* bits of max |pos_new|^2 (double) of the last frame */
 #define COSMO_ST_N_COMPLEX 10  /* flagged pairs replayed sequentially in the last frame */
+#define COSMO_ST_SLOT_LO 11    /* grid broad phase: this rank's range of the cell-sorted order */
+#define COSMO_ST_SLOT_HI 12
 #define COSMO_STATUS_LEN 16
 
 #define COSMO_ERR_PAIR_OVERFLOW 1  /* more flagged pairs than pair_cap */

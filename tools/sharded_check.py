@@ -53,6 +53,11 @@ def main():
                 rel = np.abs(d1[k] - d2[k]).max() / max(1e-300, np.abs(d1[k]).max())
                 worst = max(worst, rel)
                 fok = fok and rel <= 1e-12
+            if not fok and rank == 0:
+                print("  frame %d mismatch: ids %s mass %s events %s (%d vs %d) err %d/%d pairs %d/%d" % (
+                    f, np.array_equal(d1["id"], d2["id"]), np.array_equal(d1["mass"], d2["mass"]),
+                    np.array_equal(e1, e2), len(e1), len(e2), d1["status"]["error"], d2["status"]["error"],
+                    d1["status"]["n_pairs"], d2["status"]["n_pairs"]), flush=True)
             same = same and fok
             # every rank must hold the same replica of the sharded result, bit for bit
             digest = torch.tensor([float(np.sum(d2["pos"])), float(np.sum(d2["vel"])), float(len(e2)),
