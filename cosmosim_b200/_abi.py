@@ -12,7 +12,7 @@ STATUS_LEN = 16
 
 # flag / option / status constants (mirror the header)
 F_IMMOBILE, F_MASS_INT = 1, 2
-OPT_COLLISIONS, OPT_BOUNDED, OPT_FP32, OPT_STORE_ACC, OPT_F32_SCALAR, OPT_F32_SYM, OPT_DEFER_INTEGRATE = 1, 2, 4, 8, 16, 32, 64
+OPT_COLLISIONS, OPT_BOUNDED, OPT_FP32, OPT_STORE_ACC, OPT_F32_SCALAR, OPT_F32_SYM, OPT_DEFER_INTEGRATE, OPT_ENERGY = 1, 2, 4, 8, 16, 32, 64, 128
 ST_N_ACTIVE, ST_STEP, ST_N_EVENTS, ST_N_PAIRS, ST_N_DEAD, ST_ERROR, ST_N_ESCAPED, ST_N_CAND, ST_N_GIANTS, ST_PMAX2, ST_N_COMPLEX, ST_SLOT_LO, ST_SLOT_HI = range(13)
 SCAN_BLOCKS = 8192
 ERR_PAIR_OVERFLOW, ERR_EVENT_OVERFLOW, ERR_NAN, ERR_GIANT_OVERFLOW = 1, 2, 4, 8
@@ -24,7 +24,7 @@ class State(C.Structure):
     _fields_ = [("cap", C.c_int32), ("n_total", C.c_int32),
                 ("pos", _vp), ("vel", _vp), ("mass", _vp), ("mass_hi", _vp), ("mass_lo", _vp),
                 ("radius", _vp), ("volume", _vp), ("eaten", _vp), ("id", _vp), ("flags", _vp),
-                ("status", _vp),
+                ("status", _vp), ("energy", _vp), ("totals", _vp),
                 ("rec_mass", _vp), ("rec_mass_hi", _vp), ("rec_mass_lo", _vp), ("rec_radius", _vp),
                 ("rec_volume", _vp), ("rec_eaten", _vp), ("rec_death", _vp), ("rec_flags", _vp),
                 ("events", _vp), ("event_cap", C.c_int64)]
@@ -41,7 +41,7 @@ class Scratch(C.Structure):
                 ("pair_flag", _vp), ("cplx_list", _vp), ("ev_tmp", _vp), ("label", _vp), ("comp_items", _vp),
                 ("t_pos", _vp), ("t_vel", _vp), ("t_mass", _vp), ("t_mass_hi", _vp),
                 ("t_mass_lo", _vp), ("t_radius", _vp), ("t_volume", _vp), ("t_eaten", _vp),
-                ("t_id", _vp), ("t_flags", _vp),
+                ("t_id", _vp), ("t_flags", _vp), ("t_energy", _vp),
                 ("cell_of", _vp), ("cell_count", _vp), ("cell_start", _vp), ("cell_items", _vp),
                 ("giants", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32)]
 
@@ -65,6 +65,7 @@ SYMBOLS = {
     "cosmo_suggest_jsplit": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int32]),
     "cosmo_begin_frame": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_accel_integrate": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
+    "cosmo_energies": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_integrate": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_detect_pairs": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_resolve_commit": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),

@@ -29,13 +29,17 @@ def _randint(lo, hi):
 
 
 class Universe:
-    def __init__(self, G=6.674e-11, bounded=True, r_max=100 * AU, precision="fp64", device=None):
+    def __init__(self, G=6.674e-11, bounded=True, r_max=100 * AU, precision="fp64", device=None,
+                 track_energy=False):
         self.G = G
         self.bounded = bounded
         self.r_max = r_max
         self.planets = []
-        self.angular_momentum = 0.0
-        self.total_energy = 0.0
+        self._angular_momentum = 0.0
+        self._total_energy = 0.0
+        # energies / angular momentum are an extra O(N^2) pass (universe_old.py:181-189); the HUD
+        # numbers are only evaluated when asked for
+        self.track_energy = track_energy
         self.clicked_planet = None
         self.running = False
         self.paused = False
@@ -62,6 +66,18 @@ class Universe:
         self.bound_planets = []
         self.unbound_planets = []
         self.escaped_planets = []
+
+    @property
+    def total_energy(self):
+        """sum(K + U) of the last frame (universe_old.py:187); needs track_energy=True."""
+        self._pull_if_needed()
+        return self._total_energy
+
+    @property
+    def angular_momentum(self):
+        """sum(m * cross(p, v)) of the last frame (universe_old.py:189); needs track_energy=True."""
+        self._pull_if_needed()
+        return self._angular_momentum
 
     @property
     def merge_events(self):
@@ -184,6 +200,10 @@ class Universe:
             p._radius = float(d["radius"][k])
             p._volume = float(d["volume"][k])
             p._planets_eaten = int(d["eaten"][k])
+            if self.track_energy:
+                p._energy = float(d["energy"][k])
+        if self.track_energy:
+            self._total_energy, self._angular_momentum = d["total_energy"], d["angular_momentum"]
         for idx in np.nonzero(d["rec_death"] >= 0)[0]:
             p = self.planets[int(idx)]
             if p._alive:  # died on the device since the last pull: Planet.destroy() semantics
@@ -219,7 +239,7 @@ class Universe:
         if self._host_dirty or self._engine is None:
             self._push()
         self._engine.step(n, self.dt, self.G, self.r_max, collisions=self.collisions, bounded=self.bounded,
-                          fp32=(self.precision == "fp32"))
+                          fp32=(self.precision == "fp32"), energy=self.track_energy)
         self._frames += n
         self.iterations += n
         self._device_ahead = True
@@ -233,7 +253,7 @@ class Universe:
             self._push()
         # interact() alone never destroys escaped planets: that is simulate()'s job (:349-350)
         self._engine.step(1, self.dt, self.G, self.r_max, collisions=self.collisions, bounded=False,
-                          fp32=(self.precision == "fp32"))
+                          fp32=(self.precision == "fp32"), energy=self.track_energy)
         self._frames += 1
         self._device_ahead = True
 

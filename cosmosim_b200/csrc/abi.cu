@@ -120,6 +120,11 @@ int cosmo_accel_integrate(const cosmo_state *st, const cosmo_scratch *sc, const 
     return launch_accel(*st, *sc, *p, (cudaStream_t)stream);
 }
 
+int cosmo_energies(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p, void *stream) {
+    COSMO_TRY(check_args(st, sc, p));
+    return launch_energies(*st, *sc, *p, (cudaStream_t)stream);
+}
+
 int cosmo_integrate(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p, void *stream) {
     COSMO_TRY(check_args(st, sc, p));
     return launch_sym_integrate(*st, *sc, *p, (cudaStream_t)stream);
@@ -142,6 +147,7 @@ int cosmo_step(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_
     cudaStream_t s = (cudaStream_t)stream;
     COSMO_TRY(launch_prep(*st, *sc, *p, s));
     COSMO_TRY(launch_accel(*st, *sc, *p, s));
+    if (p->opts & COSMO_OPT_ENERGY) COSMO_TRY(launch_energies(*st, *sc, *p, s));
     COSMO_TRY(launch_detect(*st, *sc, *p, s));
     return launch_resolve_commit(*st, *sc, *p, s);
 }

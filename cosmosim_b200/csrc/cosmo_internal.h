@@ -45,6 +45,10 @@ int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const ui
 int launch_scan_exclusive(const int *in, int *out, int *blk, const int64_t *n_ptr, long long n_max,
                           long long n_add, cudaStream_t s);
 
+// energy.cu
+int launch_energies(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                    cudaStream_t s);
+
 // microbench.cu
 int launch_microbench(int kind, int blocks, int threads, int iters, double *out,
                       int64_t *ops_per_thread, cudaStream_t s);

@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(256) k_compact_scatter(cosmo_state st, cosmo_s
             sc.t_eaten[d] = st.eaten[k];
             sc.t_id[d] = st.id[k];
             sc.t_flags[d] = st.flags[k];
+            if (st.energy) sc.t_energy[d] = st.energy[k];
         }
         running += total;
     }
@@ -517,6 +518,7 @@ __global__ void __launch_bounds__(256) k_compact_copyback(cosmo_state st, cosmo_
         st.eaten[k] = sc.t_eaten[k];
         st.id[k] = sc.t_id[k];
         st.flags[k] = sc.t_flags[k];
+        if (st.energy) st.energy[k] = sc.t_energy[k];
     }
 }
 

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from ._abi import (F_IMMOBILE, F_MASS_INT, OPT_BOUNDED, OPT_COLLISIONS, OPT_DEFER_INTEGRATE, OPT_F32_SCALAR,
+from ._abi import (F_IMMOBILE, F_MASS_INT, OPT_BOUNDED, OPT_COLLISIONS, OPT_DEFER_INTEGRATE, OPT_ENERGY, OPT_F32_SCALAR,
                    OPT_F32_SYM, OPT_FP32, OPT_STORE_ACC, PAD, ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_ESCAPED, ST_N_EVENTS,
                    ST_N_PAIRS, ST_STEP, STATUS_LEN)
 
@@ -82,6 +82,9 @@ class Engine:
         self.sym_chunk = 0           # column blocks per CTA of the symmetric kernel (0 = library default)
         self.retune_every = 16      # frames between host-side refreshes of the grid tuning
         self._manual_n = False
+        self.use_graphs = True      # small N: replay a captured CUDA graph of the frame (launch-bound regime)
+        self.graph_threshold = 16384
+        self._graphs = {}
         self._since_tune = 0
 
     # ------------------------------------------------------------------ buffers
@@ -96,6 +99,7 @@ class Engine:
         t["radius"] = z(cap, dtype=f64); t["volume"] = z(cap, dtype=f64)
         t["eaten"] = z(cap, dtype=i64); t["id"] = z(cap, dtype=i32); t["flags"] = z(cap, dtype=u8)
         t["status"] = z(STATUS_LEN, dtype=i64)
+        t["energy"] = z(cap, dtype=f64); t["totals"] = z(4, dtype=f64); t["t_energy"] = z(cap, dtype=f64)
         t["rec_mass"] = z(nt, dtype=f64); t["rec_mass_hi"] = z(nt, dtype=i64); t["rec_mass_lo"] = z(nt, dtype=i64)
         t["rec_radius"] = z(nt, dtype=f64); t["rec_volume"] = z(nt, dtype=f64); t["rec_eaten"] = z(nt, dtype=i64)
         t["rec_death"] = torch.full((nt,), -1, dtype=i32, device=dev); t["rec_flags"] = z(nt, dtype=u8)
@@ -143,7 +147,7 @@ class Engine:
         st = _abi.State()
         st.cap, st.n_total = cap, self.n_total
         for k in ("pos", "vel", "mass", "mass_hi", "mass_lo", "radius", "volume", "eaten", "id", "flags",
-                  "status", "rec_mass", "rec_mass_hi", "rec_mass_lo", "rec_radius", "rec_volume",
+                  "status", "energy", "totals", "rec_mass", "rec_mass_hi", "rec_mass_lo", "rec_radius", "rec_volume",
                   "rec_eaten", "rec_death", "rec_flags", "events"):
             setattr(st, k, p(k))
         st.event_cap = self.event_cap
@@ -151,7 +155,7 @@ class Engine:
         for k in ("h", "pk_x", "pk_y", "pk_m", "acc", "rinf", "partial", "tile_ctr", "alive", "escaped",
                   "pairs", "pairs_sorted", "cur_pos", "cur_vel", "mod_row", "mod_step", "chunk_alive",
                   "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_radius", "t_volume",
-                  "t_eaten", "t_id", "t_flags", "row_count", "row_start", "pmin", "pmax", "scan_blk",
+                  "t_eaten", "t_id", "t_flags", "t_energy", "row_count", "row_start", "pmin", "pmax", "scan_blk",
                   "pair_flag", "cplx_list", "ev_tmp", "label", "comp_items", "cell_of", "cell_items", "cell_count", "cell_start",
                   "giants"):
             setattr(sc, k, p(k))
@@ -286,7 +290,10 @@ class Engine:
         st = self.status()
         n = st["n_active"]
         t = self.t
-        out = {k: t[k][:n].cpu().numpy() for k in ("pos", "vel", "mass", "radius", "volume", "eaten", "id", "flags")}
+        out = {k: t[k][:n].cpu().numpy() for k in ("pos", "vel", "mass", "radius", "volume", "eaten", "id", "flags",
+                                                   "energy")}
+        tot = t["totals"].cpu().numpy()
+        out["total_energy"], out["angular_momentum"] = float(tot[0]), float(tot[1])
         out["mass_hi"] = t["mass_hi"][:n].cpu().numpy().view(np.uint64)
         out["mass_lo"] = t["mass_lo"][:n].cpu().numpy().view(np.uint64)
         for k in ("rec_mass", "rec_radius", "rec_volume", "rec_eaten", "rec_death", "rec_flags"):
@@ -318,7 +325,7 @@ class Engine:
             self.sc.colbuf_rows = rows
 
     def params(self, dt, G, r_max, collisions=True, bounded=True, fp32=False, store_acc=False,
-               f32_scalar=False, jsplit=None, f32_sym=None):
+               f32_scalar=False, jsplit=None, f32_sym=None, energy=False):
         p = _abi.StepParams()
         p.G, p.dt, p.r_max = float(G), float(dt), float(r_max)
         n = self.n_upper
@@ -328,7 +335,7 @@ class Engine:
         p.opts = ((OPT_COLLISIONS if collisions else 0) | (OPT_BOUNDED if bounded else 0) |
                   (OPT_FP32 if fp32 else 0) | (OPT_STORE_ACC if store_acc else 0) |
                   (OPT_F32_SCALAR if f32_scalar else 0) | (OPT_F32_SYM if sym else 0) |
-                  (OPT_DEFER_INTEGRATE if (sym and self.world > 1) else 0))
+                  (OPT_DEFER_INTEGRATE if (sym and self.world > 1) else 0) | (OPT_ENERGY if energy else 0))
         p.sym_chunk = int(self.sym_chunk)
         p.reserved0 = int(os.environ.get("COSMO_SYM_VARIANT", "0"))
         p.n_upper = n
@@ -369,6 +376,9 @@ class Engine:
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         st, sc, pp = C.byref(self.st), C.byref(self.sc), C.byref(p)
         lib = self.lib
+        if (self.use_graphs and self.world == 1 and stage_events is None and n_frames >= 8
+                and self.n_upper <= self.graph_threshold):
+            return self._step_graphed(int(n_frames), dt, G, r_max, kw)
         for _ in range(int(n_frames)):
             if self._since_tune >= self.retune_every and self.n_upper >= self.grid_threshold:
                 self.retune()                      # one small D2H every retune_every frames
@@ -392,6 +402,8 @@ class Engine:
                 _abi.check(lib.cosmo_begin_frame(st, sc, pp, stream), "cosmo_begin_frame")
                 ev[1].record()
                 _abi.check(lib.cosmo_accel_integrate(st, sc, pp, stream), "cosmo_accel_integrate")
+                if p.opts & OPT_ENERGY:
+                    _abi.check(lib.cosmo_energies(st, sc, pp, stream), "cosmo_energies")
                 ev[2].record()
                 _abi.check(lib.cosmo_detect_pairs(st, sc, pp, stream), "cosmo_detect_pairs")
                 ev[3].record()
@@ -400,6 +412,36 @@ class Engine:
                 stage_events.append(ev)
             self.frames += 1
             self._status_host.copy_(self.t["status"], non_blocking=True)
+
+    def _step_graphed(self, n_frames, dt, G, r_max, kw):
+        """Launch-bound regime (N of a few thousand: a frame is ~10 kernels of a few microseconds):
+        capture cosmo_step + the status snapshot once into a CUDA graph and replay it.  Kernels read
+        the active count from the device, so a graph stays valid while planets merge; it is
+        re-captured when the launch bound has shrunk by more than 10 %."""
+        done = 0
+        while done < n_frames:
+            seen_n, seen_f = int(self._status_host[ST_N_ACTIVE]), int(self._status_host[ST_STEP])
+            if self._status_epoch <= seen_f <= self.frames and 0 < seen_n < 0.9 * self.n_upper:
+                self.n_upper = seen_n
+            p = self.params(dt, G, r_max, **kw)
+            key = bytes(memoryview(p))
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) > 16:
+                    self._graphs.clear()
+                st, sc, pp = C.byref(self.st), C.byref(self.sc), C.byref(p)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                    _abi.check(self.lib.cosmo_step(st, sc, pp, stream), "cosmo_step (graph capture)")
+                    self._status_host.copy_(self.t["status"], non_blocking=True)
+                self._graphs[key] = g
+            burst = min(n_frames - done, 64)
+            for _ in range(burst):
+                g.replay()
+            done += burst
+            self.frames += burst
 
     def launches_per_frame(self, collisions=True):
         """Kernels of this library launched per frame in the current mode (bench.py reports it)."""

@@ -65,6 +65,8 @@ def frame(eng, p, stream):
         _abi.check(lib.cosmo_integrate(st, sc, pp, stream), "cosmo_integrate")
     else:
         gather_planes(((eng._pos_new, 2), (eng._vel_new, 2), (eng._xx_new, 1)), per, eng.rank, eng.world, eng.group)
+    if p.opts & _abi.OPT_ENERGY:      # diagnostics: replicated over all rows (new positions are complete here)
+        _abi.check(lib.cosmo_energies(st, sc, pp, stream), "cosmo_energies")
     _abi.check(lib.cosmo_detect_pairs(st, sc, pp, stream), "cosmo_detect_pairs")
     status = eng.t["status"]
     if not hasattr(eng, "_xchg"):

@@ -61,6 +61,7 @@ extern "C" {
 #define COSMO_OPT_STORE_ACC 8u   /* also write the accelerations to scratch.acc */
 #define COSMO_OPT_F32_SCALAR 16u /* FP32 path: scalar FFMA inner loop instead of packed f32x2 */
 #define COSMO_OPT_F32_SYM 32u    /* FP32 path: symmetric kernel (each unordered pair once); needs colbuf */
+#define COSMO_OPT_ENERGY 128u     /* also evaluate energies / angular momentum (universe_old.py:181-189,210) */
 #define COSMO_OPT_DEFER_INTEGRATE 64u /* symmetric kernel, multi-GPU: leave this rank's partial sums in
                                          scratch.acc (to be all-reduced), integrate with cosmo_integrate */
 
@@ -100,6 +101,8 @@ typedef struct cosmo_state {
     int32_t *id;
     uint8_t *flags;
     int64_t *status;  /* [COSMO_STATUS_LEN] */
+    double *energy;   /* [cap] Planet.energy = K_i + U_i of the last frame with COSMO_OPT_ENERGY */
+    double *totals;   /* [4] total_energy, angular_momentum of the last frame (universe_old.py:187,189) */
     /* records of dead planets, indexed by insertion id (Planet keeps mass/radius after
        destroy(), planet.py:86-91) */
     double *rec_mass;      /* [n_total] */
@@ -155,6 +158,7 @@ typedef struct cosmo_scratch {
     /* compaction staging: one array per persistent field */
     double *t_pos; double *t_vel; double *t_mass; uint64_t *t_mass_hi; uint64_t *t_mass_lo;
     double *t_radius; double *t_volume; int64_t *t_eaten; int32_t *t_id; uint8_t *t_flags;
+    double *t_energy;
     /* broad phase (uniform grid) */
     int32_t *cell_of;    /* [cap] */
     int32_t *cell_count; /* [grid_cells + 1] must start zeroed (self-resetting) */
@@ -232,6 +236,15 @@ int cosmo_resolve_commit(const cosmo_state *st, const cosmo_scratch *sc,
    scratch.acc (see COSMO_OPT_DEFER_INTEGRATE). */
 int cosmo_integrate(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p,
                     void *stream);
+
+/*
+ * Optional diagnostics of the frame -- replaces universe_old.py:181-189,210: on the NEW positions
+ * and velocities and the pre-merge masses, U_i = m_i sum_{j != i} -G m_j / max(d_ij, 1),
+ * K_i = m_i |v_i|^2 / 2, energy[i] = K_i + U_i, totals = {sum(K + U), sum m (x v_y - y v_x)}.
+ * Runs between stages A and C (cosmo_step does it when COSMO_OPT_ENERGY is set); all rows.
+ */
+int cosmo_energies(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p,
+                   void *stream);
 
 /* Zeroes the per-frame counters (N_PAIRS, N_DEAD, N_CAND).  First launch of a frame. */
 int cosmo_begin_frame(const cosmo_state *st, const cosmo_scratch *sc,

@@ -278,6 +278,52 @@ void oracle_dist_rows(int64_t n, const double *p, int64_t i_begin, int64_t i_end
 }
 
 /* ---------------------------------------------------------------------------------------
+ * A7: energies and angular momentum (universe_old.py:180-189,210) on the new positions p,
+ * new velocities v and the pre-merge masses m (float(mass)):
+ *   d = clip(dist, 1, None); d_inv = 1/d; V = -G*m*d_inv (column j scaled by m_j), diag 0
+ *   U = m * sum(V, axis=1); K = 0.5*m*|v|^2; total = sum(K+U); L = sum(m * cross(p, v))
+ * numpy sums pairwise (float masses) or left-to-right (object dtype, Python int masses); the
+ * order is not restated -- agreement is to rounding (tests: 1e-12).
+ * ------------------------------------------------------------------------------------- */
+void oracle_energies(int64_t n, const double *p, const double *v, const double *m, double G,
+                     double *energy_out /* [n] */, double *totals_out /* [2] */) {
+    double *xx = (double *)malloc((size_t)n * sizeof(double));
+    for (int64_t k = 0; k < n; ++k) {
+        double x2 = p[2 * k] * p[2 * k];
+        double y2 = p[2 * k + 1] * p[2 * k + 1];
+        xx[k] = x2 + y2;
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double xi = p[2 * i], yi = p[2 * i + 1], sum = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            if (j == i) continue;
+            double dot = fma(yi, p[2 * j + 1], xi * p[2 * j]);
+            double d2 = -2.0 * dot + xx[i];
+            d2 = d2 + xx[j];
+            if (d2 < 0.0) d2 = 0.0;
+            double d = sqrt(d2);
+            if (d < 1.0) d = 1.0;
+            double vij = -G * m[j];
+            vij = vij * (1.0 / d);
+            sum += vij;
+        }
+        double vx = v[2 * i], vy = v[2 * i + 1];
+        double vmag = sqrt(vx * vx + vy * vy);
+        double K = 0.5 * m[i] * (vmag * vmag);
+        energy_out[i] = K + m[i] * sum;
+    }
+    double tot = 0.0, L = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        tot += energy_out[i];
+        L += m[i] * (p[2 * i] * v[2 * i + 1] - p[2 * i + 1] * v[2 * i]);
+    }
+    totals_out[0] = tot;
+    totals_out[1] = L;
+    free(xx);
+}
+
+/* ---------------------------------------------------------------------------------------
  * A4/A5: ordered merge loop (universe_old.py:196-210) + Planet.absorb/destroy
  * (planet.py:74-91), Python numeric semantics.
  * ------------------------------------------------------------------------------------- */

@@ -13,6 +13,7 @@ Fixtures written (all produced by reference code, none by this repo's oracle or 
                            new positions, flagged pairs and post-state (per-step parity)
   micro_merges.npz         the six 2-3 body merge micro-scenes of SURVEY.md Appendix B
   accel_n4001.npz          acc_blas on a seeded synthetic disk, N = 4001
+  energies.npz             total_energy / angular_momentum / Planet.energy over six frames
 """
 from __future__ import annotations
 
@@ -115,6 +116,34 @@ def micro_merges(out_dir):
     print("[micro] done", flush=True)
 
 
+def energy_fixture(out_dir, frames=6):
+    """HUD numbers of the reference (universe_old.py:181-189,210): total_energy, angular_momentum
+    and Planet.energy after each of a few frames of two small seeded scenes."""
+    uo, pl, fn, bl = rh.load_reference()
+    blob = {}
+    for name, builder, seed, n in (("disk", rh.build_star_with_disk, 11, 300), ("cloud", rh.build_cloud, 12, 300)):
+        u = builder(seed, n)
+        if name == "cloud":                      # make a few merges happen in six frames
+            for p in u.planets:
+                p.radius *= 300.0
+                p.volume = ((4 / 3) * np.pi) * (p.radius ** 3)
+        blob.update(flat(f"{name}_init_", rh.snapshot(u)))
+        tot, ang, en, alive = [], [], [], []
+
+        def cond(U):
+            if U.iterations > 0:
+                tot.append(float(U.total_energy)); ang.append(float(U.angular_momentum))
+                en.append(np.array([float(p.energy) for p in U.planets]))
+                alive.append(np.array([bool(p.alive) for p in U.planets]))
+            return U.iterations < frames
+        u.simulate(run_while=cond)
+        blob[f"{name}_total_energy"] = np.array(tot); blob[f"{name}_angular_momentum"] = np.array(ang)
+        blob[f"{name}_energy"] = np.array(en); blob[f"{name}_alive"] = np.array(alive)
+        blob[f"{name}_G"] = u.G
+    np.savez_compressed(os.path.join(out_dir, "energies.npz"), dt=1e6 / 33, frames=frames, **blob)
+    print("[energy] done", flush=True)
+
+
 def synthetic_disk(n, seed):
     """Config-3 style synthetic disk (float masses): shared with the tests via the fixture."""
     rng = np.random.default_rng(seed)
@@ -146,7 +175,9 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
-    todo = a.only.split(",") if a.only else ["micro", "accel", "disk", "cloud"]
+    todo = a.only.split(",") if a.only else ["micro", "accel", "energy", "disk", "cloud"]
+    if "energy" in todo:
+        energy_fixture(a.out)
     if "micro" in todo:
         micro_merges(a.out)
     if "accel" in todo:

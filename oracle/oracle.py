@@ -49,6 +49,7 @@ def lib():
         L.oracle_flags_rows.argtypes = [C.c_int64, _dp, _dp, C.c_int64, C.c_int64, _ip, C.c_int64]
         L.oracle_flags_rows.restype = C.c_int64
         L.oracle_dist_rows.argtypes = [C.c_int64, _dp, C.c_int64, C.c_int64, _dp]
+        L.oracle_energies.argtypes = [C.c_int64, _dp, _dp, _dp, C.c_double, _dp, _dp]
         L.oracle_frame.argtypes = [C.POINTER(_State), C.c_double, C.c_double, C.c_int, C.c_int,
                                    C.c_double, _ip, _dp, _dp, _dp, _ip, _ip, _ip, _ip, C.c_int64]
         L.oracle_frame.restype = C.c_int64
@@ -124,6 +125,15 @@ def dist_matrix(p, i_begin=0, i_end=None):
     return out
 
 
+def energies(p, v, m, G):
+    """A7 (universe_old.py:180-189,210): per-planet K+U, (total energy, angular momentum)."""
+    p, v, m = _c64(p), _c64(v), _c64(m)
+    n = m.shape[0]
+    e, tot = np.empty(n), np.empty(2)
+    lib().oracle_energies(n, _d(p), _d(v), _d(m), float(G), _d(e), _d(tot))
+    return e, float(tot[0]), float(tot[1])
+
+
 class OracleUniverse:
     """SoA state + frame stepping following universe_old.py:345-350 (see cosmo_oracle.c)."""
 
@@ -163,6 +173,7 @@ class OracleUniverse:
         """One frame; returns dict(events=[(absorber, absorbed)], ...) with insertion indices."""
         n = self.n
         st = self._cstate()
+        mass_pre = self.mass_f64.copy()
         nfl, nev = C.c_int64(0), C.c_int64(0)
         events = np.empty((cap, 2), dtype=np.int64)
         if record:
@@ -184,4 +195,7 @@ class OracleUniverse:
         if record:
             out.update(active_idx=act[:na].copy(), acc=acc[:na].copy(), p_new=pn[:na].copy(),
                        v_new=vn[:na].copy(), flag_pairs=fp[:nfl.value].copy())
+            if na:
+                e, tot, ang = energies(pn[:na], vn[:na], mass_pre[act[:na]], self.G)
+                out.update(energy=e, total_energy=tot, angular_momentum=ang)
         return out

@@ -80,3 +80,21 @@ def test_free_run_merge_stream(scene, prefix_steps):
     ref = [tuple(int(x) for x in r) for r in run["events"] if r[0] < prefix_steps]
     assert ev == ref
     assert len(ref) >= 8
+
+
+def test_energies_match_reference_hud_numbers():
+    """A7: total_energy, angular_momentum, Planet.energy of the reference's own frames.  The
+    fixture is a free run; the first two frames agree to rounding, later ones only as far as the
+    chaotic trajectories do (the cloud scene stays bit-identical throughout)."""
+    g = load_golden("energies.npz")
+    for name in ("disk", "cloud"):
+        ou = orc.OracleUniverse(snap_from(g, f"{name}_init_"), G=float(g[f"{name}_G"]))
+        for f in range(int(g["frames"])):
+            out = ou.frame(float(g["dt"]), record=True)
+            act = out["active_idx"]
+            tol = 1e-12 if (f < 2 or name == "cloud") else 1e-6
+            assert abs(out["total_energy"] - g[f"{name}_total_energy"][f]) <= tol * abs(g[f"{name}_total_energy"][f])
+            assert abs(out["angular_momentum"] - g[f"{name}_angular_momentum"][f]) <= tol * abs(g[f"{name}_angular_momentum"][f])
+            alive = g[f"{name}_alive"][f][act]
+            ref = g[f"{name}_energy"][f][act][alive]
+            assert np.abs(out["energy"][alive] - ref).max() <= tol * np.abs(ref).max()
