@@ -223,7 +223,7 @@ def main():
     if rank == 0:
         sampler.start()
     barrier()
-    stage_events = [] if world == 1 else None
+    stage_events = []
     status_log = torch.zeros(K + 1, 16, dtype=torch.int64).pin_memory()   # async snapshots, no sync
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -251,7 +251,9 @@ def main():
     if stage_events:
         accel_each = np.array([ev[1].elapsed_time(ev[2]) for ev in stage_events])
         accel_ms = float(np.mean(accel_each))
-        kernel_rate = float(np.sum(n_per_step ** 2) / np.sum(accel_each * 1e-3))   # interactions/s in stage A
+        # interactions/s of stage A on THIS GPU (rank 0 evaluates 1/world of the pairs; with world > 1
+        # the stage time includes the all-reduce / all-gather that follows the kernel)
+        kernel_rate = float(np.sum(n_per_step ** 2) / world / np.sum(accel_each * 1e-3))
         detect_ms = float(np.mean([ev[2].elapsed_time(ev[3]) for ev in stage_events]))
         resolve_ms = float(np.mean([ev[3].elapsed_time(ev[4]) for ev in stage_events]))
         prep_ms = float(np.mean([ev[0].elapsed_time(ev[1]) for ev in stage_events]))
@@ -272,17 +274,25 @@ def main():
         except Exception:
             pass
         hbm_peak = mp.get("hbm_gbs", 6650.0)
+        kname = "k_accel_f32_sym" if sym else "k_accel_%s" % ("f32" if prec == "fp32" else "f64")
+        traffic = None
+        try:   # DRAM bytes per launch from the committed ncu capture of this kernel on this workload
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                "%s|%s" % (kname, a.workload), {}).get("bytes")
+        except Exception:
+            pass
         roofline = {"bound": "fma_pipe_" + prec,
-                    "kernel": "k_accel_f32_sym" if sym else "k_accel_%s" % ("f32" if prec == "fp32" else "f64"),
+                    "kernel": kname,
                     "frac_vs_one_sided_9_instr_convention": (kernel_rate * INSTR_PER_INTERACTION[prec] * 2 / 1e12 / peak)
                     if peak else None,
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (achieved / peak) if peak else None, "traffic": None,
+                    "frac": (achieved / peak) if peak else None, "traffic": traffic,
                     "peak_source": "in-process %s micro-benchmark (cosmo_microbench) on this GPU; "
                                    "MEASURED_PEAKS.json holds no CUDA-core peak" % ("FFMA" if prec == "fp32" else "DFMA"),
                     "instr_per_interaction": ipi, "kernel_ms": accel_ms,
                     "interactions_per_s_kernel": kernel_rate,
-                    "stage_ms": {"prep": prep_ms, "accel_integrate": accel_ms, "detect": detect_ms,
+                    "stage_ms": {"prep": prep_ms, "accel_integrate" + ("+exchange" if world > 1 else ""): accel_ms,
+                                 "detect" + ("+exchange" if world > 1 else ""): detect_ms,
                                  "resolve_commit": resolve_ms},
                     "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in mp else "fallback"},

@@ -454,6 +454,7 @@ int launch_prep(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step
 int launch_accel(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                  cudaStream_t s) {
     if ((p.opts & COSMO_OPT_FP32) && (p.opts & COSMO_OPT_F32_SYM)) return launch_accel_sym(st, sc, p, s);
+    if (!(p.opts & COSMO_OPT_FP32) && (p.opts & COSMO_OPT_F64_SYM)) return launch_accel_sym64(st, sc, p, s);
     const int rows = p.i_end - p.i_begin;
     if (rows <= 0) return COSMO_OK;
     int jsplit = p.jsplit < 1 ? 1 : p.jsplit;

@@ -29,6 +29,8 @@ int accel_residency(int which, int *rows_per_cta, int *tile);
 // accel_sym.cu
 int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                      cudaStream_t s);
+int launch_accel_sym64(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                       cudaStream_t s);
 int launch_sym_integrate(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                          cudaStream_t s);
 

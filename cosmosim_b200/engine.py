@@ -20,6 +20,7 @@ import torch
 
 from . import _abi
 from ._abi import (F_IMMOBILE, F_MASS_INT, OPT_BOUNDED, OPT_COLLISIONS, OPT_DEFER_INTEGRATE, OPT_ENERGY, OPT_F32_SCALAR,
+                   OPT_F64_SYM,
                    OPT_F32_SYM, OPT_FP32, OPT_STORE_ACC, PAD, ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_ESCAPED, ST_N_EVENTS,
                    ST_N_PAIRS, ST_STEP, STATUS_LEN)
 
@@ -79,6 +80,7 @@ class Engine:
         self.grid_threshold = 8192  # planets from which the grid broad phase + parallel resolver pay off
         self.small_threshold = 4096  # below: small-N kernel shape (more, shorter CTAs)
         self.sym_threshold = 32768   # FP32: from here on the symmetric kernel (each pair once) wins
+        self.sym64_threshold = 16384  # FP64: same for the symmetric FP64 kernel
         self.sym_chunk = 0           # column blocks per CTA of the symmetric kernel (0 = library default)
         self.retune_every = 16      # frames between host-side refreshes of the grid tuning
         self._manual_n = False
@@ -314,28 +316,34 @@ class Engine:
         return {"acc": self.t["acc"], "pos_new": self._pos_new.view(cap, 2), "vel_new": self._vel_new.view(cap, 2)}
 
     # ------------------------------------------------------------------ stepping
-    def _ensure_colbuf(self):
+    def _ensure_colbuf(self, fp64=False):
         """Column-partial buffer of the symmetric FP32 kernel: one float2 row of `cap` per local row
         block (8 B x N^2 / 1024 / ranks: 8.6 GB at N = 2^20 on one GPU -- HBM3e capacity is what makes
         the deterministic, atomic-free reduction affordable)."""
         rows = -(-(self.cap // PAD) // self.world)
+        if fp64:                                  # 512-planet row blocks, double2 = two float2 rows each
+            rows = 2 * -(-(self.cap // 512) // self.world)
         if "colbuf" not in self.t or self.t["colbuf"].shape[0] < rows:
             self.t["colbuf"] = torch.empty(rows, self.cap, 2, dtype=torch.float32, device=self.device)
             self.sc.colbuf = C.c_void_p(self.t["colbuf"].data_ptr())
             self.sc.colbuf_rows = rows
 
     def params(self, dt, G, r_max, collisions=True, bounded=True, fp32=False, store_acc=False,
-               f32_scalar=False, jsplit=None, f32_sym=None, energy=False):
+               f32_scalar=False, jsplit=None, f32_sym=None, energy=False, f64_sym=None):
         p = _abi.StepParams()
         p.G, p.dt, p.r_max = float(G), float(dt), float(r_max)
         n = self.n_upper
         sym = bool(fp32 and not f32_scalar and (f32_sym if f32_sym is not None else n >= self.sym_threshold))
+        sym64 = bool((not fp32) and (f64_sym if f64_sym is not None else n >= self.sym64_threshold))
         if sym:
             self._ensure_colbuf()
+        if sym64:
+            self._ensure_colbuf(fp64=True)
         p.opts = ((OPT_COLLISIONS if collisions else 0) | (OPT_BOUNDED if bounded else 0) |
                   (OPT_FP32 if fp32 else 0) | (OPT_STORE_ACC if store_acc else 0) |
                   (OPT_F32_SCALAR if f32_scalar else 0) | (OPT_F32_SYM if sym else 0) |
-                  (OPT_DEFER_INTEGRATE if (sym and self.world > 1) else 0) | (OPT_ENERGY if energy else 0))
+                  (OPT_F64_SYM if sym64 else 0) |
+                  (OPT_DEFER_INTEGRATE if ((sym or sym64) and self.world > 1) else 0) | (OPT_ENERGY if energy else 0))
         p.sym_chunk = int(self.sym_chunk)
         p.reserved0 = int(os.environ.get("COSMO_SYM_VARIANT", "0"))
         p.n_upper = n
@@ -393,7 +401,7 @@ class Engine:
                 p = self.params(dt, G, r_max, **kw)
                 pp = C.byref(p)
             if self.world > 1:
-                self._step_sharded(p, stream)
+                self._step_sharded(p, stream, stage_events)
             elif stage_events is None:
                 _abi.check(lib.cosmo_step(st, sc, pp, stream), "cosmo_step")
             else:
@@ -452,9 +460,9 @@ class Engine:
             return base + 1 + 2                        # all-pairs detect | rank sort, resolve
         return base + (2 + 3 + 3) + (1 + 3 + 4 + 1 + 3 + 4)  # grid (max,count,scan x3,fill,detect,giants) | csr + components
 
-    def _step_sharded(self, p, stream):
+    def _step_sharded(self, p, stream, stage_events=None):
         from . import sharded
-        sharded.frame(self, p, stream)
+        sharded.frame(self, p, stream, stage_events)
 
     # ------------------------------------------------------------------ host-buffer (e2e) path
     E2E_IN = ("pos", "vel", "mass", "mass_hi", "mass_lo", "radius", "volume", "eaten", "id", "flags")

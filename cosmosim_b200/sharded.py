@@ -50,13 +50,21 @@ def exchange_pairs(local_pairs: torch.Tensor, local_count: torch.Tensor, xchg: t
     return xchg
 
 
-def frame(eng, p, stream):
-    """One frame on engine `eng` (params p already hold this rank's row shard)."""
+def frame(eng, p, stream, stage_events=None):
+    """One frame on engine `eng` (params p already hold this rank's row shard).
+
+    stage_events: optional list receiving (start, prep, stage A + exchange, stage B + exchange,
+    stage C) torch.cuda.Event tuples for bench.py."""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if stage_events is not None else None
+    if ev:
+        ev[0].record()
     lib = eng.lib
     st, sc, pp = C.byref(eng.st), C.byref(eng.sc), C.byref(p)
     n = p.n_upper
     _, _, per = shard_rows(n, eng.world, eng.rank)
     _abi.check(lib.cosmo_begin_frame(st, sc, pp, stream), "cosmo_begin_frame")
+    if ev:
+        ev[1].record()
     _abi.check(lib.cosmo_accel_integrate(st, sc, pp, stream), "cosmo_accel_integrate")
     if p.opts & _abi.OPT_DEFER_INTEGRATE:
         # symmetric FP32 kernel: every rank holds partial sums for ALL planets (its row blocks +
@@ -65,6 +73,8 @@ def frame(eng, p, stream):
         _abi.check(lib.cosmo_integrate(st, sc, pp, stream), "cosmo_integrate")
     else:
         gather_planes(((eng._pos_new, 2), (eng._vel_new, 2), (eng._xx_new, 1)), per, eng.rank, eng.world, eng.group)
+    if ev:
+        ev[2].record()
     if p.opts & _abi.OPT_ENERGY:      # diagnostics: replicated over all rows (new positions are complete here)
         _abi.check(lib.cosmo_energies(st, sc, pp, stream), "cosmo_energies")
     _abi.check(lib.cosmo_detect_pairs(st, sc, pp, stream), "cosmo_detect_pairs")
@@ -79,4 +89,9 @@ def frame(eng, p, stream):
         _abi.check(lib.cosmo_append_pairs(st, sc, C.c_void_p(xchg[r, 1:].data_ptr()),
                                           C.c_void_p(xchg[r, :1].data_ptr()), xchg.shape[1] - 1, stream),
                    "cosmo_append_pairs")
+    if ev:
+        ev[3].record()
     _abi.check(lib.cosmo_resolve_commit(st, sc, pp, stream), "cosmo_resolve_commit")
+    if ev:
+        ev[4].record()
+        stage_events.append(ev)

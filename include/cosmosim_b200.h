@@ -61,6 +61,7 @@ extern "C" {
 #define COSMO_OPT_STORE_ACC 8u   /* also write the accelerations to scratch.acc */
 #define COSMO_OPT_F32_SCALAR 16u /* FP32 path: scalar FFMA inner loop instead of packed f32x2 */
 #define COSMO_OPT_F32_SYM 32u    /* FP32 path: symmetric kernel (each unordered pair once); needs colbuf */
+#define COSMO_OPT_F64_SYM 256u    /* FP64 path: symmetric kernel (each unordered pair once); needs colbuf */
 #define COSMO_OPT_ENERGY 128u     /* also evaluate energies / angular momentum (universe_old.py:181-189,210) */
 #define COSMO_OPT_DEFER_INTEGRATE 64u /* symmetric kernel, multi-GPU: leave this rank's partial sums in
                                          scratch.acc (to be all-reduced), integrate with cosmo_integrate */
@@ -131,8 +132,10 @@ typedef struct cosmo_scratch {
     double *rinf;      /* [cap]      radii inflated by 2^-30 (candidate filter of stage B) */
     double *partial;   /* [jsplit_max][cap][2] partial sums of the all-pairs pass */
     int32_t jsplit_max;
-    float *colbuf;        /* [colbuf_rows][cap][2] column partial sums of the symmetric FP32 kernel */
-    int64_t colbuf_rows;  /* >= ceil(ceil(n / 1024) / ranks) */
+    float *colbuf;        /* [colbuf_rows][cap][2] column partial sums of the symmetric kernels (FP32:
+                             float2 per planet and 1024-planet row block; FP64: double2 = two rows
+                             per 512-planet row block) */
+    int64_t colbuf_rows;  /* FP32: >= ceil(ceil(n/1024)/ranks); FP64: >= 2 * ceil(ceil(n/512)/ranks) */
     int32_t *tile_ctr; /* [cap / 64 + 4] arrival counters, must start zeroed */
     uint8_t *alive;    /* [cap]      1 while the slot's planet is alive in this frame */
     uint8_t *escaped;  /* [cap]      start-of-frame escape flags (A6) */

@@ -49,6 +49,28 @@ def test_loaded_library_is_the_in_tree_cuda_build():
 
 
 # ---------------------------------------------------------------- stage A alone
+def test_accel_fp64_symmetric_kernel_vs_acc_blas_and_oracle():
+    """The symmetric FP64 kernel (each unordered pair once) against the reference's own acc_blas
+    output and the oracle, at sizes that are / are not multiples of its 512-planet block, with
+    coincident planets (d2 == 0 off the diagonal -> the masked path) thrown in."""
+    g = load_golden("accel_n4001.npz")
+    for n, dup in ((4001, False), (512, False), (1537, True)):
+        pos, mass = g["pos"][:n].copy(), g["mass"][:n].copy()
+        if dup:
+            pos[700] = pos[20]          # two pairs of coincident planets in different blocks
+            pos[1500] = pos[3]
+        arr = {"pos": pos, "vel": np.zeros((n, 2)), "mass_f64": mass, "mass_hi": np.zeros(n, np.uint64),
+               "mass_lo": np.zeros(n, np.uint64), "flags": np.zeros(n, np.uint8), "radius": np.ones(n),
+               "volume": np.ones(n), "eaten": np.zeros(n, np.int64), "id": np.arange(n, dtype=np.int32)}
+        eng = make_engine(arr)
+        eng.step(1, 0.0, float(g["G"]), 1e300, collisions=False, bounded=False, store_acc=True, f64_sym=True)
+        acc = eng.last_frame_tensors()["acc"][:n].cpu().numpy()
+        eng.check_errors()
+        assert relerr_rows(acc, orc.accel(pos, mass, float(g["G"]))).max() < 1e-13, n
+        if n == 4001:
+            assert relerr_rows(acc, g["acc"]).max() < FP64_TOL
+
+
 @pytest.mark.parametrize("jsplit", [1, 3, 16])
 def test_accel_fp64_vs_acc_blas_fixture(jsplit):
     g = load_golden("accel_n4001.npz")
@@ -466,3 +488,45 @@ def test_energies_and_angular_momentum():
     e = np.array([p.energy for p in u.planets])
     assert np.abs(e - g["disk_energy"][0]).max() <= 1e-12 * np.abs(g["disk_energy"][0]).max()
     assert len(u.get_bound_planets()) + len(u.get_unbound_planets()) == len(u.get_active_planets())
+
+
+def test_analytic_scenes_through_the_drop_in_api():
+    """Physics sanity beyond oracle parity (the reference's examples/earth_moon.py and
+    examples/lagrange_three_bodies.py as specs): a circular two-body orbit keeps its radius and
+    conserves angular momentum and energy to the integrator's accuracy; three equal masses on an
+    equilateral triangle with the matching rotation rate keep their mutual distances."""
+    import math
+    from cosmosim_b200 import Universe
+    ME_, RE_ = 5.972e24, 6.371e6
+    # Earth-Moon like pair about the common centre of mass, dt = 60 s, 2000 frames
+    u = Universe(track_energy=True)
+    m1, m2, d = ME_, 7.348e22, 3.844e8
+    r1, r2 = d * m2 / (m1 + m2), d * m1 / (m1 + m2)
+    w = math.sqrt(u.G * (m1 + m2) / d ** 3)
+    u.create_planet(mass=m1, radius=RE_, position=[-r1, 0], velocity=[0, -w * r1], color=(1, 1, 1), name="e")
+    u.create_planet(mass=m2, radius=1.7e6, position=[r2, 0], velocity=[0, w * r2], color=(1, 1, 1), name="m")
+    u.simulate(speed=60.0, fps=1, steps=1)
+    e0, l0 = u.total_energy, u.angular_momentum
+    u.simulate(speed=60.0, fps=1, steps=2000)
+    a, b = u.planets
+    sep = np.linalg.norm(a.position - b.position)
+    assert abs(sep - d) / d < 2e-3
+    assert abs(u.angular_momentum - l0) <= 1e-9 * abs(l0)      # semi-implicit Euler conserves L exactly (to rounding)
+    assert abs(u.total_energy - e0) <= 5e-3 * abs(e0)
+    assert u.merge_events == []
+    # Lagrange triangle
+    u = Universe()
+    m, side = 1.0e26, 1.0e9
+    rc = side / math.sqrt(3.0)
+    w = math.sqrt(u.G * m / (math.sqrt(3.0) * rc ** 3))
+    for k in range(3):
+        th = 2 * math.pi * k / 3
+        u.create_planet(mass=m, radius=1e6, position=[rc * math.cos(th), rc * math.sin(th)],
+                        velocity=[-w * rc * math.sin(th), w * rc * math.cos(th)], color=(1, 1, 1), name="l%d" % k)
+    period = 2 * math.pi / w
+    u.simulate(speed=period / 4000, fps=1, steps=1000)        # a quarter turn
+    p = [q.position for q in u.planets]
+    sides = [np.linalg.norm(p[0] - p[1]), np.linalg.norm(p[1] - p[2]), np.linalg.norm(p[2] - p[0])]
+    assert max(sides) / min(sides) - 1 < 1e-6 and abs(sides[0] - side) / side < 5e-3
+    ang = math.atan2(p[0][1], p[0][0])
+    assert abs(ang - math.pi / 2) < 2e-2
