@@ -257,10 +257,12 @@ def main():
         detect_ms = float(np.mean([ev[2].elapsed_time(ev[3]) for ev in stage_events]))
         resolve_ms = float(np.mean([ev[3].elapsed_time(ev[4]) for ev in stage_events]))
         prep_ms = float(np.mean([ev[0].elapsed_time(ev[1]) for ev in stage_events]))
-        sym = bool(eng.params(DT, G, R_MAX, **kw).opts & _abi.OPT_F32_SYM)
-        # the symmetric kernel evaluates each unordered pair once: 12 FMA-pipe instr per pair = 6 per
-        # ordered interaction; the one-sided kernels need 9 (FP32) / 20 (FP64)
-        ipi = 6 if sym else INSTR_PER_INTERACTION[prec]
+        opts_now = eng.params(DT, G, R_MAX, **kw).opts
+        sym = bool(opts_now & (_abi.OPT_F32_SYM | _abi.OPT_F64_SYM))
+        # the symmetric kernels evaluate each unordered pair once: 12 FMA-pipe (FP32) / 23 FP64-pipe
+        # instructions per pair = 6 / 11.5 per ordered interaction; the
+        # one-sided kernels need 9 (FP32) / 20 (FP64)
+        ipi = ({"fp32": 6.0, "fp64": 11.5}[prec]) if sym else INSTR_PER_INTERACTION[prec]
         achieved = kernel_rate * ipi * 2 / 1e12                            # FMA-equivalent TFLOP/s
         peak_key = "ffma_tflops" if prec == "fp32" else "dfma_tflops"
         peak = peaks.get(peak_key)
@@ -274,7 +276,7 @@ def main():
         except Exception:
             pass
         hbm_peak = mp.get("hbm_gbs", 6650.0)
-        kname = "k_accel_f32_sym" if sym else "k_accel_%s" % ("f32" if prec == "fp32" else "f64")
+        kname = "k_accel_%s%s" % ("f32" if prec == "fp32" else "f64", "_sym" if sym else "")
         traffic = None
         try:   # DRAM bytes per launch from the committed ncu capture of this kernel on this workload
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
@@ -283,8 +285,8 @@ def main():
             pass
         roofline = {"bound": "fma_pipe_" + prec,
                     "kernel": kname,
-                    "frac_vs_one_sided_9_instr_convention": (kernel_rate * INSTR_PER_INTERACTION[prec] * 2 / 1e12 / peak)
-                    if peak else None,
+                    "frac_vs_one_sided_convention": (kernel_rate * INSTR_PER_INTERACTION[prec] * 2 / 1e12 / peak)
+                    if peak else None,   # SURVEY 8d counts 9 (FP32) / 20 (FP64) instr per ordered interaction
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": (achieved / peak) if peak else None, "traffic": traffic,
                     "peak_source": "in-process %s micro-benchmark (cosmo_microbench) on this GPU; "

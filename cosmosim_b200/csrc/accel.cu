@@ -70,7 +70,16 @@ __global__ void k_prep(cosmo_state st, cosmo_scratch sc, double r_max, int pos_e
                 sc.pk_m[k] = (float)scalbn(st.mass[k], -mass_exp);
             }
         } else {
-            sc.h[k] = 0.0;
+            // padding slots [n, n_pad): massless planets far outside the scene.  The blocked
+            // kernels process whole blocks, so these must be benign sources AND targets: zero mass,
+            // a finite position with its own consistent chain diagonal, nothing that can cancel
+            // to d2 <= 0 against a real planet.
+            const double far = 1.0e100;
+            reinterpret_cast<double2 *>(st.pos)[k] = make_double2(far, far);
+            reinterpret_cast<double2 *>(st.vel)[k] = make_double2(0.0, 0.0);
+            st.mass[k] = 0.0;
+            double rx = __dadd_rn(__dmul_rn(-2.0 * far, far), -2.0);
+            sc.h[k] = 0.5 * __dadd_rn(__dadd_rn(rx, rx), 6.0);
             sc.rinf[k] = 0.0;
             sc.escaped[k] = 0;
             sc.alive[k] = 0;

@@ -344,7 +344,16 @@ class Engine:
                   (OPT_F32_SCALAR if f32_scalar else 0) | (OPT_F32_SYM if sym else 0) |
                   (OPT_F64_SYM if sym64 else 0) |
                   (OPT_DEFER_INTEGRATE if ((sym or sym64) and self.world > 1) else 0) | (OPT_ENERGY if energy else 0))
-        p.sym_chunk = int(self.sym_chunk)
+        if self.sym_chunk or not (sym or sym64):
+            p.sym_chunk = int(self.sym_chunk)
+        else:
+            # column blocks per CTA: enough CTAs (~8 per resident slot and rank) to keep the tail short,
+            # few enough that the row partials fit `partial` (JSPLIT_MAX rows)
+            nblk = -(-n // (512 if sym64 else 1024))
+            want = (nblk * nblk) // (2 * 8 * 2 * self.sm_count * self.world) if nblk > 1 else 1
+            p.sym_chunk = int(min(32, max(1, -(-nblk // self.JSPLIT_MAX), want)))
+        if os.environ.get("COSMO_SYM_CHUNK"):
+            p.sym_chunk = int(os.environ["COSMO_SYM_CHUNK"])
         p.reserved0 = int(os.environ.get("COSMO_SYM_VARIANT", "0"))
         p.n_upper = n
         if self.world > 1:
