@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -211,17 +211,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()              # started early: nvidia-smi needs ~0.1 s before its first sample
     # pipe peaks for the roofline denominator (tiny, before the timed region)
     peaks = measure_pipe_peaks(eng, prec) if rank == 0 else {}
-
     for _ in range(W):
         eng.step(1, DT, G, R_MAX, **kw)
         flush.zero_()
     barrier()
     n_active_start = eng.status()["n_active"]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    warm_samples = len(sampler.lines)
     barrier()
     stage_events = []
     status_log = torch.zeros(K + 1, 16, dtype=torch.int64).pin_memory()   # async snapshots, no sync
@@ -239,7 +239,13 @@ def main():
         tms = torch.tensor([ms], dtype=torch.float64, device=eng.device)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        timed_samples = len(sampler.lines) - warm_samples
+        if timed_samples >= 3:       # enough samples inside the timed region: use only those
+            sampler.lines = sampler.lines[warm_samples:]
+        clocks = sampler.stop()
+        clocks["window"] = "timed region" if timed_samples >= 3 else "warm-up + timed region (timed region < 60 ms)"
     st = eng.check_errors()
     # interactions actually evaluated: N_active^2 per frame, and N_active shrinks as planets merge
     n_per_step = status_log[:K, 0].numpy().astype(np.float64)

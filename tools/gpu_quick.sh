@@ -18,4 +18,4 @@ for f in sorted(glob.glob('gpurun_out/bench_*.json')):
     r=d.get('roofline') or {}
     print(f.split('/')[-1], 'value %.3e'%d['value'], 'ms/step %.3f'%d['ms_per_step'], 'frac', r.get('frac'), 'stage_ms', r.get('stage_ms'), 'e2e', (d.get('e2e') or {}).get('value'), 'cpu', (d.get('cpu_baseline') or {}).get('value'), d.get('final_state'), d.get('detect_mode'), 'pairs', d.get('pairs_last_frame'), 'n/step', d.get('n_active_per_step'))
 PY
-tail -3 gpurun_out/*.err
+tail -n 3 gpurun_out/bench_*.err
