@@ -251,47 +251,39 @@ __global__ void __launch_bounds__(256) k_resolve_simple(cosmo_state st, cosmo_sc
     }
 }
 
-// One CTA: stable compaction of the indices q with (pair_flag[q] & bit) into cplx_list
-// (bit == 2) or of the merge events into the log (bit == 1).
-__global__ void __launch_bounds__(1024) k_ordered_compact(cosmo_state st, cosmo_scratch sc, int bit) {
-    __shared__ int s_w[32];
-    __shared__ long long s_base;
+// Stable (order-preserving) compaction of the sorted-pair indices carrying a flag bit, multi-CTA:
+// 0/1 marks -> device-wide exclusive scan (scan.cu) -> scatter.  bit 2: indices of the clustered
+// pairs -> cplx_list; bit 1: the merge events -> appended to the log in sorted-pair order, which
+// is the visitation order of the reference's double loop.
+__global__ void __launch_bounds__(256) k_mark_bit(cosmo_state st, cosmo_scratch sc, int bit) {
+    const long long M = pair_count(st, sc);
+    if (bit == 1 && blockIdx.x == 0 && threadIdx.x == 0) st.status[COSMO_ST_EV_BASE] = st.status[COSMO_ST_N_EVENTS];
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x)
+        sc.scan_a[q] = (sc.pair_flag[q] & bit) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_scatter_bit(cosmo_state st, cosmo_scratch sc, int bit) {
     const long long M = pair_count(st, sc);
     const int stamp = (int)st.status[COSMO_ST_STEP];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_base = bit == 1 ? st.status[COSMO_ST_N_EVENTS] : 0;
-    __syncthreads();
-    for (long long q0 = 0; q0 < M; q0 += 1024) {
-        const long long q = q0 + threadIdx.x;
-        const int f = (q < M && (sc.pair_flag[q] & bit)) ? 1 : 0;
-        const unsigned ballot = __ballot_sync(0xffffffffu, f);
-        if (lane == 0) s_w[w] = __popc(ballot);
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int x = 0; x < 32; ++x) {
-            const int c = s_w[x];
-            before += x < w ? c : 0;
-            total += c;
+    const long long base = st.status[COSMO_ST_EV_BASE];
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        if (!(sc.pair_flag[q] & bit)) continue;
+        const long long pos = sc.scan_a[q];
+        if (bit == 2) {
+            sc.cplx_list[pos] = (int)q;
+        } else if (base + pos < st.event_cap) {
+            st.events[3 * (base + pos) + 0] = stamp;
+            st.events[3 * (base + pos) + 1] = sc.ev_tmp[2 * q];
+            st.events[3 * (base + pos) + 2] = sc.ev_tmp[2 * q + 1];
+        } else {
+            atomicOr(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_ERROR]),
+                     (unsigned long long)COSMO_ERR_EVENT_OVERFLOW);
         }
-        const long long pos = s_base + before + __popc(ballot & ((1u << lane) - 1));
-        if (f) {
-            if (bit == 2) {
-                sc.cplx_list[pos] = (int)q;
-            } else if (pos < st.event_cap) {
-                st.events[3 * pos + 0] = stamp;
-                st.events[3 * pos + 1] = sc.ev_tmp[2 * q];
-                st.events[3 * pos + 2] = sc.ev_tmp[2 * q + 1];
-            } else {
-                st.status[COSMO_ST_ERROR] |= COSMO_ERR_EVENT_OVERFLOW;
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_base += total;
-        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        if (bit == 2) st.status[COSMO_ST_N_COMPLEX] = s_base;
-        else st.status[COSMO_ST_N_EVENTS] = s_base;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long total = M > 0 ? sc.scan_a[M] : 0;
+        if (bit == 2) st.status[COSMO_ST_N_COMPLEX] = total;
+        else st.status[COSMO_ST_N_EVENTS] = base + total;
     }
 }
 
@@ -558,8 +550,12 @@ int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc, const 
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_csr_sort_rows"));
         k_resolve_simple<<<pb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_resolve_simple"));
-        k_ordered_compact<<<1, 1024, 0, s>>>(st, sc, 2);
-        COSMO_TRY(COSMO_LAUNCH_CHECK("k_ordered_compact(complex)"));
+        k_mark_bit<<<pb, 256, 0, s>>>(st, sc, 2);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_mark_bit(2)"));
+        COSMO_TRY(launch_scan_exclusive(sc.scan_a, sc.scan_a, sc.scan_blk, &st.status[COSMO_ST_N_PAIRS],
+                                        sc.pair_cap, 0, s));
+        k_scatter_bit<<<pb, 256, 0, s>>>(st, sc, 2);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_scatter_bit(2)"));
         k_components<<<1, 1024, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_components"));
         COSMO_TRY(launch_scan_exclusive(sc.row_count, sc.row_start, sc.scan_blk, &st.status[COSMO_ST_N_ACTIVE],
@@ -568,8 +564,12 @@ int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc, const 
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_comp_fill"));
         k_comp_resolve<<<(p.n_upper + 127) / 128 > 0 ? (p.n_upper + 127) / 128 : 1, 128, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_comp_resolve"));
-        k_ordered_compact<<<1, 1024, 0, s>>>(st, sc, 1);
-        COSMO_TRY(COSMO_LAUNCH_CHECK("k_ordered_compact(events)"));
+        k_mark_bit<<<pb, 256, 0, s>>>(st, sc, 1);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_mark_bit(1)"));
+        COSMO_TRY(launch_scan_exclusive(sc.scan_a, sc.scan_a, sc.scan_blk, &st.status[COSMO_ST_N_PAIRS],
+                                        sc.pair_cap, 0, s));
+        k_scatter_bit<<<pb, 256, 0, s>>>(st, sc, 1);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_scatter_bit(1)"));
         k_csr_cleanup<<<pb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_csr_cleanup"));
     }

@@ -126,6 +126,7 @@ class Engine:
         t["pmax"] = torch.full((cap,), -1, dtype=i32, device=dev)
         t["scan_blk"] = z(_abi.SCAN_BLOCKS + 1, dtype=i32)
         t["pair_flag"] = z(self.pair_cap, dtype=i32); t["cplx_list"] = z(self.pair_cap, dtype=i32)
+        t["scan_a"] = z(self.pair_cap + 1, dtype=i32)
         t["ev_tmp"] = z(self.pair_cap, 2, dtype=i64)
         t["label"] = z(cap, dtype=i32); t["comp_items"] = z(self.pair_cap, dtype=i32)
         # uniform-grid broad phase
@@ -158,7 +159,7 @@ class Engine:
                   "pairs", "pairs_sorted", "cur_pos", "cur_vel", "mod_row", "mod_step", "chunk_alive",
                   "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_radius", "t_volume",
                   "t_eaten", "t_id", "t_flags", "t_energy", "row_count", "row_start", "pmin", "pmax", "scan_blk",
-                  "pair_flag", "cplx_list", "ev_tmp", "label", "comp_items", "cell_of", "cell_items", "cell_count", "cell_start",
+                  "pair_flag", "cplx_list", "scan_a", "ev_tmp", "label", "comp_items", "cell_of", "cell_items", "cell_count", "cell_start",
                   "giants"):
             setattr(sc, k, p(k))
         sc.pos_new = C.c_void_p(self._pos_new.data_ptr())
@@ -467,7 +468,7 @@ class Engine:
             return base
         if self.grid is None:
             return base + 1 + 2                        # all-pairs detect | rank sort, resolve
-        return base + (2 + 3 + 3) + (1 + 3 + 4 + 1 + 3 + 4)  # grid (max,count,scan x3,fill,detect,giants) | csr + components
+        return base + (2 + 3 + 4) + (1 + 3 + 3 + 5 + 1 + 3 + 2 + 5 + 1)  # grid build+detect | csr, resolve, compactions
 
     def _step_sharded(self, p, stream, stage_events=None):
         from . import sharded

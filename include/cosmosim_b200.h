@@ -80,6 +80,7 @@ extern "C" {
 #define COSMO_ST_N_COMPLEX 10  /* flagged pairs replayed sequentially in the last frame */
 #define COSMO_ST_SLOT_LO 11    /* grid broad phase: this rank's range of the cell-sorted order */
 #define COSMO_ST_SLOT_HI 12
+#define COSMO_ST_EV_BASE 13    /* event count at the start of the frame's log append */
 #define COSMO_STATUS_LEN 16
 
 #define COSMO_ERR_PAIR_OVERFLOW 1  /* more flagged pairs than pair_cap */
@@ -154,7 +155,8 @@ typedef struct cosmo_scratch {
     int32_t *pmax;        /* [cap] largest partner, must start at -1 (self-resetting) */
     int32_t *scan_blk;    /* [COSMO_SCAN_BLOCKS] block sums of the device scans */
     int32_t *pair_flag;   /* [pair_cap] bit0: merge happened, bit1: needs sequential replay */
-    int32_t *cplx_list;   /* [pair_cap] sorted-pair indices replayed sequentially */
+    int32_t *cplx_list;   /* [pair_cap] sorted-pair indices of the clustered pairs */
+    int32_t *scan_a;      /* [pair_cap + 1] marks / exclusive scan of the ordered compactions */
     int64_t *ev_tmp;      /* [pair_cap][2] (absorber id, absorbed id) per sorted-pair slot */
     int32_t *label;       /* [cap] connected-component label of clustered planets */
     int32_t *comp_items;  /* [pair_cap] sorted-pair indices grouped by component */
