@@ -226,12 +226,14 @@ def main():
     stage_events = []
     status_log = torch.zeros(K + 1, 16, dtype=torch.int64).pin_memory()   # async snapshots, no sync
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.lib.cosmo_launch_count()
     e0.record()
     for k in range(K):
         status_log[k].copy_(eng.t["status"], non_blocking=True)
         eng.step(1, DT, G, R_MAX, stage_events=stage_events, **kw)
         flush.zero_()
     e1.record()
+    gpu_launches = int(eng.lib.cosmo_launch_count() - launches0)     # counted inside the library
     status_log[K].copy_(eng.t["status"], non_blocking=True)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -343,7 +345,7 @@ def main():
                 "steps": K, "warmup": W, "ms_per_step": ms / K, "steps_per_s": K / (ms * 1e-3),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32" if prec == "fp32" else "f64", "data": "synthetic", "config": config,
-                "clocks": clocks, "e2e": e2e, "gpu_launches": K * (eng.launches_per_frame(collisions) + (world if world > 1 else 0)),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
                 "roofline": roofline, "cpu_baseline": cpu,
                 "final_state": {"n_active": st["n_active"], "merges": st["n_events"], "escaped": st["n_escaped"]},
                 "n_active_per_step": [int(x) for x in n_per_step],

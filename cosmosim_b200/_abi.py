@@ -60,6 +60,7 @@ class StepParams(C.Structure):
 # name -> (restype, argtypes); every symbol include/cosmosim_b200.h declares
 SYMBOLS = {
     "cosmo_abi_version": (C.c_int, []),
+    "cosmo_launch_count": (C.c_longlong, []),
     "cosmo_last_error": (C.c_char_p, []),
     "cosmo_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "cosmo_suggest_jsplit": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int32]),

@@ -23,6 +23,13 @@ int check_cuda(cudaError_t e, const char *what) {
     return COSMO_E_CUDA;
 }
 
+static long long g_launches = 0;
+
+int check_launch(const char *what) {
+    ++g_launches;
+    return check_cuda(cudaGetLastError(), what);
+}
+
 static int check_args(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p) {
     if (!st || !sc || !p) {
         set_error("null state/scratch/params");
@@ -70,6 +77,8 @@ using namespace cosmo;
 extern "C" {
 
 int cosmo_abi_version(void) { return COSMO_ABI_VERSION; }
+
+long long cosmo_launch_count(void) { return g_launches; }
 
 const char *cosmo_last_error(void) { return g_err; }
 

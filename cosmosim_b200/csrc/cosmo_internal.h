@@ -10,13 +10,14 @@ namespace cosmo {
 // error plumbing (abi.cu)
 void set_error(const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
+int check_launch(const char *what);   // counts the kernel launch, then checks cudaGetLastError()
 
 #define COSMO_TRY(expr)                                  \
     do {                                                 \
         int _rc = (expr);                                \
         if (_rc != COSMO_OK) return _rc;                 \
     } while (0)
-#define COSMO_LAUNCH_CHECK(what) ::cosmo::check_cuda(cudaGetLastError(), what)
+#define COSMO_LAUNCH_CHECK(what) ::cosmo::check_launch(what)
 
 // accel.cu
 int launch_prep(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,

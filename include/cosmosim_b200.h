@@ -202,6 +202,8 @@ typedef struct cosmo_step_params {
 } cosmo_step_params;
 
 int cosmo_abi_version(void);
+/* Kernels of this library launched by this process so far (bench.py reports the difference). */
+long long cosmo_launch_count(void);
 const char *cosmo_last_error(void);
 /* Number of SMs / compute capability of the current device (host query). */
 int cosmo_device_info(int *sm_count, int *cc_major, int *cc_minor);
