@@ -100,8 +100,8 @@ k_detect_allpairs(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int 
 // Uniform-grid broad phase
 // ---------------------------------------------------------------------------------------
 struct GridParams {
-    double h, ox, oy, rg;
-    int c;
+    double h, cx, cy, rg;   // cell edge, centre of the linear box, giant radius
+    int c, w;               // cells per side (total), logarithmic cells on each side
 };
 
 // Cell edge actually used.  The reference compares the COMPUTED distance (expanded form,
@@ -109,19 +109,31 @@ struct GridParams {
 // radius <= rg) can be flagged while truly sqrt(4 rg^2 + E) apart; the cell edge is never
 // smaller than that (plus slack for the rounding of the cell coordinate itself).
 __device__ __forceinline__ GridParams grid_params(const cosmo_state &st, double h, double ox, double oy,
-                                                  double rg, int c) {
+                                                  double rg, int c, int w) {
     GridParams g;
     const double pmax2 = __longlong_as_double(st.status[COSMO_ST_PMAX2]);
     const double e = 64.0 * 1.1102230246251565e-16 * pmax2;
     const double hmin = sqrt(4.0 * rg * rg + e) * (1.0 + 1e-6);
     g.h = fmax(h, hmin);
-    g.ox = ox; g.oy = oy; g.rg = rg; g.c = c;
+    const double half_in = 0.5 * (double)(c - 2 * w) * h;   // the centre is fixed by the host's (h, origin)
+    g.cx = ox + half_in; g.cy = oy + half_in; g.rg = rg; g.c = c; g.w = w;
     return g;
 }
 
-__device__ __forceinline__ int cell_coord(double x, double o, double h, int c) {
-    double t = floor((x - o) / h);
-    t = fmin(fmax(t, 0.0), (double)(c - 1));  // outside the box: clamp (non-expansive)
+// Cell coordinate along one axis.  u = (x - centre) / h is mapped by a monotone function of
+// slope <= 1: identity inside the linear box |u| <= U0, U0 + log(1 + (|u| - U0)) outside, clamped
+// at the last cell.  Slope <= 1 means planets within one cell edge of each other land in the same
+// or in adjacent cells, which is all the broad phase needs; the logarithmic rim spreads planets
+// flung far out of the scene over many cells instead of piling them into the corners.
+__device__ __forceinline__ int cell_coord(double x, double centre, double h, int c, int w) {
+    const double u0 = 0.5 * (double)(c - 2 * w);
+    const double u = (x - centre) / h;
+    double t;
+    if (u > u0) t = u0 + fmin(log1p(u - u0), (double)w - 0.5);
+    else if (u < -u0) t = -u0 - fmin(log1p(-u - u0), (double)w - 0.5);
+    else t = u;
+    t = floor(t + u0 + (double)w);
+    t = fmin(fmax(t, 0.0), (double)(c - 1));   // NaN / overflow: clamp
     return (int)t;
 }
 
@@ -137,9 +149,9 @@ __global__ void __launch_bounds__(256) k_grid_max(cosmo_state st, cosmo_scratch 
 }
 
 __global__ void __launch_bounds__(256)
-k_grid_count(cosmo_state st, cosmo_scratch sc, double h, double ox, double oy, double rg, int c) {
+k_grid_count(cosmo_state st, cosmo_scratch sc, double h, double ox, double oy, double rg, int c, int w) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
-    const GridParams g = grid_params(st, h, ox, oy, rg, c);
+    const GridParams g = grid_params(st, h, ox, oy, rg, c, w);
     const double2 *pn = reinterpret_cast<const double2 *>(sc.pos_new);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         if (sc.rinf[k] > g.rg) {
@@ -153,7 +165,7 @@ k_grid_count(cosmo_state st, cosmo_scratch sc, double h, double ox, double oy, d
             sc.cell_of[k] = -1;
         } else {
             const double2 p = pn[k];
-            const int cell = cell_coord(p.y, g.oy, g.h, g.c) * g.c + cell_coord(p.x, g.ox, g.h, g.c);
+            const int cell = cell_coord(p.y, g.cy, g.h, g.c, g.w) * g.c + cell_coord(p.x, g.cx, g.h, g.c, g.w);
             sc.cell_of[k] = cell;
             atomicAdd(&sc.cell_count[cell], 1);
         }
@@ -180,38 +192,46 @@ __device__ __forceinline__ void test_and_emit(const cosmo_state &st, const cosmo
     if (d2 <= rs * rs && pred_exact(d2, st.radius[i], st.radius[j])) emit_pair(st, sc, i, j);
 }
 
-// This rank's share of the cell-sorted order, cut at CELL boundaries: the order of the planets
-// inside a cell comes from atomics and differs from rank to rank, the cell populations do not.
-// Rank r takes the cells whose first slot lies in [r * per, (r + 1) * per).
-__global__ void k_grid_ranges(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int c) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// The cell-sorted order is cut into chunks of GRID_CHUNK slots whose boundaries are snapped to
+// CELL boundaries (the order of the planets inside a cell comes from atomics and differs from rank
+// to rank, the cell populations do not), and the chunks are dealt round-robin to the ranks: the
+// crowded inner cells of a disk -- most of the candidate work -- are spread over all of them.
+// bounds[k] = first slot of the first cell starting at or after slot k * GRID_CHUNK.
+constexpr int GRID_CHUNK = 1024;
+
+__global__ void __launch_bounds__(128) k_grid_ranges(cosmo_state st, cosmo_scratch sc, int c) {
     const int ncell = c * c;
     const int total = sc.cell_start[ncell];
-    const int per = (total + shard_count - 1) / shard_count;
-    int bound[2];
-    for (int e = 0; e < 2; ++e) {
-        const long long target = (long long)(shard_index + e) * per;
-        if (target >= total || shard_index + e >= shard_count) { bound[e] = total; continue; }
-        int lo = 0, hi = ncell;                    // smallest cell with cell_start[cell] >= target
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (sc.cell_start[mid] >= target) hi = mid; else lo = mid + 1;
+    const int nchunk = (total + GRID_CHUNK - 1) / GRID_CHUNK;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= nchunk; k += gridDim.x * blockDim.x) {
+        const long long target = (long long)k * GRID_CHUNK;
+        int bound = total;
+        if (target < total) {
+            int lo = 0, hi = ncell;                    // smallest cell with cell_start[cell] >= target
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (sc.cell_start[mid] >= target) hi = mid; else lo = mid + 1;
+            }
+            bound = sc.cell_start[lo];
         }
-        bound[e] = sc.cell_start[lo];
+        sc.chunk_alive[k] = bound;                     // scratch shared with stage C's compaction (later)
     }
-    st.status[COSMO_ST_SLOT_LO] = bound[0];
-    st.status[COSMO_ST_SLOT_HI] = bound[1];
 }
 
 // One thread per non-giant target row, taken in CELL-SORTED order: the lanes of a warp then
 // work on planets of the same or neighbouring cells, so their candidate loops have similar trip
 // counts (the disk's surface density varies 20x between its inner and outer edge) and their
-// gathers hit the same lines.  Every row is produced by exactly one rank (k_grid_ranges).
+// gathers hit the same lines.  Every row is produced by exactly one rank.
 __global__ void __launch_bounds__(128)
-k_grid_detect(cosmo_state st, cosmo_scratch sc, int c) {
-    const int s_lo = (int)st.status[COSMO_ST_SLOT_LO], s_hi = (int)st.status[COSMO_ST_SLOT_HI];
+k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int c) {
+    const int total = sc.cell_start[c * c];
+    const int nchunk = (total + GRID_CHUNK - 1) / GRID_CHUNK;
     unsigned cand_total = 0;
-  for (int slot = s_lo + blockIdx.x * blockDim.x + threadIdx.x; slot < s_hi; slot += gridDim.x * blockDim.x) {
+  for (int chunk = shard_index + blockIdx.x * shard_count; chunk < nchunk; chunk += gridDim.x * shard_count) {
+   const int s_lo = sc.chunk_alive[chunk], s_hi = sc.chunk_alive[chunk + 1];
+   // blockIdx.y splits the chunk's slots: a normal chunk is one slot per thread, an oversized one
+   // (a crowded or border cell is never split across chunks) is still shared by gridDim.y blocks
+   for (int slot = s_lo + blockIdx.y * blockDim.x + threadIdx.x; slot < s_hi; slot += gridDim.y * blockDim.x) {
     const int i = sc.cell_items[slot];
     const int cell = sc.cell_of[i];
     const double2 p = reinterpret_cast<const double2 *>(sc.pos_new)[i];
@@ -233,6 +253,7 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int c) {
     const int ng = (int)min((long long)st.status[COSMO_ST_N_GIANTS], (long long)sc.giant_cap);
     for (int g = 0; g < ng; ++g) test_and_emit(st, sc, i, qx, qy, xxi, ri, sc.giants[g]);
     cand_total += (unsigned)cand;
+   }
   }
     // diagnostic only (all lanes are back together after the loop)
     const unsigned tot = __reduce_add_sync(0xffffffffu, cand_total);
@@ -288,7 +309,12 @@ int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_st
         if (nb > 148 * 8) nb = 148 * 8;
         k_grid_max<<<nb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_max"));
-        k_grid_count<<<nb, 256, 0, s>>>(st, sc, p.cell_size, p.grid_origin_x, p.grid_origin_y, p.giant_radius, c);
+        const int w = p.grid_log_cells < 0 ? 0 : p.grid_log_cells;
+        if (c - 2 * w < 1) {
+            set_error("grid broad phase: %d logarithmic cells per side do not fit cells_per_side=%d", w, c);
+            return COSMO_E_ARG;
+        }
+        k_grid_count<<<nb, 256, 0, s>>>(st, sc, p.cell_size, p.grid_origin_x, p.grid_origin_y, p.giant_radius, c, w);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_count"));
         COSMO_TRY(launch_scan_exclusive(sc.cell_count, sc.cell_start, sc.scan_blk, nullptr, (long long)c * c, 0, s));
         k_grid_fill<<<nb, 256, 0, s>>>(st, sc);
@@ -296,10 +322,11 @@ int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_st
         {
             const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
             const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
-            const int per = (p.n_upper + sh_n - 1) / sh_n;
-            k_grid_ranges<<<1, 32, 0, s>>>(st, sc, sh_i, sh_n, c);
+            const int nchunk = (p.n_upper + GRID_CHUNK - 1) / GRID_CHUNK + 1;
+            k_grid_ranges<<<(nchunk + 127) / 128, 128, 0, s>>>(st, sc, c);
             COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_ranges"));
-            k_grid_detect<<<(per + 127) / 128 > 0 ? (per + 127) / 128 : 1, 128, 0, s>>>(st, sc, c);
+            const int blocks = (nchunk + sh_n - 1) / sh_n;
+            k_grid_detect<<<dim3(blocks > 0 ? blocks : 1, GRID_CHUNK / 128), 128, 0, s>>>(st, sc, sh_i, sh_n, c);
             COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect"));
         }
         if (rows > 0) {

@@ -77,6 +77,7 @@ class Engine:
         self.mass_exp = 0
         self.frames = 0
         self.grid = None            # (cell_size, origin_x, origin_y, cells_per_side, giant_radius)
+        self.grid_log_cells = 32    # logarithmic rim of the broad-phase grid (cells per side)
         self.grid_threshold = 8192  # planets from which the grid broad phase + parallel resolver pay off
         self.small_threshold = 4096  # below: small-N kernel shape (more, shorter CTAs)
         self.sym_threshold = 32768   # FP32: from here on the symmetric kernel (each pair once) wins
@@ -225,9 +226,13 @@ class Engine:
             self.grid = None
             return
         r = radius * (1.0 + 2.0 ** -30)
-        lo, hi = pos.min(axis=0), pos.max(axis=0)
+        # Grid box from robust quantiles of the coordinates, NOT min/max: a handful of planets flung
+        # out by a close encounter must not stretch the cells over the whole scene (they are clamped
+        # into the border cells instead, which is exact, only a little slower for them).
+        sample = pos if n <= 131072 else pos[np.random.default_rng(0).integers(0, n, 131072)]
+        lo, hi = np.quantile(sample, 0.02, axis=0), np.quantile(sample, 0.98, axis=0)
         cx, cy = 0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1])
-        box = float(max(hi[0] - lo[0], hi[1] - lo[1]))
+        box = float(max(hi[0] - lo[0], hi[1] - lo[1], 1e-300)) * 1.25   # the bulk; tails go to the border cells
         # cost model: g giants cost g*N exact tests, the rest 9 cells * (N / area) * h^2 each
         top = min(n - 1, 1024)
         biggest = np.sort(np.partition(r, n - 1 - top)[n - 1 - top:])[::-1]     # descending, top+1 values
@@ -242,11 +247,12 @@ class Engine:
                 best = (cost, rg_g)
         rg = best[1]
         span = max(box, 4.0 * rg) * 1.1
-        cmax = int(math.isqrt(self.grid_cells))
+        w = self.grid_log_cells
+        cmax = int(math.isqrt(self.grid_cells)) - 2 * w
         h = max(2.0 * rg * 1.001, span / cmax, span * 4.0 / (3.0 * math.sqrt(n)))   # ~16 candidates per planet
         c = max(1, min(cmax, int(math.ceil(span / h))))
         rg = max(rg, h / (2.0 * 1.001))       # cells wider than 2*rg: admit larger planets for free
-        self.grid = (h, cx - 0.5 * c * h, cy - 0.5 * c * h, c, rg)
+        self.grid = (h, cx - 0.5 * c * h, cy - 0.5 * c * h, c + 2 * w, rg)   # c linear + 2w logarithmic cells
 
     def retune(self):
         """Synchronising refresh of the host-side launch parameters (active count, grid)."""
@@ -371,6 +377,7 @@ class Engine:
         if self.grid is not None and collisions:
             p.detect_mode, p.resolve_mode = 1, 1
             p.cell_size, p.grid_origin_x, p.grid_origin_y, p.cells_per_side, p.giant_radius = self.grid
+            p.grid_log_cells = self.grid_log_cells
         else:
             p.detect_mode, p.resolve_mode = 0, 0
         p.small_tiles = 1 if n <= self.small_threshold else 0

@@ -193,9 +193,13 @@ typedef struct cosmo_step_params {
     int32_t shard_count;  /* grid broad phase splits its cell-sorted planet order evenly by these */
     int32_t sym_chunk;    /* symmetric kernel: column blocks per CTA (0 = default) */
     int32_t reserved0;
+    int32_t grid_log_cells; /* detect_mode 1: logarithmic cells on each side of the linear box (>= 0) */
+    int32_t reserved1;
     double cell_size;    /* detect_mode 1 */
-    double grid_origin_x; /* detect_mode 1: the grid covers [origin, origin + cells_per_side*cell_size) */
-    double grid_origin_y; /*                per axis; planets outside are clamped to the border cells */
+    double grid_origin_x; /* detect_mode 1: lower corner of the LINEAR part of the grid, which has      */
+    double grid_origin_y; /* cells_per_side - 2*grid_log_cells cells per axis; beyond it the cell index */
+                          /* grows like log(1 + distance/cell) (non-expansive, so flagged pairs stay in */
+                          /* adjacent cells) and is finally clamped                                      */
     int32_t cells_per_side;
     int32_t jsplit_detect; /* source-range splits of the stage-B all-pairs pass */
     double giant_radius; /* detect_mode 1: planets with radius above this are brute-forced */

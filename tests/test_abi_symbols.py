@@ -37,7 +37,7 @@ def test_struct_layouts_match_header_sizes():
     import ctypes as C
     # 2 int32 + 20 pointers + int64  /  pointers and ints as declared in the header
     assert C.sizeof(_abi.State) == 8 + 22 * 8 + 8
-    assert C.sizeof(_abi.StepParams) == 3 * 8 + 14 * 4 + 3 * 8 + 2 * 4 + 8
+    assert C.sizeof(_abi.StepParams) == 3 * 8 + 16 * 4 + 3 * 8 + 2 * 4 + 8
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():

@@ -11,3 +11,8 @@ import json
 d=json.loads(open("gpurun_out/scale_1m_fp32_g$NG.json").read().strip().splitlines()[-1])
 print('n_gpus', d['n_gpus'], 'value %.3e'%d['value'], 'ms/step', d['ms_per_step'], 'e2e', (d.get('e2e') or {}).get('value'), d['final_state'], d['clocks'])
 PY
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/scale_1m_fp32_g$NG.json").read().strip().splitlines()[-1])
+print(d['roofline']['stage_ms'], 'frac', d['roofline']['frac'], 'launches', d['gpu_launches'])
+PY
