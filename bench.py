@@ -247,7 +247,7 @@ def main():
         if timed_samples >= 3:       # enough samples inside the timed region: use only those
             sampler.lines = sampler.lines[warm_samples:]
         clocks = sampler.stop()
-        clocks["window"] = "timed region" if timed_samples >= 3 else "warm-up + timed region (timed region < 60 ms)"
+        clocks["window"] = "timed region" if timed_samples >= 3 else "pipe micro-benchmark + warm-up + timed region (timed region shorter than 3 samples of 20 ms)"
     st = eng.check_errors()
     # interactions actually evaluated: N_active^2 per frame, and N_active shrinks as planets merge
     n_per_step = status_log[:K, 0].numpy().astype(np.float64)

@@ -224,6 +224,47 @@ class Universe:
         self._events_seen += ev.shape[0]
         self._merge_events.extend((int(f), int(a), int(b)) for f, a, b in ev)
 
+    # ------------------------------------------------------------------ bulk (array) interface
+    @classmethod
+    def from_arrays(cls, mass, radius, position, velocity=None, immobile=None, names=None, **universe_kw):
+        """Build a universe from SoA arrays without paying Planet.__init__ per planet (large N).
+
+        mass[n] (float or Python-int object array), radius[n], position[n,2], velocity[n,2],
+        immobile[n] bool.  Planets get slim proxies whose position/velocity are views into the
+        given arrays; no random numbers are drawn (colour is white, names are 'p<index>')."""
+        import math as _m
+        u = cls(**universe_kw)
+        n = len(radius)
+        position = np.ascontiguousarray(position, dtype=float)
+        velocity = np.zeros((n, 2)) if velocity is None else np.ascontiguousarray(velocity, dtype=float)
+        immobile = np.zeros(n, dtype=bool) if immobile is None else np.asarray(immobile, dtype=bool)
+        radius = np.asarray(radius, dtype=float)
+        planets = []
+        for k in range(n):
+            p = Planet.__new__(Planet)
+            m = mass[k]
+            p.__dict__.update(universe=u, name=names[k] if names is not None else "p%d" % k,
+                              _mass=m if isinstance(m, int) else float(m), _radius=float(radius[k]),
+                              _volume=((4 / 3) * _m.pi) * (float(radius[k]) ** 3), density=0.0,   # as Planet.__init__
+                              _position=position[k], _velocity=velocity[k],
+                              _energy=0, color=(255, 255, 255), _immobile=bool(immobile[k]), history=[],
+                              bound=False, clicked=False, tracked=False, _alive=True, _planets_eaten=0, index=k)
+            p.density = p._mass / p._volume
+            planets.append(p)
+        u.planets = planets
+        u._host_dirty = True
+        return u
+
+    def arrays(self):
+        """Current ACTIVE planets as SoA numpy arrays straight from the device (no Planet objects are
+        touched): dict(id, pos, vel, mass, radius, volume, eaten, flags[, energy])."""
+        if self._engine is None or self._host_dirty:
+            self._push()
+        d = self._engine.download()
+        if d["status"]["error"]:
+            self._engine.check_errors()
+        return {k: d[k] for k in ("id", "pos", "vel", "mass", "radius", "volume", "eaten", "flags", "energy")}
+
     # ------------------------------------------------------------------ stepping
     def step(self, n=1, dt=None, collisions=None):
         """Headless stepping: n frames of update_planet_lists -> interact -> destroy_escaped

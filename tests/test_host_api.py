@@ -103,3 +103,16 @@ def test_stepping_without_gpu_fails_loudly():
     with pytest.raises(Exception) as e:
         u.step(1)
     assert "no CPU path" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_from_arrays_builds_the_same_gather_as_planet_objects():
+    u1 = scenes.star_with_disk(4, n_planets=50)
+    g1 = u1._gather()
+    masses = np.array([p._mass for p in u1.planets], dtype=object)
+    u2 = Universe.from_arrays(masses, g1["radius"], g1["pos"], g1["vel"], immobile=(g1["flags"] & 1) != 0)
+    g2 = u2._gather()
+    for k in g1:
+        assert np.array_equal(g1[k], g2[k]), k
+    assert u2.planets[3].universe is u2 and u2.planets[3].index == 3 and u2.planets[0].immobile
+    u2.planets[7].velocity = [1.0, 2.0]          # setters still work on the slim proxies
+    assert u2._host_dirty and u2.planets[7].velocity.tolist() == [1.0, 2.0]
