@@ -350,7 +350,9 @@ def main():
                 "final_state": {"n_active": st["n_active"], "merges": st["n_events"], "escaped": st["n_escaped"]},
                 "n_active_per_step": [int(x) for x in n_per_step],
                 "pairs_last_frame": st["n_pairs"], "detect_mode": "grid" if eng.grid is not None else "all-pairs",
-                "jsplit": eng.params(DT, G, R_MAX, **kw).jsplit}
+                "jsplit": eng.params(DT, G, R_MAX, **kw).jsplit,
+                "exchange": (("nvlink peer stores + symmetric-memory barrier" if getattr(eng, "_peer", None)
+                              else "nccl (%s)" % getattr(eng, "_peer_error", "peer exchange not used")) if world > 1 else None)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

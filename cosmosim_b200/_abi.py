@@ -12,7 +12,7 @@ STATUS_LEN = 16
 
 # flag / option / status constants (mirror the header)
 F_IMMOBILE, F_MASS_INT = 1, 2
-OPT_COLLISIONS, OPT_BOUNDED, OPT_FP32, OPT_STORE_ACC, OPT_F32_SCALAR, OPT_F32_SYM, OPT_DEFER_INTEGRATE, OPT_ENERGY, OPT_F64_SYM = 1, 2, 4, 8, 16, 32, 64, 128, 256
+OPT_COLLISIONS, OPT_BOUNDED, OPT_FP32, OPT_STORE_ACC, OPT_F32_SCALAR, OPT_F32_SYM, OPT_DEFER_INTEGRATE, OPT_ENERGY, OPT_F64_SYM, OPT_PEER_EXCHANGE = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 ST_N_ACTIVE, ST_STEP, ST_N_EVENTS, ST_N_PAIRS, ST_N_DEAD, ST_ERROR, ST_N_ESCAPED, ST_N_CAND, ST_N_GIANTS, ST_PMAX2, ST_N_COMPLEX, ST_SLOT_LO, ST_SLOT_HI = range(13)
 SCAN_BLOCKS = 8192
 ERR_PAIR_OVERFLOW, ERR_EVENT_OVERFLOW, ERR_NAN, ERR_GIANT_OVERFLOW = 1, 2, 4, 8
@@ -43,7 +43,8 @@ class Scratch(C.Structure):
                 ("t_mass_lo", _vp), ("t_radius", _vp), ("t_volume", _vp), ("t_eaten", _vp),
                 ("t_id", _vp), ("t_flags", _vp), ("t_energy", _vp),
                 ("cell_of", _vp), ("cell_count", _vp), ("cell_start", _vp), ("cell_items", _vp),
-                ("giants", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32)]
+                ("giants", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32),
+                ("peer_acc", _vp * 16), ("n_peers", C.c_int32), ("reserved_scratch", C.c_int32)]
 
 
 class StepParams(C.Structure):

@@ -237,7 +237,13 @@ k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count,
     }
     ax *= unscale;
     ay *= unscale;
-    if (defer) {
+    if (defer == 2) {
+        // peer exchange: this rank's partial sums go straight into slot `shard_index` of every
+        // rank's exchange buffer (NVLink peer stores, coalesced 16 B per lane)
+        const double2 v = make_double2(ax, ay);
+        for (int r = 0; r < sc.n_peers; ++r)
+            reinterpret_cast<double2 *>(sc.peer_acc[r])[(size_t)shard_index * st.cap + k] = v;
+    } else if (defer) {
         reinterpret_cast<double2 *>(sc.acc)[k] = make_double2(ax, ay);
     } else {
         integrate_store(st, sc, k, ax, ay, G, dt, store_acc != 0);
@@ -245,11 +251,22 @@ k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count,
 }
 
 __global__ void __launch_bounds__(256)
-k_sym_integrate(cosmo_state st, cosmo_scratch sc, double G, double dt) {
+k_sym_integrate(cosmo_state st, cosmo_scratch sc, double G, double dt, int peer, int self) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const double2 a = reinterpret_cast<const double2 *>(sc.acc)[k];
+    double2 a;
+    if (peer) {   // add the ranks' slots of THIS rank's exchange buffer in rank order: deterministic
+        a = make_double2(0.0, 0.0);
+        const double2 *x = reinterpret_cast<const double2 *>(sc.peer_acc[self]);
+        for (int r = 0; r < sc.n_peers; ++r) {
+            const double2 v = __ldcg(&x[(size_t)r * st.cap + k]);
+            a.x += v.x;
+            a.y += v.y;
+        }
+    } else {
+        a = reinterpret_cast<const double2 *>(sc.acc)[k];
+    }
     // sc.acc holds the all-reduced sums S; integrate_store multiplies by G and rewrites acc = G S
     integrate_store(st, sc, k, a.x, a.y, G, dt, true);
 }
@@ -288,7 +305,7 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
         }
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_accel_f32_sym"));
     }
-    const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? 1 : 0;
+    const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? ((p.opts & COSMO_OPT_PEER_EXCHANGE) ? 2 : 1) : 0;
     k_sym_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, unscale, p.G, p.dt,
                                                  (p.opts & COSMO_OPT_STORE_ACC) ? 1 : 0, defer);
     return COSMO_LAUNCH_CHECK("k_sym_reduce");
@@ -297,7 +314,12 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
 int launch_sym_integrate(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                          cudaStream_t s) {
     if (p.n_upper <= 0) return COSMO_OK;
-    k_sym_integrate<<<(p.n_upper + 255) / 256, 256, 0, s>>>(st, sc, p.G, p.dt);
+    const int peer = (p.opts & COSMO_OPT_PEER_EXCHANGE) ? 1 : 0;
+    if (peer && (sc.n_peers < 1 || sc.n_peers > COSMO_MAX_PEERS || p.shard_index >= sc.n_peers || !sc.peer_acc[p.shard_index])) {
+        set_error("peer exchange: n_peers=%d, rank %d", sc.n_peers, p.shard_index);
+        return COSMO_E_ARG;
+    }
+    k_sym_integrate<<<(p.n_upper + 255) / 256, 256, 0, s>>>(st, sc, p.G, p.dt, peer, p.shard_index);
     return COSMO_LAUNCH_CHECK("k_sym_integrate");
 }
 

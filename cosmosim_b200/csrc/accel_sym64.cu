@@ -223,7 +223,11 @@ k_sym64_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_coun
         ax += v.x;
         ay += v.y;
     }
-    if (defer) reinterpret_cast<double2 *>(sc.acc)[k] = make_double2(ax, ay);
+    if (defer == 2) {
+        const double2 v = make_double2(ax, ay);
+        for (int r = 0; r < sc.n_peers; ++r)
+            reinterpret_cast<double2 *>(sc.peer_acc[r])[(size_t)shard_index * st.cap + k] = v;
+    } else if (defer) reinterpret_cast<double2 *>(sc.acc)[k] = make_double2(ax, ay);
     else integrate_store(st, sc, k, ax, ay, G, dt, store_acc != 0);
 }
 
@@ -248,7 +252,7 @@ int launch_accel_sym64(const cosmo_state &st, const cosmo_scratch &sc, const cos
         k_accel_f64_sym<<<grid, S64_THREADS, 0, s>>>(st, sc, sh_i, sh_n, chunk);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_accel_f64_sym"));
     }
-    const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? 1 : 0;
+    const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? ((p.opts & COSMO_OPT_PEER_EXCHANGE) ? 2 : 1) : 0;
     k_sym64_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, p.G, p.dt,
                                                    (p.opts & COSMO_OPT_STORE_ACC) ? 1 : 0, defer);
     return COSMO_LAUNCH_CHECK("k_sym64_reduce");

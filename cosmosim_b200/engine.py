@@ -351,6 +351,10 @@ class Engine:
                   (OPT_F32_SCALAR if f32_scalar else 0) | (OPT_F32_SYM if sym else 0) |
                   (OPT_F64_SYM if sym64 else 0) |
                   (OPT_DEFER_INTEGRATE if ((sym or sym64) and self.world > 1) else 0) | (OPT_ENERGY if energy else 0))
+        if (sym or sym64) and self.world > 1:
+            from . import sharded
+            if sharded.setup_peer_exchange(self):
+                p.opts |= _abi.OPT_PEER_EXCHANGE      # sharded.frame points scratch.peer_acc at the frame's parity
         if self.sym_chunk or not (sym or sym64):
             p.sym_chunk = int(self.sym_chunk)
         else:

@@ -13,6 +13,7 @@ exchange protocol without a GPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -50,6 +51,34 @@ def exchange_pairs(local_pairs: torch.Tensor, local_count: torch.Tensor, xchg: t
     return xchg
 
 
+def setup_peer_exchange(eng):
+    """Map every rank's exchange buffer into this process (NVLink peer memory) through
+    torch.distributed's symmetric-memory plumbing; the data path itself is in the CUDA kernels
+    (k_sym_reduce stores into the peers, k_sym_integrate adds the slots in rank order).
+    Two buffers (frame parity) so one barrier per frame is enough.  Returns False -- and the frame
+    falls back to an NCCL all-reduce -- if symmetric memory cannot be set up here."""
+    if getattr(eng, "_peer", None) is not None:
+        return bool(eng._peer)
+    try:
+        if os.environ.get("COSMO_PEER_EXCHANGE", "1") == "0":
+            raise RuntimeError("disabled by COSMO_PEER_EXCHANGE=0")
+        import torch.distributed._symmetric_memory as symm_mem
+        if eng.world > 16:
+            raise RuntimeError("more than COSMO_MAX_PEERS ranks")
+        numel = 2 * eng.world * eng.cap * 2                       # [parity][rank slot][cap][2] doubles
+        buf = symm_mem.empty(numel, dtype=torch.float64, device=eng.device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, eng.group if eng.group is not None else dist.group.WORLD)
+        eng._peer = {"buf": buf, "hdl": hdl, "ptrs": [int(x) for x in hdl.buffer_ptrs],
+                     "half_bytes": eng.world * eng.cap * 2 * 8}
+        eng.sc.n_peers = eng.world
+        hdl.barrier()
+    except Exception as e:                                        # no fabric / IPC support in this container
+        eng._peer = False
+        eng._peer_error = "%s: %s" % (type(e).__name__, e)
+    return bool(eng._peer)
+
+
 def frame(eng, p, stream, stage_events=None):
     """One frame on engine `eng` (params p already hold this rank's row shard).
 
@@ -62,12 +91,24 @@ def frame(eng, p, stream, stage_events=None):
     st, sc, pp = C.byref(eng.st), C.byref(eng.sc), C.byref(p)
     n = p.n_upper
     _, _, per = shard_rows(n, eng.world, eng.rank)
+    if p.opts & _abi.OPT_PEER_EXCHANGE:
+        # exchange buffer of this frame's parity, as mapped from every rank (two buffers: a rank may
+        # already store frame t+1 while a slower one still reads frame t)
+        off = (eng.frames & 1) * eng._peer["half_bytes"]
+        for r, base in enumerate(eng._peer["ptrs"]):
+            eng.sc.peer_acc[r] = base + off
     _abi.check(lib.cosmo_begin_frame(st, sc, pp, stream), "cosmo_begin_frame")
     if ev:
         ev[1].record()
     _abi.check(lib.cosmo_accel_integrate(st, sc, pp, stream), "cosmo_accel_integrate")
-    if p.opts & _abi.OPT_DEFER_INTEGRATE:
-        # symmetric FP32 kernel: every rank holds partial sums for ALL planets (its row blocks +
+    if p.opts & _abi.OPT_PEER_EXCHANGE:
+        # symmetric kernels, peer exchange: the reduce kernel above has already stored this rank's
+        # partial sums into every peer over NVLink; one device-side barrier, then every rank adds
+        # the ranks' slots in rank order (deterministic, identical everywhere) and integrates
+        eng._peer["hdl"].barrier()
+        _abi.check(lib.cosmo_integrate(st, sc, pp, stream), "cosmo_integrate")
+    elif p.opts & _abi.OPT_DEFER_INTEGRATE:
+        # symmetric kernels, NCCL: every rank holds partial sums for ALL planets (its row blocks +
         # the column sides of its pairs) -> all-reduce, then every rank integrates all rows
         dist.all_reduce(eng.t["acc"][:n], op=dist.ReduceOp.SUM, group=eng.group)
         _abi.check(lib.cosmo_integrate(st, sc, pp, stream), "cosmo_integrate")

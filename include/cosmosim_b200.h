@@ -42,6 +42,7 @@ extern "C" {
 
 #define COSMO_ABI_VERSION 1
 #define COSMO_PAD 1024 /* slot capacity granularity (tile size of the all-pairs kernels) */
+#define COSMO_MAX_PEERS 16   /* ranks of one NVLink domain */
 #define COSMO_SCAN_BLOCKS 8192 /* device scans handle up to COSMO_SCAN_BLOCKS * 4096 items */
 
 /* error codes */
@@ -61,6 +62,9 @@ extern "C" {
 #define COSMO_OPT_STORE_ACC 8u   /* also write the accelerations to scratch.acc */
 #define COSMO_OPT_F32_SCALAR 16u /* FP32 path: scalar FFMA inner loop instead of packed f32x2 */
 #define COSMO_OPT_F32_SYM 32u    /* FP32 path: symmetric kernel (each unordered pair once); needs colbuf */
+#define COSMO_OPT_PEER_EXCHANGE 512u /* with DEFER_INTEGRATE: the reduce kernel stores this rank's partial sums
+                                        straight into every peer's exchange buffer over NVLink
+                                        (scratch.peer_acc), cosmo_integrate adds the ranks' slots in rank order */
 #define COSMO_OPT_F64_SYM 256u    /* FP64 path: symmetric kernel (each unordered pair once); needs colbuf */
 #define COSMO_OPT_ENERGY 128u     /* also evaluate energies / angular momentum (universe_old.py:181-189,210) */
 #define COSMO_OPT_DEFER_INTEGRATE 64u /* symmetric kernel, multi-GPU: leave this rank's partial sums in
@@ -172,6 +176,12 @@ typedef struct cosmo_scratch {
     int32_t *giants;     /* [giant_cap] */
     int32_t grid_cells;  /* capacity of the cell arrays */
     int32_t giant_cap;
+    /* multi-GPU peer exchange (COSMO_OPT_PEER_EXCHANGE): peer_acc[r] = rank r's exchange buffer
+       double[n_peers][cap][2] as mapped into THIS process (NVLink peer memory); slot s of every
+       buffer receives rank s's partial sums */
+    double *peer_acc[COSMO_MAX_PEERS];
+    int32_t n_peers;
+    int32_t reserved_scratch;
 } cosmo_scratch;
 
 /* Parameters of one frame. */
