@@ -51,6 +51,10 @@ def exchange_pairs(local_pairs: torch.Tensor, local_count: torch.Tensor, xchg: t
     return xchg
 
 
+_PEER_CACHE = {}
+PEER_BARRIER_TIMEOUT_MS = 20000      # a lost rank turns into an error, not a hang
+
+
 def setup_peer_exchange(eng):
     """Map every rank's exchange buffer into this process (NVLink peer memory) through
     torch.distributed's symmetric-memory plumbing; the data path itself is in the CUDA kernels
@@ -60,19 +64,23 @@ def setup_peer_exchange(eng):
     if getattr(eng, "_peer", None) is not None:
         return bool(eng._peer)
     try:
-        if os.environ.get("COSMO_PEER_EXCHANGE", "1") == "0":
-            raise RuntimeError("disabled by COSMO_PEER_EXCHANGE=0")
+        # opt-in (experimental): COSMO_PEER_EXCHANGE=1.  The default exchange is NCCL.
+        if os.environ.get("COSMO_PEER_EXCHANGE", "0") != "1":
+            raise RuntimeError("not enabled (set COSMO_PEER_EXCHANGE=1)")
         import torch.distributed._symmetric_memory as symm_mem
         if eng.world > 16:
             raise RuntimeError("more than COSMO_MAX_PEERS ranks")
-        numel = 2 * eng.world * eng.cap * 2                       # [parity][rank slot][cap][2] doubles
-        buf = symm_mem.empty(numel, dtype=torch.float64, device=eng.device)
-        buf.zero_()
-        hdl = symm_mem.rendezvous(buf, eng.group if eng.group is not None else dist.group.WORLD)
-        eng._peer = {"buf": buf, "hdl": hdl, "ptrs": [int(x) for x in hdl.buffer_ptrs],
-                     "half_bytes": eng.world * eng.cap * 2 * 8}
+        key = (eng.world, eng.cap, str(eng.device))
+        if key not in _PEER_CACHE:      # one symmetric buffer per process and shape, never freed:
+            numel = 2 * eng.world * eng.cap * 2                   # [parity][rank slot][cap][2] doubles
+            buf = symm_mem.empty(numel, dtype=torch.float64, device=eng.device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, eng.group if eng.group is not None else dist.group.WORLD)
+            _PEER_CACHE[key] = {"buf": buf, "hdl": hdl, "ptrs": [int(x) for x in hdl.buffer_ptrs],
+                                "half_bytes": eng.world * eng.cap * 2 * 8}
+        eng._peer = _PEER_CACHE[key]
         eng.sc.n_peers = eng.world
-        hdl.barrier()
+        eng._peer["hdl"].barrier(0, PEER_BARRIER_TIMEOUT_MS)
     except Exception as e:                                        # no fabric / IPC support in this container
         eng._peer = False
         eng._peer_error = "%s: %s" % (type(e).__name__, e)
@@ -105,7 +113,7 @@ def frame(eng, p, stream, stage_events=None):
         # symmetric kernels, peer exchange: the reduce kernel above has already stored this rank's
         # partial sums into every peer over NVLink; one device-side barrier, then every rank adds
         # the ranks' slots in rank order (deterministic, identical everywhere) and integrates
-        eng._peer["hdl"].barrier()
+        eng._peer["hdl"].barrier(0, PEER_BARRIER_TIMEOUT_MS)
         _abi.check(lib.cosmo_integrate(st, sc, pp, stream), "cosmo_integrate")
     elif p.opts & _abi.OPT_DEFER_INTEGRATE:
         # symmetric kernels, NCCL: every rank holds partial sums for ALL planets (its row blocks +
