@@ -73,8 +73,9 @@ def main():
             single.upload(arr2, frame=f + 1)
         same = same and replicas
         if rank == 0:
-            print("%s n=%d fp32=%s frames=%d: merges=%d active=%d sharded==single: %s (worst rel %.1e) replicas_identical: %s" %
-                  (kind, n, a.fp32, a.frames, len(e1), d1["status"]["n_active"], same, worst, replicas), flush=True)
+            print("%s n=%d fp32=%s frames=%d: merges=%d active=%d sharded==single: %s (worst rel %.1e) replicas_identical: %s exchange: %s" %
+                  (kind, n, a.fp32, a.frames, len(e1), d1["status"]["n_active"], same, worst, replicas,
+                   "peer stores" if getattr(shard, "_peer", None) else "nccl"), flush=True)
         ok = ok and same
     if rank == 0:
         print("exchange:", "peer stores" if getattr(shard, "_peer", None) else "nccl (%s)" % getattr(shard, "_peer_error", "-"), flush=True)
