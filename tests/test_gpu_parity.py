@@ -557,3 +557,69 @@ def test_bulk_universe_fp32_symmetric_path_through_the_api():
     sel = np.searchsorted(a["id"], ids)
     err = np.abs(a["pos"][sel] - post["pos"][ids]).max(axis=1) / np.abs(post["pos"][ids]).max()
     assert np.median(err) < 1e-9 and np.quantile(err, 0.99) < 1e-6
+
+
+def _snapshot_from_universe(u):
+    from cosmosim_b200.engine import split_mass
+    ps = u.planets
+    n = len(ps)
+    snap = {"pos": np.zeros((n, 2)), "vel": np.zeros((n, 2)), "mass_f64": np.zeros(n),
+            "mass_int_hi": np.zeros(n, np.uint64), "mass_int_lo": np.zeros(n, np.uint64),
+            "mass_is_int": np.zeros(n, bool), "radius": np.zeros(n), "volume": np.zeros(n),
+            "alive": np.zeros(n, bool), "immobile": np.zeros(n, bool), "eaten": np.zeros(n, np.int64)}
+    for k, p in enumerate(ps):
+        f, is_int, hi, lo = split_mass(p.mass)
+        snap["mass_f64"][k], snap["mass_is_int"][k], snap["mass_int_hi"][k], snap["mass_int_lo"][k] = f, is_int, hi, lo
+        snap["radius"][k], snap["volume"][k], snap["alive"][k] = p.radius, p.volume, p.alive
+        snap["immobile"][k], snap["eaten"][k] = p.immobile, p.planets_eaten
+        if p.alive:
+            snap["pos"][k], snap["vel"][k] = p.position, p.velocity
+    return snap
+
+
+def test_drop_in_api_flows_lazy_sync_and_host_mutation():
+    """Stepping, reading planets (device -> host pull), mutating them (host -> device push),
+    adding and destroying planets between bursts: after every phase the Universe equals the
+    oracle stepped from the Universe's own state at the start of the phase."""
+    import random
+    from cosmosim_b200 import Universe
+    random.seed(5)
+    u = Universe()
+    for _ in range(300):                    # crowded: 300 planets inside 1 AU, radii inflated 30x
+        p = u.random_planet(dmax=1 * AU, max_velocity=2.0e4)
+        p.radius = p.radius * 30.0
+        p.volume = ((4 / 3) * np.pi) * (p.radius ** 3)
+    total_events = 0
+    for phase in range(5):
+        if phase == 1:                      # host-side mutation of a few planets
+            for k in (3, 50, 120):
+                if u.planets[k].alive:
+                    u.planets[k].velocity = u.planets[k].velocity * 0.5 + np.array([10.0, -5.0])
+        if phase == 2:                      # add planets after stepping (engine is re-created)
+            u.create_planet(mass=7 * 10 ** 26, radius=5.0e9, position=[1.0e12, -2.0e12], velocity=[100.0, 50.0],
+                            color=(1, 2, 3), name="late")
+            u.random_planet()
+        if phase == 3:                      # destroy from the host, flip an immobile flag
+            alive = [p for p in u.planets if p.alive]
+            alive[5].destroy()
+            alive[9].immobile = True
+        snap = _snapshot_from_universe(u)
+        ou = orc.OracleUniverse(snap, G=u.G, bounded=u.bounded, r_max=u.r_max)
+        ev0 = len(u.merge_events)
+        frames = 3 + phase
+        ref = []
+        for f in range(frames):
+            ref += [(int(a), int(b)) for a, b in ou.frame(u.dt_default)["events"]]
+        u.simulate(steps=frames)
+        got = [(a, b) for (_, a, b) in u.merge_events[ev0:]]
+        assert got == ref, (phase, got[:5], ref[:5])
+        total_events += len(got)
+        post = ou.snapshot()
+        assert [bool(p.alive) for p in u.planets] == post["alive"].tolist(), phase
+        for k, p in enumerate(u.planets):
+            if p.alive:
+                assert np.allclose(p.position, post["pos"][k], rtol=1e-11, atol=0), (phase, k)
+                assert float(p.mass) == post["mass_f64"][k] and p.planets_eaten == post["eaten"][k]
+            else:
+                assert p.position is None
+    assert total_events > 10 and u.iterations == sum(3 + k for k in range(5))
