@@ -69,32 +69,62 @@ __global__ void __launch_bounds__(256) k_sort_pairs(cosmo_state st, cosmo_scratc
 // A modification made before a mobile planet's own row is discarded when the row reaches
 // it (universe_old.py:199-201 overwrite) -- only mass/volume/radius/planets_eaten persist.
 // ---------------------------------------------------------------------------------------
+// Everything the replay of a pair may need from one planet, fetched with independent loads up
+// front: the replay threads are latency-bound (one thread per cluster), so one round trip to L2
+// per pair instead of a dozen dependent ones is what matters here.
+struct BodyRec {
+    uint8_t alive, flags;
+    double mass, volume;
+    uint64_t mhi, mlo;
+    long long eaten;
+    int id, mod_step, mod_row;
+    double2 cur_p, cur_v, new_p, new_v, old_p, old_v;
+};
+
+__device__ __forceinline__ BodyRec load_body(const cosmo_state &st, const cosmo_scratch &sc, int k) {
+    BodyRec b;
+    b.alive = sc.alive[k];
+    b.flags = st.flags[k];
+    b.mass = st.mass[k];
+    b.volume = st.volume[k];
+    b.mhi = st.mass_hi[k];
+    b.mlo = st.mass_lo[k];
+    b.eaten = st.eaten[k];
+    b.id = st.id[k];
+    b.mod_step = sc.mod_step[k];
+    b.mod_row = sc.mod_row[k];
+    b.cur_p = reinterpret_cast<const double2 *>(sc.cur_pos)[k];
+    b.cur_v = reinterpret_cast<const double2 *>(sc.cur_vel)[k];
+    b.new_p = reinterpret_cast<const double2 *>(sc.pos_new)[k];
+    b.new_v = reinterpret_cast<const double2 *>(sc.vel_new)[k];
+    b.old_p = reinterpret_cast<const double2 *>(st.pos)[k];
+    b.old_v = reinterpret_cast<const double2 *>(st.vel)[k];
+    return b;
+}
+
 struct PV {
     double2 p, v;
 };
 
-__device__ PV current_value(const cosmo_state &st, const cosmo_scratch &sc, int k, int row, int stamp) {
+// Value of planet k while row `row` of the reference's loop is being processed (see above).
+__device__ __forceinline__ PV current_value(const BodyRec &b, int k, int row, int stamp) {
     PV out;
-    const double2 *pos = reinterpret_cast<const double2 *>(st.pos);
-    const double2 *vel = reinterpret_cast<const double2 *>(st.vel);
-    if (st.flags[k] & COSMO_F_IMMOBILE) {
-        out.p = pos[k];
-        out.v = vel[k];
+    if (b.flags & COSMO_F_IMMOBILE) {
+        out.p = b.old_p;
+        out.v = b.old_v;
         return out;
     }
-    const bool mod = sc.mod_step[k] == stamp;
-    bool use_cur;
-    if (k <= row) use_cur = mod && sc.mod_row[k] >= k;
-    else use_cur = mod;
+    const bool mod = b.mod_step == stamp;
+    const bool use_cur = (k <= row) ? (mod && b.mod_row >= k) : mod;
     if (use_cur) {
-        out.p = reinterpret_cast<const double2 *>(sc.cur_pos)[k];
-        out.v = reinterpret_cast<const double2 *>(sc.cur_vel)[k];
+        out.p = b.cur_p;
+        out.v = b.cur_v;
     } else if (k <= row) {
-        out.p = reinterpret_cast<const double2 *>(sc.pos_new)[k];
-        out.v = reinterpret_cast<const double2 *>(sc.vel_new)[k];
+        out.p = b.new_p;
+        out.v = b.new_v;
     } else {
-        out.p = pos[k];
-        out.v = vel[k];
+        out.p = b.old_p;
+        out.v = b.old_v;
     }
     return out;
 }
@@ -109,16 +139,16 @@ __device__ __forceinline__ double merge1(double ma, double a, double mo, double 
 // the two already dead).  On success writes the event ids to ev[0..1].
 __device__ bool replay_pair(const cosmo_state &st, const cosmo_scratch &sc, int i, int j, int stamp,
                             int64_t *ev) {
-    if (!sc.alive[i] || !sc.alive[j]) return false;  // absorb() guard, planet.py:75
-    double2 *cur_pos = reinterpret_cast<double2 *>(sc.cur_pos);
-    double2 *cur_vel = reinterpret_cast<double2 *>(sc.cur_vel);
-    const bool i_int = st.flags[i] & COSMO_F_MASS_INT, j_int = st.flags[j] & COSMO_F_MASS_INT;
-    const u128 mi = (((u128)st.mass_hi[i]) << 64) | st.mass_lo[i];
-    const u128 mj = (((u128)st.mass_hi[j]) << 64) | st.mass_lo[j];
+    const BodyRec bi = load_body(st, sc, i), bj = load_body(st, sc, j);
+    if (!bi.alive || !bj.alive) return false;  // absorb() guard, planet.py:75
+    const bool i_int = bi.flags & COSMO_F_MASS_INT, j_int = bj.flags & COSMO_F_MASS_INT;
+    const u128 mi = (((u128)bi.mhi) << 64) | bi.mlo;
+    const u128 mj = (((u128)bj.mhi) << 64) | bj.mlo;
     // universe_old.py:206: `planet.mass >= other_planet.mass` -- the row planet wins ties
-    const bool i_wins = mass_ge(i_int, mi, st.mass[i], j_int, mj, st.mass[j]);
+    const bool i_wins = mass_ge(i_int, mi, bi.mass, j_int, mj, bj.mass);
     const int W = i_wins ? i : j, L = i_wins ? j : i;
-    const double mW = st.mass[W], mL = st.mass[L];
+    const BodyRec &bw = i_wins ? bi : bj, &bl = i_wins ? bj : bi;
+    const double mW = bw.mass, mL = bl.mass;
     double msum;
     const bool both_int = i_int && j_int;
     u128 isum = 0;
@@ -128,11 +158,13 @@ __device__ bool replay_pair(const cosmo_state &st, const cosmo_scratch &sc, int 
     } else {
         msum = __dadd_rn(mW, mL);
     }
-    if (!(st.flags[W] & COSMO_F_IMMOBILE)) {  // planet.py:76-79
-        PV w = current_value(st, sc, W, i, stamp);
-        PV l = current_value(st, sc, L, i, stamp);
-        cur_pos[W] = make_double2(merge1(mW, w.p.x, mL, l.p.x, msum), merge1(mW, w.p.y, mL, l.p.y, msum));
-        cur_vel[W] = make_double2(merge1(mW, w.v.x, mL, l.v.x, msum), merge1(mW, w.v.y, mL, l.v.y, msum));
+    if (!(bw.flags & COSMO_F_IMMOBILE)) {  // planet.py:76-79
+        const PV w = current_value(bw, W, i, stamp);
+        const PV l = current_value(bl, L, i, stamp);
+        reinterpret_cast<double2 *>(sc.cur_pos)[W] =
+            make_double2(merge1(mW, w.p.x, mL, l.p.x, msum), merge1(mW, w.p.y, mL, l.p.y, msum));
+        reinterpret_cast<double2 *>(sc.cur_vel)[W] =
+            make_double2(merge1(mW, w.v.x, mL, l.v.x, msum), merge1(mW, w.v.y, mL, l.v.y, msum));
         sc.mod_row[W] = i;
         sc.mod_step[W] = stamp;
     }
@@ -141,15 +173,15 @@ __device__ bool replay_pair(const cosmo_state &st, const cosmo_scratch &sc, int 
         st.mass_hi[W] = (uint64_t)(isum >> 64);
         st.mass_lo[W] = (uint64_t)isum;
     } else {
-        st.flags[W] &= ~COSMO_F_MASS_INT;
+        st.flags[W] = bw.flags & ~COSMO_F_MASS_INT;
     }
-    const double vol = __dadd_rn(st.volume[W], st.volume[L]);  // planet.py:81
+    const double vol = __dadd_rn(bw.volume, bl.volume);  // planet.py:81
     st.volume[W] = vol;
     st.radius[W] = pow_third(__ddiv_rn(__dmul_rn(3.0, vol), 4.0 * 3.141592653589793));  // :82
-    st.eaten[W] += 1 + st.eaten[L];  // planet.py:84
-    sc.alive[L] = 0;                 // planet.py:83,86-91
-    ev[0] = st.id[W];
-    ev[1] = st.id[L];
+    st.eaten[W] = bw.eaten + 1 + bl.eaten;  // planet.py:84
+    sc.alive[L] = 0;                        // planet.py:83,86-91
+    ev[0] = bw.id;
+    ev[1] = bl.id;
     return true;
 }
 

@@ -45,7 +45,7 @@ def _round_up(n, q):
 class Engine:
     """One GPU's replica of the world (optionally responsible for a shard of target rows)."""
 
-    JSPLIT_MAX = 32
+    JSPLIT_MAX = 64
 
     def __init__(self, n_total, device=None, pair_cap=None, event_cap=None, group=None):
         if not torch.cuda.is_available():
