@@ -304,6 +304,9 @@ def main():
                     "stage_ms": {"prep": prep_ms, "accel_integrate" + ("+exchange" if world > 1 else ""): accel_ms,
                                  "detect" + ("+exchange" if world > 1 else ""): detect_ms,
                                  "resolve_commit": resolve_ms},
+                    "exchange_ms": ({"after_stage_a": float(np.mean([ev[5].elapsed_time(ev[2]) for ev in stage_events])),
+                                     "after_stage_b": float(np.mean([ev[6].elapsed_time(ev[3]) for ev in stage_events]))}
+                                    if world > 1 else None),
                     "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in mp else "fallback"},
                     "mufu_rsq_per_s_peak": peaks.get("mufu_rsq_per_s")}

@@ -92,7 +92,7 @@ def frame(eng, p, stream, stage_events=None):
 
     stage_events: optional list receiving (start, prep, stage A + exchange, stage B + exchange,
     stage C) torch.cuda.Event tuples for bench.py."""
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if stage_events is not None else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)] if stage_events is not None else None
     if ev:
         ev[0].record()
     lib = eng.lib
@@ -109,6 +109,8 @@ def frame(eng, p, stream, stage_events=None):
     if ev:
         ev[1].record()
     _abi.check(lib.cosmo_accel_integrate(st, sc, pp, stream), "cosmo_accel_integrate")
+    if ev:
+        ev[5].record()          # stage A kernels done, exchange not yet
     if p.opts & _abi.OPT_PEER_EXCHANGE:
         # symmetric kernels, peer exchange: the reduce kernel above has already stored this rank's
         # partial sums into every peer over NVLink; one device-side barrier, then every rank adds
@@ -127,6 +129,8 @@ def frame(eng, p, stream, stage_events=None):
     if p.opts & _abi.OPT_ENERGY:      # diagnostics: replicated over all rows (new positions are complete here)
         _abi.check(lib.cosmo_energies(st, sc, pp, stream), "cosmo_energies")
     _abi.check(lib.cosmo_detect_pairs(st, sc, pp, stream), "cosmo_detect_pairs")
+    if ev:
+        ev[6].record()          # stage B kernels done, pair exchange not yet
     status = eng.t["status"]
     if not hasattr(eng, "_xchg"):
         # every rank may contribute up to its share of the pair buffer
