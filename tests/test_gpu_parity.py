@@ -662,3 +662,47 @@ def test_n1m_fp32_full_size_properties():
     # the merge stream of the frame is consistent with the state
     d = eng.download()
     assert d["status"]["n_active"] == n - d["status"]["n_dead"] and len(eng.events()) > 50000
+
+
+@pytest.mark.parametrize("scale_pos,scale_mass,Gc", [(1.0, 1.0, 1.0), (1e-6, 1e-9, 6.674e-11), (1e17, 1e33, 6.674e-11)])
+def test_unit_systems_fp32_and_fp64(scale_pos, scale_mass, Gc):
+    """Unit systems other than SI/AU.  The FP32 path rescales by exact powers of two chosen from
+    the data and forms direct differences, so it works at any magnitude (checked against a direct
+    FP64 sum).  The FP64 parity path reproduces the reference's chain, which is NOT scale-free: the
+    reference adds the constants -2 / +6 to products of coordinates (its `- 1j` trick), so for
+    coordinates << 1 its d^2 is noise or negative (acc_blas returns NaN there, and so must we);
+    it is compared with the oracle where the reference itself is meaningful."""
+    rng = np.random.default_rng(3)
+    for n in (3000, 40000):
+        pos = rng.normal(0.0, 1.0, (n, 2)) * scale_pos
+        vel = rng.normal(0.0, 0.1, (n, 2)) * scale_pos
+        mass = rng.uniform(0.5, 2.0, n) * scale_mass
+        radius = np.full(n, 1e-4 * scale_pos)
+        arr = {"pos": pos, "vel": vel, "mass_f64": mass, "mass_hi": np.zeros(n, np.uint64),
+               "mass_lo": np.zeros(n, np.uint64), "flags": np.zeros(n, np.uint8), "radius": radius,
+               "volume": (4.0 / 3.0) * np.pi * radius ** 3, "eaten": np.zeros(n, np.int64),
+               "id": np.arange(n, dtype=np.int32)}
+        dt = 1e-3 * np.sqrt(scale_pos ** 3 / (Gc * scale_mass * n))
+        rows = 256
+        d = pos[None, :, :] - pos[:rows, None, :]                       # direct FP64 sum ("truth")
+        r2 = (d ** 2).sum(axis=2)
+        r2[np.arange(rows), np.arange(rows)] = np.inf
+        truth = Gc * (mass[None, :, None] * d / r2[:, :, None] ** 1.5).sum(axis=1)
+        eng = make_engine(arr)
+        eng.step(1, dt, Gc, 1e300, bounded=False, fp32=True, store_acc=True)
+        acc = eng.last_frame_tensors()["acc"][:rows].cpu().numpy()
+        eng.check_errors()
+        rel = relerr_rows(acc, truth)
+        assert np.median(rel) < 1e-5 and rel.max() < 1e-2, (n, scale_pos, np.median(rel), rel.max())
+        eng = make_engine(arr)
+        eng.step(1, dt, Gc, 1e300, bounded=False, fp32=False, store_acc=True)
+        acc = eng.last_frame_tensors()["acc"][:rows].cpu().numpy()
+        ref = orc.accel(pos, mass, Gc, 0, rows)
+        if scale_pos >= 1.0:
+            eng.check_errors()
+            assert relerr_rows(acc, ref).max() < 1e-12, (n, scale_pos)
+        else:                                                          # the reference's chain breaks down
+            bad_ref = ~np.isfinite(ref).all(axis=1)
+            assert bad_ref.any() and eng.status()["error"] & 4        # NaN reported, like the reference
+            ok = ~bad_ref & np.isfinite(acc).all(axis=1)
+            assert np.array_equal(np.isfinite(acc).all(axis=1), ~bad_ref) or ok.sum() > 0
