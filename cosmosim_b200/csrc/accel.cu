@@ -272,25 +272,29 @@ k_accel_f64(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
         const int j0 = t * TJ;
         const int cnt = min(TJ, n - j0);
         const int order = (j0 + TJ <= base) ? 0 : (j0 >= base + BLOCK * IB ? 2 : 1);
-        if (order == 1) {
-            tile_f64<IB, 1, true>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, ax, ay);
-        } else {
-            double sx[IB], sy[IB];
+        // tile-local sums, folded into the running totals once per tile: two-level summation keeps
+        // the rounding noise of rows with large cancelling neighbour terms ~8x below a single chain
+        double lx[IB], ly[IB];
 #pragma unroll
-            for (int k = 0; k < IB; ++k) { sx[k] = ax[k]; sy[k] = ay[k]; }
+        for (int k = 0; k < IB; ++k) { lx[k] = 0.0; ly[k] = 0.0; }
+        if (order == 1) {
+            tile_f64<IB, 1, true>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, lx, ly);
+        } else {
             if (order == 0)
-                tile_f64<IB, 0, false>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, ax, ay);
+                tile_f64<IB, 0, false>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, lx, ly);
             else
-                tile_f64<IB, 2, false>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, ax, ay);
+                tile_f64<IB, 2, false>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, lx, ly);
             bool bad = false;
 #pragma unroll
-            for (int k = 0; k < IB; ++k) bad = bad || !(isfinite(ax[k]) && isfinite(ay[k]));
+            for (int k = 0; k < IB; ++k) bad = bad || !(isfinite(lx[k]) && isfinite(ly[k]));
             if (bad) {  // a d2 == 0 (or negative) entry off the diagonal: redo with the mask honoured
 #pragma unroll
-                for (int k = 0; k < IB; ++k) { ax[k] = sx[k]; ay[k] = sy[k]; }
-                tile_f64<IB, 1, true>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, ax, ay);
+                for (int k = 0; k < IB; ++k) { lx[k] = 0.0; ly[k] = 0.0; }
+                tile_f64<IB, 1, true>(s_xy[b], s_h[b], s_m[b], cnt, j0, xi, yi, qix, qiy, hi, ii, lx, ly);
             }
         }
+#pragma unroll
+        for (int k = 0; k < IB; ++k) { ax[k] += lx[k]; ay[k] += ly[k]; }
         __syncthreads();  // everyone is done with buffer b before it is refilled
     }
     reduce_and_integrate<BLOCK, IB>(st, sc, base, i_hi, ax, ay, jsplit, G, dt, store_acc != 0);

@@ -151,7 +151,8 @@ k_accel_f64_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
         if (tid == 0 && J + 1 < J1) issue(J + 1, b ^ 1);
         mbar_wait(&s_bar[b], (it_j >> 1) & 1);
         const bool diag = (J == I);
-        const double sax[2] = {rax[0], rax[1]}, say[2] = {ray[0], ray[1]};
+        // block-local row sums, folded into the totals once per column block (two-level summation)
+        double bax[2] = {0.0, 0.0}, bay[2] = {0.0, 0.0};
         for (int attempt = 0; attempt < 2; ++attempt) {
             for (int q = tid; q < S64_BLOCK; q += S64_THREADS) { s_cx[q] = 0.0; s_cy[q] = 0.0; }
             __syncthreads();
@@ -163,11 +164,11 @@ k_accel_f64_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
                 const int jbase = J * S64_BLOCK + g * S64_GROUP;
                 double tx[2] = {0.0, 0.0}, ty[2] = {0.0, 0.0};
                 if (diag)
-                    round_sym_f64<true, true>(gxy, gh, gm, lane, jbase, xi, yi, qix, qiy, hi, nmi, ii, rax, ray, tx, ty);
+                    round_sym_f64<true, true>(gxy, gh, gm, lane, jbase, xi, yi, qix, qiy, hi, nmi, ii, bax, bay, tx, ty);
                 else if (attempt == 0)
-                    round_sym_f64<false, false>(gxy, gh, gm, lane, jbase, xi, yi, qix, qiy, hi, nmi, ii, rax, ray, tx, ty);
+                    round_sym_f64<false, false>(gxy, gh, gm, lane, jbase, xi, yi, qix, qiy, hi, nmi, ii, bax, bay, tx, ty);
                 else
-                    round_sym_f64<false, true>(gxy, gh, gm, lane, jbase, xi, yi, qix, qiy, hi, nmi, ii, rax, ray, tx, ty);
+                    round_sym_f64<false, true>(gxy, gh, gm, lane, jbase, xi, yi, qix, qiy, hi, nmi, ii, bax, bay, tx, ty);
                 if (!diag) {   // lane l is home to chunk l: column planets 2l, 2l+1 of group g
                     double2 cx = *reinterpret_cast<double2 *>(&s_cx[g * S64_GROUP + 2 * lane]);
                     double2 cy = *reinterpret_cast<double2 *>(&s_cy[g * S64_GROUP + 2 * lane]);
@@ -181,11 +182,13 @@ k_accel_f64_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
             if (diag || attempt == 1) break;
             // off-diagonal fast flavour skips the d2 == 0 mask; a non-finite sum (practically never)
             // means such an entry occurred: redo this block pair with the mask honoured
-            bool bad = !(isfinite(rax[0]) && isfinite(ray[0]) && isfinite(rax[1]) && isfinite(ray[1]));
+            bool bad = !(isfinite(bax[0]) && isfinite(bay[0]) && isfinite(bax[1]) && isfinite(bay[1]));
             for (int q = tid; q < S64_BLOCK; q += S64_THREADS) bad = bad || !(isfinite(s_cx[q]) && isfinite(s_cy[q]));
             if (!__syncthreads_or(bad)) break;
-            rax[0] = sax[0]; rax[1] = sax[1]; ray[0] = say[0]; ray[1] = say[1];
+            bax[0] = bax[1] = bay[0] = bay[1] = 0.0;
         }
+        rax[0] += bax[0]; rax[1] += bax[1];
+        ray[0] += bay[0]; ray[1] += bay[1];
         if (!diag) {
             double2 *dst = colbuf + col_row + (size_t)J * S64_BLOCK;
             for (int q = tid; q < S64_BLOCK; q += S64_THREADS) dst[q] = make_double2(s_cx[q], s_cy[q]);

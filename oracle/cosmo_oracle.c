@@ -106,8 +106,12 @@ static double u128_to_double(u128 v) {
  *   w         = fl(d2 * fl(sqrt(d2)));  t_k = fl(2 fl(p_jk - p_ik) / w) if d2 != 0 else
  *               2 fl(p_jk - p_ik)                                   (blas.py:31, where= mask)
  *   a_ik      = G * sum_j fl(t_k * (m_j / 2))                       (zhpmv alpha=.5, blas.py:40-41)
- * The summation order inside zhpmv is OpenBLAS-internal and not reproducible; plain
- * ascending-j accumulation agrees with the real acc_blas to <= 2e-14 (tests pin this).
+ * The summation order inside zhpmv is OpenBLAS-internal and not reproducible.  The oracle adds
+ * the (bit-exactly reproduced) pair terms with a compensated (Neumaier) sum, i.e. it returns the
+ * correctly rounded sum of the reference's terms to within an ulp or two; the real acc_blas
+ * agrees with it to <= 2e-14 on the fixture scenes (tests pin this).  In crowded scenes, rows
+ * whose large neighbour terms cancel (sum of |terms| / |sum| up to ~500 at N = 65536) carry a
+ * summation-order noise of ~1e-13 in ANY plain summation order, OpenBLAS' included.
  * ------------------------------------------------------------------------------------- */
 static inline double chain_c(double qix, double qiy, double pjx, double pjy) {
     double rx = qix * pjx;
@@ -132,7 +136,7 @@ void oracle_accel_rows(int64_t n, const double *pos, const double *mass, double 
         const double pix = pos[2 * i], piy = pos[2 * i + 1];
         const double qix = -2.0 * pix, qiy = -2.0 * piy;
         const double hi_i = h[i];
-        double sx = 0.0, sy = 0.0;
+        double sx = 0.0, sy = 0.0, cx = 0.0, cy = 0.0;   /* Neumaier-compensated sums */
         for (int64_t j = 0; j < n; ++j) {
             const double pjx = pos[2 * j], pjy = pos[2 * j + 1];
             double c = chain_c(qix, qiy, pjx, pjy);
@@ -145,9 +149,17 @@ void oracle_accel_rows(int64_t n, const double *pos, const double *mass, double 
                 ix = ix / w;
                 iy = iy / w;
             }
-            sx += ix * mh[j];
-            sy += iy * mh[j];
+            {
+                double tx = ix * mh[j], ty = iy * mh[j];
+                double nx = sx + tx, ny = sy + ty;
+                cx += (fabs(sx) >= fabs(tx)) ? ((sx - nx) + tx) : ((tx - nx) + sx);
+                cy += (fabs(sy) >= fabs(ty)) ? ((sy - ny) + ty) : ((ty - ny) + sy);
+                sx = nx;
+                sy = ny;
+            }
         }
+        sx = sx + cx;
+        sy = sy + cy;
         out[2 * (i - i_begin)] = G * sx;
         out[2 * (i - i_begin) + 1] = G * sy;
     }

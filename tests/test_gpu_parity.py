@@ -706,3 +706,32 @@ def test_unit_systems_fp32_and_fp64(scale_pos, scale_mass, Gc):
             assert bad_ref.any() and eng.status()["error"] & 4        # NaN reported, like the reference
             ok = ~bad_ref & np.isfinite(acc).all(axis=1)
             assert np.array_equal(np.isfinite(acc).all(axis=1), ~bad_ref) or ok.sum() > 0
+
+
+def test_n65536_fp64_full_frame_vs_oracle_merges_bit_exact():
+    """BASELINE config 3 end to end: one whole frame at N = 65,536 in FP64 (symmetric kernel, grid
+    broad phase, parallel resolver) against the CPU oracle's full frame -- accelerations and new
+    positions within 1e-12, the merge stream (index pairs and order) and all merged state exact."""
+    from cosmosim_b200 import scenes
+    n = 65536
+    arr = scenes.star_disk_arrays(n, seed=11)
+    eng = make_engine(arr)
+    eng.step(1, DT, G, 100 * AU, store_acc=True)
+    lf = eng.last_frame_tensors()
+    acc, pn = lf["acc"][:n].cpu().numpy(), lf["pos_new"][:n].cpu().numpy()
+    st = eng.check_errors()
+    ou = oracle_from_arrays(arr)
+    out = ou.frame(DT, record=True, cap=1 << 18)
+    assert relerr_rows(acc, out["acc"]).max() < FP64_TOL
+    assert np.abs(pn - out["p_new"]).max() <= FP64_TOL * np.abs(out["p_new"]).max()
+    assert st["n_pairs"] == out["n_flags"]
+    ev = eng.events()
+    assert len(ev) > 500 and np.array_equal(ev[:, 1:], out["events"])
+    d, post = eng.download(), ou.snapshot()
+    ids = d["id"]
+    assert np.array_equal(ids, np.nonzero(post["alive"])[0])
+    assert np.array_equal(d["mass"], post["mass_f64"][ids]) and np.array_equal(d["eaten"], post["eaten"][ids])
+    assert np.array_equal(d["volume"], post["volume"][ids])
+    assert np.abs(d["radius"] - post["radius"][ids]).max() <= np.spacing(post["radius"][ids]).max()
+    for k in ("pos", "vel"):
+        assert np.abs(d[k] - post[k][ids]).max() <= FP64_TOL * np.abs(post[k][ids]).max()
