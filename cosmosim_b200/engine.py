@@ -472,15 +472,6 @@ class Engine:
             done += burst
             self.frames += burst
 
-    def launches_per_frame(self, collisions=True):
-        """Kernels of this library launched per frame in the current mode (bench.py reports it)."""
-        base = 2 + 4                                   # prep, accel | commit, scatter, copyback, end
-        if not collisions:
-            return base
-        if self.grid is None:
-            return base + 1 + 2                        # all-pairs detect | rank sort, resolve
-        return base + (2 + 3 + 4) + (1 + 3 + 3 + 5 + 1 + 3 + 2 + 5 + 1)  # grid build+detect | csr, resolve, compactions
-
     def _step_sharded(self, p, stream, stage_events=None):
         from . import sharded
         sharded.frame(self, p, stream, stage_events)
