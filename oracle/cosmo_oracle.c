@@ -122,8 +122,8 @@ static inline double chain_c(double qix, double qiy, double pjx, double pjy) {
     return c + 6.0;
 }
 
-void oracle_accel_rows(int64_t n, const double *pos, const double *mass, double G,
-                       int64_t i_begin, int64_t i_end, double *out /* [(i_end-i_begin)][2] */) {
+static inline void accel_rows_impl(int64_t n, const double *pos, const double *mass, double G,
+                                   int64_t i_begin, int64_t i_end, double *out, const int compensated) {
     double *h = (double *)malloc((size_t)n * sizeof(double));
     double *mh = (double *)malloc((size_t)n * sizeof(double));
     for (int64_t k = 0; k < n; ++k) {
@@ -149,13 +149,16 @@ void oracle_accel_rows(int64_t n, const double *pos, const double *mass, double 
                 ix = ix / w;
                 iy = iy / w;
             }
-            {
+            if (compensated) {
                 double tx = ix * mh[j], ty = iy * mh[j];
                 double nx = sx + tx, ny = sy + ty;
                 cx += (fabs(sx) >= fabs(tx)) ? ((sx - nx) + tx) : ((tx - nx) + sx);
                 cy += (fabs(sy) >= fabs(ty)) ? ((sy - ny) + ty) : ((ty - ny) + sy);
                 sx = nx;
                 sy = ny;
+            } else {
+                sx += ix * mh[j];
+                sy += iy * mh[j];
             }
         }
         sx = sx + cx;
@@ -165,6 +168,19 @@ void oracle_accel_rows(int64_t n, const double *pos, const double *mass, double 
     }
     free(h);
     free(mh);
+}
+
+/* parity checks: compensated sum of the reference's pair terms */
+void oracle_accel_rows(int64_t n, const double *pos, const double *mass, double G,
+                       int64_t i_begin, int64_t i_end, double *out /* [(i_end-i_begin)][2] */) {
+    accel_rows_impl(n, pos, mass, G, i_begin, i_end, out, 1);
+}
+
+/* CPU baseline timing (bench.py): same terms, plain ascending-j accumulation -- what a CPU port
+   written for speed would do (the compensated sum costs ~25 %) */
+void oracle_accel_rows_plain(int64_t n, const double *pos, const double *mass, double G,
+                             int64_t i_begin, int64_t i_end, double *out) {
+    accel_rows_impl(n, pos, mass, G, i_begin, i_end, out, 0);
 }
 
 void oracle_accel(int64_t n, const double *pos, const double *mass, double G, double *out) {

@@ -44,6 +44,7 @@ def lib():
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_threads.argtypes = [C.c_int]
         L.oracle_accel_rows.argtypes = [C.c_int64, _dp, _dp, C.c_double, C.c_int64, C.c_int64, _dp]
+        L.oracle_accel_rows_plain.argtypes = [C.c_int64, _dp, _dp, C.c_double, C.c_int64, C.c_int64, _dp]
         L.oracle_d2_rows.argtypes = [C.c_int64, _dp, C.c_int64, C.c_int64, _dp]
         L.oracle_integrate.argtypes = [C.c_int64, _dp, _dp, _dp, C.c_double, _dp, _dp]
         L.oracle_flags_rows.argtypes = [C.c_int64, _dp, _dp, C.c_int64, C.c_int64, _ip, C.c_int64]
@@ -74,13 +75,15 @@ def set_threads(n: int) -> None:
     lib().oracle_set_threads(int(n))
 
 
-def accel(pos, mass, G, i_begin=0, i_end=None):
-    """A1 (blas.py:4-41): accelerations [rows,2] of targets i_begin..i_end from all n sources."""
+def accel(pos, mass, G, i_begin=0, i_end=None, compensated=True):
+    """A1 (blas.py:4-41): accelerations [rows,2] of targets i_begin..i_end from all n sources.
+    compensated=False: plain ascending accumulation (the CPU-baseline timing leg of bench.py)."""
     pos, mass = _c64(pos), _c64(mass)
     n = mass.shape[0]
     i_end = n if i_end is None else i_end
     out = np.empty((i_end - i_begin, 2), dtype=np.float64)
-    lib().oracle_accel_rows(n, _d(pos), _d(mass), float(G), i_begin, i_end, _d(out))
+    fn = lib().oracle_accel_rows if compensated else lib().oracle_accel_rows_plain
+    fn(n, _d(pos), _d(mass), float(G), i_begin, i_end, _d(out))
     return out
 
 
