@@ -13,7 +13,7 @@ STATUS_LEN = 16
 # flag / option / status constants (mirror the header)
 F_IMMOBILE, F_MASS_INT = 1, 2
 OPT_COLLISIONS, OPT_BOUNDED, OPT_FP32, OPT_STORE_ACC, OPT_F32_SCALAR, OPT_F32_SYM, OPT_DEFER_INTEGRATE, OPT_ENERGY, OPT_F64_SYM, OPT_PEER_EXCHANGE = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
-ST_N_ACTIVE, ST_STEP, ST_N_EVENTS, ST_N_PAIRS, ST_N_DEAD, ST_ERROR, ST_N_ESCAPED, ST_N_CAND, ST_N_GIANTS, ST_PMAX2, ST_N_COMPLEX, ST_SLOT_LO, ST_SLOT_HI = range(13)
+ST_N_ACTIVE, ST_STEP, ST_N_EVENTS, ST_N_PAIRS, ST_N_DEAD, ST_ERROR, ST_N_ESCAPED, ST_N_CAND, ST_N_GIANTS, ST_PMAX2, ST_N_COMPLEX, ST_SLOT_LO, ST_SLOT_HI, ST_EV_BASE, ST_N_HEAVY = range(15)
 SCAN_BLOCKS = 8192
 ERR_PAIR_OVERFLOW, ERR_EVENT_OVERFLOW, ERR_NAN, ERR_GIANT_OVERFLOW = 1, 2, 4, 8
 
@@ -73,6 +73,7 @@ SYMBOLS = {
     "cosmo_resolve_commit": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_step": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_append_pairs": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), _vp, _vp, C.c_int64, _vp]),
+    "cosmo_append_pair_rows": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), _vp, C.c_int32, C.c_int64, _vp]),
     "cosmo_accel_workspace_bytes": (C.c_int64, [C.c_int32]),
     "cosmo_accel": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "cosmo_accel_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp,

@@ -170,6 +170,15 @@ int cosmo_append_pairs(const cosmo_state *st, const cosmo_scratch *sc, const uin
     return launch_append_pairs(*st, *sc, src, count_ptr, max_count, (cudaStream_t)stream);
 }
 
+int cosmo_append_pair_rows(const cosmo_state *st, const cosmo_scratch *sc, const int64_t *rows, int32_t n_rows,
+                           int64_t max_count, void *stream) {
+    if (!st || !sc || !rows || n_rows <= 0 || max_count <= 0) {
+        set_error("cosmo_append_pair_rows: bad argument");
+        return COSMO_E_ARG;
+    }
+    return launch_append_pair_rows(*st, *sc, rows, n_rows, max_count, (cudaStream_t)stream);
+}
+
 // ---- function-level seam: acc_blas replacement on raw arrays --------------------------
 namespace {
 struct AccelWs {

@@ -49,6 +49,7 @@ __global__ void k_prep(cosmo_state st, cosmo_scratch sc, double r_max, int pos_e
         st.status[COSMO_ST_N_GIANTS] = 0;
         st.status[COSMO_ST_PMAX2] = 0;
         st.status[COSMO_ST_N_COMPLEX] = 0;
+        st.status[COSMO_ST_N_HEAVY] = 0;
     }
     const double2 *pos = reinterpret_cast<const double2 *>(st.pos);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_pad; k += gridDim.x * blockDim.x) {

@@ -44,6 +44,9 @@ int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc,
 int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const uint64_t *src,
                         const int64_t *count_ptr, int64_t max_count, cudaStream_t s);
 
+int launch_append_pair_rows(const cosmo_state &st, const cosmo_scratch &sc, const int64_t *rows, int n_rows,
+                            long long max_count, cudaStream_t s);
+
 // scan.cu: out[k] = sum(in[0..k)), out[n] = total; n = min(*n_ptr + n_add, n_max) or n_max
 int launch_scan_exclusive(const int *in, int *out, int *blk, const int64_t *n_ptr, long long n_max,
                           long long n_add, cudaStream_t s);

@@ -198,6 +198,7 @@ __device__ __forceinline__ void test_and_emit(const cosmo_state &st, const cosmo
 // crowded inner cells of a disk -- most of the candidate work -- are spread over all of them.
 // bounds[k] = first slot of the first cell starting at or after slot k * GRID_CHUNK.
 constexpr int GRID_CHUNK = 1024;
+constexpr int GRID_HEAVY = 128;   // candidates above which a row goes to the warp-per-row pass
 
 __global__ void __launch_bounds__(128) k_grid_ranges(cosmo_state st, cosmo_scratch sc, int c) {
     const int ncell = c * c;
@@ -237,28 +238,67 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count
     const double2 p = reinterpret_cast<const double2 *>(sc.pos_new)[i];
     const double qx = -2.0 * p.x, qy = -2.0 * p.y, xxi = sc.xx_new[i], ri = sc.rinf[i];
     const int cx = cell % c, cy = cell / c;
+    // candidate ranges: the three cells of a grid row are contiguous in the sorted item array
+    int s0[3], s1[3];
     long long cand = 0;
+#pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
         const int yy = cy + dy;
-        if (yy < 0 || yy >= c) continue;
+        const bool in = yy >= 0 && yy < c;
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, c - 1);
-        // the three cells of a grid row are contiguous in the sorted item array
-        const int s0 = sc.cell_start[yy * c + x0], s1 = sc.cell_start[yy * c + x1 + 1];
-        for (int s = s0; s < s1; ++s) {
+        s0[dy + 1] = in ? sc.cell_start[yy * c + x0] : 0;
+        s1[dy + 1] = in ? sc.cell_start[yy * c + x1 + 1] : 0;
+        cand += s1[dy + 1] - s0[dy + 1];
+    }
+    const int ng = (int)min((long long)st.status[COSMO_ST_N_GIANTS], (long long)sc.giant_cap);
+    cand_total += (unsigned)cand;
+    if (cand + ng > GRID_HEAVY) {
+        // a crowded neighbourhood (dense inner disk, logarithmic rim): one thread walking thousands
+        // of candidates would be the critical path of the whole frame -> warp-per-row pass
+        const unsigned long long h =
+            atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_HEAVY]), 1ull);
+        sc.label[h] = i;       // `label` is free until stage C
+        continue;
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        for (int s = s0[d]; s < s1[d]; ++s) {
             const int j = sc.cell_items[s];
             if (j != i) test_and_emit(st, sc, i, qx, qy, xxi, ri, j);
         }
-        cand += s1 - s0;
-    }
-    const int ng = (int)min((long long)st.status[COSMO_ST_N_GIANTS], (long long)sc.giant_cap);
     for (int g = 0; g < ng; ++g) test_and_emit(st, sc, i, qx, qy, xxi, ri, sc.giants[g]);
-    cand_total += (unsigned)cand;
    }
   }
     // diagnostic only (all lanes are back together after the loop)
     const unsigned tot = __reduce_add_sync(0xffffffffu, cand_total);
     if ((threadIdx.x & 31) == 0 && tot)
         atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_CAND]), (unsigned long long)tot);
+}
+
+// Warp-per-row pass for the rows k_grid_detect set aside: the lanes stride over the candidates.
+__global__ void __launch_bounds__(256) k_grid_detect_heavy(cosmo_state st, cosmo_scratch sc, int c) {
+    const int nh = (int)st.status[COSMO_ST_N_HEAVY];
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    const int ng = (int)min((long long)st.status[COSMO_ST_N_GIANTS], (long long)sc.giant_cap);
+    for (int h = warp; h < nh; h += nwarp) {
+        const int i = sc.label[h];
+        const int cell = sc.cell_of[i];
+        const double2 p = reinterpret_cast<const double2 *>(sc.pos_new)[i];
+        const double qx = -2.0 * p.x, qy = -2.0 * p.y, xxi = sc.xx_new[i], ri = sc.rinf[i];
+        const int cx = cell % c, cy = cell / c;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = cy + dy;
+            if (yy < 0 || yy >= c) continue;
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, c - 1);
+            const int s0 = sc.cell_start[yy * c + x0], s1 = sc.cell_start[yy * c + x1 + 1];
+            for (int s = s0 + lane; s < s1; s += 32) {
+                const int j = sc.cell_items[s];
+                if (j != i) test_and_emit(st, sc, i, qx, qy, xxi, ri, j);
+            }
+        }
+        for (int g = lane; g < ng; g += 32) test_and_emit(st, sc, i, qx, qy, xxi, ri, sc.giants[g]);
+    }
 }
 
 // rows of the giants: giant g against every planet (blockIdx.y strides over the giants)
@@ -328,6 +368,8 @@ int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_st
             const int blocks = (nchunk + sh_n - 1) / sh_n;
             k_grid_detect<<<dim3(blocks > 0 ? blocks : 1, GRID_CHUNK / 128), 128, 0, s>>>(st, sc, sh_i, sh_n, c);
             COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect"));
+            k_grid_detect_heavy<<<296, 256, 0, s>>>(st, sc, c);
+            COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect_heavy"));
         }
         if (rows > 0) {
             k_giant_rows<<<dim3(nb > 296 ? 296 : nb, 8), 256, 0, s>>>(st, sc, p.i_begin, p.i_end);

@@ -30,6 +30,22 @@ __global__ void k_append_pairs(cosmo_state st, cosmo_scratch sc, const uint64_t 
     }
 }
 
+// all ranks' lists at once: row r = (count | pairs[max_count]); blockIdx.y = row
+__global__ void k_append_pair_rows(cosmo_state st, cosmo_scratch sc, const int64_t *rows, long long max_count) {
+    const int64_t *row = rows + (size_t)blockIdx.y * (size_t)(max_count + 1);
+    long long cnt = row[0];
+    if (cnt > max_count) {
+        cnt = max_count;
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            atomicOr(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_ERROR]),
+                     (unsigned long long)COSMO_ERR_PAIR_OVERFLOW);
+    }
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < cnt; k += (long long)gridDim.x * blockDim.x) {
+        const uint64_t key = (uint64_t)row[1 + k];
+        emit_pair(st, sc, (int)(key >> 32), (int)(key & 0xffffffffu));
+    }
+}
+
 // Rank sort of the (unique) keys i<<32|j: row-major order = the order in which the
 // reference's double loop meets the flags.  O(M^2) compares spread over the grid; M is
 // normally a handful.
@@ -560,6 +576,12 @@ int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const ui
                         const int64_t *count_ptr, int64_t max_count, cudaStream_t s) {
     k_append_pairs<<<32, 256, 0, s>>>(st, sc, src, count_ptr, (long long)max_count);
     return COSMO_LAUNCH_CHECK("k_append_pairs");
+}
+
+int launch_append_pair_rows(const cosmo_state &st, const cosmo_scratch &sc, const int64_t *rows, int n_rows,
+                            long long max_count, cudaStream_t s) {
+    k_append_pair_rows<<<dim3(32, n_rows), 256, 0, s>>>(st, sc, rows, max_count);
+    return COSMO_LAUNCH_CHECK("k_append_pair_rows");
 }
 
 int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,

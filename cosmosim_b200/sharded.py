@@ -134,14 +134,14 @@ def frame(eng, p, stream, stage_events=None):
     status = eng.t["status"]
     if not hasattr(eng, "_xchg"):
         # every rank may contribute up to its share of the pair buffer
-        eng._xchg = torch.zeros(eng.world, 1 + max(1024, eng.pair_cap // eng.world), dtype=torch.int64,
-                                device=eng.device)
+        # a rank's share of the flagged pairs: balanced by the round-robin chunking of stage B, so a
+        # fraction of pair_cap is plenty (overflow raises COSMO_ERR_PAIR_OVERFLOW, never silent)
+        xcap = min(eng.pair_cap // eng.world, max(1 << 16, eng.cap // eng.world))
+        eng._xchg = torch.zeros(eng.world, 1 + max(1024, xcap), dtype=torch.int64, device=eng.device)
     xchg = exchange_pairs(eng.t["pairs"], status[ST_N_PAIRS], eng._xchg, eng.rank, eng.world, eng.group)
     status[ST_N_PAIRS] = 0
-    for r in range(eng.world):
-        _abi.check(lib.cosmo_append_pairs(st, sc, C.c_void_p(xchg[r, 1:].data_ptr()),
-                                          C.c_void_p(xchg[r, :1].data_ptr()), xchg.shape[1] - 1, stream),
-                   "cosmo_append_pairs")
+    _abi.check(lib.cosmo_append_pair_rows(st, sc, C.c_void_p(xchg.data_ptr()), eng.world, xchg.shape[1] - 1, stream),
+               "cosmo_append_pair_rows")
     if ev:
         ev[3].record()
     _abi.check(lib.cosmo_resolve_commit(st, sc, pp, stream), "cosmo_resolve_commit")

@@ -85,6 +85,7 @@ extern "C" {
 #define COSMO_ST_SLOT_LO 11    /* grid broad phase: this rank's range of the cell-sorted order */
 #define COSMO_ST_SLOT_HI 12
 #define COSMO_ST_EV_BASE 13    /* event count at the start of the frame's log append */
+#define COSMO_ST_N_HEAVY 14    /* grid broad phase: rows handed to the warp-per-row pass in the last frame */
 #define COSMO_STATUS_LEN 16
 
 #define COSMO_ERR_PAIR_OVERFLOW 1  /* more flagged pairs than pair_cap */
@@ -284,6 +285,10 @@ int cosmo_step(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_
    a count above max_count raises COSMO_ERR_PAIR_OVERFLOW in the status block. */
 int cosmo_append_pairs(const cosmo_state *st, const cosmo_scratch *sc, const uint64_t *src,
                        const int64_t *count_ptr, int64_t max_count, void *stream);
+/* Same for `n_rows` lists laid out as rows of (count | pairs[max_count]) int64 words, i.e. the
+   all-gathered exchange buffer of the multi-GPU frame, in one launch. */
+int cosmo_append_pair_rows(const cosmo_state *st, const cosmo_scratch *sc, const int64_t *rows,
+                           int32_t n_rows, int64_t max_count, void *stream);
 
 /*
  * Function-level seam for callers that only want the reference's acc_blas replaced:

@@ -400,6 +400,7 @@ def _detect_pairs(eng, p):
     from cosmosim_b200 import _abi
     eng.t["status"][_abi.ST_N_PAIRS] = 0
     eng.t["status"][_abi.ST_N_GIANTS] = 0
+    eng.t["status"][_abi.ST_N_HEAVY] = 0
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     _abi.check(eng.lib.cosmo_detect_pairs(C.byref(eng.st), C.byref(eng.sc), C.byref(p), stream), "detect")
     torch.cuda.synchronize()
