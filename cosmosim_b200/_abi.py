@@ -38,7 +38,7 @@ class Scratch(C.Structure):
                 ("pair_cap", C.c_int64), ("cur_pos", _vp), ("cur_vel", _vp), ("mod_row", _vp),
                 ("mod_step", _vp), ("chunk_alive", _vp),
                 ("row_count", _vp), ("row_start", _vp), ("pmin", _vp), ("pmax", _vp), ("scan_blk", _vp),
-                ("pair_flag", _vp), ("cplx_list", _vp), ("scan_a", _vp), ("ev_tmp", _vp), ("label", _vp), ("comp_items", _vp),
+                ("pair_flag", _vp), ("cplx_list", _vp), ("scan_a", _vp), ("ev_tmp", _vp), ("label", _vp), ("comp_items", _vp), ("comp_root", _vp),
                 ("t_pos", _vp), ("t_vel", _vp), ("t_mass", _vp), ("t_mass_hi", _vp),
                 ("t_mass_lo", _vp), ("t_radius", _vp), ("t_volume", _vp), ("t_eaten", _vp),
                 ("t_id", _vp), ("t_flags", _vp), ("t_energy", _vp),

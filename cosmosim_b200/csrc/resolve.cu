@@ -335,54 +335,85 @@ __global__ void __launch_bounds__(256) k_scatter_bit(cosmo_state st, cosmo_scrat
     }
 }
 
-// Pairs that are not simple form small clusters (chains, triples).  Clusters are disjoint
-// sets of planets, so they are independent of each other; inside a cluster the reference's
-// order matters.  One CTA labels the connected components by min-label propagation over the
-// cluster edges (iterating to the fixed point: __syncthreads_or), then a counting sort groups
-// the pairs by component and one thread per component replays its pairs in sorted order.
-__global__ void __launch_bounds__(1024) k_components(cosmo_state st, cosmo_scratch sc) {
+// Pairs that are not simple form clusters (chains, triples, in a crowded disk also larger blobs).
+// Clusters are disjoint sets of planets, so they are independent of each other; inside a cluster
+// the reference's order matters.  Connected components by lock-free union-find over the cluster
+// edges (hook the larger root under the smaller with atomicCAS, path halving on find): three
+// multi-CTA kernels, no iteration to a fixed point; the representative is the smallest planet
+// index of the component.  A counting sort then groups the pairs by component, a parallel rank
+// sort orders every group by sorted-pair index (= visitation order), and one thread per component
+// replays its pairs.
+__device__ __forceinline__ int uf_find(int *parent, int v) {
+    int p = *(volatile int *)&parent[v];
+    while (p != v) {
+        const int gp = *(volatile int *)&parent[p];
+        if (gp != p) parent[v] = gp;     // path halving (benign race: only ever moves towards the root)
+        v = p;
+        p = gp;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_uf_init(cosmo_state st, cosmo_scratch sc) {
     const long long C = st.status[COSMO_ST_N_COMPLEX];
-    if (C == 0) return;
-    for (long long c = threadIdx.x; c < C; c += blockDim.x) {
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
         const uint64_t key = sc.pairs_sorted[sc.cplx_list[c]];
         const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
         sc.label[i] = i;
         sc.label[j] = j;
     }
-    __syncthreads();
-    for (int iter = 0; iter < (1 << 20); ++iter) {
-        int changed = 0;
-        for (long long c = threadIdx.x; c < C; c += blockDim.x) {
-            const uint64_t key = sc.pairs_sorted[sc.cplx_list[c]];
-            const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
-            const int li = *(volatile int *)&sc.label[i], lj = *(volatile int *)&sc.label[j];
-            if (li != lj) {
-                const int m = min(li, lj);
-                atomicMin(&sc.label[i], m);
-                atomicMin(&sc.label[j], m);
-                changed = 1;
-            }
+}
+
+__global__ void __launch_bounds__(256) k_uf_union(cosmo_state st, cosmo_scratch sc) {
+    const long long C = st.status[COSMO_ST_N_COMPLEX];
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
+        const uint64_t key = sc.pairs_sorted[sc.cplx_list[c]];
+        int a = uf_find(sc.label, (int)(key >> 32)), b = uf_find(sc.label, (int)(key & 0xffffffffu));
+        while (a != b) {
+            const int hi = max(a, b), lo = min(a, b);
+            const int old = atomicCAS(&sc.label[hi], hi, lo);    // hook root `hi` under `lo`
+            if (old == hi) break;
+            a = uf_find(sc.label, old);                           // someone else moved it: retry from the new roots
+            b = uf_find(sc.label, lo);
         }
-        if (!__syncthreads_or(changed)) break;
     }
-    for (long long c = threadIdx.x; c < C; c += blockDim.x) {
-        const int i = (int)(sc.pairs_sorted[sc.cplx_list[c]] >> 32);
-        atomicAdd(&sc.row_count[*(volatile int *)&sc.label[i]], 1);
+}
+
+// flatten (label = root = smallest index of the component) and count the pairs per component
+__global__ void __launch_bounds__(256) k_uf_count(cosmo_state st, cosmo_scratch sc) {
+    const long long C = st.status[COSMO_ST_N_COMPLEX];
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
+        const uint64_t key = sc.pairs_sorted[sc.cplx_list[c]];
+        const int root = uf_find(sc.label, (int)(key >> 32));
+        sc.comp_root[c] = root;
+        atomicAdd(&sc.row_count[root], 1);
     }
 }
 
 __global__ void __launch_bounds__(256) k_comp_fill(cosmo_state st, cosmo_scratch sc) {
     const long long C = st.status[COSMO_ST_N_COMPLEX];
     for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
-        const int q = sc.cplx_list[c];
-        const int root = sc.label[(int)(sc.pairs_sorted[q] >> 32)];
+        const int root = sc.comp_root[c];
         const int slot = sc.row_start[root] + atomicSub(&sc.row_count[root], 1) - 1;
-        sc.comp_items[slot] = q;
+        sc.comp_items[slot] = sc.cplx_list[c];
     }
 }
 
-// one thread per component root: order the component's pairs (ascending sorted-pair index =
-// visitation order) and replay them
+// order every component's pairs by sorted-pair index: rank of a pair = number of smaller indices in
+// its component (all pairs in parallel; components are small to moderate)
+__global__ void __launch_bounds__(256) k_comp_rank(cosmo_state st, cosmo_scratch sc) {
+    const long long C = st.status[COSMO_ST_N_COMPLEX];
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
+        const int q = sc.cplx_list[c];
+        const int root = sc.comp_root[c];
+        const int s0 = sc.row_start[root], s1 = sc.row_start[root + 1];
+        int rank = 0;
+        for (int s = s0; s < s1; ++s) rank += sc.comp_items[s] < q;
+        sc.scan_a[s0 + rank] = q;          // scan_a is free between the two ordered compactions
+    }
+}
+
+// one thread per component root: replay the component's pairs in visitation order
 __global__ void __launch_bounds__(128) k_comp_resolve(cosmo_state st, cosmo_scratch sc) {
     if (st.status[COSMO_ST_N_COMPLEX] == 0) return;
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
@@ -391,17 +422,8 @@ __global__ void __launch_bounds__(128) k_comp_resolve(cosmo_state st, cosmo_scra
     const int s0 = sc.row_start[v], s1 = sc.row_start[v + 1];
     if (s1 <= s0) return;
     const int stamp = (int)st.status[COSMO_ST_STEP];
-    for (int a = s0 + 1; a < s1; ++a) {
-        const int q = sc.comp_items[a];
-        int b = a - 1;
-        while (b >= s0 && sc.comp_items[b] > q) {
-            sc.comp_items[b + 1] = sc.comp_items[b];
-            --b;
-        }
-        sc.comp_items[b + 1] = q;
-    }
     for (int a = s0; a < s1; ++a) {
-        const int q = sc.comp_items[a];
+        const int q = sc.scan_a[a];
         const uint64_t key = sc.pairs_sorted[q];
         if (replay_pair(st, sc, (int)(key >> 32), (int)(key & 0xffffffffu), stamp, &sc.ev_tmp[2 * q]))
             sc.pair_flag[q] |= 1;
@@ -610,12 +632,18 @@ int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc, const 
                                         sc.pair_cap, 0, s));
         k_scatter_bit<<<pb, 256, 0, s>>>(st, sc, 2);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_scatter_bit(2)"));
-        k_components<<<1, 1024, 0, s>>>(st, sc);
-        COSMO_TRY(COSMO_LAUNCH_CHECK("k_components"));
+        k_uf_init<<<pb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_uf_init"));
+        k_uf_union<<<pb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_uf_union"));
+        k_uf_count<<<pb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_uf_count"));
         COSMO_TRY(launch_scan_exclusive(sc.row_count, sc.row_start, sc.scan_blk, &st.status[COSMO_ST_N_ACTIVE],
                                         p.n_upper, 0, s));
         k_comp_fill<<<pb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_comp_fill"));
+        k_comp_rank<<<pb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_comp_rank"));
         k_comp_resolve<<<(p.n_upper + 127) / 128 > 0 ? (p.n_upper + 127) / 128 : 1, 128, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_comp_resolve"));
         k_mark_bit<<<pb, 256, 0, s>>>(st, sc, 1);

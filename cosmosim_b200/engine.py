@@ -130,6 +130,7 @@ class Engine:
         t["scan_a"] = z(self.pair_cap + 1, dtype=i32)
         t["ev_tmp"] = z(self.pair_cap, 2, dtype=i64)
         t["label"] = z(cap, dtype=i32); t["comp_items"] = z(self.pair_cap, dtype=i32)
+        t["comp_root"] = z(self.pair_cap, dtype=i32)
         # uniform-grid broad phase
         self.grid_cells = int(min(_abi.SCAN_BLOCKS * 4096 - 1, max(1 << 16, 8 * cap)))
         self.giant_cap = 1 << 16
@@ -160,7 +161,7 @@ class Engine:
                   "pairs", "pairs_sorted", "cur_pos", "cur_vel", "mod_row", "mod_step", "chunk_alive",
                   "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_radius", "t_volume",
                   "t_eaten", "t_id", "t_flags", "t_energy", "row_count", "row_start", "pmin", "pmax", "scan_blk",
-                  "pair_flag", "cplx_list", "scan_a", "ev_tmp", "label", "comp_items", "cell_of", "cell_items", "cell_count", "cell_start",
+                  "pair_flag", "cplx_list", "scan_a", "ev_tmp", "label", "comp_items", "comp_root", "cell_of", "cell_items", "cell_count", "cell_start",
                   "giants"):
             setattr(sc, k, p(k))
         sc.pos_new = C.c_void_p(self._pos_new.data_ptr())

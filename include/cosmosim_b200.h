@@ -165,6 +165,7 @@ typedef struct cosmo_scratch {
     int64_t *ev_tmp;      /* [pair_cap][2] (absorber id, absorbed id) per sorted-pair slot */
     int32_t *label;       /* [cap] connected-component label of clustered planets */
     int32_t *comp_items;  /* [pair_cap] sorted-pair indices grouped by component */
+    int32_t *comp_root;   /* [pair_cap] component representative of every clustered pair */
     /* compaction staging: one array per persistent field */
     double *t_pos; double *t_vel; double *t_mass; uint64_t *t_mass_hi; uint64_t *t_mass_lo;
     double *t_radius; double *t_volume; int64_t *t_eaten; int32_t *t_id; uint8_t *t_flags;
