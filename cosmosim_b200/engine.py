@@ -45,7 +45,7 @@ def _round_up(n, q):
 class Engine:
     """One GPU's replica of the world (optionally responsible for a shard of target rows)."""
 
-    JSPLIT_MAX = 64
+    JSPLIT_MAX = 128
 
     def __init__(self, n_total, device=None, pair_cap=None, event_cap=None, group=None):
         if not torch.cuda.is_available():
@@ -359,10 +359,10 @@ class Engine:
         if self.sym_chunk or not (sym or sym64):
             p.sym_chunk = int(self.sym_chunk)
         else:
-            # column blocks per CTA: enough CTAs (~8 per resident slot and rank) to keep the tail short,
+            # column blocks per CTA: enough CTAs (~16 per resident slot and rank) to keep the tail short,
             # few enough that the row partials fit `partial` (JSPLIT_MAX rows)
             nblk = -(-n // (512 if sym64 else 1024))
-            want = (nblk * nblk) // (2 * 8 * 2 * self.sm_count * self.world) if nblk > 1 else 1
+            want = (nblk * nblk) // (2 * 16 * 2 * self.sm_count * self.world) if nblk > 1 else 1
             p.sym_chunk = int(min(32, max(1, -(-nblk // self.JSPLIT_MAX), want)))
         if os.environ.get("COSMO_SYM_CHUNK"):
             p.sym_chunk = int(os.environ["COSMO_SYM_CHUNK"])
