@@ -1,0 +1,142 @@
+"""The 3-D oracle (oracle/state3d_oracle.c = the reference's new-API step, State.interact,
+cosmosim/core/universe.py:94-129) against the committed reference fixtures
+(tests/golden/state3d_*.npz, oracle/gen_golden3d.py) and, in the build container, against the
+live reference.  CPU only."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, relerr_rows
+from oracle import oracle3d as o3
+from oracle import ref_harness as rh
+
+S3_KEYS = ("pos", "vel", "mass_f64", "mass_int_hi", "mass_int_lo", "mass_is_int", "dens_f64", "dens_is_int", "id")
+
+
+def snap3(npz, prefix):
+    return {k: npz[prefix + k] for k in S3_KEYS}
+
+
+def test_int_true_division_is_pythons():
+    rnd = random.Random(11)
+    cases = [(1, 3), (2 ** 53 + 1, 1), (2 ** 100 + 1, 2 ** 47), (5972000000000000327155712 * 3000, 7), (10, 4),
+             (2 ** 127 - 1, 2 ** 64 + 1), (3, 2 ** 120), (2 ** 54 + 2, 4), (2 ** 54 + 6, 4)]
+    cases += [(rnd.getrandbits(rnd.randint(1, 127)) + 1, rnd.getrandbits(rnd.randint(1, 100)) + 1) for _ in range(20000)]
+    for a, b in cases:
+        assert o3.truediv(a, b) == a / b, (a, b)
+
+
+def test_accel_fixture():
+    g = load_golden("state3d_accel_n2001.npz")
+    got = o3.accel(g["pos"], g["mass"], float(g["G"]))
+    assert relerr_rows(got, g["acc"]).max() < 1e-13
+
+
+@pytest.mark.parametrize("name", ["disk_planar", "disk_thick", "inmemory"])
+def test_kept_steps_match_reference(name):
+    g = load_golden("state3d_%s.npz" % name)
+    for s in g["kept"]:
+        pre = snap3(g, "s%d_pre_" % s)
+        o = o3.OracleState(pre, dt=float(g["dt"]), G=float(g["G"]))
+        assert np.array_equal(o.radii(), g["s%d_radius" % s])        # glibc pow on both sides
+        out = o.interact(True, record=True)
+        assert relerr_rows(out["acc"], g["s%d_acc" % s]).max() < 1e-12
+        assert np.abs(out["p_new"] - g["s%d_p_new" % s]).max() <= 1e-12 * np.abs(g["s%d_p_new" % s]).max()
+        assert np.array_equal(out["flag_pairs"], g["s%d_flag_pairs" % s])
+        assert np.array_equal(out["events"], g["s%d_events" % s])
+        post, want = o.snapshot(), snap3(g, "s%d_post_" % s)
+        for k in ("mass_f64", "mass_int_hi", "mass_int_lo", "mass_is_int", "dens_f64", "dens_is_int", "id"):
+            assert np.array_equal(post[k], want[k]), (s, k)
+        for k in ("pos", "vel"):
+            assert np.abs(post[k] - want[k]).max() <= 1e-12 * np.abs(want[k]).max(), (s, k)
+
+
+@pytest.mark.parametrize("name", ["disk_planar", "disk_thick"])
+def test_free_run_absorb_stream(name):
+    g = load_golden("state3d_%s.npz" % name)
+    o = o3.OracleState(snap3(g, "init_"), dt=float(g["dt"]), G=float(g["G"]))
+    ev = []
+    for s in range(int(g["steps"])):
+        out = o.interact(True)
+        ev += [(s, int(a), int(b), int(c)) for a, b, c in out["events"]]
+        assert o.n == g["n_objects"][s]
+    assert np.array_equal(np.array(ev, dtype=np.int64).reshape(-1, 4), g["events"])
+    assert (g["events"][:, 3] == 0).sum() >= 1          # the fixture exercises the destroyed-object re-absorb
+    post, want = o.snapshot(), snap3(g, "final_")
+    assert np.array_equal(post["id"], want["id"])
+    assert np.array_equal(post["mass_is_int"], want["mass_is_int"])
+    assert np.allclose(post["mass_f64"], want["mass_f64"], rtol=1e-15, atol=0)
+    assert np.abs(post["pos"] - want["pos"]).max() <= 1e-9 * np.abs(want["pos"]).max()
+
+
+def test_micro_scenes():
+    g = load_golden("state3d_micro.npz")
+    for name in g["names"]:
+        o = o3.OracleState(snap3(g, "%s_pre_" % name), dt=1.0, G=float(g["%s_G" % name]))
+        ev = []
+        for s in (0, 1):
+            out = o.interact(True, record=True)
+            ev += [(s, int(a), int(b), int(c)) for a, b, c in out["events"]]
+            assert np.array_equal(out["radius"], g["%s_radius%d" % (name, s)]), name
+            assert np.abs(out["acc"] - g["%s_acc%d" % (name, s)]).max() <= 1e-13 * np.abs(g["%s_acc%d" % (name, s)]).max()
+            post, want = o.snapshot(), snap3(g, "%s_post%d_" % (name, s))
+            for k in S3_KEYS:
+                if k in ("pos", "vel"):
+                    assert np.abs(post[k] - want[k]).max() <= 1e-13 * max(np.abs(want[k]).max(), 1e-300), (name, s, k)
+                else:
+                    assert np.array_equal(post[k], want[k]), (name, s, k)
+            o.pos[:o.n], o.vel[:o.n] = want["pos"], want["vel"]
+        assert np.array_equal(np.array(ev, dtype=np.int64).reshape(-1, 4), g["%s_events" % name]), name
+
+
+# ------------------------------------------------------------------------------------------
+# live reference (build container only)
+# ------------------------------------------------------------------------------------------
+live = pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
+
+
+@live
+@pytest.mark.parametrize("n", [600, 704])
+def test_live_d2_chain_and_distances_bit_exact(n):
+    from scipy.linalg.blas import dspr2, zhpr
+    from sklearn.metrics import pairwise_distances
+    rng = np.random.default_rng(n)
+    pos = rng.normal(size=(n, 3)) * 1.5e11 * np.array([1.0, 0.8, 0.05])
+    packed = np.zeros((3, n * (n + 1) // 2), complex)
+    for row, p in zip(packed, pos.T - 1j):
+        zhpr(n, -2, p, row, 1, 0, 0, 1)
+    c = packed.real.sum(0) + 6
+    dspr2(n, -0.5, c[np.r_[0, 2:n + 1].cumsum()], np.ones((n,)), c, 1, 0, 1, 0, 0, 1)
+    iu = np.triu_indices(n)
+    mine = o3.d2_matrix(pos)
+    assert np.array_equal(mine[iu[0], iu[1]], c[iu[0] + iu[1] * (iu[1] + 1) // 2])
+    mine_d = o3.dist_matrix(pos)
+    for jobs in (1, -1):
+        want = pairwise_distances(pos, n_jobs=jobs)
+        bad = np.argwhere(mine_d != want)
+        if n % 8 < 4 and jobs == 1:
+            assert len(bad) == 0
+        if len(bad):
+            assert np.abs(mine_d - want).max() <= 1e-11 * want.max()
+
+
+@live
+def test_live_short_run():
+    from oracle import ref_harness3d as r3
+    objs = r3.build_disk(7, 250, 0.1 * r3.AU, 0.115 * r3.AU, 25, 1e8)
+    init = r3.snapshot_with_ids(objs)
+    rec = r3.Recorder3D(objs, 600.0, keep_steps=range(25)).run(25)
+    assert len(rec.events) > 5
+    o = o3.OracleState(init, dt=600.0)
+    ev = []
+    for s in range(25):
+        out = o.interact(True, record=True)
+        ev += [(s, int(a), int(b), int(c)) for a, b, c in out["events"]]
+        st = rec.steps[s]
+        assert np.array_equal(out["flag_pairs"], st["flag_pairs"])
+        post = o.snapshot()
+        for k in ("mass_f64", "mass_is_int", "dens_f64", "dens_is_int", "id"):
+            assert np.array_equal(post[k], st["post"][k]), (s, k)
+        o.pos[:o.n], o.vel[:o.n] = st["post"]["pos"], st["post"]["vel"]
+    assert ev == rec.events
