@@ -1,4 +1,4 @@
-"""ctypes binding of include/cosmosim_b200.h.  No fallback: a missing library is an error."""
+"""ctypes binding of include/cosmosim_b200.h and include/cosmosim_b200_state3d.h.  No fallback: a missing library is an error."""
 from __future__ import annotations
 
 import ctypes as C
@@ -58,8 +58,45 @@ class StepParams(C.Structure):
                 ("giant_radius", C.c_double)]
 
 
-# name -> (restype, argtypes); every symbol include/cosmosim_b200.h declares
+# include/cosmosim_b200_state3d.h
+F3_MASS_INT, F3_DENS_INT = 1, 2
+OPT3_COLLISIONS, OPT3_FP32, OPT3_STORE_ACC = 1, 4, 8
+ERR3_INT_OVERFLOW = 16
+
+
+class State3(C.Structure):
+    _fields_ = [("cap", C.c_int32), ("n_total", C.c_int32), ("pos", _vp), ("vel", _vp), ("mass", _vp),
+                ("mass_hi", _vp), ("mass_lo", _vp), ("density", _vp), ("radius", _vp), ("id", _vp),
+                ("flags", _vp), ("status", _vp), ("events", _vp), ("event_cap", C.c_int64)]
+
+
+class Scratch3(C.Structure):
+    _fields_ = [("h", _vp), ("pk", _vp), ("acc", _vp), ("pos_new", _vp), ("vel_new", _vp), ("xx_new", _vp),
+                ("rinf", _vp), ("partial", _vp), ("jsplit_max", C.c_int32), ("reserved0", C.c_int32),
+                ("tile_ctr", _vp), ("pairs", _vp), ("pairs_sorted", _vp), ("pair_cap", C.c_int64),
+                ("exists", _vp), ("cur_pos", _vp), ("cur_vel", _vp), ("touched", _vp), ("scan_in", _vp),
+                ("scan_out", _vp), ("scan_blk", _vp),
+                ("t_pos", _vp), ("t_vel", _vp), ("t_mass", _vp), ("t_mass_hi", _vp), ("t_mass_lo", _vp),
+                ("t_density", _vp), ("t_radius", _vp), ("t_id", _vp), ("t_flags", _vp)]
+
+
+class StepParams3(C.Structure):
+    _fields_ = [("G", C.c_double), ("dt", C.c_double), ("opts", C.c_uint32), ("n_upper", C.c_int32),
+                ("i_begin", C.c_int32), ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
+                ("jsplit", C.c_int32), ("jsplit_detect", C.c_int32)]
+
+
+_S3 = [C.POINTER(State3), C.POINTER(Scratch3), C.POINTER(StepParams3), _vp]
+
+# name -> (restype, argtypes); every symbol the headers under include/ declare
 SYMBOLS = {
+    "cosmo3_accel_integrate": (C.c_int, _S3),
+    "cosmo3_detect_pairs": (C.c_int, _S3),
+    "cosmo3_resolve_commit": (C.c_int, _S3),
+    "cosmo3_step": (C.c_int, _S3),
+    "cosmo3_suggest_jsplit": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int32]),
+    "cosmo3_host_truediv": (C.c_double, [C.c_uint64] * 4),
+    "cosmo3_host_radius": (C.c_double, [C.c_int, C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_double]),
     "cosmo_abi_version": (C.c_int, []),
     "cosmo_launch_count": (C.c_longlong, []),
     "cosmo_last_error": (C.c_char_p, []),

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcosmosim_b200.so")
-SOURCES = ("accel.cu", "accel_sym.cu", "accel_sym64.cu", "detect.cu", "resolve.cu", "energy.cu", "scan.cu", "microbench.cu", "abi.cu")
+SOURCES = ("accel.cu", "accel_sym.cu", "accel_sym64.cu", "detect.cu", "resolve.cu", "energy.cu", "scan.cu", "microbench.cu", "abi.cu", "state3d.cu")
 HEADERS = ("cosmo_device.cuh", "cosmo_internal.h", "pred.cuh", "integrate.cuh")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -30,7 +30,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(INCLUDE, "cosmosim_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(INCLUDE, h) for h in ("cosmosim_b200.h", "cosmosim_b200_state3d.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -1,0 +1,240 @@
+"""Device-resident SoA object state and launch sequence of the 3-D step (the reference's new API,
+``State.interact``, cosmosim/core/universe.py:94-129) -- binds include/cosmosim_b200_state3d.h.
+
+As in engine.py, PyTorch only owns the device buffers; all arithmetic is in libcosmosim_b200.so.
+The reference rebuilds numpy arrays from its Object list on every step (universe.py:95-98); here
+the SoA buffers are the source of truth while stepping.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import (ERR3_INT_OVERFLOW, F3_DENS_INT, F3_MASS_INT, OPT3_COLLISIONS, OPT3_FP32, OPT3_STORE_ACC, PAD,
+                   ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_EVENTS, ST_N_PAIRS, ST_STEP, STATUS_LEN)
+from .engine import _round_up, split_mass
+
+MAX_INT_DENSITY = 1 << 53
+
+
+def split_density(density):
+    """Python density -> (float(density), is_int).  Integer densities are held as exact doubles."""
+    if isinstance(density, (int, np.integer)) and not isinstance(density, (bool, np.bool_)):
+        d = int(density)
+        return float(d), 0 <= d < MAX_INT_DENSITY
+    return float(density), False
+
+
+class Engine3D:
+    JSPLIT_MAX = 64
+
+    def __init__(self, n_total, device=None, pair_cap=None, event_cap=None):
+        if not torch.cuda.is_available():
+            raise _abi.CosmoError("cosmosim_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _abi.lib()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib.cosmo_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), "cosmo_device_info")
+        self.n_total = int(n_total)
+        self.cap = max(PAD, _round_up(self.n_total, PAD))
+        self.pair_cap = int(pair_cap or max(1 << 16, 4 * self.cap))
+        self.event_cap = int(event_cap or max(1 << 16, 4 * self.n_total))
+        self._alloc()
+        self._status_host = torch.zeros(STATUS_LEN, dtype=torch.int64).pin_memory()
+        self._status_event = None
+        self.n_upper = 0
+        self.pos_exp = 0
+        self.mass_exp = 0
+        self.steps = 0
+        self._jsplit_cache = {}
+
+    def _alloc(self):
+        dev, cap = self.device, self.cap
+        f64, i64, i32, u8, f32 = torch.float64, torch.int64, torch.int32, torch.uint8, torch.float32
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+        self.t = t = {}
+        t["pos"] = z(3, cap, dtype=f64); t["vel"] = z(3, cap, dtype=f64)
+        t["mass"] = z(cap, dtype=f64); t["mass_hi"] = z(cap, dtype=i64); t["mass_lo"] = z(cap, dtype=i64)
+        t["density"] = z(cap, dtype=f64); t["radius"] = z(cap, dtype=f64)
+        t["id"] = z(cap, dtype=i32); t["flags"] = z(cap, dtype=u8)
+        t["status"] = z(STATUS_LEN, dtype=i64)
+        t["events"] = z(self.event_cap, 4, dtype=i64)
+        t["h"] = z(cap, dtype=f64); t["pk"] = z(4, cap, dtype=f32); t["acc"] = z(3, cap, dtype=f64)
+        t["pos_new"] = z(3, cap, dtype=f64); t["vel_new"] = z(3, cap, dtype=f64); t["xx_new"] = z(cap, dtype=f64)
+        t["rinf"] = z(cap, dtype=f64)
+        t["partial"] = z(self.JSPLIT_MAX, 3, cap, dtype=f64)
+        t["tile_ctr"] = z(cap // 64 + 4, dtype=i32)
+        t["pairs"] = z(self.pair_cap, dtype=i64); t["pairs_sorted"] = z(self.pair_cap, dtype=i64)
+        t["exists"] = z(cap, dtype=u8)
+        t["cur_pos"] = z(3, cap, dtype=f64); t["cur_vel"] = z(3, cap, dtype=f64)
+        t["touched"] = torch.full((cap,), -1, dtype=i32, device=dev)
+        t["scan_in"] = z(cap + 1, dtype=i32); t["scan_out"] = z(cap + 1, dtype=i32)
+        t["scan_blk"] = z(_abi.SCAN_BLOCKS + 1, dtype=i32)
+        t["t_pos"] = z(3, cap, dtype=f64); t["t_vel"] = z(3, cap, dtype=f64)
+        for k, dt_ in (("mass", f64), ("mass_hi", i64), ("mass_lo", i64), ("density", f64), ("radius", f64),
+                       ("id", i32), ("flags", u8)):
+            t["t_" + k] = z(cap, dtype=dt_)
+        p = lambda k: C.c_void_p(t[k].data_ptr())  # noqa: E731
+        st = _abi.State3()
+        st.cap, st.n_total, st.event_cap = cap, self.n_total, self.event_cap
+        for k in ("pos", "vel", "mass", "mass_hi", "mass_lo", "density", "radius", "id", "flags", "status", "events"):
+            setattr(st, k, p(k))
+        sc = _abi.Scratch3()
+        for k in ("h", "pk", "acc", "pos_new", "vel_new", "xx_new", "rinf", "partial", "tile_ctr", "pairs",
+                  "pairs_sorted", "exists", "cur_pos", "cur_vel", "touched", "scan_in", "scan_out", "scan_blk",
+                  "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_density", "t_radius", "t_id", "t_flags"):
+            setattr(sc, k, p(k))
+        sc.jsplit_max, sc.pair_cap = self.JSPLIT_MAX, self.pair_cap
+        self.st, self.sc = st, sc
+
+    # ------------------------------------------------------------------ host <-> device
+    def upload(self, arrays, iteration=0):
+        """arrays: pos[n,3], vel[n,3], mass_f64[n], mass_hi[n], mass_lo[n] (uint64), density[n], radius[n]
+        (Object.get_radius() evaluated by the caller), flags[n] (F3_* bits), id[n]."""
+        n = int(arrays["mass_f64"].shape[0])
+        if n > self.cap:
+            raise ValueError("upload of %d objects exceeds capacity %d" % (n, self.cap))
+        t = self.t
+
+        def put(key, src, dtype, planes=False):
+            a = np.ascontiguousarray(src, dtype=dtype)
+            if planes:
+                a = np.ascontiguousarray(a.reshape(n, 3).T)
+            if a.dtype == np.uint64:
+                a = a.view(np.int64)
+            h = torch.from_numpy(a)
+            if planes:
+                t[key][:, :n].copy_(h)
+            else:
+                t[key][:n].copy_(h)
+
+        put("pos", arrays["pos"], np.float64, True); put("vel", arrays["vel"], np.float64, True)
+        put("mass", arrays["mass_f64"], np.float64)
+        put("mass_hi", arrays["mass_hi"], np.uint64); put("mass_lo", arrays["mass_lo"], np.uint64)
+        put("density", arrays["density"], np.float64); put("radius", arrays["radius"], np.float64)
+        put("id", arrays["id"], np.int32); put("flags", arrays["flags"], np.uint8)
+        status = torch.zeros(STATUS_LEN, dtype=torch.int64)
+        status[ST_N_ACTIVE] = n
+        status[ST_STEP] = int(iteration)
+        status[ST_N_EVENTS] = self.t["status"].cpu()[ST_N_EVENTS]
+        t["status"].copy_(status)
+        t["touched"].fill_(-1)
+        self.n_upper = n
+        self.steps = int(iteration)
+        torch.cuda.current_stream(self.device).synchronize()
+        self._status_event = None
+        pos = np.asarray(arrays["pos"], dtype=np.float64)
+        mass = np.asarray(arrays["mass_f64"], dtype=np.float64)
+        pmax = float(np.max(np.abs(pos))) if pos.size else 1.0
+        mmax = float(np.max(np.abs(mass))) if mass.size else 1.0
+        self.pos_exp = (math.frexp(pmax)[1] - 6) if pmax > 0 and math.isfinite(pmax) else 0
+        self.mass_exp = (math.frexp(mmax)[1] - 20) if mmax > 0 and math.isfinite(mmax) else 0
+
+    def status(self):
+        s = self.t["status"].cpu().numpy()
+        self.n_upper = int(s[ST_N_ACTIVE])
+        return {"n_active": int(s[ST_N_ACTIVE]), "iteration": int(s[ST_STEP]), "n_events": int(s[ST_N_EVENTS]),
+                "n_pairs": int(s[ST_N_PAIRS]), "n_dead": int(s[ST_N_DEAD]), "error": int(s[ST_ERROR])}
+
+    def check_errors(self):
+        st = self.status()
+        err = st["error"]
+        if err:
+            what = [name for bit, name in ((1, "flagged-pair buffer overflow"), (2, "event log overflow"),
+                                           (4, "non-finite acceleration (d^2 < 0 or NaN input)"),
+                                           (ERR3_INT_OVERFLOW, "integer mass x density beyond 128 bits")) if err & bit]
+            raise _abi.CosmoError("device reported: " + ", ".join(what or ["error bits 0x%x" % err]))
+        return st
+
+    def download(self):
+        """Objects of State.objects in list order (numpy, positions/velocities as [n,3])."""
+        st = self.status()
+        n = st["n_active"]
+        t = self.t
+        out = {k: t[k][:n].cpu().numpy() for k in ("mass", "density", "radius", "id", "flags")}
+        out["pos"] = np.ascontiguousarray(t["pos"][:, :n].cpu().numpy().T)
+        out["vel"] = np.ascontiguousarray(t["vel"][:, :n].cpu().numpy().T)
+        out["mass_hi"] = t["mass_hi"][:n].cpu().numpy().view(np.uint64)
+        out["mass_lo"] = t["mass_lo"][:n].cpu().numpy().view(np.uint64)
+        out["status"] = st
+        return out
+
+    def events(self, start=0):
+        """Object.absorb call stream rows (iteration, absorber id, absorbed id, absorbed existed)."""
+        n = min(self.status()["n_events"], self.event_cap)
+        return self.t["events"][start:n].cpu().numpy()
+
+    def last_step_tensors(self, n):
+        """acc / pos_new / vel_new ([n,3] numpy) and the flagged pairs of the last step, in the slot
+        order the step STARTED with."""
+        t = self.t
+        out = {k: np.ascontiguousarray(t[k][:, :n].cpu().numpy().T) for k in ("acc", "pos_new", "vel_new")}
+        m = min(int(self.t["status"].cpu()[ST_N_PAIRS]), self.pair_cap)
+        keys = np.sort(t["pairs"][:m].cpu().numpy().view(np.uint64))
+        out["flag_pairs"] = np.stack([(keys >> np.uint64(32)).astype(np.int64),
+                                      (keys & np.uint64(0xffffffff)).astype(np.int64)], axis=1).reshape(-1, 2)
+        return out
+
+    # ------------------------------------------------------------------ stepping
+    def params(self, dt, G, collisions=True, fp32=False, store_acc=False, i_begin=0, i_end=None):
+        n = self.n_upper
+        p = _abi.StepParams3()
+        p.G, p.dt = float(G), float(dt)
+        p.opts = (OPT3_COLLISIONS if collisions else 0) | (OPT3_FP32 if fp32 else 0) | (OPT3_STORE_ACC if store_acc else 0)
+        p.n_upper, p.i_begin, p.i_end = n, int(i_begin), int(n if i_end is None else i_end)
+        p.pos_exp, p.mass_exp = self.pos_exp, self.mass_exp
+        rows = p.i_end - p.i_begin
+        key = (rows, n, bool(fp32))
+        js = self._jsplit_cache.get(key)
+        if js is None:
+            if len(self._jsplit_cache) > 4096:
+                self._jsplit_cache.clear()
+            js = (self.lib.cosmo3_suggest_jsplit(rows, n, 1 if fp32 else 0, self.JSPLIT_MAX),
+                  self.lib.cosmo3_suggest_jsplit(rows, n, 2, 256))
+            self._jsplit_cache[key] = js
+        p.jsplit, p.jsplit_detect = js
+        return p
+
+    def _refresh_n_upper(self):
+        ev = self._status_event
+        if ev is not None and ev.query():
+            self.n_upper = min(self.n_upper, int(self._status_host[ST_N_ACTIVE]))
+
+    def step(self, dt, G, collisions=True, fp32=False, store_acc=False, steps=1):
+        """`steps` x State.interact on this device; asynchronous (no host sync)."""
+        stream = torch.cuda.current_stream(self.device)
+        sp = C.c_void_p(stream.cuda_stream)
+        with torch.cuda.device(self.device):
+            for _ in range(int(steps)):
+                self._refresh_n_upper()
+                p = self.params(dt, G, collisions, fp32, store_acc)
+                _abi.check(self.lib.cosmo3_step(C.byref(self.st), C.byref(self.sc), C.byref(p), sp), "cosmo3_step")
+                self.steps += 1
+                self._status_host.copy_(self.t["status"], non_blocking=True)
+                self._status_event = torch.cuda.Event()
+                self._status_event.record(stream)
+
+
+def arrays_from_objects(objects):
+    """Host Object list (reference attribute names: mass, density, position, velocity) -> upload arrays.
+    The radius is Object.get_radius() evaluated by Python itself, exactly as the reference does."""
+    n = len(objects)
+    out = {"pos": np.zeros((n, 3)), "vel": np.zeros((n, 3)), "mass_f64": np.zeros(n),
+           "mass_hi": np.zeros(n, dtype=np.uint64), "mass_lo": np.zeros(n, dtype=np.uint64),
+           "density": np.zeros(n), "radius": np.zeros(n), "flags": np.zeros(n, dtype=np.uint8),
+           "id": np.arange(n, dtype=np.int32)}
+    for k, o in enumerate(objects):
+        out["pos"][k] = o.position
+        out["vel"][k] = o.velocity
+        f, is_int, hi, lo = split_mass(o.mass)
+        d, d_int = split_density(o.density)
+        out["mass_f64"][k], out["mass_hi"][k], out["mass_lo"][k] = f, hi, lo
+        out["density"][k] = d
+        out["flags"][k] = (F3_MASS_INT if is_int else 0) | (F3_DENS_INT if d_int else 0)
+        out["radius"][k] = ((3 * (o.mass / o.density)) / (4 * math.pi)) ** (1 / 3)
+    return out

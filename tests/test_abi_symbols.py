@@ -1,4 +1,4 @@
-"""The C-ABI library loads and exports every symbol include/cosmosim_b200.h declares; the
+"""The C-ABI library loads and exports every symbol the headers under include/ declare; the
 host-callable exact-arithmetic helpers agree with Python's own numeric semantics.  No GPU."""
 import math
 import os
@@ -9,13 +9,16 @@ import pytest
 
 from cosmosim_b200 import _abi, _build
 
-HEADER = os.path.join(os.path.dirname(_build.INCLUDE), "include", "cosmosim_b200.h")
+HEADERS = [os.path.join(_build.INCLUDE, h) for h in sorted(os.listdir(_build.INCLUDE)) if h.endswith(".h")]
 
 
 def header_functions():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(cosmo_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for header in HEADERS:
+        src = open(header).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names.update(re.findall(r"\b(cosmo3?_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_library_builds_and_loads():

@@ -1,0 +1,240 @@
+"""Parity of the CUDA 3-D step (include/cosmosim_b200_state3d.h; the reference's State.interact,
+cosmosim/core/universe.py:94-129) against the reference fixtures and the CPU oracle.  B200 only.
+
+Bars: absorb-call stream, flagged pairs, ids, masses and densities bit-exact; accelerations,
+positions and velocities within 1e-12 (summation order is the only freedom); merged radii within
+one ulp (glibc pow is not correctly rounded, the device's pow(x, 1/3) is); FP32 flavour within the
+bounds stated in the test."""
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+
+from conftest import engine3d_arrays_from_snapshot, load_golden, python_numbers3, relerr_rows, snap3_from
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    from cosmosim_b200 import _abi, engine3d
+    from oracle import oracle3d
+    assert torch.cuda.is_available()
+    return engine3d, oracle3d, _abi
+
+
+def synthetic_cloud(n, seed, thick=0.2):
+    rng = np.random.default_rng(seed)
+    AU, ME, MS = 1.496e11, 5.972e24, 1.989e30
+    pos = rng.normal(size=(n, 3)) * AU * np.array([1.0, 0.7, thick])
+    vel = rng.normal(size=(n, 3)) * 1e4
+    mass = rng.uniform(0.1, 100.0, n) * ME
+    mass[0] = MS
+    dens = np.full(n, 3000.0)
+    snap = {"pos": pos, "vel": vel, "mass_f64": mass, "mass_int_hi": np.zeros(n, np.uint64),
+            "mass_int_lo": np.zeros(n, np.uint64), "mass_is_int": np.zeros(n, bool), "dens_f64": dens,
+            "dens_is_int": np.zeros(n, bool), "id": np.arange(n)}
+    return snap
+
+
+def step_once(engine3d, snap, dt, G, collisions=True, fp32=False):
+    arr = engine3d_arrays_from_snapshot(snap)
+    n = len(arr["mass_f64"])
+    eng = engine3d.Engine3D(n)
+    eng.upload(arr)
+    eng.step(dt, G, collisions=collisions, fp32=fp32, store_acc=True)
+    eng.check_errors()
+    return eng, eng.last_step_tensors(n)
+
+
+def test_accel_fixture_against_reference(mods):
+    engine3d, o3, _ = mods
+    g = load_golden("state3d_accel_n2001.npz")
+    n = len(g["mass"])
+    snap = synthetic_cloud(n, 0)
+    snap["pos"], snap["mass_f64"] = g["pos"], g["mass"]
+    eng, out = step_once(engine3d, snap, 1.0, float(g["G"]), collisions=False)
+    assert relerr_rows(out["acc"], g["acc"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,rows", [(1000, None), (9001, None), (65536, 3000)])
+def test_accel_against_oracle(mods, n, rows):
+    engine3d, o3, _ = mods
+    snap = synthetic_cloud(n, n)
+    eng, out = step_once(engine3d, snap, 60.0, 6.674e-11, collisions=False)
+    i0, i1 = (0, n) if rows is None else (n // 2 - rows // 2, n // 2 + rows // 2)
+    want = o3.accel(snap["pos"], snap["mass_f64"], 6.674e-11, i0, i1)
+    assert relerr_rows(out["acc"][i0:i1], want).max() < 1e-12
+    p, v = o3.integrate(snap["pos"][i0:i1], snap["vel"][i0:i1], out["acc"][i0:i1], 60.0)
+    assert np.array_equal(out["pos_new"][i0:i1], p) and np.array_equal(out["vel_new"][i0:i1], v)
+    # Newton's third law as a whole-matrix property: sum m a = 0 up to rounding
+    ma = out["acc"] * snap["mass_f64"][:, None]
+    assert np.abs(ma.sum(0)).max() < 1e-9 * np.abs(ma).sum(0).max()
+
+
+@pytest.mark.parametrize("name", ["disk_planar", "disk_thick", "inmemory"])
+def test_kept_steps_match_reference(mods, name):
+    engine3d, o3, _ = mods
+    g = load_golden("state3d_%s.npz" % name)
+    for s in g["kept"]:
+        pre = snap3_from(g, "s%d_pre_" % s)
+        arr = engine3d_arrays_from_snapshot(pre)
+        assert np.array_equal(arr["radius"], g["s%d_radius" % s])
+        n = len(arr["mass_f64"])
+        eng = engine3d.Engine3D(n)
+        eng.upload(arr, iteration=int(s))
+        eng.step(float(g["dt"]), float(g["G"]), store_acc=True)
+        eng.check_errors()
+        out = eng.last_step_tensors(n)
+        assert relerr_rows(out["acc"], g["s%d_acc" % s]).max() < 1e-12
+        assert np.abs(out["pos_new"] - g["s%d_p_new" % s]).max() <= 1e-12 * np.abs(g["s%d_p_new" % s]).max()
+        assert np.array_equal(out["flag_pairs"], g["s%d_flag_pairs" % s])
+        ev = eng.events()
+        want_ev = g["s%d_events" % s]
+        assert np.array_equal(ev[:, 1:].reshape(-1, 3), want_ev.reshape(-1, 3))
+        assert np.all(ev[:, 0] == s)
+        d, want = eng.download(), snap3_from(g, "s%d_post_" % s)
+        assert np.array_equal(d["id"], want["id"])
+        assert np.array_equal(d["mass"], want["mass_f64"])
+        assert np.array_equal(d["mass_hi"], want["mass_int_hi"]) and np.array_equal(d["mass_lo"], want["mass_int_lo"])
+        assert np.array_equal(d["density"], want["dens_f64"])
+        assert np.array_equal(d["flags"] & 1, want["mass_is_int"].astype(np.uint8))
+        assert np.array_equal((d["flags"] >> 1) & 1, want["dens_is_int"].astype(np.uint8))
+        for k, w in (("pos", want["pos"]), ("vel", want["vel"])):
+            assert np.abs(d[k] - w).max() <= 1e-12 * np.abs(w).max(), (s, k)
+        masses, dens = python_numbers3(want)
+        r_want = np.array([((3 * (m / q)) / (4 * math.pi)) ** (1 / 3) for m, q in zip(masses, dens)])
+        assert np.all(np.abs(d["radius"] - r_want) <= np.spacing(r_want))
+
+
+@pytest.mark.parametrize("name", ["disk_planar", "disk_thick"])
+def test_free_run_absorb_stream(mods, name):
+    engine3d, o3, _ = mods
+    g = load_golden("state3d_%s.npz" % name)
+    init = snap3_from(g, "init_")
+    arr = engine3d_arrays_from_snapshot(init)
+    eng = engine3d.Engine3D(len(arr["mass_f64"]))
+    eng.upload(arr)
+    counts = []
+    for s in range(int(g["steps"])):
+        eng.step(float(g["dt"]), float(g["G"]))
+        counts.append(eng.status()["n_active"])
+    eng.check_errors()
+    assert np.array_equal(eng.events(), g["events"])
+    assert np.array_equal(np.array(counts), g["n_objects"])
+    d, want = eng.download(), snap3_from(g, "final_")
+    assert np.array_equal(d["id"], want["id"])
+    assert np.array_equal(d["flags"] & 1, want["mass_is_int"].astype(np.uint8))
+    assert np.allclose(d["mass"], want["mass_f64"], rtol=1e-15, atol=0)
+    assert np.abs(d["pos"] - want["pos"]).max() <= 1e-9 * np.abs(want["pos"]).max()
+
+
+def test_micro_scenes(mods):
+    engine3d, o3, _ = mods
+    g = load_golden("state3d_micro.npz")
+    for name in g["names"]:
+        snap = snap3_from(g, "%s_pre_" % name)
+        ev = []
+        for s in (0, 1):
+            arr = engine3d_arrays_from_snapshot(snap)
+            assert np.array_equal(arr["radius"], g["%s_radius%d" % (name, s)]), name
+            n = len(arr["mass_f64"])
+            eng = engine3d.Engine3D(n)
+            eng.upload(arr, iteration=s)
+            eng.step(1.0, float(g["%s_G" % name]), store_acc=True)
+            eng.check_errors()
+            acc = eng.last_step_tensors(n)["acc"]
+            want_acc = g["%s_acc%d" % (name, s)]
+            assert np.abs(acc - want_acc).max() <= 1e-13 * np.abs(want_acc).max(), (name, s)
+            ev += [(int(a), int(b), int(c), int(e)) for a, b, c, e in eng.events()]
+            d, want = eng.download(), snap3_from(g, "%s_post%d_" % (name, s))
+            assert np.array_equal(d["id"], want["id"]), (name, s)
+            assert np.array_equal(d["mass"], want["mass_f64"]) and np.array_equal(d["density"], want["dens_f64"]), (name, s)
+            assert np.array_equal(d["mass_hi"], want["mass_int_hi"]) and np.array_equal(d["mass_lo"], want["mass_int_lo"])
+            assert np.array_equal(d["flags"] & 1, want["mass_is_int"].astype(np.uint8)), (name, s)
+            assert np.array_equal((d["flags"] >> 1) & 1, want["dens_is_int"].astype(np.uint8)), (name, s)
+            # merged velocities can cancel to (almost) zero: the scale is the step's own velocity change
+            scale = {"pos": np.abs(want["pos"]).max(), "vel": max(np.abs(want["vel"]).max(), np.abs(want_acc).max())}
+            for k in ("pos", "vel"):
+                assert np.abs(d[k] - want[k]).max() <= 1e-13 * scale[k], (name, s, k)
+            snap = want
+        assert np.array_equal(np.array(ev, dtype=np.int64).reshape(-1, 4), g["%s_events" % name]), name
+
+
+def test_crowded_step_against_oracle(mods):
+    """A crowded 3-D cloud (hundreds of flagged pairs, chains, destroyed-object re-absorbs) for one
+    step: pairs and the absorb stream must equal the oracle's exactly."""
+    engine3d, o3, _ = mods
+    n = 6000
+    snap = synthetic_cloud(n, 77, thick=0.5)
+    snap["pos"] *= 0.02                      # squeeze: radii ~ 1e7 m in a ~3e9 m cloud
+    rnd = random.Random(5)
+    ints = [rnd.randint(int(0.1 * 5.972e24), int(100 * 5.972e24)) for _ in range(n)]
+    snap["mass_is_int"][:] = True
+    snap["mass_int_hi"] = np.array([m >> 64 for m in ints], dtype=np.uint64)
+    snap["mass_int_lo"] = np.array([m & ((1 << 64) - 1) for m in ints], dtype=np.uint64)
+    snap["mass_f64"] = np.array([float(m) for m in ints])
+    snap["dens_f64"][:] = 30.0
+    snap["dens_is_int"][:] = True
+    orc = o3.OracleState(snap, dt=60.0)
+    want = orc.interact(True, record=True, cap=1 << 18)
+    assert len(want["events"]) > 100 and (want["events"][:, 2] == 0).sum() > 0
+    eng, out = step_once(engine3d, snap, 60.0, 6.674e-11)
+    assert np.array_equal(out["flag_pairs"], want["flag_pairs"])
+    assert np.array_equal(eng.events()[:, 1:], want["events"])
+    d, post = eng.download(), orc.snapshot()
+    assert np.array_equal(d["id"], post["id"])
+    assert np.array_equal(d["mass"], post["mass_f64"]) and np.array_equal(d["density"], post["dens_f64"])
+    assert np.array_equal(d["mass_hi"], post["mass_int_hi"]) and np.array_equal(d["mass_lo"], post["mass_int_lo"])
+    assert np.abs(d["pos"] - post["pos"]).max() <= 1e-12 * np.abs(post["pos"]).max()
+    assert np.abs(d["vel"] - post["vel"]).max() <= 1e-10 * np.abs(post["vel"]).max()
+
+
+def test_fp32_flavour_accuracy(mods):
+    """FP32 all-pairs sum against the FP64 oracle: direct differences after an exact power-of-two
+    rescaling, so the error is the FP32 rounding of the pair terms: median < 1e-5, 99 % < 1e-4,
+    max < 1e-2 of |a| (rows with a near neighbour carry the largest relative error)."""
+    engine3d, o3, _ = mods
+    n = 8192
+    snap = synthetic_cloud(n, 3)
+    eng, out = step_once(engine3d, snap, 60.0, 6.674e-11, collisions=False, fp32=True)
+    want = o3.accel(snap["pos"], snap["mass_f64"], 6.674e-11)
+    err = relerr_rows(out["acc"], want)
+    assert np.median(err) < 1e-5 and np.quantile(err, 0.99) < 1e-4 and err.max() < 1e-2
+    a = out["acc"]
+    v = snap["vel"] + a * 60.0
+    assert np.array_equal(out["vel_new"], v) and np.array_equal(out["pos_new"], snap["pos"] + v * 60.0)
+
+
+def test_host_api_run_and_pickles(mods, tmp_path):
+    """Object / State / Universe.run through the drop-in module: in-memory run vs the reference
+    fixture, and the on-disk pickle stream (universe.py:151-158) read back."""
+    from cosmosim_b200.core import state as S
+    g = load_golden("state3d_inmemory.npz")
+    init = snap3_from(g, "init_")
+    masses, dens = python_numbers3(init)
+
+    def build():
+        return [S.Object(m, q, p, v, name="o%d" % k, color=(1, 2, 3))
+                for k, (m, q, p, v) in enumerate(zip(masses, dens, init["pos"], init["vel"]))]
+
+    st = S.State(build(), dt=float(g["dt"]))
+    st.step(int(g["steps"]))
+    want = snap3_from(g, "final_")
+    assert st.iteration == int(g["steps"]) and len(st.objects) == len(want["id"])
+    assert np.abs(st.positions() - want["pos"]).max() <= 1e-9 * np.abs(want["pos"]).max()
+    assert st.absorb_calls == [tuple(int(x) for x in e) for e in g["events"]]
+    assert all(isinstance(o.mass, int) for o in st.objects[1:]) and isinstance(st.objects[0].mass, float)
+
+    out = str(tmp_path / "run") + os.sep
+    S.Universe(build(), float(g["dt"]), 5, outpath=out, filesize=3).run()
+    assert sorted(os.listdir(out)) == ["0.dat", "1.dat"]
+    states = S.load_states(out)
+    assert sorted(s.iteration for s in states) == [1, 2, 3, 4, 5]
+    mem = S.Universe(build(), float(g["dt"]), 5).run()
+    last = [s for s in states if s.iteration == 5][0]
+    assert np.array_equal(last.positions(), mem[-1].positions())
+    assert b"ccosmosim.core.universe\nState\n" in open(os.path.join(out, "0.dat"), "rb").read()
