@@ -46,7 +46,14 @@ WORKLOADS = {
     "star_disk_64k_fp64": ("star_disk", 1 << 16, "fp64", True),
     "cloud_256k_fp32": ("cloud", 1 << 18, "fp32", True),
     "star_disk_1001_fp64": ("star_disk", 1001, "fp64", True),
+    # the reference's NEW (3-D, batch) API, State.interact: 1-GPU lines
+    "state3d_64k_fp64": ("disk3d", 1 << 16, "fp64", True),
+    "state3d_10k_fp64": ("disk3d", 10001, "fp64", True),     # size of examples/testing/save-data.py
+    "state3d_256k_fp32": ("disk3d", 1 << 18, "fp32", True),
 }
+DT3 = 60.0          # dt of examples/testing/in-memory.py
+# pipe instructions per ordered interaction of the 3-D kernels
+INSTR3_PER_INTERACTION = {"fp32": 12.0, "fp64": 25.0}
 # FMA-pipe instructions per ordered interaction of the dominant kernel
 INSTR_PER_INTERACTION = {"fp32": 9, "fp64": 20}
 
@@ -171,6 +178,9 @@ def main():
     config = {"workload": a.workload, "scene": kind, "n_bodies": n, "precision": prec, "collisions": collisions,
               "dt": DT, "parallelism": "rows%d" % world if world > 1 else "single",
               "l2": "256 MiB memset between steps (inside the timed region)"}
+
+    if kind == "disk3d":
+        return main_state3d(a, n, prec, collisions, rank, world, local_rank, W, K, config)
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if a.impl == "reference":
@@ -359,6 +369,155 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------------------------ 3-D step
+def cpu_oracle3_leg(arrays, seconds_target=12.0, steps=1, warmup=0):
+    """CPU oracle of State.interact (oracle/state3d_oracle.c: accel + integrate + collision predicate)
+    on a bounded sample of target rows of the same scene, all host threads."""
+    from oracle import oracle as orc
+    from oracle import oracle3d as o3
+    n = arrays["mass_f64"].shape[0]
+    pos, vel, mass, rad = arrays["pos"], arrays["vel"], arrays["mass_f64"], arrays["radius"]
+    cores = orc.num_threads()
+
+    def sample(rows):
+        t0 = time.perf_counter()
+        acc = o3.accel(pos, mass, G, 0, rows, compensated=False)
+        p, v = o3.integrate(pos[:rows], vel[:rows], acc, DT3)
+        pn = pos.copy()
+        pn[:rows] = p
+        o3.flags(pn, rad, 0, rows)
+        return time.perf_counter() - t0
+
+    rows = min(n, max(cores, 8))
+    sample(rows)
+    for _ in range(4):
+        t = sample(rows)
+        want = int(min(n, max(rows, seconds_target * rows / max(t, 1e-9))))
+        if want <= rows * 1.25 or t >= 0.5 * seconds_target:
+            break
+        rows = min(want, rows * 16)
+    for _ in range(warmup):
+        sample(rows)
+    t = float(np.mean([sample(rows) for _ in range(max(1, steps))]))
+    return {"value": rows * n / t, "unit": "interactions/s", "cores": cores, "kind": "port",
+            "sample": "oracle/state3d_oracle.c accel+integrate+collision predicate on target rows [0,%d) of the "
+                      "N=%d 3-D scene (%d x %d ordered pairs, %.1f s per step, OpenMP %d threads)"
+                      % (rows, n, rows, n, t, cores), "ms_per_step_sample": t * 1e3, "rows": rows}
+
+
+def main_state3d(a, n, prec, collisions, rank, world, local_rank, W, K, config):
+    """Bench lines of the 3-D step (one GPU): same JSON contract as the main path."""
+    from cosmosim_b200 import scenes
+    config = dict(config, dt=DT3, scene="disk3d (star + thick disk, 0.1-2 AU)", api="State.interact (universe.py:94-129)")
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"error": "the 3-D step is single-GPU in this round; run with --gpus 1", "config": config}))
+        return 2
+    arrays = scenes.disk3d_arrays(n, seed=0)
+    if a.impl == "reference":
+        leg = cpu_oracle3_leg(arrays, seconds_target=min(a.cpu_seconds, 100.0 / (K + W)), steps=K, warmup=W)
+        print(json.dumps({"impl": "reference", "metric": "pairwise_interactions_per_s", "value": leg["value"],
+                          "unit": "interactions/s", "n_gpus": 0, "steps": K, "warmup": W,
+                          "ms_per_step": leg["ms_per_step_sample"], "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                          "e2e": {"value": leg["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}), flush=True)
+        return 0
+    import torch
+    from cosmosim_b200.engine3d import Engine3D
+    torch.cuda.set_device(local_rank)
+    eng = Engine3D(n, device="cuda:%d" % local_rank)
+    eng.sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    eng.upload(arrays)
+    kw = dict(collisions=collisions, fp32=(prec == "fp32"))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    peaks = measure_pipe_peaks(eng, prec)
+    for _ in range(W):
+        eng.step(DT3, G, **kw)
+        flush.zero_()
+    torch.cuda.synchronize()
+    warm_samples = len(sampler.lines)
+    stage_events = []
+    status_log = torch.zeros(K + 1, 16, dtype=torch.int64).pin_memory()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.lib.cosmo_launch_count()
+    e0.record()
+    for k in range(K):
+        status_log[k].copy_(eng.t["status"], non_blocking=True)
+        eng.step(DT3, G, stage_events=stage_events, **kw)
+        flush.zero_()
+    e1.record()
+    gpu_launches = int(eng.lib.cosmo_launch_count() - launches0)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    timed_samples = len(sampler.lines) - warm_samples
+    if timed_samples >= 3:
+        sampler.lines = sampler.lines[warm_samples:]
+    clocks = sampler.stop()
+    clocks["window"] = "timed region" if timed_samples >= 3 else "pipe micro-benchmark + warm-up + timed region"
+    st = eng.check_errors()
+    n_per_step = status_log[:K, 0].numpy().astype(np.float64)
+    interactions = float(np.sum(n_per_step ** 2))
+    value = interactions / (ms * 1e-3)
+    accel_each = np.array([ev[0].elapsed_time(ev[1]) for ev in stage_events])
+    accel_ms = float(np.mean(accel_each))
+    kernel_rate = float(interactions / np.sum(accel_each * 1e-3))
+    ipi = INSTR3_PER_INTERACTION[prec]
+    achieved = kernel_rate * ipi * 2 / 1e12
+    peak = peaks.get("ffma_tflops" if prec == "fp32" else "dfma_tflops")
+    kname = "k3_accel_%s" % ("f32" if prec == "fp32" else "f64")
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+            "%s|%s" % (kname, a.workload), {}).get("bytes")
+    except Exception:
+        pass
+    roofline = {"bound": "fma_pipe_" + prec, "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if peak else None, "traffic": traffic,
+                "peak_source": "in-process %s micro-benchmark (cosmo_microbench) on this GPU"
+                               % ("FFMA" if prec == "fp32" else "DFMA"),
+                "instr_per_interaction": ipi, "kernel_ms": accel_ms, "interactions_per_s_kernel": kernel_rate,
+                "stage_ms": {"prep+accel_integrate": accel_ms,
+                             "detect": float(np.mean([ev[1].elapsed_time(ev[2]) for ev in stage_events])),
+                             "resolve_commit": float(np.mean([ev[2].elapsed_time(ev[3]) for ev in stage_events]))}}
+    e2e = None
+    if not a.no_e2e:
+        eng.upload(arrays)
+        stg = eng.make_host_staging(arrays)
+        for _ in range(2):
+            eng.step_from_host(stg, DT3, G, **kw)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        f0.record()
+        for _ in range(K):
+            eng.step_from_host(stg, DT3, G, **kw)
+        f1.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e_ms = f0.elapsed_time(f1)
+        e2e = {"value": float(n) * n * K / (e_ms * 1e-3), "unit": "interactions/s",
+               "h2d_bytes_per_step": int(stg["h2d_bytes"]), "d2h_bytes_per_step": int(stg["d2h_bytes"]),
+               "ms_per_step": e_ms / K, "wall_ms_per_step": wall_ms / K,
+               "path": "Engine3D.step_from_host: pinned host SoA -> H2D -> cosmo3_step -> D2H, stream sync per step"}
+    cpu = None
+    if not a.no_cpu_baseline:
+        cpu = cpu_oracle3_leg(arrays, seconds_target=a.cpu_seconds)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps({"metric": "pairwise_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": 1,
+                      "steps": K, "warmup": W, "ms_per_step": ms / K, "steps_per_s": K / (ms * 1e-3),
+                      "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "f32" if prec == "fp32" else "f64", "data": "synthetic", "config": config,
+                      "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
+                      "cpu_baseline": cpu, "final_state": {"n_active": st["n_active"], "absorb_calls": st["n_events"]},
+                      "n_active_per_step": [int(x) for x in n_per_step], "pairs_last_step": st["n_pairs"],
+                      "jsplit": eng.params(DT3, G, **kw).jsplit}), flush=True)
     return 0
 
 

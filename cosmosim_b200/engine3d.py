@@ -205,19 +205,78 @@ class Engine3D:
         if ev is not None and ev.query():
             self.n_upper = min(self.n_upper, int(self._status_host[ST_N_ACTIVE]))
 
-    def step(self, dt, G, collisions=True, fp32=False, store_acc=False, steps=1):
-        """`steps` x State.interact on this device; asynchronous (no host sync)."""
+    def step(self, dt, G, collisions=True, fp32=False, store_acc=False, steps=1, stage_events=None):
+        """`steps` x State.interact on this device; asynchronous (no host sync).  stage_events: a list
+        that receives, per step, four CUDA events bracketing stages A, B and C (bench.py)."""
         stream = torch.cuda.current_stream(self.device)
         sp = C.c_void_p(stream.cuda_stream)
+        L, st, sc = self.lib, self.st, self.sc
         with torch.cuda.device(self.device):
             for _ in range(int(steps)):
                 self._refresh_n_upper()
                 p = self.params(dt, G, collisions, fp32, store_acc)
-                _abi.check(self.lib.cosmo3_step(C.byref(self.st), C.byref(self.sc), C.byref(p), sp), "cosmo3_step")
+                if stage_events is None:
+                    _abi.check(L.cosmo3_step(C.byref(st), C.byref(sc), C.byref(p), sp), "cosmo3_step")
+                else:
+                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                    ev[0].record(stream)
+                    _abi.check(L.cosmo3_accel_integrate(C.byref(st), C.byref(sc), C.byref(p), sp), "cosmo3_accel_integrate")
+                    ev[1].record(stream)
+                    _abi.check(L.cosmo3_detect_pairs(C.byref(st), C.byref(sc), C.byref(p), sp), "cosmo3_detect_pairs")
+                    ev[2].record(stream)
+                    _abi.check(L.cosmo3_resolve_commit(C.byref(st), C.byref(sc), C.byref(p), sp), "cosmo3_resolve_commit")
+                    ev[3].record(stream)
+                    stage_events.append(ev)
                 self.steps += 1
                 self._status_host.copy_(self.t["status"], non_blocking=True)
                 self._status_event = torch.cuda.Event()
                 self._status_event.record(stream)
+
+
+    # ------------------------------------------------------------------ host-buffer path (e2e)
+    E2E_IN = ("pos", "vel", "mass", "mass_hi", "mass_lo", "density", "radius", "id", "flags")
+    E2E_OUT = ("pos", "vel", "mass", "mass_hi", "mass_lo", "density", "radius", "id", "flags")
+
+    def make_host_staging(self, arrays):
+        """Pinned host mirrors of the state (what a host-resident caller hands over per step)."""
+        n = int(arrays["mass_f64"].shape[0])
+        src = {"pos": np.ascontiguousarray(np.asarray(arrays["pos"], dtype=np.float64).T),
+               "vel": np.ascontiguousarray(np.asarray(arrays["vel"], dtype=np.float64).T),
+               "mass": arrays["mass_f64"], "mass_hi": np.asarray(arrays["mass_hi"]).view(np.int64),
+               "mass_lo": np.asarray(arrays["mass_lo"]).view(np.int64), "density": arrays["density"],
+               "radius": arrays["radius"], "id": arrays["id"], "flags": arrays["flags"]}
+        stg = {"n": n, "in": {}, "out": {}}
+        for k in self.E2E_IN:
+            stg["in"][k] = torch.from_numpy(np.ascontiguousarray(src[k])).pin_memory()
+        for k in self.E2E_OUT:
+            shape = (3, n) if k in ("pos", "vel") else (n,)
+            stg["out"][k] = torch.empty(shape, dtype=self.t[k].dtype).pin_memory()
+        stg["status_in"] = torch.zeros(STATUS_LEN, dtype=torch.int64).pin_memory()
+        stg["status_out"] = torch.zeros(STATUS_LEN, dtype=torch.int64).pin_memory()
+        stg["h2d_bytes"] = sum(v.numel() * v.element_size() for v in stg["in"].values()) + STATUS_LEN * 8
+        stg["d2h_bytes"] = sum(v.numel() * v.element_size() for v in stg["out"].values()) + STATUS_LEN * 8
+        return stg
+
+    def step_from_host(self, stg, dt, G, **kw):
+        """One State.interact the way a host-resident caller sees it: state H2D from pinned memory, the
+        step, the new state D2H, stream synchronised."""
+        n, t = stg["n"], self.t
+        for k in self.E2E_IN:
+            dst = t[k][:, :n] if k in ("pos", "vel") else t[k][:n]
+            dst.copy_(stg["in"][k], non_blocking=True)
+        stg["status_in"].zero_()
+        stg["status_in"][ST_N_ACTIVE] = n
+        stg["status_in"][ST_STEP] = self.steps
+        t["status"].copy_(stg["status_in"], non_blocking=True)
+        self.n_upper = n
+        self._status_event = None
+        self.step(dt, G, **kw)
+        for k in self.E2E_OUT:
+            src = t[k][:, :n] if k in ("pos", "vel") else t[k][:n]
+            stg["out"][k].copy_(src, non_blocking=True)
+        stg["status_out"].copy_(t["status"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return stg["status_out"]
 
 
 def arrays_from_objects(objects):
