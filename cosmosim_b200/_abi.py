@@ -77,13 +77,18 @@ class Scratch3(C.Structure):
                 ("exists", _vp), ("cur_pos", _vp), ("cur_vel", _vp), ("touched", _vp), ("scan_in", _vp),
                 ("scan_out", _vp), ("scan_blk", _vp),
                 ("t_pos", _vp), ("t_vel", _vp), ("t_mass", _vp), ("t_mass_hi", _vp), ("t_mass_lo", _vp),
-                ("t_density", _vp), ("t_radius", _vp), ("t_id", _vp), ("t_flags", _vp)]
+                ("t_density", _vp), ("t_radius", _vp), ("t_id", _vp), ("t_flags", _vp),
+                ("cell_of", _vp), ("cell_count", _vp), ("cell_start", _vp), ("cell_items", _vp), ("giants", _vp),
+                ("chunk_bounds", _vp), ("heavy_rows", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32)]
 
 
 class StepParams3(C.Structure):
     _fields_ = [("G", C.c_double), ("dt", C.c_double), ("opts", C.c_uint32), ("n_upper", C.c_int32),
                 ("i_begin", C.c_int32), ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
-                ("jsplit", C.c_int32), ("jsplit_detect", C.c_int32)]
+                ("jsplit", C.c_int32), ("jsplit_detect", C.c_int32),
+                ("detect_mode", C.c_int32), ("grid_log_cells", C.c_int32), ("cells_per_side", C.c_int32),
+                ("reserved1", C.c_int32), ("cell_size", C.c_double), ("grid_origin_x", C.c_double),
+                ("grid_origin_y", C.c_double), ("giant_radius", C.c_double)]
 
 
 _S3 = [C.POINTER(State3), C.POINTER(Scratch3), C.POINTER(StepParams3), _vp]

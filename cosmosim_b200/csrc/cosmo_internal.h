@@ -39,6 +39,10 @@ int launch_sym_integrate(const cosmo_state &st, const cosmo_scratch &sc, const c
 int detect_residency(int *rows_per_cta, int *tile);
 int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                   cudaStream_t s);
+// uniform-grid broad phase; planes3: sc.pos_new holds three planes double[3][cap] and the exact test is
+// the 3-D predicate of state3d.cu (st/sc are then shadow structs filled by that file)
+int launch_detect_grid(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p, cudaStream_t s,
+                       bool planes3);
 int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc,
                           const cosmo_step_params &p, cudaStream_t s);
 int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const uint64_t *src,

@@ -148,11 +148,22 @@ __global__ void __launch_bounds__(256) k_grid_max(cosmo_state st, cosmo_scratch 
                   (unsigned long long)__double_as_longlong(m));
 }
 
+// D3 = true serves the 3-D step (state3d.cu): sc.pos_new then holds three PLANES double[3][cap] and
+// the exact test is the three-column predicate without the clip of d to 1 (universe.py:107-108).  The
+// grid itself stays two-dimensional: it bins the (x, y) projection, and planets within a flagged
+// 3-D distance of each other are at least as close in projection, so the candidate set is still a
+// superset (for a thin disk the projection costs nothing; for a thick cloud it is only less selective).
+template <bool D3>
+__device__ __forceinline__ double2 xy_of(const cosmo_state &st, const cosmo_scratch &sc, int k) {
+    if (D3) return make_double2(sc.pos_new[k], sc.pos_new[(size_t)st.cap + k]);
+    return reinterpret_cast<const double2 *>(sc.pos_new)[k];
+}
+
+template <bool D3>
 __global__ void __launch_bounds__(256)
 k_grid_count(cosmo_state st, cosmo_scratch sc, double h, double ox, double oy, double rg, int c, int w) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const GridParams g = grid_params(st, h, ox, oy, rg, c, w);
-    const double2 *pn = reinterpret_cast<const double2 *>(sc.pos_new);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         if (sc.rinf[k] > g.rg) {
             unsigned long long idx =
@@ -164,7 +175,7 @@ k_grid_count(cosmo_state st, cosmo_scratch sc, double h, double ox, double oy, d
                          (unsigned long long)COSMO_ERR_GIANT_OVERFLOW);
             sc.cell_of[k] = -1;
         } else {
-            const double2 p = pn[k];
+            const double2 p = xy_of<D3>(st, sc, k);
             const int cell = cell_coord(p.y, g.cy, g.h, g.c, g.w) * g.c + cell_coord(p.x, g.cx, g.h, g.c, g.w);
             sc.cell_of[k] = cell;
             atomicAdd(&sc.cell_count[cell], 1);
@@ -184,12 +195,36 @@ __global__ void __launch_bounds__(256) k_grid_fill(cosmo_state st, cosmo_scratch
     }
 }
 
-__device__ __forceinline__ void test_and_emit(const cosmo_state &st, const cosmo_scratch &sc, int i, double qx,
-                                              double qy, double xxi, double ri, int j) {
-    const double2 pj = reinterpret_cast<const double2 *>(sc.pos_new)[j];
-    const double d2 = pred_d2(qx, qy, xxi, pj.x, pj.y, sc.xx_new[j]);
-    const double rs = ri + sc.rinf[j];
-    if (d2 <= rs * rs && pred_exact(d2, st.radius[i], st.radius[j])) emit_pair(st, sc, i, j);
+struct GridRow {
+    double qx, qy, qz, xxi, ri;
+};
+
+template <bool D3>
+__device__ __forceinline__ GridRow load_row(const cosmo_state &st, const cosmo_scratch &sc, int i) {
+    GridRow r;
+    const double2 p = xy_of<D3>(st, sc, i);
+    r.qx = -2.0 * p.x; r.qy = -2.0 * p.y;
+    r.qz = D3 ? -2.0 * sc.pos_new[2 * (size_t)st.cap + i] : 0.0;
+    r.xxi = sc.xx_new[i]; r.ri = sc.rinf[i];
+    return r;
+}
+
+template <bool D3>
+__device__ __forceinline__ void test_and_emit(const cosmo_state &st, const cosmo_scratch &sc, int i, const GridRow &r,
+                                              int j) {
+    const double2 pj = xy_of<D3>(st, sc, j);
+    double d2;
+    if (D3) {
+        const double m2dot = __fma_rn(r.qz, sc.pos_new[2 * (size_t)st.cap + j], __fma_rn(r.qy, pj.y, __dmul_rn(r.qx, pj.x)));
+        d2 = __dadd_rn(__dadd_rn(m2dot, r.xxi), sc.xx_new[j]);
+    } else {
+        d2 = pred_d2(r.qx, r.qy, r.xxi, pj.x, pj.y, sc.xx_new[j]);
+    }
+    const double rs = r.ri + sc.rinf[j];
+    if (!(d2 <= rs * rs)) return;
+    const bool hit = D3 ? sqrt(fmax(d2, 0.0)) <= __dadd_rn(st.radius[i], st.radius[j])
+                        : pred_exact(d2, st.radius[i], st.radius[j]);
+    if (hit) emit_pair(st, sc, i, j);
 }
 
 // The cell-sorted order is cut into chunks of GRID_CHUNK slots whose boundaries are snapped to
@@ -223,6 +258,7 @@ __global__ void __launch_bounds__(128) k_grid_ranges(cosmo_state st, cosmo_scrat
 // work on planets of the same or neighbouring cells, so their candidate loops have similar trip
 // counts (the disk's surface density varies 20x between its inner and outer edge) and their
 // gathers hit the same lines.  Every row is produced by exactly one rank.
+template <bool D3>
 __global__ void __launch_bounds__(128)
 k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int c) {
     const int total = sc.cell_start[c * c];
@@ -235,8 +271,7 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count
    for (int slot = s_lo + blockIdx.y * blockDim.x + threadIdx.x; slot < s_hi; slot += gridDim.y * blockDim.x) {
     const int i = sc.cell_items[slot];
     const int cell = sc.cell_of[i];
-    const double2 p = reinterpret_cast<const double2 *>(sc.pos_new)[i];
-    const double qx = -2.0 * p.x, qy = -2.0 * p.y, xxi = sc.xx_new[i], ri = sc.rinf[i];
+    const GridRow row = load_row<D3>(st, sc, i);
     const int cx = cell % c, cy = cell / c;
     // candidate ranges: the three cells of a grid row are contiguous in the sorted item array
     int s0[3], s1[3];
@@ -264,9 +299,9 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count
     for (int d = 0; d < 3; ++d)
         for (int s = s0[d]; s < s1[d]; ++s) {
             const int j = sc.cell_items[s];
-            if (j != i) test_and_emit(st, sc, i, qx, qy, xxi, ri, j);
+            if (j != i) test_and_emit<D3>(st, sc, i, row, j);
         }
-    for (int g = 0; g < ng; ++g) test_and_emit(st, sc, i, qx, qy, xxi, ri, sc.giants[g]);
+    for (int g = 0; g < ng; ++g) test_and_emit<D3>(st, sc, i, row, sc.giants[g]);
    }
   }
     // diagnostic only (all lanes are back together after the loop)
@@ -276,6 +311,7 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count
 }
 
 // Warp-per-row pass for the rows k_grid_detect set aside: the lanes stride over the candidates.
+template <bool D3>
 __global__ void __launch_bounds__(256) k_grid_detect_heavy(cosmo_state st, cosmo_scratch sc, int c) {
     const int nh = (int)st.status[COSMO_ST_N_HEAVY];
     const int lane = threadIdx.x & 31;
@@ -284,8 +320,7 @@ __global__ void __launch_bounds__(256) k_grid_detect_heavy(cosmo_state st, cosmo
     for (int h = warp; h < nh; h += nwarp) {
         const int i = sc.label[h];
         const int cell = sc.cell_of[i];
-        const double2 p = reinterpret_cast<const double2 *>(sc.pos_new)[i];
-        const double qx = -2.0 * p.x, qy = -2.0 * p.y, xxi = sc.xx_new[i], ri = sc.rinf[i];
+        const GridRow row = load_row<D3>(st, sc, i);
         const int cx = cell % c, cy = cell / c;
         for (int dy = -1; dy <= 1; ++dy) {
             const int yy = cy + dy;
@@ -294,14 +329,15 @@ __global__ void __launch_bounds__(256) k_grid_detect_heavy(cosmo_state st, cosmo
             const int s0 = sc.cell_start[yy * c + x0], s1 = sc.cell_start[yy * c + x1 + 1];
             for (int s = s0 + lane; s < s1; s += 32) {
                 const int j = sc.cell_items[s];
-                if (j != i) test_and_emit(st, sc, i, qx, qy, xxi, ri, j);
+                if (j != i) test_and_emit<D3>(st, sc, i, row, j);
             }
         }
-        for (int g = lane; g < ng; g += 32) test_and_emit(st, sc, i, qx, qy, xxi, ri, sc.giants[g]);
+        for (int g = lane; g < ng; g += 32) test_and_emit<D3>(st, sc, i, row, sc.giants[g]);
     }
 }
 
 // rows of the giants: giant g against every planet (blockIdx.y strides over the giants)
+template <bool D3>
 __global__ void __launch_bounds__(256)
 k_giant_rows(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
@@ -310,10 +346,9 @@ k_giant_rows(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end) {
     for (int gi = blockIdx.y; gi < ng; gi += gridDim.y) {
         const int g = sc.giants[gi];
         if (g < i_begin || g >= i_hi) continue;
-        const double2 p = reinterpret_cast<const double2 *>(sc.pos_new)[g];
-        const double qx = -2.0 * p.x, qy = -2.0 * p.y, xxg = sc.xx_new[g], rg = sc.rinf[g];
+        const GridRow row = load_row<D3>(st, sc, g);
         for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
-            if (j != g) test_and_emit(st, sc, g, qx, qy, xxg, rg, j);
+            if (j != g) test_and_emit<D3>(st, sc, g, row, j);
     }
 }
 
@@ -333,50 +368,57 @@ int detect_residency(int *rows_per_cta, int *tile) {
     return nb;
 }
 
+template <bool D3>
+static int launch_grid(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p, cudaStream_t s) {
+    const int rows = p.i_end - p.i_begin;
+    const int c = p.cells_per_side;
+    if (c < 1 || (long long)c * c > sc.grid_cells || !sc.cell_count || !sc.giants) {
+        set_error("grid broad phase: cells_per_side=%d does not fit grid_cells=%d", c, sc.grid_cells);
+        return COSMO_E_ARG;
+    }
+    int nb = (p.n_upper + 255) / 256;
+    if (nb < 1) nb = 1;
+    if (nb > 148 * 8) nb = 148 * 8;
+    k_grid_max<<<nb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_max"));
+    const int w = p.grid_log_cells < 0 ? 0 : p.grid_log_cells;
+    if (c - 2 * w < 1) {
+        set_error("grid broad phase: %d logarithmic cells per side do not fit cells_per_side=%d", w, c);
+        return COSMO_E_ARG;
+    }
+    k_grid_count<D3><<<nb, 256, 0, s>>>(st, sc, p.cell_size, p.grid_origin_x, p.grid_origin_y, p.giant_radius, c, w);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_count"));
+    COSMO_TRY(launch_scan_exclusive(sc.cell_count, sc.cell_start, sc.scan_blk, nullptr, (long long)c * c, 0, s));
+    k_grid_fill<<<nb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_fill"));
+    const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
+    const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
+    const int nchunk = (p.n_upper + GRID_CHUNK - 1) / GRID_CHUNK + 1;
+    k_grid_ranges<<<(nchunk + 127) / 128, 128, 0, s>>>(st, sc, c);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_ranges"));
+    const int blocks = (nchunk + sh_n - 1) / sh_n;
+    k_grid_detect<D3><<<dim3(blocks > 0 ? blocks : 1, GRID_CHUNK / 128), 128, 0, s>>>(st, sc, sh_i, sh_n, c);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect"));
+    k_grid_detect_heavy<D3><<<296, 256, 0, s>>>(st, sc, c);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect_heavy"));
+    if (rows > 0) {
+        k_giant_rows<D3><<<dim3(nb > 296 ? 296 : nb, 8), 256, 0, s>>>(st, sc, p.i_begin, p.i_end);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_giant_rows"));
+    }
+    return COSMO_OK;
+}
+
+int launch_detect_grid(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p, cudaStream_t s,
+                       bool planes3) {
+    return planes3 ? launch_grid<true>(st, sc, p, s) : launch_grid<false>(st, sc, p, s);
+}
+
 int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                   cudaStream_t s) {
     if (!(p.opts & COSMO_OPT_COLLISIONS)) return COSMO_OK;
     const int rows = p.i_end - p.i_begin;
     if (rows <= 0 && p.detect_mode == 0) return COSMO_OK;
-    if (p.detect_mode == 1) {
-        const int c = p.cells_per_side;
-        if (c < 1 || (long long)c * c > sc.grid_cells || !sc.cell_count || !sc.giants) {
-            set_error("grid broad phase: cells_per_side=%d does not fit grid_cells=%d", c, sc.grid_cells);
-            return COSMO_E_ARG;
-        }
-        int nb = (p.n_upper + 255) / 256;
-        if (nb < 1) nb = 1;
-        if (nb > 148 * 8) nb = 148 * 8;
-        k_grid_max<<<nb, 256, 0, s>>>(st, sc);
-        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_max"));
-        const int w = p.grid_log_cells < 0 ? 0 : p.grid_log_cells;
-        if (c - 2 * w < 1) {
-            set_error("grid broad phase: %d logarithmic cells per side do not fit cells_per_side=%d", w, c);
-            return COSMO_E_ARG;
-        }
-        k_grid_count<<<nb, 256, 0, s>>>(st, sc, p.cell_size, p.grid_origin_x, p.grid_origin_y, p.giant_radius, c, w);
-        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_count"));
-        COSMO_TRY(launch_scan_exclusive(sc.cell_count, sc.cell_start, sc.scan_blk, nullptr, (long long)c * c, 0, s));
-        k_grid_fill<<<nb, 256, 0, s>>>(st, sc);
-        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_fill"));
-        {
-            const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
-            const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
-            const int nchunk = (p.n_upper + GRID_CHUNK - 1) / GRID_CHUNK + 1;
-            k_grid_ranges<<<(nchunk + 127) / 128, 128, 0, s>>>(st, sc, c);
-            COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_ranges"));
-            const int blocks = (nchunk + sh_n - 1) / sh_n;
-            k_grid_detect<<<dim3(blocks > 0 ? blocks : 1, GRID_CHUNK / 128), 128, 0, s>>>(st, sc, sh_i, sh_n, c);
-            COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect"));
-            k_grid_detect_heavy<<<296, 256, 0, s>>>(st, sc, c);
-            COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect_heavy"));
-        }
-        if (rows > 0) {
-            k_giant_rows<<<dim3(nb > 296 ? 296 : nb, 8), 256, 0, s>>>(st, sc, p.i_begin, p.i_end);
-            COSMO_TRY(COSMO_LAUNCH_CHECK("k_giant_rows"));
-        }
-        return COSMO_OK;
-    }
+    if (p.detect_mode == 1) return launch_detect_grid(st, sc, p, s, false);
     int jsplit = p.jsplit_detect < 1 ? 1 : p.jsplit_detect;
     if (p.small_tiles) {
         const int per = DETS_BLOCK * DETS_IB;

@@ -151,6 +151,10 @@ __global__ void k3_prep(cosmo3_state st, cosmo3_scratch sc, int pos_exp, int mas
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st.status[COSMO_ST_N_PAIRS] = 0;
         st.status[COSMO_ST_N_DEAD] = 0;
+        st.status[COSMO_ST_N_CAND] = 0;
+        st.status[COSMO_ST_N_GIANTS] = 0;
+        st.status[COSMO_ST_PMAX2] = 0;
+        st.status[COSMO_ST_N_HEAVY] = 0;
     }
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_pad; k += gridDim.x * blockDim.x) {
         if (k < n) {
@@ -802,6 +806,24 @@ static int launch_stage_b(const cosmo3_state &st, const cosmo3_scratch &sc, cons
                           cudaStream_t s) {
     if (!(p.opts & COSMO3_OPT_COLLISIONS)) return COSMO_OK;
     const int rows = p.i_end - p.i_begin;
+    if (p.detect_mode == 1) {
+        // the 2-D grid kernels of detect.cu on shadow structs: planes for pos_new, 3-D exact predicate
+        cosmo_state s2 = {};
+        cosmo_scratch c2 = {};
+        s2.cap = st.cap; s2.n_total = st.n_total; s2.status = st.status; s2.radius = st.radius;
+        c2.pos_new = sc.pos_new; c2.xx_new = sc.xx_new; c2.rinf = sc.rinf;
+        c2.pairs = sc.pairs; c2.pair_cap = sc.pair_cap;
+        c2.cell_of = sc.cell_of; c2.cell_count = sc.cell_count; c2.cell_start = sc.cell_start;
+        c2.cell_items = sc.cell_items; c2.giants = sc.giants; c2.grid_cells = sc.grid_cells;
+        c2.giant_cap = sc.giant_cap; c2.chunk_alive = sc.chunk_bounds; c2.label = sc.heavy_rows;
+        c2.scan_blk = sc.scan_blk;
+        cosmo_step_params p2 = {};
+        p2.opts = COSMO_OPT_COLLISIONS; p2.n_upper = p.n_upper; p2.i_begin = p.i_begin; p2.i_end = p.i_end;
+        p2.detect_mode = 1; p2.grid_log_cells = p.grid_log_cells; p2.cells_per_side = p.cells_per_side;
+        p2.cell_size = p.cell_size; p2.grid_origin_x = p.grid_origin_x; p2.grid_origin_y = p.grid_origin_y;
+        p2.giant_radius = p.giant_radius; p2.shard_index = 0; p2.shard_count = 1;
+        return launch_detect_grid(s2, c2, p2, s, true);
+    }
     if (rows <= 0) return COSMO_OK;
     int jsplit = p.jsplit_detect < 1 ? 1 : p.jsplit_detect;
     const int per = DET_BLOCK * DET_IB;

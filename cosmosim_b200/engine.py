@@ -42,6 +42,44 @@ def _round_up(n, q):
     return (int(n) + q - 1) // q * q
 
 
+def tune_grid(pos, radius, grid_cells, log_cells):
+    """Broad-phase grid (cell edge, origin x, origin y, cells per side, giant radius) for planets at
+    `pos` [n,2] with radii `radius` (host side, O(N)).
+
+    giant_radius: planets with (inflated) radius above it are tested against everybody;
+    cell edge >= 2 * giant_radius so flagged non-giant pairs are always in adjacent cells
+    (the device enlarges the edge further by the rounding slack of the reference's d^2)."""
+    n = radius.shape[0]
+    r = radius * (1.0 + 2.0 ** -30)
+    # Grid box from robust quantiles of the coordinates, NOT min/max: a handful of planets flung
+    # out by a close encounter must not stretch the cells over the whole scene (they are clamped
+    # into the border cells instead, which is exact, only a little slower for them).
+    sample = pos if n <= 131072 else pos[np.random.default_rng(0).integers(0, n, 131072)]
+    lo, hi = np.quantile(sample, 0.02, axis=0), np.quantile(sample, 0.98, axis=0)
+    cx, cy = 0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1])
+    box = float(max(hi[0] - lo[0], hi[1] - lo[1], 1e-300)) * 1.25   # the bulk; tails go to the border cells
+    # cost model: g giants cost g*N exact tests, the rest 9 cells * (N / area) * h^2 each
+    top = min(n - 1, 1024)
+    biggest = np.sort(np.partition(r, n - 1 - top)[n - 1 - top:])[::-1]     # descending, top+1 values
+    area = max(box * box, 1.0)
+    best = None
+    for g in (0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
+        if g > top:
+            break
+        rg_g = float(biggest[g]) * 1.3                   # headroom: merged planets grow until the next retune
+        cost = g * n + n * 9.0 * (n / area) * (2.0 * rg_g) ** 2
+        if best is None or cost < best[0]:
+            best = (cost, rg_g)
+    rg = best[1]
+    span = max(box, 4.0 * rg) * 1.1
+    w = log_cells
+    cmax = int(math.isqrt(grid_cells)) - 2 * w
+    h = max(2.0 * rg * 1.001, span / cmax, span * 4.0 / (3.0 * math.sqrt(n)))   # ~16 candidates per planet
+    c = max(1, min(cmax, int(math.ceil(span / h))))
+    rg = max(rg, h / (2.0 * 1.001))       # cells wider than 2*rg: admit larger planets for free
+    return (h, cx - 0.5 * c * h, cy - 0.5 * c * h, c + 2 * w, rg)   # c linear + 2w logarithmic cells
+
+
 class Engine:
     """One GPU's replica of the world (optionally responsible for a shard of target rows)."""
 
@@ -217,43 +255,11 @@ class Engine:
         self._since_tune = 0
 
     def _tune_grid(self, pos, radius):
-        """Pick the broad-phase grid from the current positions and radii (host side, O(N)).
-
-        giant_radius: planets with (inflated) radius above it are tested against everybody;
-        cell edge >= 2 * giant_radius so flagged non-giant pairs are always in adjacent cells
-        (the device enlarges the edge further by the rounding slack of the reference's d^2)."""
-        n = radius.shape[0]
-        if n < self.grid_threshold:
+        """Pick the broad-phase grid from the current positions and radii (host side, O(N))."""
+        if radius.shape[0] < self.grid_threshold:
             self.grid = None
             return
-        r = radius * (1.0 + 2.0 ** -30)
-        # Grid box from robust quantiles of the coordinates, NOT min/max: a handful of planets flung
-        # out by a close encounter must not stretch the cells over the whole scene (they are clamped
-        # into the border cells instead, which is exact, only a little slower for them).
-        sample = pos if n <= 131072 else pos[np.random.default_rng(0).integers(0, n, 131072)]
-        lo, hi = np.quantile(sample, 0.02, axis=0), np.quantile(sample, 0.98, axis=0)
-        cx, cy = 0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1])
-        box = float(max(hi[0] - lo[0], hi[1] - lo[1], 1e-300)) * 1.25   # the bulk; tails go to the border cells
-        # cost model: g giants cost g*N exact tests, the rest 9 cells * (N / area) * h^2 each
-        top = min(n - 1, 1024)
-        biggest = np.sort(np.partition(r, n - 1 - top)[n - 1 - top:])[::-1]     # descending, top+1 values
-        area = max(box * box, 1.0)
-        best = None
-        for g in (0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
-            if g > top:
-                break
-            rg_g = float(biggest[g]) * 1.3                   # headroom: merged planets grow until the next retune
-            cost = g * n + n * 9.0 * (n / area) * (2.0 * rg_g) ** 2
-            if best is None or cost < best[0]:
-                best = (cost, rg_g)
-        rg = best[1]
-        span = max(box, 4.0 * rg) * 1.1
-        w = self.grid_log_cells
-        cmax = int(math.isqrt(self.grid_cells)) - 2 * w
-        h = max(2.0 * rg * 1.001, span / cmax, span * 4.0 / (3.0 * math.sqrt(n)))   # ~16 candidates per planet
-        c = max(1, min(cmax, int(math.ceil(span / h))))
-        rg = max(rg, h / (2.0 * 1.001))       # cells wider than 2*rg: admit larger planets for free
-        self.grid = (h, cx - 0.5 * c * h, cy - 0.5 * c * h, c + 2 * w, rg)   # c linear + 2w logarithmic cells
+        self.grid = tune_grid(pos, radius, self.grid_cells, self.grid_log_cells)
 
     def retune(self):
         """Synchronising refresh of the host-side launch parameters (active count, grid)."""

@@ -16,7 +16,7 @@ import torch
 from . import _abi
 from ._abi import (ERR3_INT_OVERFLOW, F3_DENS_INT, F3_MASS_INT, OPT3_COLLISIONS, OPT3_FP32, OPT3_STORE_ACC, PAD,
                    ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_EVENTS, ST_N_PAIRS, ST_STEP, STATUS_LEN)
-from .engine import _round_up, split_mass
+from .engine import _round_up, split_mass, tune_grid
 
 MAX_INT_DENSITY = 1 << 53
 
@@ -52,6 +52,11 @@ class Engine3D:
         self.mass_exp = 0
         self.steps = 0
         self._jsplit_cache = {}
+        self.grid = None             # (cell edge, origin x, origin y, cells per side, giant radius)
+        self.grid_log_cells = 32
+        self.grid_threshold = 16384  # objects from which the grid broad phase beats the all-pairs test
+        self.retune_every = 16       # steps between host-side refreshes of the grid tuning
+        self._since_tune = 0
 
     def _alloc(self):
         dev, cap = self.device, self.cap
@@ -79,6 +84,12 @@ class Engine3D:
         for k, dt_ in (("mass", f64), ("mass_hi", i64), ("mass_lo", i64), ("density", f64), ("radius", f64),
                        ("id", i32), ("flags", u8)):
             t["t_" + k] = z(cap, dtype=dt_)
+        self.grid_cells = int(min(_abi.SCAN_BLOCKS * 4096 - 1, max(1 << 16, 8 * cap)))
+        self.giant_cap = 1 << 16
+        t["cell_of"] = z(cap, dtype=i32); t["cell_items"] = z(cap, dtype=i32)
+        t["cell_count"] = z(self.grid_cells + 1, dtype=i32); t["cell_start"] = z(self.grid_cells + 1, dtype=i32)
+        t["giants"] = z(self.giant_cap, dtype=i32)
+        t["chunk_bounds"] = z(cap // 1024 + 2, dtype=i32); t["heavy_rows"] = z(cap, dtype=i32)
         p = lambda k: C.c_void_p(t[k].data_ptr())  # noqa: E731
         st = _abi.State3()
         st.cap, st.n_total, st.event_cap = cap, self.n_total, self.event_cap
@@ -87,9 +98,11 @@ class Engine3D:
         sc = _abi.Scratch3()
         for k in ("h", "pk", "acc", "pos_new", "vel_new", "xx_new", "rinf", "partial", "tile_ctr", "pairs",
                   "pairs_sorted", "exists", "cur_pos", "cur_vel", "touched", "scan_in", "scan_out", "scan_blk",
-                  "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_density", "t_radius", "t_id", "t_flags"):
+                  "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_density", "t_radius", "t_id", "t_flags",
+                  "cell_of", "cell_count", "cell_start", "cell_items", "giants", "chunk_bounds", "heavy_rows"):
             setattr(sc, k, p(k))
         sc.jsplit_max, sc.pair_cap = self.JSPLIT_MAX, self.pair_cap
+        sc.grid_cells, sc.giant_cap = self.grid_cells, self.giant_cap
         self.st, self.sc = st, sc
 
     # ------------------------------------------------------------------ host <-> device
@@ -134,6 +147,27 @@ class Engine3D:
         mmax = float(np.max(np.abs(mass))) if mass.size else 1.0
         self.pos_exp = (math.frexp(pmax)[1] - 6) if pmax > 0 and math.isfinite(pmax) else 0
         self.mass_exp = (math.frexp(mmax)[1] - 20) if mmax > 0 and math.isfinite(mmax) else 0
+        self._tune(pos[:, :2], np.asarray(arrays["radius"], dtype=np.float64))
+
+    def _tune(self, pos_xy, radius):
+        """Grid of the stage-B broad phase from the (x, y) projection (host side, O(N))."""
+        self._since_tune = 0
+        if radius.shape[0] < self.grid_threshold:
+            self.grid = None
+        else:
+            self.grid = tune_grid(np.ascontiguousarray(pos_xy), radius, self.grid_cells, self.grid_log_cells)
+
+    def retune(self):
+        """Synchronising refresh of the active count and the grid tuning."""
+        st = self.status()
+        n = st["n_active"]
+        if n >= self.grid_threshold:
+            xy = self.t["pos"][:2, :n].cpu().numpy().T
+            self._tune(xy, self.t["radius"][:n].cpu().numpy())
+        else:
+            self.grid = None
+            self._since_tune = 0
+        return st
 
     def status(self):
         s = self.t["status"].cpu().numpy()
@@ -147,6 +181,7 @@ class Engine3D:
         if err:
             what = [name for bit, name in ((1, "flagged-pair buffer overflow"), (2, "event log overflow"),
                                            (4, "non-finite acceleration (d^2 < 0 or NaN input)"),
+                                           (8, "broad-phase giant list overflow"),
                                            (ERR3_INT_OVERFLOW, "integer mass x density beyond 128 bits")) if err & bit]
             raise _abi.CosmoError("device reported: " + ", ".join(what or ["error bits 0x%x" % err]))
         return st
@@ -198,6 +233,9 @@ class Engine3D:
                   self.lib.cosmo3_suggest_jsplit(rows, n, 2, 256))
             self._jsplit_cache[key] = js
         p.jsplit, p.jsplit_detect = js
+        if collisions and self.grid is not None and n >= self.grid_threshold:
+            p.detect_mode, p.grid_log_cells = 1, self.grid_log_cells
+            p.cell_size, p.grid_origin_x, p.grid_origin_y, p.cells_per_side, p.giant_radius = self.grid
         return p
 
     def _refresh_n_upper(self):
@@ -214,6 +252,9 @@ class Engine3D:
         with torch.cuda.device(self.device):
             for _ in range(int(steps)):
                 self._refresh_n_upper()
+                if collisions and self.grid is not None and self._since_tune >= self.retune_every:
+                    self.retune()
+                self._since_tune += 1
                 p = self.params(dt, G, collisions, fp32, store_acc)
                 if stage_events is None:
                     _abi.check(L.cosmo3_step(C.byref(st), C.byref(sc), C.byref(p), sp), "cosmo3_step")

@@ -89,6 +89,16 @@ typedef struct cosmo3_scratch {
     /* compaction staging */
     double *t_pos; double *t_vel; double *t_mass; uint64_t *t_mass_hi; uint64_t *t_mass_lo;
     double *t_density; double *t_radius; int32_t *t_id; uint8_t *t_flags;
+    /* uniform-grid broad phase of stage B (detect_mode 1; same arrays as cosmo_scratch) */
+    int32_t *cell_of;      /* [cap] */
+    int32_t *cell_count;   /* [grid_cells + 1] must start zeroed (self-resetting) */
+    int32_t *cell_start;   /* [grid_cells + 1] */
+    int32_t *cell_items;   /* [cap] */
+    int32_t *giants;       /* [giant_cap] */
+    int32_t *chunk_bounds; /* [cap / 1024 + 2] */
+    int32_t *heavy_rows;   /* [cap] */
+    int32_t grid_cells;
+    int32_t giant_cap;
 } cosmo3_scratch;
 
 typedef struct cosmo3_step_params {
@@ -102,6 +112,17 @@ typedef struct cosmo3_step_params {
     int32_t mass_exp;
     int32_t jsplit;        /* source-range splits of the all-pairs pass */
     int32_t jsplit_detect; /* source-range splits of the detection pass */
+    /* stage B mode: 0 = all-pairs predicate; 1 = uniform-grid broad phase on the (x, y) projection
+       (objects close in 3-D are at least as close in projection, so the candidates stay a superset;
+       every candidate goes through the exact 3-D predicate).  Fields as in cosmo_step_params. */
+    int32_t detect_mode;
+    int32_t grid_log_cells;
+    int32_t cells_per_side;
+    int32_t reserved1;
+    double cell_size;
+    double grid_origin_x;
+    double grid_origin_y;
+    double giant_radius;
 } cosmo3_step_params;
 
 /* Stage A: per-step preparation + all-pairs acceleration (FP64: the reference's rounding sequence

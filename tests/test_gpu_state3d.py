@@ -75,8 +75,10 @@ def test_accel_against_oracle(mods, n, rows):
     assert np.abs(ma.sum(0)).max() < 1e-9 * np.abs(ma).sum(0).max()
 
 
-@pytest.mark.parametrize("name", ["disk_planar", "disk_thick", "inmemory"])
-def test_kept_steps_match_reference(mods, name):
+@pytest.mark.parametrize("name,grid", [("disk_planar", False), ("disk_thick", False), ("inmemory", False),
+                                       ("disk_planar", True), ("disk_thick", True)])
+def test_kept_steps_match_reference(mods, name, grid):
+    """grid=True forces the uniform-grid broad phase (normally used from 16384 objects on)."""
     engine3d, o3, _ = mods
     g = load_golden("state3d_%s.npz" % name)
     for s in g["kept"]:
@@ -85,7 +87,10 @@ def test_kept_steps_match_reference(mods, name):
         assert np.array_equal(arr["radius"], g["s%d_radius" % s])
         n = len(arr["mass_f64"])
         eng = engine3d.Engine3D(n)
+        if grid:
+            eng.grid_threshold = 0
         eng.upload(arr, iteration=int(s))
+        assert (eng.grid is not None) == grid
         eng.step(float(g["dt"]), float(g["G"]), store_acc=True)
         eng.check_errors()
         out = eng.last_step_tensors(n)
@@ -191,6 +196,34 @@ def test_crowded_step_against_oracle(mods):
     assert np.array_equal(d["mass_hi"], post["mass_int_hi"]) and np.array_equal(d["mass_lo"], post["mass_int_lo"])
     assert np.abs(d["pos"] - post["pos"]).max() <= 1e-12 * np.abs(post["pos"]).max()
     assert np.abs(d["vel"] - post["vel"]).max() <= 1e-10 * np.abs(post["vel"]).max()
+
+
+@pytest.mark.parametrize("thick", [0.02, 0.6])
+def test_grid_broad_phase_equals_all_pairs(mods, thick):
+    """N = 40000 (grid broad phase on the (x, y) projection, thin disk and thick cloud): flagged pairs
+    and absorb stream must equal the all-pairs kernel's and the oracle's flagged set."""
+    engine3d, o3, _ = mods
+    n = 40000
+    snap = synthetic_cloud(n, 9, thick=thick)
+    snap["pos"] *= 0.05
+    snap["dens_f64"][:] = 100.0
+    arr = engine3d_arrays_from_snapshot(snap)
+    res = []
+    for force_all_pairs in (False, True):
+        eng = engine3d.Engine3D(n)
+        if force_all_pairs:
+            eng.grid_threshold = 1 << 30
+        eng.upload(arr)
+        assert (eng.grid is None) == force_all_pairs
+        eng.step(60.0, 6.674e-11)
+        st = eng.check_errors()
+        res.append((eng.last_step_tensors(n), eng.events(), eng.download(), st))
+    (ta, ea, da, sa), (tb, eb, db, sb) = res
+    assert len(ta["flag_pairs"]) > 50
+    assert np.array_equal(ta["flag_pairs"], tb["flag_pairs"]) and np.array_equal(ea, eb)
+    assert np.array_equal(da["id"], db["id"]) and np.array_equal(da["pos"], db["pos"])
+    want = o3.flags(ta["pos_new"], arr["radius"])
+    assert np.array_equal(ta["flag_pairs"], want)
 
 
 def test_fp32_flavour_accuracy(mods):
