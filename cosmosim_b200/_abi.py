@@ -60,7 +60,7 @@ class StepParams(C.Structure):
 
 # include/cosmosim_b200_state3d.h
 F3_MASS_INT, F3_DENS_INT = 1, 2
-OPT3_COLLISIONS, OPT3_FP32, OPT3_STORE_ACC = 1, 4, 8
+OPT3_COLLISIONS, OPT3_FP32, OPT3_STORE_ACC, OPT3_F64_SYM = 1, 4, 8, 16
 ERR3_INT_OVERFLOW = 16
 
 
@@ -79,7 +79,8 @@ class Scratch3(C.Structure):
                 ("t_pos", _vp), ("t_vel", _vp), ("t_mass", _vp), ("t_mass_hi", _vp), ("t_mass_lo", _vp),
                 ("t_density", _vp), ("t_radius", _vp), ("t_id", _vp), ("t_flags", _vp),
                 ("cell_of", _vp), ("cell_count", _vp), ("cell_start", _vp), ("cell_items", _vp), ("giants", _vp),
-                ("chunk_bounds", _vp), ("heavy_rows", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32)]
+                ("chunk_bounds", _vp), ("heavy_rows", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32),
+                ("colbuf", _vp), ("colbuf_rows", C.c_int64)]
 
 
 class StepParams3(C.Structure):
@@ -87,7 +88,7 @@ class StepParams3(C.Structure):
                 ("i_begin", C.c_int32), ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
                 ("jsplit", C.c_int32), ("jsplit_detect", C.c_int32),
                 ("detect_mode", C.c_int32), ("grid_log_cells", C.c_int32), ("cells_per_side", C.c_int32),
-                ("reserved1", C.c_int32), ("cell_size", C.c_double), ("grid_origin_x", C.c_double),
+                ("sym_chunk", C.c_int32), ("cell_size", C.c_double), ("grid_origin_x", C.c_double),
                 ("grid_origin_y", C.c_double), ("giant_radius", C.c_double)]
 
 

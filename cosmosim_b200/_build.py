@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcosmosim_b200.so")
-SOURCES = ("accel.cu", "accel_sym.cu", "accel_sym64.cu", "detect.cu", "resolve.cu", "energy.cu", "scan.cu", "microbench.cu", "abi.cu", "state3d.cu")
-HEADERS = ("cosmo_device.cuh", "cosmo_internal.h", "pred.cuh", "integrate.cuh")
+SOURCES = ("accel.cu", "accel_sym.cu", "accel_sym64.cu", "detect.cu", "resolve.cu", "energy.cu", "scan.cu", "microbench.cu", "abi.cu", "state3d.cu", "state3d_sym.cu")
+HEADERS = ("cosmo_device.cuh", "cosmo_internal.h", "pred.cuh", "integrate.cuh", "state3d.cuh")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -20,7 +20,7 @@
 
 #include "cosmo_device.cuh"
 #include "cosmo_internal.h"
-#include "cosmosim_b200_state3d.h"
+#include "state3d.cuh"
 
 namespace cosmo {
 namespace s3 {
@@ -137,13 +137,6 @@ __device__ __forceinline__ PyNum load_dens(const cosmo3_state &st, int k) {
 // ---------------------------------------------------------------------------------------
 // stage A
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double chain_c(double qx, double qy, double qz, double x, double y, double z) {
-    double rx = __dadd_rn(__dmul_rn(qx, x), -2.0);
-    double ry = __dadd_rn(__dmul_rn(qy, y), -2.0);
-    double rz = __dadd_rn(__dmul_rn(qz, z), -2.0);
-    return __dadd_rn(__dadd_rn(__dadd_rn(rx, ry), rz), 6.0);
-}
-
 __global__ void k3_prep(cosmo3_state st, cosmo3_scratch sc, int pos_exp, int mass_exp, int do_f32) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int n_pad = min(st.cap, (n + COSMO_PAD - 1) / COSMO_PAD * COSMO_PAD);
@@ -180,31 +173,6 @@ __global__ void k3_prep(cosmo3_state st, cosmo3_scratch sc, int pos_exp, int mas
                 for (int d = 0; d < 4; ++d) sc.pk[d * cap + k] = 0.f;
         }
     }
-}
-
-// a = G*S, v = v0 + a dt, p = p0 + v dt (two roundings per update like numpy, universe.py:103-104),
-// squared row norm of p as sklearn's row_norms forms it for three columns: fl(fl(x^2 + z^2) + y^2)
-__device__ __forceinline__ void integrate_store3(const cosmo3_state &st, const cosmo3_scratch &sc, int i,
-                                                 double sx, double sy, double sz, double G, double dt,
-                                                 bool store_acc) {
-    const size_t cap = (size_t)st.cap;
-    const double s[3] = {sx, sy, sz};
-    double p[3];
-    bool finite = true;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        const double a = __dmul_rn(G, s[d]);
-        const double v = __dadd_rn(st.vel[d * cap + i], __dmul_rn(a, dt));
-        p[d] = __dadd_rn(st.pos[d * cap + i], __dmul_rn(v, dt));
-        sc.vel_new[d * cap + i] = v;
-        sc.pos_new[d * cap + i] = p[d];
-        if (store_acc) sc.acc[d * cap + i] = a;
-        finite = finite && isfinite(a);
-    }
-    sc.xx_new[i] = __dadd_rn(__dadd_rn(__dmul_rn(p[0], p[0]), __dmul_rn(p[2], p[2])), __dmul_rn(p[1], p[1]));
-    if (!finite)
-        atomicOr(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_ERROR]),
-                 (unsigned long long)COSMO_ERR_NAN);
 }
 
 template <int BLOCK, int IB>
@@ -787,6 +755,13 @@ static int launch_stage_a(const cosmo3_state &st, const cosmo3_scratch &sc, cons
         k3_accel_f32<A32_BLOCK, A32_IB, A32_TJ><<<grid, A32_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit, p.G,
                                                                            p.dt, unscale, store_acc);
         return COSMO_LAUNCH_CHECK("k3_accel_f32");
+    }
+    if (p.opts & COSMO3_OPT_F64_SYM) {
+        if (p.i_begin != 0 || p.i_end < p.n_upper) {
+            set_error("symmetric 3-D accel needs all target rows (i_begin = 0, i_end >= n_upper)");
+            return COSMO_E_ARG;
+        }
+        return launch_accel3_sym64(st, sc, p, s);
     }
     if (p.n_upper <= SMALL_N) {
         const int per = A64S_BLOCK * A64S_IB;

@@ -1,0 +1,263 @@
+// Stage A of the 3-D step, FP64 parity flavour, SYMMETRIC variant.  The reference's d^2 chain is
+// symmetric in (i, j) bit for bit (commutative products, hi/lo ordering by index) and its pair term is
+// exactly antisymmetric, so every unordered pair is evaluated once: 29 FP64-pipe instructions per
+// pair = 14.5 per ordered interaction instead of 25.  Same decomposition as accel_sym64.cu: a CTA
+// owns a 512-object row block in registers (2 + 2 objects per lane, 8 warps) and walks column blocks
+// staged in shared memory by the TMA engine's bulk copy; inside a 64 x 64 sub-block the 32 lanes
+// rotate over the column chunks, the column sums travelling through the warp by SHFL; column
+// partials go to `colbuf` (one row of three planes per row block), row partials to `partial`, and
+// k3_sym64_reduce adds both in a fixed order (deterministic) and integrates.
+// Replaces acc_blas on (N,3) input (cosmosim/util/blas.py:4-41, call site universe.py:101) + the
+// integrator (universe.py:103-104).
+#include <math.h>
+
+#include "state3d.cuh"
+
+namespace cosmo {
+namespace s3 {
+
+constexpr int T_BLOCK = 512;
+constexpr int T_GROUP = 64;
+constexpr int T_WARPS = 8;
+constexpr int T_THREADS = T_WARPS * 32;
+// dynamic shared memory: 2 stages x 5 planes (x, y, z, h, m) + 3 planes of column sums + 2 mbarriers
+constexpr size_t T_SMEM = (size_t)(2 * 5 + 3) * T_BLOCK * sizeof(double) + 2 * sizeof(uint64_t);
+
+__device__ __forceinline__ double shfl_f64(double v, int src_lane) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src_lane);
+    hi = __shfl_sync(0xffffffffu, hi, src_lane);
+    return __hiloint2double(hi, lo);
+}
+
+// One unordered pair {i, j}.  DIAG: i and j come from the same block (index order varies, self pairs
+// occur, only the row side is accumulated).  CHECK0: honour the where= mask (blas.py:31).
+template <bool DIAG, bool CHECK0>
+__device__ __forceinline__ void pair3_sym(const double (&pi)[3], const double (&qi)[3], double hi, double nmi,
+                                          int i, double xj, double yj, double zj, double hj, double mj, int j,
+                                          double (&ai)[3], double &axj, double &ayj, double &azj) {
+    const double c = chain_c(qi[0], qi[1], qi[2], xj, yj, zj);
+    double d2;
+    if (!DIAG) {
+        d2 = __dadd_rn(__dadd_rn(c, -hj), -hi);   // every column index is above every row index
+    } else {
+        const bool ge = j >= i;
+        d2 = __dadd_rn(__dadd_rn(c, -(ge ? hj : hi)), -(ge ? hi : hj));
+    }
+    const double dx = xj - pi[0], dy = yj - pi[1], dz = zj - pi[2];
+    double y = rsqrt_approx_f64(d2);
+    const double t = d2 * y;
+    const double e = __fma_rn(-t, y, 1.0);
+    const double p = __fma_rn(e, 0.375, 0.5);
+    const double ye = y * e;
+    y = __fma_rn(ye, p, y);
+    const double y3 = (y * y) * y;
+    double sj = mj * y3;
+    double nsi = nmi * y3;
+    if (CHECK0) {
+        const bool zero = ((__double2hiint(d2) << 1) | __double2loint(d2)) == 0;
+        sj = zero ? mj : sj;
+        nsi = zero ? nmi : nsi;
+    }
+    ai[0] = __fma_rn(dx, sj, ai[0]);
+    ai[1] = __fma_rn(dy, sj, ai[1]);
+    ai[2] = __fma_rn(dz, sj, ai[2]);
+    if (!DIAG) {
+        axj = __fma_rn(dx, nsi, axj);
+        ayj = __fma_rn(dy, nsi, ayj);
+        azj = __fma_rn(dz, nsi, azj);
+    }
+}
+
+// 64 row objects (2 per lane) x 64 column objects (chunk c = columns 2c, 2c+1): 32 rotation steps
+template <bool DIAG, bool CHECK0>
+__device__ __forceinline__ void round3_sym(const double *__restrict__ gp, int lane, int jbase,
+                                           const double (&pi)[2][3], const double (&qi)[2][3],
+                                           const double (&hi)[2], const double (&nmi)[2], const int (&ii)[2],
+                                           double (&ra)[2][3], double (&tc)[2][3]) {
+    // gp points at plane 0 of the group inside the stage; planes are T_BLOCK doubles apart
+#pragma unroll 1
+    for (int s = 0; s < 32; ++s) {
+        const int c = (lane + s) & 31;
+        const double2 X = *reinterpret_cast<const double2 *>(gp + 2 * c);
+        const double2 Y = *reinterpret_cast<const double2 *>(gp + T_BLOCK + 2 * c);
+        const double2 Z = *reinterpret_cast<const double2 *>(gp + 2 * T_BLOCK + 2 * c);
+        const double2 H = *reinterpret_cast<const double2 *>(gp + 3 * T_BLOCK + 2 * c);
+        const double2 M = *reinterpret_cast<const double2 *>(gp + 4 * T_BLOCK + 2 * c);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            pair3_sym<DIAG, CHECK0>(pi[k], qi[k], hi[k], nmi[k], ii[k], X.x, Y.x, Z.x, H.x, M.x, jbase + 2 * c,
+                                    ra[k], tc[0][0], tc[0][1], tc[0][2]);
+            pair3_sym<DIAG, CHECK0>(pi[k], qi[k], hi[k], nmi[k], ii[k], X.y, Y.y, Z.y, H.y, M.y, jbase + 2 * c + 1,
+                                    ra[k], tc[1][0], tc[1][1], tc[1][2]);
+        }
+        if (!DIAG) {
+            const int src = (lane + 1) & 31;
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) tc[q][d] = shfl_f64(tc[q][d], src);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(T_THREADS, 2)
+k3_accel_f64_sym(cosmo3_state st, cosmo3_scratch sc, int chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_p = reinterpret_cast<double *>(smem_raw);          // [2][5][T_BLOCK]
+    double *s_c = s_p + 2 * 5 * T_BLOCK;                         // [3][T_BLOCK]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_c + 3 * T_BLOCK);
+
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int nblk = (n + T_BLOCK - 1) / T_BLOCK;
+    const int I = blockIdx.x;
+    if (I >= nblk) return;
+    const int J0 = I + blockIdx.y * chunk;
+    if (J0 >= nblk) return;
+    const int J1 = min(nblk, J0 + chunk);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const size_t cap = (size_t)st.cap;
+
+    double pi[2][3], qi[2][3], hi[2], nmi[2], ra[2][3];
+    int ii[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int r = I * T_BLOCK + w * T_GROUP + k * 32 + lane;   // slots past n are massless pads (k3_prep)
+        ii[k] = r;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            pi[k][d] = st.pos[d * cap + r];
+            qi[k][d] = -2.0 * pi[k][d];
+            asm volatile("" : "+d"(qi[k][d]));
+            ra[k][d] = 0.0;
+        }
+        hi[k] = sc.h[r];
+        nmi[k] = -st.mass[r];
+    }
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    constexpr uint32_t kBytes = T_BLOCK * 5 * sizeof(double);
+    auto issue = [&](int J, int b) {
+        const size_t j0 = (size_t)J * T_BLOCK;
+        double *dst = s_p + (size_t)b * 5 * T_BLOCK;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar[b], kBytes);
+        bulk_g2s(dst, st.pos + j0, T_BLOCK * sizeof(double), &s_bar[b]);
+        bulk_g2s(dst + T_BLOCK, st.pos + cap + j0, T_BLOCK * sizeof(double), &s_bar[b]);
+        bulk_g2s(dst + 2 * T_BLOCK, st.pos + 2 * cap + j0, T_BLOCK * sizeof(double), &s_bar[b]);
+        bulk_g2s(dst + 3 * T_BLOCK, sc.h + j0, T_BLOCK * sizeof(double), &s_bar[b]);
+        bulk_g2s(dst + 4 * T_BLOCK, st.mass + j0, T_BLOCK * sizeof(double), &s_bar[b]);
+    };
+    if (tid == 0) issue(J0, 0);
+    double *colrow = sc.colbuf + (size_t)blockIdx.x * 3 * cap;
+
+    for (int J = J0; J < J1; ++J) {
+        const int it_j = J - J0;
+        const int b = it_j & 1;
+        if (tid == 0 && J + 1 < J1) issue(J + 1, b ^ 1);
+        mbar_wait(&s_bar[b], (it_j >> 1) & 1);
+        const double *stage = s_p + (size_t)b * 5 * T_BLOCK;
+        const bool diag = (J == I);
+        double ba[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};   // block-local row sums (two-level summation)
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            for (int q = tid; q < 3 * T_BLOCK; q += T_THREADS) s_c[q] = 0.0;
+            __syncthreads();
+            for (int it = 0; it < T_WARPS; ++it) {
+                const int g = (w + it) & (T_WARPS - 1);
+                const double *gp = stage + g * T_GROUP;
+                const int jbase = J * T_BLOCK + g * T_GROUP;
+                double tc[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+                if (diag) round3_sym<true, true>(gp, lane, jbase, pi, qi, hi, nmi, ii, ba, tc);
+                else if (attempt == 0) round3_sym<false, false>(gp, lane, jbase, pi, qi, hi, nmi, ii, ba, tc);
+                else round3_sym<false, true>(gp, lane, jbase, pi, qi, hi, nmi, ii, ba, tc);
+                if (!diag) {   // lane l is home to chunk l: column objects 2l, 2l+1 of group g
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        double2 *cell = reinterpret_cast<double2 *>(&s_c[d * T_BLOCK + g * T_GROUP + 2 * lane]);
+                        double2 v = *cell;
+                        v.x += tc[0][d];
+                        v.y += tc[1][d];
+                        *cell = v;
+                    }
+                }
+                __syncthreads();
+            }
+            if (diag || attempt == 1) break;
+            // the off-diagonal fast flavour skips the d2 == 0 mask; a non-finite sum (practically never)
+            // means such an entry occurred: redo this block pair with the mask honoured
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) bad = bad || !(isfinite(ba[k][0]) && isfinite(ba[k][1]) && isfinite(ba[k][2]));
+            for (int q = tid; q < 3 * T_BLOCK; q += T_THREADS) bad = bad || !isfinite(s_c[q]);
+            if (!__syncthreads_or(bad)) break;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) ba[k][0] = ba[k][1] = ba[k][2] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { ra[k][0] += ba[k][0]; ra[k][1] += ba[k][1]; ra[k][2] += ba[k][2]; }
+        if (!diag) {
+            for (int q = tid; q < 3 * T_BLOCK; q += T_THREADS) {
+                const int d = q / T_BLOCK, o = q - d * T_BLOCK;
+                colrow[d * cap + (size_t)J * T_BLOCK + o] = s_c[q];
+            }
+        }
+        __syncthreads();
+    }
+    double *part = sc.partial + (size_t)blockIdx.y * 3 * cap;
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) part[d * cap + ii[k]] = ra[k][d];
+}
+
+// row partials of the object's own row block (in chunk order) + column partials of every row block
+// above it (in block order): a fixed summation order, independent of scheduling
+__global__ void __launch_bounds__(256)
+k3_sym64_reduce(cosmo3_state st, cosmo3_scratch sc, int chunk, double G, double dt, int store_acc) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t cap = (size_t)st.cap;
+    const int nblk = (n + T_BLOCK - 1) / T_BLOCK;
+    const int K = k / T_BLOCK;
+    double a[3] = {0.0, 0.0, 0.0};
+    const int nchunk = (nblk - K + chunk - 1) / chunk;
+    for (int c = 0; c < nchunk; ++c)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a[d] += sc.partial[((size_t)c * 3 + d) * cap + k];
+    for (int I = 0; I < K; ++I)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a[d] += __ldcs(&sc.colbuf[((size_t)I * 3 + d) * cap + k]);
+    integrate_store3(st, sc, k, a[0], a[1], a[2], G, dt, store_acc != 0);
+}
+
+int launch_accel3_sym64(const cosmo3_state &st, const cosmo3_scratch &sc, const cosmo3_step_params &p,
+                        cudaStream_t s) {
+    const int n = p.n_upper;
+    if (n <= 0) return COSMO_OK;
+    const int nblk = (n + T_BLOCK - 1) / T_BLOCK;
+    int chunk = p.sym_chunk > 0 ? p.sym_chunk : 4;
+    while ((nblk + chunk - 1) / chunk > sc.jsplit_max) ++chunk;
+    if (!sc.colbuf || (long long)nblk > sc.colbuf_rows) {
+        set_error("symmetric 3-D accel: colbuf has %lld rows, %d needed", (long long)sc.colbuf_rows, nblk);
+        return COSMO_E_ARG;
+    }
+    static bool configured = false;
+    if (!configured) {
+        COSMO_TRY(check_cuda(cudaFuncSetAttribute(k3_accel_f64_sym, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)T_SMEM), "cudaFuncSetAttribute(k3_accel_f64_sym)"));
+        configured = true;
+    }
+    dim3 grid(nblk, (nblk + chunk - 1) / chunk);
+    k3_accel_f64_sym<<<grid, T_THREADS, T_SMEM, s>>>(st, sc, chunk);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k3_accel_f64_sym"));
+    k3_sym64_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, chunk, p.G, p.dt, (p.opts & COSMO3_OPT_STORE_ACC) ? 1 : 0);
+    return COSMO_LAUNCH_CHECK("k3_sym64_reduce");
+}
+
+}  // namespace s3
+}  // namespace cosmo

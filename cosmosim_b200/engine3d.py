@@ -9,12 +9,13 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
 
 from . import _abi
-from ._abi import (ERR3_INT_OVERFLOW, F3_DENS_INT, F3_MASS_INT, OPT3_COLLISIONS, OPT3_FP32, OPT3_STORE_ACC, PAD,
+from ._abi import (ERR3_INT_OVERFLOW, F3_DENS_INT, F3_MASS_INT, OPT3_COLLISIONS, OPT3_F64_SYM, OPT3_FP32, OPT3_STORE_ACC, PAD,
                    ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_EVENTS, ST_N_PAIRS, ST_STEP, STATUS_LEN)
 from .engine import _round_up, split_mass, tune_grid
 
@@ -30,7 +31,7 @@ def split_density(density):
 
 
 class Engine3D:
-    JSPLIT_MAX = 64
+    JSPLIT_MAX = 128
 
     def __init__(self, n_total, device=None, pair_cap=None, event_cap=None):
         if not torch.cuda.is_available():
@@ -57,6 +58,9 @@ class Engine3D:
         self.grid_threshold = 16384  # objects from which the grid broad phase beats the all-pairs test
         self.retune_every = 16       # steps between host-side refreshes of the grid tuning
         self._since_tune = 0
+        self.sym64_threshold = 16384 # FP64: from here on the symmetric kernel (each pair once) wins
+        self.sym_chunk = 0           # column blocks per CTA of the symmetric kernel (0 = automatic)
+        self._colbuf = None
 
     def _alloc(self):
         dev, cap = self.device, self.cap
@@ -216,11 +220,31 @@ class Engine3D:
         return out
 
     # ------------------------------------------------------------------ stepping
-    def params(self, dt, G, collisions=True, fp32=False, store_acc=False, i_begin=0, i_end=None):
+    def _ensure_colbuf(self, n):
+        """Column-partial buffer of the symmetric kernel: three planes of `cap` doubles per 512-object
+        row block (24 B x N^2 / 512: 201 MB at N = 65536, 3.2 GB at 262144)."""
+        rows = -(-n // 512)
+        if self._colbuf is None or self._colbuf.shape[0] < rows:
+            self._colbuf = torch.empty(rows, 3, self.cap, dtype=torch.float64, device=self.device)
+            self.sc.colbuf = C.c_void_p(self._colbuf.data_ptr())
+            self.sc.colbuf_rows = rows
+
+    def params(self, dt, G, collisions=True, fp32=False, store_acc=False, i_begin=0, i_end=None, sym=None):
         n = self.n_upper
         p = _abi.StepParams3()
         p.G, p.dt = float(G), float(dt)
         p.opts = (OPT3_COLLISIONS if collisions else 0) | (OPT3_FP32 if fp32 else 0) | (OPT3_STORE_ACC if store_acc else 0)
+        whole = int(i_begin) == 0 and (i_end is None or int(i_end) >= n)
+        if sym is None:
+            sym = n >= self.sym64_threshold
+        if sym and not fp32 and whole and n > 512:
+            self._ensure_colbuf(n)
+            p.opts |= OPT3_F64_SYM
+            nblk = -(-n // 512)
+            want = (nblk * nblk) // (2 * 16 * 2 * 148)
+            p.sym_chunk = int(self.sym_chunk or min(32, max(1, -(-nblk // self.JSPLIT_MAX), want)))
+            if os.environ.get("COSMO3_SYM_CHUNK"):
+                p.sym_chunk = max(int(os.environ["COSMO3_SYM_CHUNK"]), -(-nblk // self.JSPLIT_MAX))
         p.n_upper, p.i_begin, p.i_end = n, int(i_begin), int(n if i_end is None else i_end)
         p.pos_exp, p.mass_exp = self.pos_exp, self.mass_exp
         rows = p.i_end - p.i_begin
@@ -243,7 +267,7 @@ class Engine3D:
         if ev is not None and ev.query():
             self.n_upper = min(self.n_upper, int(self._status_host[ST_N_ACTIVE]))
 
-    def step(self, dt, G, collisions=True, fp32=False, store_acc=False, steps=1, stage_events=None):
+    def step(self, dt, G, collisions=True, fp32=False, store_acc=False, steps=1, stage_events=None, sym=None):
         """`steps` x State.interact on this device; asynchronous (no host sync).  stage_events: a list
         that receives, per step, four CUDA events bracketing stages A, B and C (bench.py)."""
         stream = torch.cuda.current_stream(self.device)
@@ -255,7 +279,7 @@ class Engine3D:
                 if collisions and self.grid is not None and self._since_tune >= self.retune_every:
                     self.retune()
                 self._since_tune += 1
-                p = self.params(dt, G, collisions, fp32, store_acc)
+                p = self.params(dt, G, collisions, fp32, store_acc, sym=sym)
                 if stage_events is None:
                     _abi.check(L.cosmo3_step(C.byref(st), C.byref(sc), C.byref(p), sp), "cosmo3_step")
                 else:

@@ -42,6 +42,7 @@ extern "C" {
 #define COSMO3_OPT_COLLISIONS 1u /* State.interact(collisions=True) */
 #define COSMO3_OPT_FP32 4u       /* FP32 fast path for the all-pairs sum (state stays FP64) */
 #define COSMO3_OPT_STORE_ACC 8u  /* also write the accelerations to scratch.acc */
+#define COSMO3_OPT_F64_SYM 16u   /* FP64 path: symmetric kernel (each unordered pair once); needs colbuf, all rows */
 
 #define COSMO3_ERR_INT_OVERFLOW 16 /* an integer mass x density product exceeded 128 bits (status ERROR bit) */
 
@@ -99,6 +100,9 @@ typedef struct cosmo3_scratch {
     int32_t *heavy_rows;   /* [cap] */
     int32_t grid_cells;
     int32_t giant_cap;
+    /* column partial sums of the symmetric kernel: [colbuf_rows][3][cap], one row per 512-object row block */
+    double *colbuf;
+    int64_t colbuf_rows;   /* >= ceil(n / 512) */
 } cosmo3_scratch;
 
 typedef struct cosmo3_step_params {
@@ -118,7 +122,7 @@ typedef struct cosmo3_step_params {
     int32_t detect_mode;
     int32_t grid_log_cells;
     int32_t cells_per_side;
-    int32_t reserved1;
+    int32_t sym_chunk;     /* symmetric kernel: column blocks per CTA (0 = default) */
     double cell_size;
     double grid_origin_x;
     double grid_origin_y;

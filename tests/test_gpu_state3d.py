@@ -26,6 +26,10 @@ def mods():
     return engine3d, oracle3d, _abi
 
 
+def _abi_bits(mods):
+    return mods[2]
+
+
 def synthetic_cloud(n, seed, thick=0.2):
     rng = np.random.default_rng(seed)
     AU, ME, MS = 1.496e11, 5.972e24, 1.989e30
@@ -40,12 +44,12 @@ def synthetic_cloud(n, seed, thick=0.2):
     return snap
 
 
-def step_once(engine3d, snap, dt, G, collisions=True, fp32=False):
+def step_once(engine3d, snap, dt, G, collisions=True, fp32=False, sym=None):
     arr = engine3d_arrays_from_snapshot(snap)
     n = len(arr["mass_f64"])
     eng = engine3d.Engine3D(n)
     eng.upload(arr)
-    eng.step(dt, G, collisions=collisions, fp32=fp32, store_acc=True)
+    eng.step(dt, G, collisions=collisions, fp32=fp32, store_acc=True, sym=sym)
     eng.check_errors()
     return eng, eng.last_step_tensors(n)
 
@@ -60,11 +64,14 @@ def test_accel_fixture_against_reference(mods):
     assert relerr_rows(out["acc"], g["acc"]).max() < 1e-12
 
 
-@pytest.mark.parametrize("n,rows", [(1000, None), (9001, None), (65536, 3000)])
-def test_accel_against_oracle(mods, n, rows):
+@pytest.mark.parametrize("n,rows,sym", [(1000, None, False), (9001, None, False), (9001, None, True), (1537, None, True),
+                                        (65536, 3000, False), (65536, 3000, True)])
+def test_accel_against_oracle(mods, n, rows, sym):
+    """sym: the symmetric kernel (each unordered pair once; default from 16384 objects on)."""
     engine3d, o3, _ = mods
     snap = synthetic_cloud(n, n)
-    eng, out = step_once(engine3d, snap, 60.0, 6.674e-11, collisions=False)
+    eng, out = step_once(engine3d, snap, 60.0, 6.674e-11, collisions=False, sym=sym)
+    assert bool(eng.params(60.0, 6.674e-11, False, sym=sym).opts & _abi_bits(mods).OPT3_F64_SYM) == sym
     i0, i1 = (0, n) if rows is None else (n // 2 - rows // 2, n // 2 + rows // 2)
     want = o3.accel(snap["pos"], snap["mass_f64"], 6.674e-11, i0, i1)
     assert relerr_rows(out["acc"][i0:i1], want).max() < 1e-12

@@ -35,18 +35,19 @@ def timed(fn, reps):
     return a.elapsed_time(b) / reps
 
 
-for n, fp32, reps in ((1001, False, 200), (10001, False, 50), (65536, False, 10), (65536, True, 20), (262144, True, 5)):
-    eng = engine3d.Engine3D(n)
-    eng.upload(cloud(n))
-    L, st, sc = eng.lib, eng.st, eng.sc
-    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    p = eng.params(60.0, 6.674e-11, True, fp32)
-    ta = timed(lambda: L.cosmo3_accel_integrate(C.byref(st), C.byref(sc), C.byref(p), sp), reps)
-    tb = timed(lambda: L.cosmo3_detect_pairs(C.byref(st), C.byref(sc), C.byref(p), sp), reps)
-    eng.t["status"][3] = 0
-    tc = timed(lambda: L.cosmo3_resolve_commit(C.byref(st), C.byref(sc), C.byref(p), sp), reps)
-    eng.upload(cloud(n))
-    tall = timed(lambda: eng.step(60.0, 6.674e-11, True, fp32), reps)
-    ops = 12.5 if fp32 else 25.0
-    print("n=%d fp32=%s jsplit=%d/%d  A %.3f ms (%.3e int/s, %.2e pipe-instr/s)  B %.3f ms  C %.3f ms  step %.3f ms  status %s"
-          % (n, fp32, p.jsplit, p.jsplit_detect, ta, n * n / ta * 1e3, n * n * ops / ta * 1e3, tb, tc, tall, eng.check_errors()))
+if __name__ == "__main__":
+  for n, fp32, reps in ((1001, False, 200), (10001, False, 50), (65536, False, 10), (65536, True, 20), (262144, True, 5)):
+      eng = engine3d.Engine3D(n)
+      eng.upload(cloud(n))
+      L, st, sc = eng.lib, eng.st, eng.sc
+      sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+      p = eng.params(60.0, 6.674e-11, True, fp32)
+      ta = timed(lambda: L.cosmo3_accel_integrate(C.byref(st), C.byref(sc), C.byref(p), sp), reps)
+      tb = timed(lambda: L.cosmo3_detect_pairs(C.byref(st), C.byref(sc), C.byref(p), sp), reps)
+      eng.t["status"][3] = 0
+      tc = timed(lambda: L.cosmo3_resolve_commit(C.byref(st), C.byref(sc), C.byref(p), sp), reps)
+      eng.upload(cloud(n))
+      tall = timed(lambda: eng.step(60.0, 6.674e-11, True, fp32), reps)
+      ops = 12.5 if fp32 else 25.0
+      print("n=%d fp32=%s jsplit=%d/%d  A %.3f ms (%.3e int/s, %.2e pipe-instr/s)  B %.3f ms  C %.3f ms  step %.3f ms  status %s"
+            % (n, fp32, p.jsplit, p.jsplit_detect, ta, n * n / ta * 1e3, n * n * ops / ta * 1e3, tb, tc, tall, eng.check_errors()))
