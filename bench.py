@@ -468,10 +468,13 @@ def main_state3d(a, n, prec, collisions, rank, world, local_rank, W, K, config):
     accel_each = np.array([ev[0].elapsed_time(ev[1]) for ev in stage_events])
     accel_ms = float(np.mean(accel_each))
     kernel_rate = float(interactions / np.sum(accel_each * 1e-3))
-    ipi = INSTR3_PER_INTERACTION[prec]
+    from cosmosim_b200 import _abi
+    sym = bool(eng.params(DT3, G, **kw).opts & _abi.OPT3_F64_SYM)
+    # the symmetric FP64 kernel evaluates each unordered pair once: 29 FP64-pipe instructions per pair
+    ipi = 14.5 if sym else INSTR3_PER_INTERACTION[prec]
     achieved = kernel_rate * ipi * 2 / 1e12
     peak = peaks.get("ffma_tflops" if prec == "fp32" else "dfma_tflops")
-    kname = "k3_accel_%s" % ("f32" if prec == "fp32" else "f64")
+    kname = "k3_accel_%s%s" % ("f32" if prec == "fp32" else "f64", "_sym" if sym else "")
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
@@ -480,6 +483,8 @@ def main_state3d(a, n, prec, collisions, rank, world, local_rank, W, K, config):
         pass
     roofline = {"bound": "fma_pipe_" + prec, "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if peak else None, "traffic": traffic,
+                "frac_vs_one_sided_convention": (kernel_rate * INSTR3_PER_INTERACTION[prec] * 2 / 1e12 / peak)
+                if peak else None,
                 "peak_source": "in-process %s micro-benchmark (cosmo_microbench) on this GPU"
                                % ("FFMA" if prec == "fp32" else "DFMA"),
                 "instr_per_interaction": ipi, "kernel_ms": accel_ms, "interactions_per_s_kernel": kernel_rate,

@@ -241,7 +241,7 @@ class Engine3D:
             self._ensure_colbuf(n)
             p.opts |= OPT3_F64_SYM
             nblk = -(-n // 512)
-            want = (nblk * nblk) // (2 * 16 * 2 * 148)
+            want = (nblk * nblk) // (2 * 64 * 2 * 148)     # >= ~64 block pairs per resident CTA slot
             p.sym_chunk = int(self.sym_chunk or min(32, max(1, -(-nblk // self.JSPLIT_MAX), want)))
             if os.environ.get("COSMO3_SYM_CHUNK"):
                 p.sym_chunk = max(int(os.environ["COSMO3_SYM_CHUNK"]), -(-nblk // self.JSPLIT_MAX))
