@@ -412,12 +412,10 @@ def main_state3d(a, n, prec, collisions, rank, world, local_rank, W, K, config):
     """Bench lines of the 3-D step (one GPU): same JSON contract as the main path."""
     from cosmosim_b200 import scenes
     config = dict(config, dt=DT3, scene="disk3d (star + thick disk, 0.1-2 AU)", api="State.interact (universe.py:94-129)")
-    if world > 1:
-        if rank == 0:
-            print(json.dumps({"error": "the 3-D step is single-GPU in this round; run with --gpus 1", "config": config}))
-        return 2
     arrays = scenes.disk3d_arrays(n, seed=0)
     if a.impl == "reference":
+        if rank != 0:
+            return 0
         leg = cpu_oracle3_leg(arrays, seconds_target=min(a.cpu_seconds, 100.0 / (K + W)), steps=K, warmup=W)
         print(json.dumps({"impl": "reference", "metric": "pairwise_interactions_per_s", "value": leg["value"],
                           "unit": "interactions/s", "n_gpus": 0, "steps": K, "warmup": W,
@@ -428,20 +426,32 @@ def main_state3d(a, n, prec, collisions, rank, world, local_rank, W, K, config):
                                   "d2h_bytes_per_step": 0}}), flush=True)
         return 0
     import torch
+    import torch.distributed as dist
     from cosmosim_b200.engine3d import Engine3D
     torch.cuda.set_device(local_rank)
-    eng = Engine3D(n, device="cuda:%d" % local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        group = dist.group.WORLD
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = Engine3D(n, device="cuda:%d" % local_rank, group=group)
     eng.sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     eng.upload(arrays)
     kw = dict(collisions=collisions, fp32=(prec == "fp32"))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    peaks = measure_pipe_peaks(eng, prec)
+    if rank == 0:
+        sampler.start()
+    peaks = measure_pipe_peaks(eng, prec) if rank == 0 else {}
     for _ in range(W):
         eng.step(DT3, G, **kw)
         flush.zero_()
-    torch.cuda.synchronize()
+    barrier()
     warm_samples = len(sampler.lines)
     stage_events = []
     status_log = torch.zeros(K + 1, 16, dtype=torch.int64).pin_memory()
@@ -454,20 +464,26 @@ def main_state3d(a, n, prec, collisions, rank, world, local_rank, W, K, config):
         flush.zero_()
     e1.record()
     gpu_launches = int(eng.lib.cosmo_launch_count() - launches0)
-    torch.cuda.synchronize()
+    barrier()
     ms = e0.elapsed_time(e1)
-    timed_samples = len(sampler.lines) - warm_samples
-    if timed_samples >= 3:
-        sampler.lines = sampler.lines[warm_samples:]
-    clocks = sampler.stop()
-    clocks["window"] = "timed region" if timed_samples >= 3 else "pipe micro-benchmark + warm-up + timed region"
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    clocks = None
+    if rank == 0:
+        timed_samples = len(sampler.lines) - warm_samples
+        if timed_samples >= 3:
+            sampler.lines = sampler.lines[warm_samples:]
+        clocks = sampler.stop()
+        clocks["window"] = "timed region" if timed_samples >= 3 else "pipe micro-benchmark + warm-up + timed region"
     st = eng.check_errors()
     n_per_step = status_log[:K, 0].numpy().astype(np.float64)
     interactions = float(np.sum(n_per_step ** 2))
     value = interactions / (ms * 1e-3)
     accel_each = np.array([ev[0].elapsed_time(ev[1]) for ev in stage_events])
     accel_ms = float(np.mean(accel_each))
-    kernel_rate = float(interactions / np.sum(accel_each * 1e-3))
+    kernel_rate = float(interactions / world / np.sum(accel_each * 1e-3))   # this GPU's share of the pairs
     from cosmosim_b200 import _abi
     sym = bool(eng.params(DT3, G, **kw).opts & _abi.OPT3_F64_SYM)
     # the symmetric FP64 kernel evaluates each unordered pair once: 29 FP64-pipe instructions per pair
@@ -488,7 +504,7 @@ def main_state3d(a, n, prec, collisions, rank, world, local_rank, W, K, config):
                 "peak_source": "in-process %s micro-benchmark (cosmo_microbench) on this GPU"
                                % ("FFMA" if prec == "fp32" else "DFMA"),
                 "instr_per_interaction": ipi, "kernel_ms": accel_ms, "interactions_per_s_kernel": kernel_rate,
-                "stage_ms": {"prep+accel_integrate": accel_ms,
+                "stage_ms": {"prep+accel_integrate" + ("+exchange" if world > 1 else ""): accel_ms,
                              "detect": float(np.mean([ev[1].elapsed_time(ev[2]) for ev in stage_events])),
                              "resolve_commit": float(np.mean([ev[2].elapsed_time(ev[3]) for ev in stage_events]))}}
     e2e = None
@@ -497,25 +513,33 @@ def main_state3d(a, n, prec, collisions, rank, world, local_rank, W, K, config):
         stg = eng.make_host_staging(arrays)
         for _ in range(2):
             eng.step_from_host(stg, DT3, G, **kw)
-        torch.cuda.synchronize()
+        barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         f0.record()
         for _ in range(K):
             eng.step_from_host(stg, DT3, G, **kw)
         f1.record()
-        torch.cuda.synchronize()
+        barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         e_ms = f0.elapsed_time(f1)
+        if world > 1:
+            tms = torch.tensor([e_ms], dtype=torch.float64, device=eng.device)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            e_ms = float(tms.item())
         e2e = {"value": float(n) * n * K / (e_ms * 1e-3), "unit": "interactions/s",
                "h2d_bytes_per_step": int(stg["h2d_bytes"]), "d2h_bytes_per_step": int(stg["d2h_bytes"]),
                "ms_per_step": e_ms / K, "wall_ms_per_step": wall_ms / K,
                "path": "Engine3D.step_from_host: pinned host SoA -> H2D -> cosmo3_step -> D2H, stream sync per step"}
     cpu = None
-    if not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_oracle3_leg(arrays, seconds_target=a.cpu_seconds)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps({"metric": "pairwise_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": 1,
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    print(json.dumps({"metric": "pairwise_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world,
                       "steps": K, "warmup": W, "ms_per_step": ms / K, "steps_per_s": K / (ms * 1e-3),
                       "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                       "dtype": "f32" if prec == "fp32" else "f64", "data": "synthetic", "config": config,

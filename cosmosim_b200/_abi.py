@@ -60,7 +60,7 @@ class StepParams(C.Structure):
 
 # include/cosmosim_b200_state3d.h
 F3_MASS_INT, F3_DENS_INT = 1, 2
-OPT3_COLLISIONS, OPT3_FP32, OPT3_STORE_ACC, OPT3_F64_SYM = 1, 4, 8, 16
+OPT3_COLLISIONS, OPT3_FP32, OPT3_STORE_ACC, OPT3_F64_SYM, OPT3_DEFER_INTEGRATE = 1, 4, 8, 16, 32
 ERR3_INT_OVERFLOW = 16
 
 
@@ -89,7 +89,8 @@ class StepParams3(C.Structure):
                 ("jsplit", C.c_int32), ("jsplit_detect", C.c_int32),
                 ("detect_mode", C.c_int32), ("grid_log_cells", C.c_int32), ("cells_per_side", C.c_int32),
                 ("sym_chunk", C.c_int32), ("cell_size", C.c_double), ("grid_origin_x", C.c_double),
-                ("grid_origin_y", C.c_double), ("giant_radius", C.c_double)]
+                ("grid_origin_y", C.c_double), ("giant_radius", C.c_double),
+                ("shard_index", C.c_int32), ("shard_count", C.c_int32)]
 
 
 _S3 = [C.POINTER(State3), C.POINTER(Scratch3), C.POINTER(StepParams3), _vp]
@@ -100,6 +101,8 @@ SYMBOLS = {
     "cosmo3_detect_pairs": (C.c_int, _S3),
     "cosmo3_resolve_commit": (C.c_int, _S3),
     "cosmo3_step": (C.c_int, _S3),
+    "cosmo3_integrate": (C.c_int, _S3),
+    "cosmo3_append_pair_rows": (C.c_int, [C.POINTER(State3), C.POINTER(Scratch3), _vp, C.c_int32, C.c_int64, _vp]),
     "cosmo3_suggest_jsplit": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int32]),
     "cosmo3_host_truediv": (C.c_double, [C.c_uint64] * 4),
     "cosmo3_host_radius": (C.c_double, [C.c_int, C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_double]),

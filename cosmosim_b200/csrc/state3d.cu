@@ -757,11 +757,7 @@ static int launch_stage_a(const cosmo3_state &st, const cosmo3_scratch &sc, cons
         return COSMO_LAUNCH_CHECK("k3_accel_f32");
     }
     if (p.opts & COSMO3_OPT_F64_SYM) {
-        if (p.i_begin != 0 || p.i_end < p.n_upper) {
-            set_error("symmetric 3-D accel needs all target rows (i_begin = 0, i_end >= n_upper)");
-            return COSMO_E_ARG;
-        }
-        return launch_accel3_sym64(st, sc, p, s);
+        return launch_accel3_sym64(st, sc, p, s);   // rows by shard_index / shard_count, not i_begin / i_end
     }
     if (p.n_upper <= SMALL_N) {
         const int per = A64S_BLOCK * A64S_IB;
@@ -796,7 +792,9 @@ static int launch_stage_b(const cosmo3_state &st, const cosmo3_scratch &sc, cons
         p2.opts = COSMO_OPT_COLLISIONS; p2.n_upper = p.n_upper; p2.i_begin = p.i_begin; p2.i_end = p.i_end;
         p2.detect_mode = 1; p2.grid_log_cells = p.grid_log_cells; p2.cells_per_side = p.cells_per_side;
         p2.cell_size = p.cell_size; p2.grid_origin_x = p.grid_origin_x; p2.grid_origin_y = p.grid_origin_y;
-        p2.giant_radius = p.giant_radius; p2.shard_index = 0; p2.shard_count = 1;
+        p2.giant_radius = p.giant_radius;
+        p2.shard_index = p.shard_count > 0 ? p.shard_index : 0;
+        p2.shard_count = p.shard_count > 0 ? p.shard_count : 1;
         return launch_detect_grid(s2, c2, p2, s, true);
     }
     if (rows <= 0) return COSMO_OK;
@@ -865,6 +863,24 @@ int cosmo3_resolve_commit(const cosmo3_state *st, const cosmo3_scratch *sc, cons
                           void *stream) {
     COSMO_TRY(check_args3(st, sc, p));
     return launch_stage_c(*st, *sc, *p, (cudaStream_t)stream);
+}
+
+int cosmo3_integrate(const cosmo3_state *st, const cosmo3_scratch *sc, const cosmo3_step_params *p, void *stream) {
+    COSMO_TRY(check_args3(st, sc, p));
+    return launch_integrate3(*st, *sc, *p, (cudaStream_t)stream);
+}
+
+int cosmo3_append_pair_rows(const cosmo3_state *st, const cosmo3_scratch *sc, const int64_t *rows, int32_t n_rows,
+                            int64_t max_count, void *stream) {
+    if (!st || !sc || !rows || n_rows < 0 || max_count < 0) {
+        set_error("bad argument (cosmo3_append_pair_rows)");
+        return COSMO_E_ARG;
+    }
+    cosmo_state s2 = {};
+    cosmo_scratch c2 = {};
+    s2.cap = st->cap; s2.status = st->status;
+    c2.pairs = sc->pairs; c2.pair_cap = sc->pair_cap;
+    return launch_append_pair_rows(s2, c2, rows, n_rows, (long long)max_count, (cudaStream_t)stream);
 }
 
 int cosmo3_step(const cosmo3_state *st, const cosmo3_scratch *sc, const cosmo3_step_params *p, void *stream) {

@@ -102,7 +102,7 @@ __device__ __forceinline__ void round3_sym(const double *__restrict__ gp, int la
 }
 
 __global__ void __launch_bounds__(T_THREADS, 2)
-k3_accel_f64_sym(cosmo3_state st, cosmo3_scratch sc, int chunk) {
+k3_accel_f64_sym(cosmo3_state st, cosmo3_scratch sc, int shard_index, int shard_count, int chunk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_p = reinterpret_cast<double *>(smem_raw);          // [2][5][T_BLOCK]
     double *s_c = s_p + 2 * 5 * T_BLOCK;                         // [3][T_BLOCK]
@@ -110,7 +110,7 @@ k3_accel_f64_sym(cosmo3_state st, cosmo3_scratch sc, int chunk) {
 
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int nblk = (n + T_BLOCK - 1) / T_BLOCK;
-    const int I = blockIdx.x;
+    const int I = shard_index + blockIdx.x * shard_count;   // row blocks dealt round-robin to the ranks
     if (I >= nblk) return;
     const int J0 = I + blockIdx.y * chunk;
     if (J0 >= nblk) return;
@@ -217,7 +217,8 @@ k3_accel_f64_sym(cosmo3_state st, cosmo3_scratch sc, int chunk) {
 // row partials of the object's own row block (in chunk order) + column partials of every row block
 // above it (in block order): a fixed summation order, independent of scheduling
 __global__ void __launch_bounds__(256)
-k3_sym64_reduce(cosmo3_state st, cosmo3_scratch sc, int chunk, double G, double dt, int store_acc) {
+k3_sym64_reduce(cosmo3_state st, cosmo3_scratch sc, int shard_index, int shard_count, int chunk, double G, double dt,
+                int store_acc, int defer) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -225,14 +226,38 @@ k3_sym64_reduce(cosmo3_state st, cosmo3_scratch sc, int chunk, double G, double 
     const int nblk = (n + T_BLOCK - 1) / T_BLOCK;
     const int K = k / T_BLOCK;
     double a[3] = {0.0, 0.0, 0.0};
-    const int nchunk = (nblk - K + chunk - 1) / chunk;
-    for (int c = 0; c < nchunk; ++c)
+    if (K % shard_count == shard_index) {
+        const int nchunk = (nblk - K + chunk - 1) / chunk;
+        for (int c = 0; c < nchunk; ++c)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) a[d] += sc.partial[((size_t)c * 3 + d) * cap + k];
-    for (int I = 0; I < K; ++I)
+            for (int d = 0; d < 3; ++d) a[d] += sc.partial[((size_t)c * 3 + d) * cap + k];
+    }
+    int r = 0;
+    for (int I = shard_index; I < K; I += shard_count, ++r)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) a[d] += __ldcs(&sc.colbuf[((size_t)I * 3 + d) * cap + k]);
-    integrate_store3(st, sc, k, a[0], a[1], a[2], G, dt, store_acc != 0);
+        for (int d = 0; d < 3; ++d) a[d] += __ldcs(&sc.colbuf[((size_t)r * 3 + d) * cap + k]);
+    if (defer) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) sc.acc[d * cap + k] = a[d];
+    } else {
+        integrate_store3(st, sc, k, a[0], a[1], a[2], G, dt, store_acc != 0);
+    }
+}
+
+// multi-GPU: every rank integrates all rows from the all-reduced sums (identical on every rank)
+__global__ void __launch_bounds__(256) k3_integrate_all(cosmo3_state st, cosmo3_scratch sc, double G, double dt,
+                                                        int store_acc) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t cap = (size_t)st.cap;
+    integrate_store3(st, sc, k, sc.acc[k], sc.acc[cap + k], sc.acc[2 * cap + k], G, dt, store_acc != 0);
+}
+
+int launch_integrate3(const cosmo3_state &st, const cosmo3_scratch &sc, const cosmo3_step_params &p, cudaStream_t s) {
+    if (p.n_upper <= 0) return COSMO_OK;
+    k3_integrate_all<<<(p.n_upper + 255) / 256, 256, 0, s>>>(st, sc, p.G, p.dt, (p.opts & COSMO3_OPT_STORE_ACC) ? 1 : 0);
+    return COSMO_LAUNCH_CHECK("k3_integrate_all");
 }
 
 int launch_accel3_sym64(const cosmo3_state &st, const cosmo3_scratch &sc, const cosmo3_step_params &p,
@@ -242,8 +267,11 @@ int launch_accel3_sym64(const cosmo3_state &st, const cosmo3_scratch &sc, const 
     const int nblk = (n + T_BLOCK - 1) / T_BLOCK;
     int chunk = p.sym_chunk > 0 ? p.sym_chunk : 4;
     while ((nblk + chunk - 1) / chunk > sc.jsplit_max) ++chunk;
-    if (!sc.colbuf || (long long)nblk > sc.colbuf_rows) {
-        set_error("symmetric 3-D accel: colbuf has %lld rows, %d needed", (long long)sc.colbuf_rows, nblk);
+    const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
+    const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
+    const int rows_local = (nblk - sh_i + sh_n - 1) / sh_n;
+    if (!sc.colbuf || (long long)rows_local > sc.colbuf_rows) {
+        set_error("symmetric 3-D accel: colbuf has %lld rows, %d needed", (long long)sc.colbuf_rows, rows_local);
         return COSMO_E_ARG;
     }
     static bool configured = false;
@@ -252,10 +280,14 @@ int launch_accel3_sym64(const cosmo3_state &st, const cosmo3_scratch &sc, const 
                                                   (int)T_SMEM), "cudaFuncSetAttribute(k3_accel_f64_sym)"));
         configured = true;
     }
-    dim3 grid(nblk, (nblk + chunk - 1) / chunk);
-    k3_accel_f64_sym<<<grid, T_THREADS, T_SMEM, s>>>(st, sc, chunk);
-    COSMO_TRY(COSMO_LAUNCH_CHECK("k3_accel_f64_sym"));
-    k3_sym64_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, chunk, p.G, p.dt, (p.opts & COSMO3_OPT_STORE_ACC) ? 1 : 0);
+    if (rows_local > 0) {
+        dim3 grid(rows_local, (nblk + chunk - 1) / chunk);
+        k3_accel_f64_sym<<<grid, T_THREADS, T_SMEM, s>>>(st, sc, sh_i, sh_n, chunk);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k3_accel_f64_sym"));
+    }
+    k3_sym64_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, p.G, p.dt,
+                                                    (p.opts & COSMO3_OPT_STORE_ACC) ? 1 : 0,
+                                                    (p.opts & COSMO3_OPT_DEFER_INTEGRATE) ? 1 : 0);
     return COSMO_LAUNCH_CHECK("k3_sym64_reduce");
 }
 

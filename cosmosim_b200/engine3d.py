@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from ._abi import (ERR3_INT_OVERFLOW, F3_DENS_INT, F3_MASS_INT, OPT3_COLLISIONS, OPT3_F64_SYM, OPT3_FP32, OPT3_STORE_ACC, PAD,
+from ._abi import (ERR3_INT_OVERFLOW, F3_DENS_INT, F3_MASS_INT, OPT3_COLLISIONS, OPT3_DEFER_INTEGRATE, OPT3_F64_SYM, OPT3_FP32, OPT3_STORE_ACC, PAD,
                    ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_EVENTS, ST_N_PAIRS, ST_STEP, STATUS_LEN)
 from .engine import _round_up, split_mass, tune_grid
 
@@ -33,7 +33,7 @@ def split_density(density):
 class Engine3D:
     JSPLIT_MAX = 128
 
-    def __init__(self, n_total, device=None, pair_cap=None, event_cap=None):
+    def __init__(self, n_total, device=None, pair_cap=None, event_cap=None, group=None):
         if not torch.cuda.is_available():
             raise _abi.CosmoError("cosmosim_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = _abi.lib()
@@ -43,6 +43,13 @@ class Engine3D:
             _abi.check(self.lib.cosmo_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), "cosmo_device_info")
         self.n_total = int(n_total)
         self.cap = max(PAD, _round_up(self.n_total, PAD))
+        self.group = group
+        self.rank, self.world = 0, 1
+        if group is not None:
+            import torch.distributed as dist
+            from . import sharded
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+            self.cap = sharded.required_capacity(self.n_total, self.world)
         self.pair_cap = int(pair_cap or max(1 << 16, 4 * self.cap))
         self.event_cap = int(event_cap or max(1 << 16, 4 * self.n_total))
         self._alloc()
@@ -223,7 +230,7 @@ class Engine3D:
     def _ensure_colbuf(self, n):
         """Column-partial buffer of the symmetric kernel: three planes of `cap` doubles per 512-object
         row block (24 B x N^2 / 512: 201 MB at N = 65536, 3.2 GB at 262144)."""
-        rows = -(-n // 512)
+        rows = -(-(-(-n // 512)) // self.world)          # row blocks are dealt round-robin to the ranks
         if self._colbuf is None or self._colbuf.shape[0] < rows:
             self._colbuf = torch.empty(rows, 3, self.cap, dtype=torch.float64, device=self.device)
             self.sc.colbuf = C.c_void_p(self._colbuf.data_ptr())
@@ -234,14 +241,20 @@ class Engine3D:
         p = _abi.StepParams3()
         p.G, p.dt = float(G), float(dt)
         p.opts = (OPT3_COLLISIONS if collisions else 0) | (OPT3_FP32 if fp32 else 0) | (OPT3_STORE_ACC if store_acc else 0)
-        whole = int(i_begin) == 0 and (i_end is None or int(i_end) >= n)
+        if self.world > 1:
+            from . import sharded
+            i_begin, i_end, _ = sharded.shard_rows(n, self.world, self.rank)
+            p.shard_index, p.shard_count = self.rank, self.world
+        else:
+            p.shard_index, p.shard_count = 0, 1
+        whole = self.world > 1 or (int(i_begin) == 0 and (i_end is None or int(i_end) >= n))
         if sym is None:
             sym = n >= self.sym64_threshold
         if sym and not fp32 and whole and n > 512:
             self._ensure_colbuf(n)
-            p.opts |= OPT3_F64_SYM
+            p.opts |= OPT3_F64_SYM | (OPT3_DEFER_INTEGRATE if self.world > 1 else 0)
             nblk = -(-n // 512)
-            want = (nblk * nblk) // (2 * 64 * 2 * 148)     # >= ~64 block pairs per resident CTA slot
+            want = (nblk * nblk) // (2 * 64 * 2 * 148 * self.world)     # >= ~64 block pairs per resident CTA slot
             p.sym_chunk = int(self.sym_chunk or min(32, max(1, -(-nblk // self.JSPLIT_MAX), want)))
             if os.environ.get("COSMO3_SYM_CHUNK"):
                 p.sym_chunk = max(int(os.environ["COSMO3_SYM_CHUNK"]), -(-nblk // self.JSPLIT_MAX))
@@ -275,12 +288,16 @@ class Engine3D:
         L, st, sc = self.lib, self.st, self.sc
         with torch.cuda.device(self.device):
             for _ in range(int(steps)):
-                self._refresh_n_upper()
-                if collisions and self.grid is not None and self._since_tune >= self.retune_every:
-                    self.retune()
+                if self.world == 1:
+                    self._refresh_n_upper()
+                if self._since_tune >= self.retune_every and ((collisions and self.grid is not None) or self.world > 1):
+                    self.retune()       # sharded: every rank refreshes n_upper at the same step (identical state)
                 self._since_tune += 1
                 p = self.params(dt, G, collisions, fp32, store_acc, sym=sym)
-                if stage_events is None:
+                if self.world > 1:
+                    from . import sharded
+                    sharded.frame3d(self, p, sp, stage_events)
+                elif stage_events is None:
                     _abi.check(L.cosmo3_step(C.byref(st), C.byref(sc), C.byref(p), sp), "cosmo3_step")
                 else:
                     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]

@@ -148,3 +148,42 @@ def frame(eng, p, stream, stage_events=None):
     if ev:
         ev[4].record()
         stage_events.append(ev)
+
+
+def frame3d(eng, p, stream, stage_events=None):
+    """One State.interact on Engine3D `eng`, rows sharded over the ranks (params p hold this rank's
+    shard).  Same protocol as `frame`: stage A on the shard -> all-gather of the seven new planes (or,
+    with the symmetric kernel, all-reduce of the partial sums + replicated integrate) -> stage B on
+    the shard -> all-gather of the pair lists -> replicated stage C."""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if stage_events is not None else None
+    if ev:
+        ev[0].record()
+    lib = eng.lib
+    st, sc, pp = C.byref(eng.st), C.byref(eng.sc), C.byref(p)
+    n = p.n_upper
+    _, _, per = shard_rows(n, eng.world, eng.rank)
+    _abi.check(lib.cosmo3_accel_integrate(st, sc, pp, stream), "cosmo3_accel_integrate")
+    if p.opts & _abi.OPT3_DEFER_INTEGRATE:
+        dist.all_reduce(eng.t["acc"], op=dist.ReduceOp.SUM, group=eng.group)
+        _abi.check(lib.cosmo3_integrate(st, sc, pp, stream), "cosmo3_integrate")
+    else:
+        planes = [(eng.t[k][d], 1) for k in ("pos_new", "vel_new") for d in range(3)] + [(eng.t["xx_new"], 1)]
+        gather_planes(planes, per, eng.rank, eng.world, eng.group)
+    if ev:
+        ev[1].record()
+    if p.opts & _abi.OPT3_COLLISIONS:
+        _abi.check(lib.cosmo3_detect_pairs(st, sc, pp, stream), "cosmo3_detect_pairs")
+        status = eng.t["status"]
+        if not hasattr(eng, "_xchg"):
+            xcap = min(eng.pair_cap // eng.world, max(1 << 16, eng.cap // eng.world))
+            eng._xchg = torch.zeros(eng.world, 1 + max(1024, xcap), dtype=torch.int64, device=eng.device)
+        xchg = exchange_pairs(eng.t["pairs"], status[ST_N_PAIRS], eng._xchg, eng.rank, eng.world, eng.group)
+        status[ST_N_PAIRS] = 0
+        _abi.check(lib.cosmo3_append_pair_rows(st, sc, C.c_void_p(xchg.data_ptr()), eng.world, xchg.shape[1] - 1,
+                                               stream), "cosmo3_append_pair_rows")
+    if ev:
+        ev[2].record()
+    _abi.check(lib.cosmo3_resolve_commit(st, sc, pp, stream), "cosmo3_resolve_commit")
+    if ev:
+        ev[3].record()
+        stage_events.append(ev)

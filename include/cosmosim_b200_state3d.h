@@ -42,7 +42,10 @@ extern "C" {
 #define COSMO3_OPT_COLLISIONS 1u /* State.interact(collisions=True) */
 #define COSMO3_OPT_FP32 4u       /* FP32 fast path for the all-pairs sum (state stays FP64) */
 #define COSMO3_OPT_STORE_ACC 8u  /* also write the accelerations to scratch.acc */
-#define COSMO3_OPT_F64_SYM 16u   /* FP64 path: symmetric kernel (each unordered pair once); needs colbuf, all rows */
+#define COSMO3_OPT_F64_SYM 16u   /* FP64 path: symmetric kernel (each unordered pair once); needs colbuf; row
+                                    blocks are dealt round-robin to shard_count ranks */
+#define COSMO3_OPT_DEFER_INTEGRATE 32u /* symmetric kernel, multi-GPU: leave this rank's partial sums in
+                                          scratch.acc (to be all-reduced), integrate with cosmo3_integrate */
 
 #define COSMO3_ERR_INT_OVERFLOW 16 /* an integer mass x density product exceeded 128 bits (status ERROR bit) */
 
@@ -127,6 +130,8 @@ typedef struct cosmo3_step_params {
     double grid_origin_x;
     double grid_origin_y;
     double giant_radius;
+    int32_t shard_index;   /* this rank / number of ranks sharing the step (0 / 1 if single): the grid broad */
+    int32_t shard_count;   /* phase and the symmetric kernel deal their chunks / row blocks round-robin      */
 } cosmo3_step_params;
 
 /* Stage A: per-step preparation + all-pairs acceleration (FP64: the reference's rounding sequence
@@ -143,6 +148,13 @@ int cosmo3_detect_pairs(const cosmo3_state *st, const cosmo3_scratch *sc, const 
    removal of the absorbed objects, State.iteration += 1. */
 int cosmo3_resolve_commit(const cosmo3_state *st, const cosmo3_scratch *sc, const cosmo3_step_params *p,
                           void *stream);
+/* Multi-GPU symmetric path: integrates ALL rows from the all-reduced sums in scratch.acc
+   (see COSMO3_OPT_DEFER_INTEGRATE). */
+int cosmo3_integrate(const cosmo3_state *st, const cosmo3_scratch *sc, const cosmo3_step_params *p, void *stream);
+/* Appends `n_rows` pair lists laid out as rows of (count | pairs[max_count]) int64 words -- the
+   all-gathered exchange buffer of the multi-GPU step -- to scratch.pairs in one launch. */
+int cosmo3_append_pair_rows(const cosmo3_state *st, const cosmo3_scratch *sc, const int64_t *rows, int32_t n_rows,
+                            int64_t max_count, void *stream);
 /* A + B + C on one device. */
 int cosmo3_step(const cosmo3_state *st, const cosmo3_scratch *sc, const cosmo3_step_params *p, void *stream);
 /* Suggested source-range split; kernel: 0 FP64 accel, 1 FP32 accel, 2 detection. */

@@ -90,3 +90,65 @@ def test_two_rank_exchange_equals_unsharded_oracle():
     pairs = orc.flags(p_ref, arr["radius"])
     ref = np.sort((pairs[:, 0] << 32 | pairs[:, 1]).astype(np.int64))
     assert len(ref) > 10 and np.array_equal(merged, ref)     # same flagged set on every rank
+
+
+# ---------------------------------------------------------------------------------------------
+# 3-D step (cosmosim_b200.sharded.frame3d): seven planes of width 1 instead of three interleaved ones
+# ---------------------------------------------------------------------------------------------
+def _worker3d(rank, world, port, n, out_q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cosmosim_b200 import scenes, sharded
+        from oracle import oracle3d as o3
+        arr = scenes.disk3d_arrays(n, seed=4, r_in=0.1, r_out=0.2, density=10.0)
+        G, dt = 6.674e-11, 600.0
+        b, e, per = sharded.shard_rows(n, world, rank)
+        cap = sharded.required_capacity(n, world)
+        acc = o3.accel(arr["pos"], arr["mass_f64"], G, b, e)
+        p_loc, v_loc = o3.integrate(arr["pos"][b:e], arr["vel"][b:e], acc, dt)
+        pos_new, vel_new = torch.zeros(3, cap, dtype=torch.float64), torch.zeros(3, cap, dtype=torch.float64)
+        xx_new = torch.zeros(cap, dtype=torch.float64)
+        pos_new[:, b:e] = torch.from_numpy(np.ascontiguousarray(p_loc.T))
+        vel_new[:, b:e] = torch.from_numpy(np.ascontiguousarray(v_loc.T))
+        xx_new[b:e] = torch.from_numpy((p_loc[:, 0] ** 2 + p_loc[:, 2] ** 2) + p_loc[:, 1] ** 2)
+        planes = [(t[d], 1) for t in (pos_new, vel_new) for d in range(3)] + [(xx_new, 1)]
+        sharded.gather_planes(planes, per, rank, world)
+        p_all = np.ascontiguousarray(pos_new[:, :n].numpy().T)
+        pairs = o3.flags(p_all, arr["radius"], b, e)
+        keys = torch.from_numpy((pairs[:, 0] << 32 | pairs[:, 1]).astype(np.int64))
+        xcap = 1 << 14
+        local = torch.zeros(xcap, dtype=torch.int64)
+        local[: len(keys)] = keys
+        xchg = torch.zeros(world, 1 + xcap, dtype=torch.int64)
+        sharded.exchange_pairs(local, torch.tensor(len(keys)), xchg, rank, world)
+        merged = torch.cat([xchg[r, 1:1 + int(xchg[r, 0])] for r in range(world)]).numpy()
+        if rank == 0:
+            out_q.put((p_all.copy(), np.sort(merged)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_exchange_equals_unsharded_oracle_3d():
+    from cosmosim_b200 import scenes
+    from oracle import oracle3d as o3
+    n, world = 1500, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker3d, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    p_all, merged = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    arr = scenes.disk3d_arrays(n, seed=4, r_in=0.1, r_out=0.2, density=10.0)
+    acc = o3.accel(arr["pos"], arr["mass_f64"], 6.674e-11)
+    p_ref, _ = o3.integrate(arr["pos"], arr["vel"], acc, 600.0)
+    assert np.array_equal(p_all, p_ref)
+    pairs = o3.flags(p_ref, arr["radius"])
+    ref = np.sort((pairs[:, 0] << 32 | pairs[:, 1]).astype(np.int64))
+    assert len(ref) > 10 and np.array_equal(merged, ref)
