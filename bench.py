@@ -485,9 +485,9 @@ def main_state3d(a, n, prec, collisions, rank, world, local_rank, W, K, config):
     accel_ms = float(np.mean(accel_each))
     kernel_rate = float(interactions / world / np.sum(accel_each * 1e-3))   # this GPU's share of the pairs
     from cosmosim_b200 import _abi
-    sym = bool(eng.params(DT3, G, **kw).opts & _abi.OPT3_F64_SYM)
-    # the symmetric FP64 kernel evaluates each unordered pair once: 29 FP64-pipe instructions per pair
-    ipi = 14.5 if sym else INSTR3_PER_INTERACTION[prec]
+    sym = bool(eng.params(DT3, G, **kw).opts & (_abi.OPT3_F64_SYM | _abi.OPT3_F32_SYM))
+    # the symmetric kernels evaluate each unordered pair once: 29 FP64-pipe / 16 FMA-pipe instructions per pair
+    ipi = ({"fp32": 8.0, "fp64": 14.5}[prec]) if sym else INSTR3_PER_INTERACTION[prec]
     achieved = kernel_rate * ipi * 2 / 1e12
     peak = peaks.get("ffma_tflops" if prec == "fp32" else "dfma_tflops")
     kname = "k3_accel_%s%s" % ("f32" if prec == "fp32" else "f64", "_sym" if sym else "")

@@ -60,7 +60,7 @@ class StepParams(C.Structure):
 
 # include/cosmosim_b200_state3d.h
 F3_MASS_INT, F3_DENS_INT = 1, 2
-OPT3_COLLISIONS, OPT3_FP32, OPT3_STORE_ACC, OPT3_F64_SYM, OPT3_DEFER_INTEGRATE = 1, 4, 8, 16, 32
+OPT3_COLLISIONS, OPT3_FP32, OPT3_STORE_ACC, OPT3_F64_SYM, OPT3_DEFER_INTEGRATE, OPT3_F32_SYM = 1, 4, 8, 16, 32, 64
 ERR3_INT_OVERFLOW = 16
 
 

@@ -748,6 +748,7 @@ static int launch_stage_a(const cosmo3_state &st, const cosmo3_scratch &sc, cons
     int jsplit = p.jsplit < 1 ? 1 : p.jsplit;
     if (jsplit > sc.jsplit_max) jsplit = sc.jsplit_max;
     const int store_acc = (p.opts & COSMO3_OPT_STORE_ACC) ? 1 : 0;
+    if (f32 && (p.opts & COSMO3_OPT_F32_SYM)) return launch_accel3_sym32(st, sc, p, s);
     if (f32) {
         const int per = A32_BLOCK * A32_IB;
         dim3 grid((rows + per - 1) / per, jsplit);

@@ -43,6 +43,8 @@ __device__ __forceinline__ void integrate_store3(const cosmo3_state &st, const c
 
 // symmetric FP64 flavour (state3d_sym.cu)
 int launch_integrate3(const cosmo3_state &st, const cosmo3_scratch &sc, const cosmo3_step_params &p, cudaStream_t s);
+int launch_accel3_sym32(const cosmo3_state &st, const cosmo3_scratch &sc, const cosmo3_step_params &p,
+                        cudaStream_t s);
 int launch_accel3_sym64(const cosmo3_state &st, const cosmo3_scratch &sc, const cosmo3_step_params &p,
                         cudaStream_t s);
 

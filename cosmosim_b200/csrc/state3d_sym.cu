@@ -291,5 +291,239 @@ int launch_accel3_sym64(const cosmo3_state &st, const cosmo3_scratch &sc, const 
     return COSMO_LAUNCH_CHECK("k3_sym64_reduce");
 }
 
+
+// ---------------------------------------------------------------------------------------
+// FP32 fast flavour, SYMMETRIC: direct differences on packed f32x2, every unordered pair once --
+// 16 packed FMA-pipe instructions per two pairs = 8 per ORDERED interaction (scalar-equivalent)
+// and half a MUFU.RSQ instead of 12 and 1.  Decomposition of accel_sym.cu: 1024-object blocks,
+// 8 warps, 4 row objects per lane, column chunks of 4 rotating through the warp (12 SHFL per step).
+// Column sums in float planes of `colbuf`, row sums folded into FP64 once per column block.
+// ---------------------------------------------------------------------------------------
+constexpr int U_BLOCK = 1024;
+constexpr int U_GROUP = 128;
+constexpr int U_WARPS = 8;
+constexpr int U_THREADS = U_WARPS * 32;
+// dynamic shared memory: 2 stages x 4 planes (x, y, z, m) + 3 planes of column sums (floats) + 2 mbarriers
+constexpr size_t U_SMEM = (size_t)(2 * 4 + 3) * U_BLOCK * sizeof(float) + 2 * sizeof(uint64_t);
+#define COSMO3_F32_TINY_SYM 8.673617379884035e-19f /* 2^-60 softening (scaled units), see state3d.cu */
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src_lane) {
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    lo = __shfl_sync(0xffffffffu, lo, src_lane);
+    hi = __shfl_sync(0xffffffffu, hi, src_lane);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(U_THREADS, 2)
+k3_accel_f32_sym(cosmo3_state st, cosmo3_scratch sc, int shard_index, int shard_count, int chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_p = reinterpret_cast<float *>(smem_raw);            // [2][4][U_BLOCK]
+    float *s_c = s_p + 2 * 4 * U_BLOCK;                          // [3][U_BLOCK]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_c + 3 * U_BLOCK);
+
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int nblk = (n + U_BLOCK - 1) / U_BLOCK;
+    const int I = shard_index + blockIdx.x * shard_count;
+    if (I >= nblk) return;
+    const int J0 = I + blockIdx.y * chunk;
+    if (J0 >= nblk) return;
+    const int J1 = min(nblk, J0 + chunk);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const size_t cap = (size_t)st.cap;
+
+    float xi[4], yi[4], zi[4], nmi[4];
+    double ra[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = I * U_BLOCK + w * U_GROUP + k * 32 + lane;   // slots past n: zero mass (k3_prep)
+        xi[k] = sc.pk[r];
+        yi[k] = sc.pk[cap + r];
+        zi[k] = sc.pk[2 * cap + r];
+        nmi[k] = -sc.pk[3 * cap + r];
+        ra[k][0] = 0.0; ra[k][1] = 0.0; ra[k][2] = 0.0;
+    }
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    constexpr uint32_t kBytes = U_BLOCK * 4 * sizeof(float);
+    auto issue = [&](int J, int b) {
+        const size_t j0 = (size_t)J * U_BLOCK;
+        float *dst = s_p + (size_t)b * 4 * U_BLOCK;
+        fence_proxy_async();
+        mbar_expect_tx(&s_bar[b], kBytes);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) bulk_g2s(dst + d * U_BLOCK, sc.pk + d * cap + j0, U_BLOCK * sizeof(float), &s_bar[b]);
+    };
+    if (tid == 0) issue(J0, 0);
+    const uint64_t eps2 = pack2(COSMO3_F32_TINY_SYM, COSMO3_F32_TINY_SYM);
+    float *colrow = reinterpret_cast<float *>(sc.colbuf) + (size_t)blockIdx.x * 3 * cap;
+
+    for (int J = J0; J < J1; ++J) {
+        const int it_j = J - J0;
+        const int b = it_j & 1;
+        if (tid == 0 && J + 1 < J1) issue(J + 1, b ^ 1);
+        for (int q = tid; q < 3 * U_BLOCK; q += U_THREADS) s_c[q] = 0.f;
+        mbar_wait(&s_bar[b], (it_j >> 1) & 1);
+        __syncthreads();
+        const float *stage = s_p + (size_t)b * 4 * U_BLOCK;
+        const bool diag = (J == I);
+        uint64_t rx2[4], ry2[4], rz2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { rx2[k] = 0ull; ry2[k] = 0ull; rz2[k] = 0ull; }
+
+        for (int it = 0; it < U_WARPS; ++it) {
+            const int g = (w + it) & (U_WARPS - 1);
+            const float *gp = stage + g * U_GROUP;
+            uint64_t tx2[2] = {0ull, 0ull}, ty2[2] = {0ull, 0ull}, tz2[2] = {0ull, 0ull};
+#pragma unroll 1
+            for (int s = 0; s < 32; ++s) {
+                const int c = (lane + s) & 31;
+                const float4 X = *reinterpret_cast<const float4 *>(gp + 4 * c);
+                const float4 Y = *reinterpret_cast<const float4 *>(gp + U_BLOCK + 4 * c);
+                const float4 Z = *reinterpret_cast<const float4 *>(gp + 2 * U_BLOCK + 4 * c);
+                const float4 M = *reinterpret_cast<const float4 *>(gp + 3 * U_BLOCK + 4 * c);
+                const uint64_t xj2[2] = {pack2(X.x, X.y), pack2(X.z, X.w)};
+                const uint64_t yj2[2] = {pack2(Y.x, Y.y), pack2(Y.z, Y.w)};
+                const uint64_t zj2[2] = {pack2(Z.x, Z.y), pack2(Z.z, Z.w)};
+                const uint64_t mj2[2] = {pack2(M.x, M.y), pack2(M.z, M.w)};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t xik = pack2(xi[k], xi[k]), yik = pack2(yi[k], yi[k]), zik = pack2(zi[k], zi[k]);
+                    const uint64_t nmik = pack2(nmi[k], nmi[k]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint64_t dx = sub2(xj2[h], xik);
+                        const uint64_t dy = sub2(yj2[h], yik);
+                        const uint64_t dz = sub2(zj2[h], zik);
+                        const uint64_t r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, eps2)));
+                        float r2a, r2b;
+                        unpack2(r2, r2a, r2b);
+                        const uint64_t rinv = pack2(rsqrt_approx_f32(r2a), rsqrt_approx_f32(r2b));
+                        const uint64_t rinv3 = mul2(mul2(rinv, rinv), rinv);
+                        const uint64_t sj = mul2(mj2[h], rinv3);
+                        const uint64_t nsi = mul2(rinv3, nmik);
+                        rx2[k] = fma2(dx, sj, rx2[k]);
+                        ry2[k] = fma2(dy, sj, ry2[k]);
+                        rz2[k] = fma2(dz, sj, rz2[k]);
+                        tx2[h] = fma2(dx, nsi, tx2[h]);
+                        ty2[h] = fma2(dy, nsi, ty2[h]);
+                        tz2[h] = fma2(dz, nsi, tz2[h]);
+                    }
+                }
+                const int src = (lane + 1) & 31;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tx2[h] = shfl_u64(tx2[h], src);
+                    ty2[h] = shfl_u64(ty2[h], src);
+                    tz2[h] = shfl_u64(tz2[h], src);
+                }
+            }
+            if (!diag) {   // home again: lane l holds the sums of chunk l of group g
+                const uint64_t *t2[3] = {tx2, ty2, tz2};
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float a0, a1, a2, a3;
+                    unpack2(t2[d][0], a0, a1);
+                    unpack2(t2[d][1], a2, a3);
+                    float4 *cell = reinterpret_cast<float4 *>(&s_c[d * U_BLOCK + g * U_GROUP + 4 * lane]);
+                    float4 v = *cell;
+                    v.x += a0; v.y += a1; v.z += a2; v.w += a3;
+                    *cell = v;
+                }
+            }
+            __syncthreads();   // the next round moves every warp to another column group
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // fold this block's FP32 row sums into the FP64 accumulators
+            float u, v;
+            unpack2(rx2[k], u, v); ra[k][0] += (double)u + (double)v;
+            unpack2(ry2[k], u, v); ra[k][1] += (double)u + (double)v;
+            unpack2(rz2[k], u, v); ra[k][2] += (double)u + (double)v;
+        }
+        if (!diag) {
+            for (int q = tid; q < 3 * U_BLOCK; q += U_THREADS) {
+                const int d = q / U_BLOCK, o = q - d * U_BLOCK;
+                colrow[d * cap + (size_t)J * U_BLOCK + o] = s_c[q];
+            }
+        }
+        __syncthreads();   // column accumulators and buffer b are free again
+    }
+    double *part = sc.partial + (size_t)blockIdx.y * 3 * cap;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = I * U_BLOCK + w * U_GROUP + k * 32 + lane;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) part[d * cap + r] = ra[k][d];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k3_sym32_reduce(cosmo3_state st, cosmo3_scratch sc, int shard_index, int shard_count, int chunk, double unscale,
+                double G, double dt, int store_acc, int defer) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t cap = (size_t)st.cap;
+    const int nblk = (n + U_BLOCK - 1) / U_BLOCK;
+    const int K = k / U_BLOCK;
+    double a[3] = {0.0, 0.0, 0.0};
+    if (K % shard_count == shard_index) {
+        const int nchunk = (nblk - K + chunk - 1) / chunk;
+        for (int c = 0; c < nchunk; ++c)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) a[d] += sc.partial[((size_t)c * 3 + d) * cap + k];
+    }
+    const float *colbuf = reinterpret_cast<const float *>(sc.colbuf);
+    int r = 0;
+    for (int I = shard_index; I < K; I += shard_count, ++r)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a[d] += (double)__ldcs(&colbuf[((size_t)r * 3 + d) * cap + k]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) a[d] *= unscale;
+    if (defer) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) sc.acc[d * cap + k] = a[d];
+    } else {
+        integrate_store3(st, sc, k, a[0], a[1], a[2], G, dt, store_acc != 0);
+    }
+}
+
+int launch_accel3_sym32(const cosmo3_state &st, const cosmo3_scratch &sc, const cosmo3_step_params &p,
+                        cudaStream_t s) {
+    const int n = p.n_upper;
+    if (n <= 0) return COSMO_OK;
+    const int nblk = (n + U_BLOCK - 1) / U_BLOCK;
+    const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
+    const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
+    const int rows_local = (nblk - sh_i + sh_n - 1) / sh_n;
+    int chunk = p.sym_chunk > 0 ? p.sym_chunk : 4;
+    while ((nblk + chunk - 1) / chunk > sc.jsplit_max) ++chunk;
+    // colbuf rows are counted in units of three planes of `cap` DOUBLES; a float row takes half of one
+    if (!sc.colbuf || (long long)(rows_local + 1) / 2 > sc.colbuf_rows) {
+        set_error("symmetric 3-D FP32 accel: colbuf has %lld rows, %d needed", (long long)sc.colbuf_rows,
+                  (rows_local + 1) / 2);
+        return COSMO_E_ARG;
+    }
+    static bool configured = false;
+    if (!configured) {
+        COSMO_TRY(check_cuda(cudaFuncSetAttribute(k3_accel_f32_sym, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)U_SMEM), "cudaFuncSetAttribute(k3_accel_f32_sym)"));
+        configured = true;
+    }
+    if (rows_local > 0) {
+        dim3 grid(rows_local, (nblk + chunk - 1) / chunk);
+        k3_accel_f32_sym<<<grid, U_THREADS, U_SMEM, s>>>(st, sc, sh_i, sh_n, chunk);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k3_accel_f32_sym"));
+    }
+    const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
+    k3_sym32_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, unscale, p.G, p.dt,
+                                                    (p.opts & COSMO3_OPT_STORE_ACC) ? 1 : 0,
+                                                    (p.opts & COSMO3_OPT_DEFER_INTEGRATE) ? 1 : 0);
+    return COSMO_LAUNCH_CHECK("k3_sym32_reduce");
+}
+
 }  // namespace s3
 }  // namespace cosmo

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from ._abi import (ERR3_INT_OVERFLOW, F3_DENS_INT, F3_MASS_INT, OPT3_COLLISIONS, OPT3_DEFER_INTEGRATE, OPT3_F64_SYM, OPT3_FP32, OPT3_STORE_ACC, PAD,
+from ._abi import (ERR3_INT_OVERFLOW, F3_DENS_INT, F3_MASS_INT, OPT3_COLLISIONS, OPT3_DEFER_INTEGRATE, OPT3_F32_SYM, OPT3_F64_SYM, OPT3_FP32, OPT3_STORE_ACC, PAD,
                    ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_EVENTS, ST_N_PAIRS, ST_STEP, STATUS_LEN)
 from .engine import _round_up, split_mass, tune_grid
 
@@ -66,6 +66,7 @@ class Engine3D:
         self.retune_every = 16       # steps between host-side refreshes of the grid tuning
         self._since_tune = 0
         self.sym64_threshold = 16384 # FP64: from here on the symmetric kernel (each pair once) wins
+        self.sym32_threshold = 32768 # FP32: same for the symmetric FP32 kernel
         self.sym_chunk = 0           # column blocks per CTA of the symmetric kernel (0 = automatic)
         self._colbuf = None
 
@@ -249,11 +250,11 @@ class Engine3D:
             p.shard_index, p.shard_count = 0, 1
         whole = self.world > 1 or (int(i_begin) == 0 and (i_end is None or int(i_end) >= n))
         if sym is None:
-            sym = n >= self.sym64_threshold
-        if sym and not fp32 and whole and n > 512:
+            sym = n >= (self.sym32_threshold if fp32 else self.sym64_threshold)
+        if sym and whole and n > (1024 if fp32 else 512):
             self._ensure_colbuf(n)
-            p.opts |= OPT3_F64_SYM | (OPT3_DEFER_INTEGRATE if self.world > 1 else 0)
-            nblk = -(-n // 512)
+            p.opts |= (OPT3_F32_SYM if fp32 else OPT3_F64_SYM) | (OPT3_DEFER_INTEGRATE if self.world > 1 else 0)
+            nblk = -(-n // (1024 if fp32 else 512))
             want = (nblk * nblk) // (2 * 64 * 2 * 148 * self.world)     # >= ~64 block pairs per resident CTA slot
             p.sym_chunk = int(self.sym_chunk or min(32, max(1, -(-nblk // self.JSPLIT_MAX), want)))
             if os.environ.get("COSMO3_SYM_CHUNK"):

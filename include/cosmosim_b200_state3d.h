@@ -44,6 +44,7 @@ extern "C" {
 #define COSMO3_OPT_STORE_ACC 8u  /* also write the accelerations to scratch.acc */
 #define COSMO3_OPT_F64_SYM 16u   /* FP64 path: symmetric kernel (each unordered pair once); needs colbuf; row
                                     blocks are dealt round-robin to shard_count ranks */
+#define COSMO3_OPT_F32_SYM 64u   /* FP32 path: symmetric kernel, same requirements as COSMO3_OPT_F64_SYM */
 #define COSMO3_OPT_DEFER_INTEGRATE 32u /* symmetric kernel, multi-GPU: leave this rank's partial sums in
                                           scratch.acc (to be all-reduced), integrate with cosmo3_integrate */
 
@@ -105,7 +106,7 @@ typedef struct cosmo3_scratch {
     int32_t giant_cap;
     /* column partial sums of the symmetric kernel: [colbuf_rows][3][cap], one row per 512-object row block */
     double *colbuf;
-    int64_t colbuf_rows;   /* >= ceil(n / 512) */
+    int64_t colbuf_rows;   /* FP64: >= ceil(ceil(n / 512) / ranks); FP32 (1024-object blocks, float planes): a quarter of that */
 } cosmo3_scratch;
 
 typedef struct cosmo3_step_params {

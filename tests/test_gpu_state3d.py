@@ -233,14 +233,16 @@ def test_grid_broad_phase_equals_all_pairs(mods, thick):
     assert np.array_equal(ta["flag_pairs"], want)
 
 
-def test_fp32_flavour_accuracy(mods):
+@pytest.mark.parametrize("sym", [False, True])
+def test_fp32_flavour_accuracy(mods, sym):
     """FP32 all-pairs sum against the FP64 oracle: direct differences after an exact power-of-two
     rescaling, so the error is the FP32 rounding of the pair terms: median < 1e-5, 99 % < 1e-4,
     max < 1e-2 of |a| (rows with a near neighbour carry the largest relative error)."""
     engine3d, o3, _ = mods
     n = 8192
     snap = synthetic_cloud(n, 3)
-    eng, out = step_once(engine3d, snap, 60.0, 6.674e-11, collisions=False, fp32=True)
+    eng, out = step_once(engine3d, snap, 60.0, 6.674e-11, collisions=False, fp32=True, sym=sym)
+    assert bool(eng.params(60.0, 6.674e-11, False, True, sym=sym).opts & _abi_bits(mods).OPT3_F32_SYM) == sym
     want = o3.accel(snap["pos"], snap["mass_f64"], 6.674e-11)
     err = relerr_rows(out["acc"], want)
     assert np.median(err) < 1e-5 and np.quantile(err, 0.99) < 1e-4 and err.max() < 1e-2

@@ -32,7 +32,8 @@ def main():
     DT, G = 600.0, 6.674e-11
     ok = True
     # (n, fp32, symmetric kernel): one-sided gather path, all-pairs and grid detection, symmetric all-reduce path
-    for n, fp32, sym in ((3000, False, False), (20000, False, False), (20000, False, True), (40000, True, False)):
+    for n, fp32, sym in ((3000, False, False), (20000, False, False), (20000, False, True), (40000, True, False),
+                         (40000, True, True)):
         arr = crowded(n, 3)
         single = Engine3D(n, device="cuda:%d" % local)
         shard = Engine3D(n, device="cuda:%d" % local, group=dist.group.WORLD)
