@@ -8,7 +8,7 @@ timeout 600 $RUN tools/sharded3d_check.py --steps 3 > gpurun_out/sharded3d_check
 grep -E "sharded==single|mismatch|ALL OK|FAILED|Error|error" gpurun_out/sharded3d_check_$NG.log | tail -20
 for w in state3d_64k_fp64 state3d_256k_fp32; do
   timeout 600 $RUN bench.py --gpus $NG --workload $w --no-cpu-baseline > gpurun_out/bench_${w}_${NG}gpu.json 2> gpurun_out/bench_${w}_${NG}gpu.err; echo "$w rc=$?"
-  tail -c 1500 gpurun_out/bench_${w}_${NG}gpu.json | python -c "
+  tail -n 1 gpurun_out/bench_${w}_${NG}gpu.json | python -c "
 import sys,json
 try:
     d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
