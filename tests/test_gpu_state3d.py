@@ -280,3 +280,70 @@ def test_host_api_run_and_pickles(mods, tmp_path):
     last = [s for s in states if s.iteration == 5][0]
     assert np.array_equal(last.positions(), mem[-1].positions())
     assert b"ccosmosim.core.universe\nState\n" in open(os.path.join(out, "0.dat"), "rb").read()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 63, 64, 65, 1023, 1024, 1025, 2049])
+def test_ragged_sizes_against_oracle(mods, n):
+    """Object counts around the tile / padding boundaries (incl. a lone object): one crowded step must
+    equal the oracle's (pairs, absorb stream, survivors)."""
+    engine3d, o3, _ = mods
+    snap = synthetic_cloud(max(n, 2), 100 + n, thick=0.3)
+    snap = {k: v[:n].copy() for k, v in snap.items()}
+    snap["pos"] *= 1e-3 * max(1.0, n / 64.0) ** (1.0 / 3.0)   # constant density: radii ~1e7 m, plenty of contacts
+    snap["vel"] *= 0.0
+    snap["mass_f64"][:] = np.random.default_rng(n).uniform(0.1, 100.0, n) * 5.972e24
+    orc = o3.OracleState(snap, dt=10.0)
+    want = orc.interact(True, record=True, cap=1 << 18)
+    eng, out = step_once(engine3d, snap, 10.0, 6.674e-11)
+    assert np.array_equal(out["flag_pairs"], want["flag_pairs"])
+    assert np.array_equal(eng.events()[:, 1:].reshape(-1, 3), want["events"].reshape(-1, 3))
+    d, post = eng.download(), orc.snapshot()
+    assert d["status"]["n_active"] == orc.n and d["status"]["iteration"] == 1
+    assert np.array_equal(d["id"], post["id"]) and np.array_equal(d["mass"], post["mass_f64"])
+    if n > 1:
+        assert relerr_rows(out["acc"], want["acc"]).max() < 1e-11
+        assert np.abs(d["pos"] - post["pos"]).max() <= 1e-12 * np.abs(post["pos"]).max()
+    else:
+        assert np.array_equal(out["acc"], np.zeros((1, 3))) and np.array_equal(d["pos"], post["pos"])
+
+
+def test_empty_state_and_collisions_off(mods):
+    engine3d, o3, _ = mods
+    eng = engine3d.Engine3D(0)
+    snap = synthetic_cloud(2, 1)
+    empty = {k: v[:0] for k, v in snap.items()}
+    eng.upload(engine3d_arrays_from_snapshot(empty))
+    eng.step(60.0, 6.674e-11, steps=3)
+    st = eng.check_errors()
+    assert st["n_active"] == 0 and st["iteration"] == 3 and st["n_events"] == 0
+    # collisions=False: overlapping objects pass through each other (universe.py:106,115)
+    snap = synthetic_cloud(500, 2)
+    snap["pos"] *= 1e-4
+    eng, out = step_once(engine3d, snap, 1.0, 6.674e-11, collisions=False)
+    st = eng.check_errors()
+    assert st["n_active"] == 500 and st["n_events"] == 0 and st["n_pairs"] == 0
+
+
+def test_overflow_is_reported_not_silent(mods):
+    """More flagged pairs than the pair buffer holds: the step must raise, never drop pairs silently."""
+    engine3d, o3, abi = mods
+    n = 600
+    snap = synthetic_cloud(n, 5)
+    snap["pos"] *= 1e-6                       # everything overlaps everything: n (n - 1) flagged pairs
+    snap["vel"] *= 0.0
+    dt = 1e-6                                 # (the pull of the 1 M_sun object at 1e5 m would scatter them in 1 s)
+    arr = engine3d_arrays_from_snapshot(snap)
+    eng = engine3d.Engine3D(n, pair_cap=1024)
+    eng.upload(arr)
+    eng.step(dt, 6.674e-11)
+    with pytest.raises(abi.CosmoError, match="pair buffer overflow"):
+        eng.check_errors()
+    # with room for all pairs the same scene collapses into the heaviest row objects, like the oracle
+    eng = engine3d.Engine3D(n, pair_cap=n * n)
+    eng.upload(arr)
+    eng.step(dt, 6.674e-11)
+    orc = o3.OracleState(snap, dt=dt)
+    want = orc.interact(True, cap=1 << 20)
+    assert want["n_pairs"] == n * (n - 1)
+    assert eng.check_errors()["n_active"] == orc.n
+    assert np.array_equal(eng.events()[:, 1:], want["events"])
