@@ -572,8 +572,7 @@ __global__ void __launch_bounds__(256) k3_sort_pairs(cosmo3_state st, cosmo3_scr
 // absorbed something); an object j > i not yet visited still holds its OLD position; a destroyed
 // object holds mass 0.0 and zero vectors -- and is absorbed again by any row that still flags it,
 // because the reference tests only `obj.mass >= other.mass`.
-__global__ void k3_resolve(cosmo3_state st, cosmo3_scratch sc) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ void resolve_loop(const cosmo3_state &st, const cosmo3_scratch &sc) {
     long long M = st.status[COSMO_ST_N_PAIRS];
     if (M > sc.pair_cap) M = sc.pair_cap;
     if (M == 0) return;
@@ -647,6 +646,11 @@ __global__ void k3_resolve(cosmo3_state st, cosmo3_scratch sc) {
     if (ovf) st.status[COSMO_ST_ERROR] |= COSMO3_ERR_INT_OVERFLOW;
 }
 
+__global__ void k3_resolve(cosmo3_state st, cosmo3_scratch sc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    resolve_loop(st, sc);
+}
+
 // obj.velocity = v[i]; obj.position = p[i] (universe.py:113-114) for every object that still exists,
 // or the merged values of an absorber; marks the survivors for the compaction.
 __global__ void __launch_bounds__(256) k3_commit(cosmo3_state st, cosmo3_scratch sc) {
@@ -714,6 +718,108 @@ __global__ void k3_end_step(cosmo3_state st) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Stage C for small scenes (n_upper <= TAIL_N) in ONE launch of ONE CTA: rank sort of the pairs,
+// the sequential absorb loop, commit, stable compaction and the step counter.  At the size of the
+// reference's example scenes a step is launch-bound; this replaces nine launches.
+// ---------------------------------------------------------------------------------------
+constexpr int TAIL_N = 4096;
+constexpr int TAIL_THREADS = 1024;
+constexpr int TAIL_PER = TAIL_N / TAIL_THREADS;
+
+__global__ void __launch_bounds__(TAIL_THREADS) k3_tail_small(cosmo3_state st, cosmo3_scratch sc, int collisions) {
+    __shared__ uint64_t s_keys[TAIL_THREADS];
+    __shared__ int s_warp[TAIL_THREADS / 32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x;
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int stamp = (int)st.status[COSMO_ST_STEP];
+    const size_t cap = (size_t)st.cap;
+    if (collisions) {
+        long long M = st.status[COSMO_ST_N_PAIRS];
+        if (M > sc.pair_cap) M = sc.pair_cap;
+        // rank sort (keys are unique): row-major order of the reference's double loop
+        for (long long k0 = 0; k0 < M; k0 += TAIL_THREADS) {
+            const long long k = k0 + tid;
+            const uint64_t key = k < M ? sc.pairs[k] : ~0ull;
+            long long rank = 0;
+            for (long long b0 = 0; b0 < M; b0 += TAIL_THREADS) {
+                __syncthreads();
+                s_keys[tid] = b0 + tid < M ? sc.pairs[b0 + tid] : ~0ull;
+                __syncthreads();
+                const int lim = (int)min((long long)TAIL_THREADS, M - b0);
+                for (int q = 0; q < lim; ++q) rank += s_keys[q] < key;
+            }
+            if (k < M) sc.pairs_sorted[rank] = key;
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (tid == 0 && M > 0) resolve_loop(st, sc);
+        __threadfence_block();
+        __syncthreads();
+    }
+    // commit + gather of the survivors into registers (TAIL_PER consecutive slots per thread)
+    double pv[TAIL_PER][6], ms[TAIL_PER], dn[TAIL_PER], rd[TAIL_PER];
+    uint64_t mh[TAIL_PER], ml[TAIL_PER];
+    int idv[TAIL_PER];
+    uint8_t fl[TAIL_PER];
+    int live[TAIL_PER], mine = 0;
+#pragma unroll
+    for (int q = 0; q < TAIL_PER; ++q) {
+        const int k = tid * TAIL_PER + q;
+        live[q] = (k < n && sc.exists[k]) ? 1 : 0;
+        if (live[q]) {
+            const bool t = sc.touched[k] == stamp;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                pv[q][d] = t ? sc.cur_pos[d * cap + k] : sc.pos_new[d * cap + k];
+                pv[q][3 + d] = t ? sc.cur_vel[d * cap + k] : sc.vel_new[d * cap + k];
+            }
+            ms[q] = st.mass[k]; mh[q] = st.mass_hi[k]; ml[q] = st.mass_lo[k];
+            dn[q] = st.density[k]; rd[q] = st.radius[k]; idv[q] = st.id[k]; fl[q] = st.flags[k];
+        }
+        mine += live[q];
+    }
+    // block-wide exclusive scan of `mine`
+    const int lane = tid & 31, w = tid >> 5;
+    int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int v = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        s_warp[lane] = v;
+        if (lane == 31) s_total = v;
+    }
+    __syncthreads();   // every source slot has been read into registers above: in-place scatter is safe
+    int dst = incl - mine + (w ? s_warp[w - 1] : 0);
+#pragma unroll
+    for (int q = 0; q < TAIL_PER; ++q) {
+        if (!live[q]) continue;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            st.pos[d * cap + dst] = pv[q][d];
+            st.vel[d * cap + dst] = pv[q][3 + d];
+        }
+        st.mass[dst] = ms[q]; st.mass_hi[dst] = mh[q]; st.mass_lo[dst] = ml[q];
+        st.density[dst] = dn[q]; st.radius[dst] = rd[q]; st.id[dst] = idv[q]; st.flags[dst] = fl[q];
+        ++dst;
+    }
+    if (tid == 0) {
+        st.status[COSMO_ST_N_DEAD] = n - s_total;
+        st.status[COSMO_ST_N_ACTIVE] = s_total;
+        st.status[COSMO_ST_STEP] += 1;  // State.iteration += 1 (universe.py:129)
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
@@ -721,6 +827,7 @@ constexpr int A64_BLOCK = 128, A64_IB = 2, A64_TJ = 256;
 constexpr int A64S_BLOCK = 64, A64S_IB = 1, A64S_TJ = 64;   // small-N shape
 constexpr int A32_BLOCK = 256, A32_IB = 4, A32_TJ = 512;
 constexpr int DET_BLOCK = 128, DET_IB = 2, DET_TJ = 256;
+constexpr int DETS_BLOCK = 64, DETS_IB = 1, DETS_TJ = 64;   // small-N shape
 constexpr int SMALL_N = 8192;
 static_assert(COSMO_PAD % A64_TJ == 0 && COSMO_PAD % A32_TJ == 0 && COSMO_PAD % DET_TJ == 0, "tiles must divide the padding");
 
@@ -800,6 +907,12 @@ static int launch_stage_b(const cosmo3_state &st, const cosmo3_scratch &sc, cons
     }
     if (rows <= 0) return COSMO_OK;
     int jsplit = p.jsplit_detect < 1 ? 1 : p.jsplit_detect;
+    if (p.n_upper <= SMALL_N) {   // many short CTAs: at this size the pass is latency-bound
+        const int per = DETS_BLOCK * DETS_IB;
+        dim3 grid((rows + per - 1) / per, jsplit);
+        k3_detect<DETS_BLOCK, DETS_IB, DETS_TJ><<<grid, DETS_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit);
+        return COSMO_LAUNCH_CHECK("k3_detect(small)");
+    }
     const int per = DET_BLOCK * DET_IB;
     dim3 grid((rows + per - 1) / per, jsplit);
     k3_detect<DET_BLOCK, DET_IB, DET_TJ><<<grid, DET_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit);
@@ -808,6 +921,10 @@ static int launch_stage_b(const cosmo3_state &st, const cosmo3_scratch &sc, cons
 
 static int launch_stage_c(const cosmo3_state &st, const cosmo3_scratch &sc, const cosmo3_step_params &p,
                           cudaStream_t s) {
+    if (p.n_upper <= TAIL_N) {
+        k3_tail_small<<<1, TAIL_THREADS, 0, s>>>(st, sc, (p.opts & COSMO3_OPT_COLLISIONS) ? 1 : 0);
+        return COSMO_LAUNCH_CHECK("k3_tail_small");
+    }
     int blocks = (p.n_upper + 255) / 256;
     blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
     if (p.opts & COSMO3_OPT_COLLISIONS) {
@@ -906,6 +1023,8 @@ int cosmo3_suggest_jsplit(int32_t rows, int32_t n, int kernel, int32_t jsplit_ma
     if (kernel == 1) {
         per = A32_BLOCK * A32_IB; tile = A32_TJ; res = residency(k3_accel_f32<A32_BLOCK, A32_IB, A32_TJ>, A32_BLOCK);
         if (res <= 0) res = 3;
+    } else if (kernel == 2 && n <= SMALL_N) {
+        per = DETS_BLOCK * DETS_IB; tile = DETS_TJ; res = 16;
     } else if (kernel == 2) {
         per = DET_BLOCK * DET_IB; tile = DET_TJ; res = residency(k3_detect<DET_BLOCK, DET_IB, DET_TJ>, DET_BLOCK);
         if (res <= 0) res = 6;

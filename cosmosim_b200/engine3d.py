@@ -53,8 +53,13 @@ class Engine3D:
         self.pair_cap = int(pair_cap or max(1 << 16, 4 * self.cap))
         self.event_cap = int(event_cap or max(1 << 16, 4 * self.n_total))
         self._alloc()
+        # last completed step's status block, refreshed by an async D2H copy after every step: the
+        # object count only shrinks, so a slightly stale value is a safe, tight upper bound
         self._status_host = torch.zeros(STATUS_LEN, dtype=torch.int64).pin_memory()
-        self._status_event = None
+        self._epoch = 0              # step counter at the last upload (guards against stale snapshots)
+        self.use_graphs = True       # small N: replay a captured CUDA graph of the step (launch-bound regime)
+        self.graph_threshold = 16384
+        self._graphs = {}
         self.n_upper = 0
         self.pos_exp = 0
         self.mass_exp = 0
@@ -152,7 +157,8 @@ class Engine3D:
         self.n_upper = n
         self.steps = int(iteration)
         torch.cuda.current_stream(self.device).synchronize()
-        self._status_event = None
+        self._status_host.copy_(status)
+        self._epoch = int(iteration)
         pos = np.asarray(arrays["pos"], dtype=np.float64)
         mass = np.asarray(arrays["mass_f64"], dtype=np.float64)
         pmax = float(np.max(np.abs(pos))) if pos.size else 1.0
@@ -276,10 +282,39 @@ class Engine3D:
             p.cell_size, p.grid_origin_x, p.grid_origin_y, p.cells_per_side, p.giant_radius = self.grid
         return p
 
-    def _refresh_n_upper(self):
-        ev = self._status_event
-        if ev is not None and ev.query():
-            self.n_upper = min(self.n_upper, int(self._status_host[ST_N_ACTIVE]))
+    def _refresh_n_upper(self, margin=1.0):
+        """Non-blocking refresh of the launch bound from the newest COMPLETED step's snapshot."""
+        seen_n, seen_s = int(self._status_host[ST_N_ACTIVE]), int(self._status_host[ST_STEP])
+        if self._epoch <= seen_s <= self.steps and 0 < seen_n < margin * self.n_upper:
+            self.n_upper = seen_n
+
+    def _step_graphed(self, steps, dt, G, collisions, fp32, sym):
+        """Launch-bound regime (a step is ~13 kernels of a few microseconds): capture cosmo3_step + the
+        status snapshot once into a CUDA graph and replay it.  The kernels read the object count from
+        the device, so a graph stays valid while objects merge; it is re-captured when the launch
+        bound has shrunk by more than 10 %."""
+        done = 0
+        while done < steps:
+            self._refresh_n_upper(0.9)
+            p = self.params(dt, G, collisions, fp32, False, sym=sym)
+            key = bytes(memoryview(p))
+            g = self._graphs.get(key)
+            if g is None:
+                if len(self._graphs) > 16:
+                    self._graphs.clear()
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    sp = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                    _abi.check(self.lib.cosmo3_step(C.byref(self.st), C.byref(self.sc), C.byref(p), sp),
+                               "cosmo3_step (graph capture)")
+                    self._status_host.copy_(self.t["status"], non_blocking=True)
+                self._graphs[key] = g
+            burst = min(steps - done, 64)
+            for _ in range(burst):
+                g.replay()
+            done += burst
+            self.steps += burst
 
     def step(self, dt, G, collisions=True, fp32=False, store_acc=False, steps=1, stage_events=None, sym=None):
         """`steps` x State.interact on this device; asynchronous (no host sync).  stage_events: a list
@@ -288,6 +323,9 @@ class Engine3D:
         sp = C.c_void_p(stream.cuda_stream)
         L, st, sc = self.lib, self.st, self.sc
         with torch.cuda.device(self.device):
+            if (self.use_graphs and self.world == 1 and stage_events is None and not store_acc and int(steps) >= 8
+                    and self.n_upper <= self.graph_threshold and self.grid is None):
+                return self._step_graphed(int(steps), dt, G, collisions, fp32, sym)
             for _ in range(int(steps)):
                 if self.world == 1:
                     self._refresh_n_upper()
@@ -312,8 +350,6 @@ class Engine3D:
                     stage_events.append(ev)
                 self.steps += 1
                 self._status_host.copy_(self.t["status"], non_blocking=True)
-                self._status_event = torch.cuda.Event()
-                self._status_event.record(stream)
 
 
     # ------------------------------------------------------------------ host-buffer path (e2e)
@@ -352,7 +388,7 @@ class Engine3D:
         stg["status_in"][ST_STEP] = self.steps
         t["status"].copy_(stg["status_in"], non_blocking=True)
         self.n_upper = n
-        self._status_event = None
+        self._epoch = self.steps + 1      # ignore status snapshots of earlier steps
         self.step(dt, G, **kw)
         for k in self.E2E_OUT:
             src = t[k][:, :n] if k in ("pos", "vel") else t[k][:n]

@@ -122,21 +122,30 @@ def test_kept_steps_match_reference(mods, name, grid):
         assert np.all(np.abs(d["radius"] - r_want) <= np.spacing(r_want))
 
 
-@pytest.mark.parametrize("name", ["disk_planar", "disk_thick"])
-def test_free_run_absorb_stream(mods, name):
+@pytest.mark.parametrize("name,graphed", [("disk_planar", False), ("disk_thick", False), ("disk_planar", True),
+                                          ("disk_thick", True)])
+def test_free_run_absorb_stream(mods, name, graphed):
+    """graphed: all steps in one call, i.e. through the CUDA-graph replay used for small N."""
     engine3d, o3, _ = mods
     g = load_golden("state3d_%s.npz" % name)
     init = snap3_from(g, "init_")
     arr = engine3d_arrays_from_snapshot(init)
     eng = engine3d.Engine3D(len(arr["mass_f64"]))
     eng.upload(arr)
-    counts = []
-    for s in range(int(g["steps"])):
-        eng.step(float(g["dt"]), float(g["G"]))
-        counts.append(eng.status()["n_active"])
+    if graphed:
+        eng.step(float(g["dt"]), float(g["G"]), steps=int(g["steps"]))
+        assert len(eng._graphs) >= 1
+        counts = [eng.status()["n_active"]]
+        assert counts[0] == g["n_objects"][-1]
+    else:
+        counts = []
+        for s in range(int(g["steps"])):
+            eng.step(float(g["dt"]), float(g["G"]))
+            counts.append(eng.status()["n_active"])
+        assert np.array_equal(np.array(counts), g["n_objects"])
     eng.check_errors()
+    assert eng.status()["iteration"] == int(g["steps"])
     assert np.array_equal(eng.events(), g["events"])
-    assert np.array_equal(np.array(counts), g["n_objects"])
     d, want = eng.download(), snap3_from(g, "final_")
     assert np.array_equal(d["id"], want["id"])
     assert np.array_equal(d["flags"] & 1, want["mass_is_int"].astype(np.uint8))

@@ -48,6 +48,10 @@ if __name__ == "__main__":
       tc = timed(lambda: L.cosmo3_resolve_commit(C.byref(st), C.byref(sc), C.byref(p), sp), reps)
       eng.upload(cloud(n))
       tall = timed(lambda: eng.step(60.0, 6.674e-11, True, fp32), reps)
+      if n <= 16384:
+          eng.step(60.0, 6.674e-11, True, fp32, steps=64)      # captures the graph
+          tg = timed(lambda: eng.step(60.0, 6.674e-11, True, fp32, steps=64), 4) / 64
+          print("n=%d graph replay: %.4f ms per step" % (n, tg))
       ops = (8.0 if n >= 32768 else 12.0) if fp32 else (14.5 if n >= 16384 else 25.0)
       print("n=%d fp32=%s jsplit=%d/%d  A %.3f ms (%.3e int/s, %.2e pipe-instr/s)  B %.3f ms  C %.3f ms  step %.3f ms  status %s"
             % (n, fp32, p.jsplit, p.jsplit_detect, ta, n * n / ta * 1e3, n * n * ops / ta * 1e3, tb, tc, tall, eng.check_errors()))
