@@ -101,8 +101,9 @@ class State:
     """universe.py:73-133.  `precision`: "fp64" reproduces the reference's arithmetic; "fp32" is the
     fast all-pairs flavour (state and integrator stay FP64)."""
 
-    def __init__(self, objects, dt=1, G=_G, iteration=0, precision="fp64", device=None):
+    def __init__(self, objects, dt=1, G=_G, iteration=0, precision="fp64", device=None, group=None):
         self._objects = objects
+        self.group = group           # torch.distributed process group: rows sharded over its ranks
         self.dt = dt
         self.G = G
         self._iteration = iteration
@@ -153,7 +154,7 @@ class State:
                 o._cosmo_index = self._next_index
                 self._next_index += 1
         if self._engine is None or self._engine.cap < len(objs):
-            self._engine = engine3d.Engine3D(len(objs), device=self.device)
+            self._engine = engine3d.Engine3D(len(objs), device=self.device, group=self.group)
         self._engine.upload(engine3d.arrays_from_objects(objs), iteration=self._iteration)
         self._uploaded = list(objs)
         self._events_seen = self._engine.status()["n_events"]
@@ -235,7 +236,7 @@ class State:
 
     def __deepcopy__(self, memo):
         return State(copy.deepcopy(self._host_objects(), memo), dt=self.dt, G=self.G, iteration=self._iteration,
-                     precision=self.precision, device=self.device)
+                     precision=self.precision, device=self.device, group=self.group)
 
     def save(self, f):
         """universe.py:131-132: one pickle of the State appended to the open file."""
