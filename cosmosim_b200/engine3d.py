@@ -234,10 +234,13 @@ class Engine3D:
         return out
 
     # ------------------------------------------------------------------ stepping
-    def _ensure_colbuf(self, n):
-        """Column-partial buffer of the symmetric kernel: three planes of `cap` doubles per 512-object
-        row block (24 B x N^2 / 512: 201 MB at N = 65536, 3.2 GB at 262144)."""
-        rows = -(-(-(-n // 512)) // self.world)          # row blocks are dealt round-robin to the ranks
+    def _ensure_colbuf(self, n, fp32=False):
+        """Column-partial buffer of the symmetric kernels.  FP64: three planes of `cap` doubles per
+        512-object row block (24 B x N^2 / 512: 201 MB at N = 65536); FP32: three planes of floats per
+        1024-object row block (12 B x N^2 / 1024: 0.8 GB at N = 262144).  Rows are counted in units of
+        three planes of doubles (a float row takes half of one)."""
+        rows_local = -(-(-(-n // (1024 if fp32 else 512))) // self.world)   # row blocks are dealt round-robin to the ranks
+        rows = -(-rows_local // 2) if fp32 else rows_local
         if self._colbuf is None or self._colbuf.shape[0] < rows:
             self._colbuf = torch.empty(rows, 3, self.cap, dtype=torch.float64, device=self.device)
             self.sc.colbuf = C.c_void_p(self._colbuf.data_ptr())
@@ -258,7 +261,7 @@ class Engine3D:
         if sym is None:
             sym = n >= (self.sym32_threshold if fp32 else self.sym64_threshold)
         if sym and whole and n > (1024 if fp32 else 512):
-            self._ensure_colbuf(n)
+            self._ensure_colbuf(n, fp32)
             p.opts |= (OPT3_F32_SYM if fp32 else OPT3_F64_SYM) | (OPT3_DEFER_INTEGRATE if self.world > 1 else 0)
             nblk = -(-n // (1024 if fp32 else 512))
             want = (nblk * nblk) // (2 * 64 * 2 * 148 * self.world)     # >= ~64 block pairs per resident CTA slot
