@@ -202,8 +202,7 @@ __device__ bool replay_pair(const cosmo_state &st, const cosmo_scratch &sc, int 
 }
 
 // resolve_mode 0: one thread walks the rank-sorted pair list (few pairs, few launches)
-__global__ void k_resolve(cosmo_state st, cosmo_scratch sc) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+__device__ void resolve_sequential(const cosmo_state &st, const cosmo_scratch &sc) {
     long long M = st.status[COSMO_ST_N_PAIRS];
     if (M > sc.pair_cap) M = sc.pair_cap;
     if (M == 0) return;
@@ -224,6 +223,11 @@ __global__ void k_resolve(cosmo_state st, cosmo_scratch sc) {
     }
     st.status[COSMO_ST_N_EVENTS] = nev;
     st.status[COSMO_ST_N_COMPLEX] = M;
+}
+
+__global__ void k_resolve(cosmo_state st, cosmo_scratch sc) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    resolve_sequential(st, sc);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -591,6 +595,135 @@ __global__ void k_end_frame(cosmo_state st) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Stage C for small scenes (n_upper <= TAIL_N, resolve_mode 0) in ONE launch of ONE CTA: rank sort
+// of the pairs, the sequential replay, commit (universe_old.py:199-201,349-350), stable compaction
+// held in registers, frame counter.  At the size of the reference's example scenes a frame is
+// launch-bound; this replaces six launches.
+// ---------------------------------------------------------------------------------------
+constexpr int TAIL_N = 2048;
+constexpr int TAIL_THREADS = 1024;
+constexpr int TAIL_PER = TAIL_N / TAIL_THREADS;
+
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail_small(cosmo_state st, cosmo_scratch sc, int collisions,
+                                                             int bounded) {
+    __shared__ uint64_t s_keys[TAIL_THREADS];
+    __shared__ int s_warp[TAIL_THREADS / 32];
+    __shared__ int s_esc[TAIL_THREADS / 32];
+    __shared__ int s_total, s_escaped;
+    const int tid = threadIdx.x;
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int stamp = (int)st.status[COSMO_ST_STEP];
+    if (collisions) {
+        long long M = st.status[COSMO_ST_N_PAIRS];
+        if (M > sc.pair_cap) M = sc.pair_cap;
+        for (long long k0 = 0; k0 < M; k0 += TAIL_THREADS) {   // rank sort of the unique keys
+            const long long k = k0 + tid;
+            const uint64_t key = k < M ? sc.pairs[k] : ~0ull;
+            long long rank = 0;
+            for (long long b0 = 0; b0 < M; b0 += TAIL_THREADS) {
+                __syncthreads();
+                s_keys[tid] = b0 + tid < M ? sc.pairs[b0 + tid] : ~0ull;
+                __syncthreads();
+                const int lim = (int)min((long long)TAIL_THREADS, M - b0);
+                for (int q = 0; q < lim; ++q) rank += s_keys[q] < key;
+            }
+            if (k < M) sc.pairs_sorted[rank] = key;
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (tid == 0) resolve_sequential(st, sc);
+        __threadfence_block();
+        __syncthreads();
+    }
+    // commit (k_commit) + gather of the survivors into registers: TAIL_PER consecutive slots per thread
+    double2 ps[TAIL_PER], vs[TAIL_PER];
+    double ms[TAIL_PER], rd[TAIL_PER], vo[TAIL_PER], en[TAIL_PER];
+    uint64_t mh[TAIL_PER], ml[TAIL_PER];
+    long long ea[TAIL_PER];
+    int idv[TAIL_PER];
+    uint8_t flv[TAIL_PER];
+    int live[TAIL_PER], mine = 0, esc_mine = 0;
+#pragma unroll
+    for (int q = 0; q < TAIL_PER; ++q) {
+        const int k = tid * TAIL_PER + q;
+        live[q] = 0;
+        if (k >= n) continue;
+        const bool alive = sc.alive[k] != 0;
+        const uint8_t fl = st.flags[k];
+        const bool esc = bounded && sc.escaped[k];   // flagged BEFORE interact, universe_old.py:345-350
+        if (alive && esc) ++esc_mine;
+        if (alive && !esc) {
+            live[q] = 1;
+            if (!(fl & COSMO_F_IMMOBILE)) {
+                const bool use_cur = sc.mod_step[k] == stamp && sc.mod_row[k] >= k;
+                ps[q] = use_cur ? reinterpret_cast<const double2 *>(sc.cur_pos)[k]
+                                : reinterpret_cast<const double2 *>(sc.pos_new)[k];
+                vs[q] = use_cur ? reinterpret_cast<const double2 *>(sc.cur_vel)[k]
+                                : reinterpret_cast<const double2 *>(sc.vel_new)[k];
+            } else {
+                ps[q] = reinterpret_cast<const double2 *>(st.pos)[k];
+                vs[q] = reinterpret_cast<const double2 *>(st.vel)[k];
+            }
+            ms[q] = st.mass[k]; mh[q] = st.mass_hi[k]; ml[q] = st.mass_lo[k];
+            rd[q] = st.radius[k]; vo[q] = st.volume[k]; ea[q] = st.eaten[k]; idv[q] = st.id[k]; flv[q] = fl;
+            en[q] = st.energy ? st.energy[k] : 0.0;
+        } else {
+            const int id = st.id[k];                 // Planet keeps mass / radius after destroy()
+            st.rec_mass[id] = st.mass[k];
+            st.rec_mass_hi[id] = st.mass_hi[k];
+            st.rec_mass_lo[id] = st.mass_lo[k];
+            st.rec_radius[id] = st.radius[k];
+            st.rec_volume[id] = st.volume[k];
+            st.rec_eaten[id] = st.eaten[k];
+            st.rec_flags[id] = fl;
+            st.rec_death[id] = stamp;
+        }
+        mine += live[q];
+    }
+    // block-wide exclusive scan of `mine`, block sum of the escape count
+    const int lane = tid & 31, w = tid >> 5;
+    int incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int esc_warp = __reduce_add_sync(0xffffffffu, esc_mine);
+    if (lane == 31) s_warp[w] = incl;
+    if (lane == 0) s_esc[w] = esc_warp;
+    __syncthreads();
+    if (w == 0) {
+        int v = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        s_warp[lane] = v;
+        const int e = __reduce_add_sync(0xffffffffu, s_esc[lane]);
+        if (lane == 31) { s_total = v; s_escaped = e; }
+    }
+    __syncthreads();   // every source slot has been read into registers above: the in-place scatter is safe
+    int dst = incl - mine + (w ? s_warp[w - 1] : 0);
+#pragma unroll
+    for (int q = 0; q < TAIL_PER; ++q) {
+        if (!live[q]) continue;
+        reinterpret_cast<double2 *>(st.pos)[dst] = ps[q];
+        reinterpret_cast<double2 *>(st.vel)[dst] = vs[q];
+        st.mass[dst] = ms[q]; st.mass_hi[dst] = mh[q]; st.mass_lo[dst] = ml[q];
+        st.radius[dst] = rd[q]; st.volume[dst] = vo[q]; st.eaten[dst] = ea[q]; st.id[dst] = idv[q];
+        st.flags[dst] = flv[q];
+        if (st.energy) st.energy[dst] = en[q];
+        ++dst;
+    }
+    if (tid == 0) {
+        st.status[COSMO_ST_N_DEAD] = n - s_total;
+        st.status[COSMO_ST_N_ESCAPED] += s_escaped;
+        st.status[COSMO_ST_N_ACTIVE] = s_total;
+        st.status[COSMO_ST_STEP] += 1;  // universe_old.py:361
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
@@ -608,6 +741,11 @@ int launch_append_pair_rows(const cosmo_state &st, const cosmo_scratch &sc, cons
 
 int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                           cudaStream_t s) {
+    if (p.n_upper <= TAIL_N && (p.resolve_mode == 0 || !(p.opts & COSMO_OPT_COLLISIONS))) {
+        k_tail_small<<<1, TAIL_THREADS, 0, s>>>(st, sc, (p.opts & COSMO_OPT_COLLISIONS) ? 1 : 0,
+                                                (p.opts & COSMO_OPT_BOUNDED) ? 1 : 0);
+        return COSMO_LAUNCH_CHECK("k_tail_small");
+    }
     const int chunks = (p.n_upper + CHUNK - 1) / CHUNK > 0 ? (p.n_upper + CHUNK - 1) / CHUNK : 1;
     if ((p.opts & COSMO_OPT_COLLISIONS) && p.resolve_mode == 0) {
         k_sort_pairs<<<64, 256, 0, s>>>(st, sc);
