@@ -850,12 +850,15 @@ static int launch_stage_a(const cosmo3_state &st, const cosmo3_scratch &sc, cons
     const int f32 = (p.opts & COSMO3_OPT_FP32) ? 1 : 0;
     k3_prep<<<blocks, 256, 0, s>>>(st, sc, p.pos_exp, p.mass_exp, f32);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k3_prep"));
+    // the symmetric kernels take their rows from shard_index / shard_count (round-robin row blocks), not
+    // from [i_begin, i_end): a rank whose contiguous range is empty still owns row blocks
+    if (f32 && (p.opts & COSMO3_OPT_F32_SYM)) return launch_accel3_sym32(st, sc, p, s);
+    if (!f32 && (p.opts & COSMO3_OPT_F64_SYM)) return launch_accel3_sym64(st, sc, p, s);
     const int rows = p.i_end - p.i_begin;
     if (rows <= 0) return COSMO_OK;
     int jsplit = p.jsplit < 1 ? 1 : p.jsplit;
     if (jsplit > sc.jsplit_max) jsplit = sc.jsplit_max;
     const int store_acc = (p.opts & COSMO3_OPT_STORE_ACC) ? 1 : 0;
-    if (f32 && (p.opts & COSMO3_OPT_F32_SYM)) return launch_accel3_sym32(st, sc, p, s);
     if (f32) {
         const int per = A32_BLOCK * A32_IB;
         dim3 grid((rows + per - 1) / per, jsplit);
@@ -863,9 +866,6 @@ static int launch_stage_a(const cosmo3_state &st, const cosmo3_scratch &sc, cons
         k3_accel_f32<A32_BLOCK, A32_IB, A32_TJ><<<grid, A32_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit, p.G,
                                                                            p.dt, unscale, store_acc);
         return COSMO_LAUNCH_CHECK("k3_accel_f32");
-    }
-    if (p.opts & COSMO3_OPT_F64_SYM) {
-        return launch_accel3_sym64(st, sc, p, s);   // rows by shard_index / shard_count, not i_begin / i_end
     }
     if (p.n_upper <= SMALL_N) {
         const int per = A64S_BLOCK * A64S_IB;

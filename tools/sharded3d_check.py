@@ -32,7 +32,8 @@ def main():
     DT, G = 600.0, 6.674e-11
     ok = True
     # (n, fp32, symmetric kernel): one-sided gather path, all-pairs and grid detection, symmetric all-reduce path
-    for n, fp32, sym in ((3000, False, False), (20000, False, False), (20000, False, True), (40000, True, False),
+    # n = 1000: the last rank's CONTIGUOUS row range is empty while it still owns symmetric row blocks
+    for n, fp32, sym in ((1000, False, True), (1000, False, False), (3000, False, False), (20000, False, False), (20000, False, True), (40000, True, False),
                          (40000, True, True)):
         arr = crowded(n, 3)
         single = Engine3D(n, device="cuda:%d" % local)
