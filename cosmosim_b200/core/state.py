@@ -192,19 +192,19 @@ class State:
 
     # -------------------------------------------------------------- the reference's getters
     def masses(self):
-        return np.array([o.mass for o in self.objects])
+        return np.array([o.mass for o in self._host_objects()])
 
     def radii(self):
-        return np.array([o.get_radius() for o in self.objects])
+        return np.array([o.get_radius() for o in self._host_objects()])
 
     def positions(self):
-        return np.array([o.position for o in self.objects])
+        return np.array([o.position for o in self._host_objects()])
 
     def velocities(self):
-        return np.array([o.velocity for o in self.objects])
+        return np.array([o.velocity for o in self._host_objects()])
 
     def colors(self):
-        return [o.color for o in self.objects]
+        return [o.color for o in self._host_objects()]
 
     # -------------------------------------------------------------- stepping
     def step(self, n=1, collisions=True):
@@ -262,7 +262,8 @@ class _Unpickler(pickle.Unpickler):
 
 def load_states(path):
     """Read every State of a data directory (Universe.run(outpath=...)) or of one .dat file, written by
-    this package or by the reference; mirrors the loader of cosmosim/core/animation.py:32-45."""
+    this package or by the reference; mirrors the loader of cosmosim/core/animation.py:32-45.
+    The format is the reference's (a stream of pickles): only load files you trust."""
     files = [path] if os.path.isfile(path) else [os.path.join(path, f) for f in os.listdir(path)]
     states = []
     for fn in files:
