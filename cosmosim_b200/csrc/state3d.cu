@@ -1010,6 +1010,7 @@ int cosmo3_step(const cosmo3_state *st, const cosmo3_scratch *sc, const cosmo3_s
 }
 
 int cosmo3_suggest_jsplit(int32_t rows, int32_t n, int kernel, int32_t jsplit_max) {
+    configure_sym_kernels();   // first host call of an engine: never inside a graph capture
     if (rows <= 0 || n <= 0) return 1;
     if (jsplit_max < 1) jsplit_max = 1;
     int sms = 148, dev = 0;

@@ -41,7 +41,8 @@ __device__ __forceinline__ void integrate_store3(const cosmo3_state &st, const c
                  (unsigned long long)COSMO_ERR_NAN);
 }
 
-// symmetric FP64 flavour (state3d_sym.cu)
+// symmetric flavours (state3d_sym.cu)
+int configure_sym_kernels();
 int launch_integrate3(const cosmo3_state &st, const cosmo3_scratch &sc, const cosmo3_step_params &p, cudaStream_t s);
 int launch_accel3_sym32(const cosmo3_state &st, const cosmo3_scratch &sc, const cosmo3_step_params &p,
                         cudaStream_t s);

@@ -23,6 +23,8 @@ constexpr int T_THREADS = T_WARPS * 32;
 // dynamic shared memory: 2 stages x 5 planes (x, y, z, h, m) + 3 planes of column sums + 2 mbarriers
 constexpr size_t T_SMEM = (size_t)(2 * 5 + 3) * T_BLOCK * sizeof(double) + 2 * sizeof(uint64_t);
 
+int configure_sym_kernels();
+
 __device__ __forceinline__ double shfl_f64(double v, int src_lane) {
     int lo = __double2loint(v), hi = __double2hiint(v);
     lo = __shfl_sync(0xffffffffu, lo, src_lane);
@@ -274,12 +276,7 @@ int launch_accel3_sym64(const cosmo3_state &st, const cosmo3_scratch &sc, const 
         set_error("symmetric 3-D accel: colbuf has %lld rows, %d needed", (long long)sc.colbuf_rows, rows_local);
         return COSMO_E_ARG;
     }
-    static bool configured = false;
-    if (!configured) {
-        COSMO_TRY(check_cuda(cudaFuncSetAttribute(k3_accel_f64_sym, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)T_SMEM), "cudaFuncSetAttribute(k3_accel_f64_sym)"));
-        configured = true;
-    }
+    COSMO_TRY(configure_sym_kernels());
     if (rows_local > 0) {
         dim3 grid(rows_local, (nblk + chunk - 1) / chunk);
         k3_accel_f64_sym<<<grid, T_THREADS, T_SMEM, s>>>(st, sc, sh_i, sh_n, chunk);
@@ -507,12 +504,7 @@ int launch_accel3_sym32(const cosmo3_state &st, const cosmo3_scratch &sc, const 
                   (rows_local + 1) / 2);
         return COSMO_E_ARG;
     }
-    static bool configured = false;
-    if (!configured) {
-        COSMO_TRY(check_cuda(cudaFuncSetAttribute(k3_accel_f32_sym, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)U_SMEM), "cudaFuncSetAttribute(k3_accel_f32_sym)"));
-        configured = true;
-    }
+    COSMO_TRY(configure_sym_kernels());
     if (rows_local > 0) {
         dim3 grid(rows_local, (nblk + chunk - 1) / chunk);
         k3_accel_f32_sym<<<grid, U_THREADS, U_SMEM, s>>>(st, sc, sh_i, sh_n, chunk);
@@ -523,6 +515,25 @@ int launch_accel3_sym32(const cosmo3_state &st, const cosmo3_scratch &sc, const 
                                                     (p.opts & COSMO3_OPT_STORE_ACC) ? 1 : 0,
                                                     (p.opts & COSMO3_OPT_DEFER_INTEGRATE) ? 1 : 0);
     return COSMO_LAUNCH_CHECK("k3_sym32_reduce");
+}
+
+// Opt-in to > 48 KB of dynamic shared memory for both symmetric kernels, once per process (one process
+// drives one GPU).  Called from every host entry point of the 3-D step, so it has always happened
+// before a step is captured into a CUDA graph.
+int configure_sym_kernels() {
+    static bool configured = false;
+    if (configured) return COSMO_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {   // no device (symbol / argument tests on a CPU box)
+        cudaGetLastError();
+        return COSMO_OK;
+    }
+    COSMO_TRY(check_cuda(cudaFuncSetAttribute(k3_accel_f64_sym, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)T_SMEM), "cudaFuncSetAttribute(k3_accel_f64_sym)"));
+    COSMO_TRY(check_cuda(cudaFuncSetAttribute(k3_accel_f32_sym, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)U_SMEM), "cudaFuncSetAttribute(k3_accel_f32_sym)"));
+    configured = true;
+    return COSMO_OK;
 }
 
 }  // namespace s3
