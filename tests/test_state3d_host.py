@@ -92,3 +92,24 @@ def test_pickles_load_with_the_reference_classes_and_back():
     buf2.seek(0)
     mine = S._Unpickler(buf2).load()
     assert isinstance(mine, S.State) and mine.objects[3].mass == 10 and mine.iteration == 3
+
+
+def test_scene_builder_reproduces_the_reference_initial_state():
+    """scenes.star_with_disk_objects(seed) = examples/testing/in-memory.py:12-42 on this package's Object:
+    positions, velocities, masses (Python ints) and densities equal the reference's for the same seed
+    (fixture written by the unmodified reference, oracle/gen_golden3d.py)."""
+    from conftest import load_golden, python_numbers3, snap3_from
+    from cosmosim_b200 import scenes
+    g = load_golden("state3d_inmemory.npz")
+    init = snap3_from(g, "init_")
+    objs = scenes.star_with_disk_objects(0, 1000)
+    assert len(objs) == 1001
+    assert np.array_equal(np.array([o.position for o in objs]), init["pos"])
+    assert np.array_equal(np.array([o.velocity for o in objs]), init["vel"])
+    masses, dens = python_numbers3(init)
+    assert [o.mass for o in objs] == masses and [type(o.mass) for o in objs] == [type(m) for m in masses]
+    assert [o.density for o in objs] == dens
+    from cosmosim_b200.engine3d import arrays_from_objects
+    arr = arrays_from_objects(objs)
+    assert np.array_equal(arr["radius"], g["s0_radius"]) and arr["pos"].shape == (1001, 3)
+    assert np.array_equal(arr["flags"] & 1, init["mass_is_int"].astype(np.uint8))
