@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from ._abi import (F_IMMOBILE, F_MASS_INT, OPT_BOUNDED, OPT_COLLISIONS, OPT_DEFER_INTEGRATE, OPT_ENERGY, OPT_F32_SCALAR,
+from ._abi import (OPT_BOUNDED, OPT_COLLISIONS, OPT_DEFER_INTEGRATE, OPT_ENERGY, OPT_F32_SCALAR,
                    OPT_F64_SYM,
                    OPT_F32_SYM, OPT_FP32, OPT_STORE_ACC, PAD, ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_ESCAPED, ST_N_EVENTS,
                    ST_N_PAIRS, ST_STEP, STATUS_LEN)

@@ -5,7 +5,6 @@ import os
 import random
 import re
 
-import pytest
 
 from cosmosim_b200 import _abi, _build
 

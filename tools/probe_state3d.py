@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from cosmosim_b200 import _abi, engine3d  # noqa: E402
+from cosmosim_b200 import engine3d  # noqa: E402
 
 
 def cloud(n, seed=0):
