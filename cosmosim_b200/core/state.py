@@ -118,18 +118,57 @@ class State:
         # Object.absorb calls so far: (iteration, absorber, absorbed, absorbed still existed), objects
         # numbered in the order this State first saw them (the initial list order)
         self.absorb_calls = []
+        self._bulk = None            # from_arrays(): the host truth is a dict of arrays, not Object instances
+
+    @classmethod
+    def from_arrays(cls, mass, density, position, velocity=None, dt=1, G=_G, iteration=0, precision="fp64",
+                    device=None, group=None):
+        """A State of len(mass) bodies from column data, without a Python Object per body (large N).
+        mass / density: numpy arrays or sequences of Python numbers (ints stay exact, as with Object);
+        position / velocity: [n, 3].  `state.objects` materialises Object instances on first use;
+        masses() / positions() / velocities() / radii() / arrays() read the arrays directly."""
+        from .. import engine3d
+        st = cls(None, dt=dt, G=G, iteration=iteration, precision=precision, device=device, group=group)
+        st._bulk = engine3d.arrays_from_columns(mass, density, position, velocity)
+        return st
+
+    def _materialise(self):
+        """Bulk mode -> Object instances (numbered by their original row)."""
+        b = self._bulk
+        objs = []
+        for k in range(b["mass_f64"].shape[0]):
+            fl = int(b["flags"][k])
+            o = Object(_python_mass(fl, b["mass_hi"][k], b["mass_lo"][k], b["mass_f64"][k]),
+                       int(b["density"][k]) if fl & 2 else float(b["density"][k]), b["pos"][k], b["vel"][k],
+                       name="body%d" % int(b["id"][k]), color=(255, 255, 255))
+            o._cosmo_index = int(b["id"][k])
+            objs.append(o)
+        self._next_index = max([self._next_index] + [o._cosmo_index + 1 for o in objs])
+        self._objects, self._bulk = objs, None
+        self._host_dirty = True      # device ids are re-issued from the new list at the next step
 
     # -------------------------------------------------------------- host <-> device
     @property
     def objects(self):
         self._pull()
+        if self._objects is None:
+            self._materialise()
         self._host_dirty = True      # the caller may edit what it gets
         return self._objects
 
     def _host_objects(self):
         """The up-to-date Object list for internal readers that do not edit it."""
         self._pull()
+        if self._objects is None:
+            self._materialise()
         return self._objects
+
+    def _column(self, key):
+        """Bulk mode: one column of the up-to-date arrays (None when the State holds Objects)."""
+        if self._objects is not None:
+            return None
+        self._pull()
+        return self._bulk[key]
 
     @objects.setter
     def objects(self, value):
@@ -148,6 +187,16 @@ class State:
 
     def _push(self):
         from .. import engine3d
+        if self._objects is None:                # bulk mode: the arrays go up as they are
+            n = self._bulk["mass_f64"].shape[0]
+            if self._engine is None or self._engine.cap < n:
+                self._engine = engine3d.Engine3D(n, device=self.device, group=self.group)
+            self._engine.upload(self._bulk, iteration=self._iteration)
+            self._uploaded = None
+            self._events_seen = self._engine.status()["n_events"]
+            self._host_dirty = False
+            self._device_ahead = False
+            return
         objs = self._objects
         for o in objs:
             if getattr(o, "_cosmo_index", None) is None:
@@ -169,6 +218,14 @@ class State:
         d = eng.download()
         ev = eng.events(self._events_seen)
         self._events_seen += len(ev)
+        if self._objects is None:                # bulk mode: ids are the original rows
+            self.absorb_calls.extend((int(a), int(b), int(c), int(e)) for a, b, c, e in ev)
+            self._bulk = {"pos": d["pos"], "vel": d["vel"], "mass_f64": d["mass"], "mass_hi": d["mass_hi"],
+                          "mass_lo": d["mass_lo"], "density": d["density"], "radius": d["radius"],
+                          "flags": d["flags"], "id": d["id"]}
+            self._iteration = d["status"]["iteration"]
+            self._device_ahead = False
+            return
         src = self._uploaded
         self.absorb_calls.extend((int(a), src[int(b)]._cosmo_index, src[int(c)]._cosmo_index, int(e))
                                  for a, b, c, e in ev)
@@ -192,16 +249,20 @@ class State:
 
     # -------------------------------------------------------------- the reference's getters
     def masses(self):
-        return np.array([o.mass for o in self._host_objects()])
+        col = self._column("mass_f64")
+        return col.copy() if col is not None else np.array([o.mass for o in self._host_objects()])
 
     def radii(self):
-        return np.array([o.get_radius() for o in self._host_objects()])
+        col = self._column("radius")
+        return col.copy() if col is not None else np.array([o.get_radius() for o in self._host_objects()])
 
     def positions(self):
-        return np.array([o.position for o in self._host_objects()])
+        col = self._column("pos")
+        return col.copy() if col is not None else np.array([o.position for o in self._host_objects()])
 
     def velocities(self):
-        return np.array([o.velocity for o in self._host_objects()])
+        col = self._column("vel")
+        return col.copy() if col is not None else np.array([o.velocity for o in self._host_objects()])
 
     def colors(self):
         return [o.color for o in self._host_objects()]

@@ -419,3 +419,27 @@ def arrays_from_objects(objects):
         out["flags"][k] = (F3_MASS_INT if is_int else 0) | (F3_DENS_INT if d_int else 0)
         out["radius"][k] = ((3 * (o.mass / o.density)) / (4 * math.pi)) ** (1 / 3)
     return out
+
+
+def arrays_from_columns(mass, density, position, velocity=None):
+    """Column data -> upload arrays, without a Python Object per body.  `mass` / `density` may be numpy
+    float arrays or sequences of Python numbers (ints stay exact ints, as with Object)."""
+    pos = np.ascontiguousarray(np.asarray(position, dtype=np.float64).reshape(-1, 3))
+    n = pos.shape[0]
+    vel = np.zeros((n, 3)) if velocity is None else np.ascontiguousarray(np.asarray(velocity, dtype=np.float64).reshape(n, 3))
+    masses = mass.tolist() if isinstance(mass, np.ndarray) else list(mass)
+    dens = density.tolist() if isinstance(density, np.ndarray) else (list(density) if np.ndim(density) else [density] * n)
+    if len(masses) != n or len(dens) != n:
+        raise ValueError("mass / density / position lengths differ")
+    out = {"pos": pos, "vel": vel, "mass_f64": np.zeros(n), "mass_hi": np.zeros(n, dtype=np.uint64),
+           "mass_lo": np.zeros(n, dtype=np.uint64), "density": np.zeros(n), "radius": np.zeros(n),
+           "flags": np.zeros(n, dtype=np.uint8), "id": np.arange(n, dtype=np.int32)}
+    four_pi = 4 * math.pi
+    for k in range(n):
+        m, d = masses[k], dens[k]
+        f, is_int, hi, lo = split_mass(m)
+        df, d_int = split_density(d)
+        out["mass_f64"][k], out["mass_hi"][k], out["mass_lo"][k], out["density"][k] = f, hi, lo, df
+        out["flags"][k] = (F3_MASS_INT if is_int else 0) | (F3_DENS_INT if d_int else 0)
+        out["radius"][k] = ((3 * (m / d)) / four_pi) ** (1 / 3)      # Object.get_radius() in Python arithmetic
+    return out

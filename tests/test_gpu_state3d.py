@@ -356,3 +356,31 @@ def test_overflow_is_reported_not_silent(mods):
     assert want["n_pairs"] == n * (n - 1)
     assert eng.check_errors()["n_active"] == orc.n
     assert np.array_equal(eng.events()[:, 1:], want["events"])
+
+
+def test_bulk_state_from_arrays_equals_object_state(mods):
+    """State.from_arrays (no Python Object per body) steps exactly like a State built from Objects,
+    reports the same absorb calls, and can be turned into Objects mid-run."""
+    from cosmosim_b200.core import state as S
+    g = load_golden("state3d_disk_planar.npz")
+    init = snap3_from(g, "init_")
+    masses, dens = python_numbers3(init)
+    objs = [S.Object(m, q, p, v, name="o%d" % k, color=(1, 2, 3))
+            for k, (m, q, p, v) in enumerate(zip(masses, dens, init["pos"], init["vel"]))]
+    a = S.State(objs, dt=float(g["dt"]))
+    b = S.State.from_arrays(masses, dens, init["pos"], init["vel"], dt=float(g["dt"]))
+    assert np.array_equal(a.radii(), b.radii()) and np.array_equal(b.positions(), init["pos"])
+    a.step(12)
+    b.step(12)
+    assert np.array_equal(a.positions(), b.positions()) and np.array_equal(a.velocities(), b.velocities())
+    want = [tuple(int(x) for x in e) for e in g["events"] if e[0] < 12]
+    assert a.absorb_calls == want and b.absorb_calls == want and b.iteration == 12
+    assert b._objects is None                                   # still arrays only
+    bo = b.objects                                              # materialise mid-run
+    assert len(bo) == len(a.objects) and [type(o.mass) for o in bo] == [type(o.mass) for o in a.objects]
+    assert [o._cosmo_index for o in bo] == [o._cosmo_index for o in a.objects]
+    a.step(8)
+    b.step(8)
+    assert np.array_equal(a.positions(), b.positions())
+    want = [tuple(int(x) for x in e) for e in g["events"] if e[0] < 20]
+    assert a.absorb_calls == want and b.absorb_calls == want
