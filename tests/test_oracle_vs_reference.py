@@ -88,3 +88,32 @@ def test_short_run_merge_stream_and_state(ref):
         post = ou.snapshot()
         for k in ("alive", "mass_f64", "radius", "volume", "eaten"):
             assert np.array_equal(post[k], st["post"][k]), (s, k)
+
+
+@pytest.mark.parametrize("n", [4001, 16001])
+def test_acc_blas_and_flags_at_survey_sizes(ref, n):
+    """SURVEY 8c gate: the restatement agrees with the real acc_blas to <= 1e-13 and flags exactly the
+    pairs of the real pairwise_distances at N = 4001 and 16001 (acc_blas needs 36 N^2 bytes: 9.2 GB
+    at 16001 -- skipped when the box has less than 24 GB free)."""
+    import psutil
+    from sklearn.metrics import pairwise_distances
+    if n > 8000 and psutil.virtual_memory().available < 24 << 30:
+        pytest.skip("not enough memory for acc_blas at N = %d" % n)
+    uo, pl, fn, bl = ref
+    from oracle.gen_golden import synthetic_disk
+    pos, mass = synthetic_disk(n, seed=n)
+    want = bl.acc_blas(pos, mass, 6.674e-11)[:, :2]
+    rows = slice(0, n) if n < 8000 else slice(n // 2 - 1000, n // 2 + 1000)
+    got = orc.accel(pos, mass, 6.674e-11, rows.start, rows.stop)
+    rel = np.linalg.norm(got - want[rows], axis=1) / np.linalg.norm(want[rows], axis=1)
+    assert rel.max() < 1e-13
+    del want
+    rng = np.random.default_rng(n)
+    radii = rng.uniform(2e6, 4e7, n) * 3.0
+    d = pairwise_distances(pos, n_jobs=-1)
+    flags = np.clip(d, 1, None) <= np.add.outer(radii, radii)
+    del d
+    np.fill_diagonal(flags, False)
+    ii, jj = np.nonzero(flags)
+    mine = orc.flags(pos, radii)
+    assert len(ii) > 10 and np.array_equal(mine, np.stack([ii, jj], axis=1))
