@@ -140,3 +140,25 @@ def test_live_short_run():
             assert np.array_equal(post[k], st["post"][k]), (s, k)
         o.pos[:o.n], o.vel[:o.n] = st["post"]["pos"], st["post"]["vel"]
     assert ev == rec.events
+
+
+@live
+def test_live_gate_at_n4001():
+    """acc_blas on (4001, 3) positions and sklearn's flags (no clip) vs the restatement."""
+    from sklearn.metrics import pairwise_distances
+    rh.load_reference()
+    import cosmosim.util.blas as bl
+    n = 4001
+    rng = np.random.default_rng(n)
+    pos = rng.normal(size=(n, 3)) * 1.496e11 * np.array([1.0, 0.7, 0.1])
+    mass = rng.uniform(0.1, 100.0, n) * 5.972e24
+    mass[0] = 1.989e30
+    want = bl.acc_blas(pos, mass, 6.674e-11)
+    got = o3.accel(pos, mass, 6.674e-11)
+    assert relerr_rows(got, want).max() < 1e-13
+    radii = rng.uniform(2e6, 4e7, n) * 40.0
+    d = pairwise_distances(pos, n_jobs=-1)
+    flags = d <= np.add.outer(radii, radii)
+    np.fill_diagonal(flags, False)
+    ii, jj = np.nonzero(flags)
+    assert len(ii) > 10 and np.array_equal(o3.flags(pos, radii), np.stack([ii, jj], axis=1))
