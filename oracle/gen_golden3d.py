@@ -9,6 +9,8 @@ Fixtures (all produced by reference code through oracle/ref_harness3d.py):
                             objects per step, final state, selected steps in full
   state3d_disk_thick.npz    same with out-of-plane offsets (400 planets, density 20): true 3-D
   state3d_inmemory.npz      examples/testing/in-memory.py scene (seed 0), 200 of its 1000 steps
+  state3d_savedata.npz      examples/testing/save-data.py scene (10000 planets, 0.1-0.5 AU, dt 600, seed 0),
+                            4 of its 5000 steps: init, absorb stream, final state, acc / pairs of step 0
   state3d_micro.npz         2-3 body scenes for every branch of the absorb loop
   state3d_accel_n2001.npz   acc_blas on a seeded 3-D cloud
 """
@@ -68,6 +70,26 @@ def run_scene(name, out_dir, steps, dt, n_keep=6, **build_kw):
           f"objects), kept {keep}, {time.time() - t0:.0f}s", flush=True)
 
 
+def savedata(out_dir, steps=4):
+    """The reference needs ~40 s per step at this size (its absorb loop walks all N^2 flags in Python)."""
+    t0 = time.time()
+    kw = dict(seed=0, n_planets=10000, d_min=0.1 * r3.AU, d_max=0.5 * r3.AU, density=3000)
+    objs = r3.build_disk(**kw)
+    init = r3.snapshot_with_ids(objs)
+    rec = r3.Recorder3D(objs, 600, keep_steps=[0]).run(steps)
+    events = np.array(rec.events, dtype=np.int64).reshape(-1, 4)
+    final = r3.snapshot(rec.state.objects)
+    st0 = rec.steps[0]
+    blob = {"dt": 600.0, "G": 6.674e-11, "steps": steps, "events": events,
+            "n_objects": np.array(rec.n_objects, dtype=np.int64), "s0_acc": st0["acc"],
+            "s0_flag_pairs": st0["flag_pairs"], "s0_radius": st0["radius"]}
+    blob.update(flat("init_", init))
+    blob.update(flat("final_", final))
+    np.savez_compressed(os.path.join(out_dir, "state3d_savedata.npz"), **blob)
+    print(f"[savedata] {steps} steps, {len(events)} absorb calls, {len(st0['flag_pairs'])} flagged pairs in step 0, "
+          f"{time.time() - t0:.0f}s", flush=True)
+
+
 def micro(out_dir):
     un = r3.load_reference3d()
     # (mass, density, x, vx): bodies on a line, radii ~ (3 m / (4 pi rho))^(1/3)
@@ -118,7 +140,7 @@ if __name__ == "__main__":
                                                    "tests", "golden"))
     ap.add_argument("--only", default="")
     a = ap.parse_args()
-    todo = a.only.split(",") if a.only else ["micro", "accel", "planar", "thick", "inmemory"]
+    todo = a.only.split(",") if a.only else ["micro", "accel", "planar", "thick", "inmemory", "savedata"]
     if "micro" in todo:
         micro(a.out)
     if "accel" in todo:
@@ -131,3 +153,5 @@ if __name__ == "__main__":
                   density=20, z_sigma=2e8)
     if "inmemory" in todo:
         run_scene("inmemory", a.out, 200, 60, n_keep=3, seed=0, n_planets=1000)
+    if "savedata" in todo:
+        savedata(a.out)

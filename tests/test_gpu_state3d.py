@@ -384,3 +384,31 @@ def test_bulk_state_from_arrays_equals_object_state(mods):
     assert np.array_equal(a.positions(), b.positions())
     want = [tuple(int(x) for x in e) for e in g["events"] if e[0] < 20]
     assert a.absorb_calls == want and b.absorb_calls == want
+
+
+@pytest.mark.parametrize("sym", [False, True])
+def test_savedata_scene_free_run(mods, sym):
+    """examples/testing/save-data.py at its real size (10001 objects, dt = 600) against the reference's own
+    run: 4 steps, 66 absorb calls; one-sided kernel (the default at this size) and the symmetric one."""
+    engine3d, o3, _ = mods
+    g = load_golden("state3d_savedata.npz")
+    arr = engine3d_arrays_from_snapshot(snap3_from(g, "init_"))
+    n = len(arr["mass_f64"])
+    assert np.array_equal(arr["radius"], g["s0_radius"])
+    eng = engine3d.Engine3D(n)
+    eng.upload(arr)
+    counts = []
+    for s in range(int(g["steps"])):
+        eng.step(float(g["dt"]), float(g["G"]), store_acc=(s == 0), sym=sym)
+        if s == 0:
+            out = eng.last_step_tensors(n)
+            assert relerr_rows(out["acc"], g["s0_acc"]).max() < 1e-12
+            assert np.array_equal(out["flag_pairs"], g["s0_flag_pairs"])
+        counts.append(eng.status()["n_active"])
+    eng.check_errors()
+    assert np.array_equal(np.array(counts), g["n_objects"])
+    assert np.array_equal(eng.events(), g["events"])
+    d, want = eng.download(), snap3_from(g, "final_")
+    assert np.array_equal(d["id"], want["id"]) and np.array_equal(d["mass"], want["mass_f64"])
+    assert np.array_equal(d["density"], want["dens_f64"])
+    assert np.abs(d["pos"] - want["pos"]).max() <= 1e-11 * np.abs(want["pos"]).max()

@@ -162,3 +162,23 @@ def test_live_gate_at_n4001():
     np.fill_diagonal(flags, False)
     ii, jj = np.nonzero(flags)
     assert len(ii) > 10 and np.array_equal(o3.flags(pos, radii), np.stack([ii, jj], axis=1))
+
+
+def test_savedata_scene_free_run():
+    """examples/testing/save-data.py (10000 planets around a star, dt = 600): 4 steps, 66 absorb calls."""
+    g = load_golden("state3d_savedata.npz")
+    o = o3.OracleState(snap3(g, "init_"), dt=float(g["dt"]), G=float(g["G"]))
+    ev = []
+    for s in range(int(g["steps"])):
+        out = o.interact(True, record=(s == 0))
+        if s == 0:
+            assert np.array_equal(out["radius"], g["s0_radius"])
+            assert relerr_rows(out["acc"], g["s0_acc"]).max() < 1e-12
+            assert np.array_equal(out["flag_pairs"], g["s0_flag_pairs"])
+        ev += [(s, int(a), int(b), int(c)) for a, b, c in out["events"]]
+        assert o.n == g["n_objects"][s]
+    assert np.array_equal(np.array(ev, dtype=np.int64).reshape(-1, 4), g["events"]) and len(ev) > 50
+    post, want = o.snapshot(), snap3(g, "final_")
+    assert np.array_equal(post["id"], want["id"]) and np.array_equal(post["mass_f64"], want["mass_f64"])
+    assert np.array_equal(post["dens_f64"], want["dens_f64"])
+    assert np.abs(post["pos"] - want["pos"]).max() <= 1e-11 * np.abs(want["pos"]).max()
