@@ -13,6 +13,8 @@ Fixtures written (all produced by reference code, none by this repo's oracle or 
                            new positions, flagged pairs and post-state (per-step parity)
   micro_merges.npz         the six 2-3 body merge micro-scenes of SURVEY.md Appendix B
   accel_n4001.npz          acc_blas on a seeded synthetic disk, N = 4001
+  scene_disk6001.npz       star + 6000 planets (radii x4 so that merges are plentiful), 3 frames of the
+                           reference: initial state, merge stream, final state, acc / flagged pairs of frame 0
   energies.npz             total_energy / angular_momentum / Planet.energy over six frames
 """
 from __future__ import annotations
@@ -158,6 +160,25 @@ def synthetic_disk(n, seed):
     return pos, mass
 
 
+def disk6001(out_dir, n_planets=6000, seed=3, frames=3, inflate=4.0):
+    """A scene beyond the small-N kernel shapes (N > 4096), run by the reference itself."""
+    t0 = time.time()
+    u = rh.build_star_with_disk(seed, n_planets)
+    for p in u.planets[1:]:
+        p.radius *= inflate
+        p.volume = ((4 / 3) * np.pi) * (p.radius ** 3)
+    init = rh.snapshot(u)
+    rec = rh.Recorder(u, keep_steps=[0]).run(frames)
+    events = np.array(rec.events, dtype=np.int64).reshape(-1, 3)
+    blob = {"dt": 1e6 / 33, "G": u.G, "frames": frames, "events": events, "s0_acc": rec.steps[0]["acc"],
+            "s0_flag_pairs": rec.steps[0]["flag_pairs"], "s0_active_idx": rec.steps[0]["active_idx"]}
+    blob.update(flat("init_", init))
+    blob.update(flat("final_", rh.snapshot(u)))
+    np.savez_compressed(os.path.join(out_dir, "scene_disk6001.npz"), **blob)
+    print(f"[disk6001] {frames} frames, {len(events)} merges, {len(rec.steps[0]['flag_pairs'])} flagged pairs in "
+          f"frame 0, {time.time() - t0:.0f}s", flush=True)
+
+
 def accel_fixture(out_dir, n=4001, seed=7):
     uo, pl, fn, bl = rh.load_reference()
     pos, mass = synthetic_disk(n, seed)
@@ -175,7 +196,9 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
-    todo = a.only.split(",") if a.only else ["micro", "accel", "energy", "disk", "cloud"]
+    todo = a.only.split(",") if a.only else ["micro", "accel", "energy", "disk", "cloud", "disk6001"]
+    if "disk6001" in todo:
+        disk6001(a.out)
     if "energy" in todo:
         energy_fixture(a.out)
     if "micro" in todo:

@@ -736,3 +736,32 @@ def test_n65536_fp64_full_frame_vs_oracle_merges_bit_exact():
     assert np.abs(d["radius"] - post["radius"][ids]).max() <= np.spacing(post["radius"][ids]).max()
     for k in ("pos", "vel"):
         assert np.abs(d[k] - post[k][ids]).max() <= FP64_TOL * np.abs(post[k][ids]).max()
+
+
+@pytest.mark.parametrize("grid", [False, True])
+def test_disk6001_three_frames_of_the_reference(grid):
+    """N = 6001 (beyond the small-N kernel shapes), 3 frames run by the reference itself with 391
+    merges: frame-0 accelerations and flagged pairs, the whole merge stream and the final state."""
+    g = load_golden("scene_disk6001.npz")
+    pre, ref = snap_from(g, "init_"), snap_from(g, "final_")
+    arr = engine_arrays_from_snapshot(pre)
+    eng = make_engine(arr, n_total=len(pre["alive"]), grid=grid)
+    n = arr["id"].shape[0]
+    eng.step(1, float(g["dt"]), float(g["G"]), 100 * AU, store_acc=True)
+    assert (eng.grid is not None) == grid
+    acc = eng.last_frame_tensors()["acc"][:n].cpu().numpy()
+    assert relerr_rows(acc, g["s0_acc"]).max() < FP64_TOL
+    pairs = np.sort(eng.t["pairs"][: eng.status()["n_pairs"]].cpu().numpy().view(np.uint64))
+    got = np.stack([(pairs >> np.uint64(32)).astype(np.int64), (pairs & np.uint64(0xffffffff)).astype(np.int64)], axis=1)
+    assert np.array_equal(got, g["s0_flag_pairs"])
+    for _ in range(int(g["frames"]) - 1):
+        eng.step(1, float(g["dt"]), float(g["G"]), 100 * AU)
+    eng.check_errors()
+    assert np.array_equal(eng.events(), g["events"])                       # 391 merges, order bit-exact
+    d = eng.download()
+    ids = d["id"]
+    assert np.array_equal(ids, np.nonzero(ref["alive"])[0])
+    assert np.array_equal(d["mass"], ref["mass_f64"][ids]) and np.array_equal(d["volume"], ref["volume"][ids])
+    assert np.array_equal(d["eaten"], ref["eaten"][ids])
+    assert np.abs(d["radius"] - ref["radius"][ids]).max() <= np.spacing(ref["radius"][ids]).max()
+    assert np.abs(d["pos"] - ref["pos"][ids]).max() <= 1e-11 * np.abs(ref["pos"][ids]).max()

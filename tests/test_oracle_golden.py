@@ -98,3 +98,27 @@ def test_energies_match_reference_hud_numbers():
             alive = g[f"{name}_alive"][f][act]
             ref = g[f"{name}_energy"][f][act][alive]
             assert np.abs(out["energy"][alive] - ref).max() <= tol * np.abs(ref).max()
+
+
+def test_disk6001_three_frames_of_the_reference():
+    """Star + 6000 planets with inflated radii, run by the reference for 3 frames (391 merges): the
+    oracle reproduces frame 0's acc_blas output and flagged pairs, the whole merge stream and the
+    final masses / radii / volumes exactly."""
+    g = load_golden("scene_disk6001.npz")
+    ou = orc.OracleUniverse(snap_from(g, "init_"), G=float(g["G"]))
+    ev = []
+    for f in range(int(g["frames"])):
+        out = ou.frame(float(g["dt"]), record=(f == 0), cap=1 << 16)
+        if f == 0:
+            assert np.array_equal(out["active_idx"], g["s0_active_idx"])
+            rel = np.linalg.norm(out["acc"] - g["s0_acc"], axis=1) / np.linalg.norm(g["s0_acc"], axis=1)
+            assert rel.max() < 1e-12
+            assert np.array_equal(out["flag_pairs"], g["s0_flag_pairs"])
+        ev += [(f, int(a), int(b)) for a, b in out["events"]]
+    assert ev == [tuple(int(x) for x in r) for r in g["events"]] and len(ev) > 300
+    post, ref = ou.snapshot(), snap_from(g, "final_")
+    assert np.array_equal(post["alive"], ref["alive"])
+    for k in ("mass_f64", "radius", "volume", "eaten"):
+        assert np.array_equal(post[k], ref[k]), k
+    al = ref["alive"]
+    assert np.abs(post["pos"][al] - ref["pos"][al]).max() <= 1e-11 * np.abs(ref["pos"][al]).max()
