@@ -117,3 +117,68 @@ def test_acc_blas_and_flags_at_survey_sizes(ref, n):
     ii, jj = np.nonzero(flags)
     mine = orc.flags(pos, radii)
     assert len(ii) > 10 and np.array_equal(mine, np.stack([ii, jj], axis=1))
+
+
+def _example_scenes(uo, pl, fn):
+    """The reference's three-body example scripts as functions (examples/earth_moon.py:8-45,
+    figure_8.py:8-26, lagrange_three_bodies.py:13-30) on the REFERENCE classes; returns (universe, speed)."""
+    import math
+    import random
+
+    def earth_moon():
+        random.seed(6)
+        ME, RE = 5.972e24, 6.371e6
+        u = uo.Universe()
+        earth = pl.Planet(mass=ME, radius=RE, name="Terra", position=[0, 0], color=(3, 90, 252))
+        u.add_planet(earth)
+        earth.create_satellite(distance=62 * RE, mass=7.3459e22, radius=1.7374e6, name="Luna", color=(136, 138, 143))
+        earth.create_satellite(distance=7e6, mass=4.5e6, radius=100, name="ISS")
+        return u, 300
+
+    def figure_8():
+        ME, RE, k = 5.972e18, 6.371, 100
+        u = uo.Universe()
+        p1 = [0.97000436 * k * RE, -0.24308753 * k * RE]
+        v3 = [-0.93240737, -0.86473146]
+        v2 = [-v3[0] / 2, -v3[1] / 2]
+        u.create_planet(mass=ME, radius=RE, position=p1, velocity=v2)
+        u.create_planet(mass=ME, radius=RE, position=[-p1[0], -p1[1]], velocity=v2)
+        u.create_planet(mass=ME, radius=RE, position=[0, 0], velocity=v3)
+        return u, 100
+
+    def lagrange():
+        ME, RE = 5.972e24, 6.371e6
+        u = uo.Universe()
+        r = 10 * RE
+        omega = math.sqrt((u.G * ME) / (math.sqrt(3) * r ** 3))
+        for theta in (0.0, 2 * math.pi / 3, 4 * math.pi / 3):
+            p = fn.to_cartesian(r, theta)
+            u.add_planet(pl.Planet(mass=ME, radius=RE, position=p, velocity=fn.rotation(omega * np.array(p), math.pi / 2)))
+        return u, 1e4
+
+    return {"earth_moon": earth_moon, "figure_8": figure_8, "lagrange": lagrange}
+
+
+@pytest.mark.parametrize("name", ["earth_moon", "figure_8", "lagrange"])
+def test_three_body_example_scripts(ref, name):
+    """150 frames of each analytic example through the reference's own simulate(): the oracle's frame
+    from the reference's pre-state gives the reference's acc_blas output (<= 1e-12; these scenes have
+    coordinates from 6e2 to 4e8 m, i.e. very different conditioning of the expanded d^2) and post-state."""
+    uo, pl, fn, bl = ref
+    u, speed = _example_scenes(uo, pl, fn)[name]()
+    steps = 150
+    rec = rh.Recorder(u, keep_steps=range(steps)).run(steps, speed=speed)
+    assert rec.events == []
+    worst = 0.0
+    for s in range(steps):
+        st = rec.steps[s]
+        ou = orc.OracleUniverse(st["pre"], G=u.G)
+        out = ou.frame(speed / 33, record=True)
+        # scale = the largest acceleration of the frame: the body at the centre of the figure-8 starts
+        # with an exactly cancelling (zero) net pull
+        rel = np.linalg.norm(out["acc"] - st["acc"], axis=1) / np.linalg.norm(st["acc"], axis=1).max()
+        worst = max(worst, rel.max())
+        post = ou.snapshot()
+        assert np.abs(post["pos"] - st["post"]["pos"]).max() <= 1e-12 * np.abs(st["post"]["pos"]).max()
+        assert np.array_equal(post["alive"], st["post"]["alive"])
+    assert worst < 1e-12
