@@ -156,14 +156,28 @@ def _example_scenes(uo, pl, fn):
             u.add_planet(pl.Planet(mass=ME, radius=RE, position=p, velocity=fn.rotation(omega * np.array(p), math.pi / 2)))
         return u, 1e4
 
-    return {"earth_moon": earth_moon, "figure_8": figure_8, "lagrange": lagrange}
+    def solar_system():
+        random.seed(8)
+        u = uo.Universe()
+        star_mass, star_radius = 333000, fn.get_radius(333000, 1 / 4)
+        sol = pl.Planet(star_mass, star_radius, [0, 0], immobile=True, name="Sol", color=(255, 255, 0))
+        u.add_planet(sol)
+        au = star_radius * 215
+        for dist, mass, radius in ((0.4, 1, 1), (0.7, 1, 1), (1, 1, 1), (1.5, 1, 1), (5.2, 320, 11), (9.5, 95, 9),
+                                   (19, 15, 4), (30, 17, 4)):
+            sol.create_satellite(distance=dist * au, mass=mass, radius=radius, name="p", color=(1, 2, 3))
+        return u, 1e6
+
+    return {"earth_moon": earth_moon, "figure_8": figure_8, "lagrange": lagrange, "solar_system": solar_system}
 
 
-@pytest.mark.parametrize("name", ["earth_moon", "figure_8", "lagrange"])
+@pytest.mark.parametrize("name", ["earth_moon", "figure_8", "lagrange", "solar_system"])
 def test_three_body_example_scripts(ref, name):
     """150 frames of each analytic example through the reference's own simulate(): the oracle's frame
     from the reference's pre-state gives the reference's acc_blas output (<= 1e-12; these scenes have
-    coordinates from 6e2 to 4e8 m, i.e. very different conditioning of the expanded d^2) and post-state."""
+    coordinates from 6e2 to 4e8 m, i.e. very different conditioning of the expanded d^2) and post-state.
+    solar_system.py (examples/solar_system.py:11-90) adds an immobile star, small integer masses and
+    the reference's default G in a unit system where gravity is almost absent."""
     uo, pl, fn, bl = ref
     u, speed = _example_scenes(uo, pl, fn)[name]()
     steps = 150
