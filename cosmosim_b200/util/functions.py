@@ -43,3 +43,23 @@ def get_radius(mass, density):
     """Radius of a homogeneous sphere of the given mass and density."""
     volume = mass / density
     return ((3 * volume) / (4 * math.pi)) ** (1 / 3)
+
+
+def to_cartesian_3d(r, theta, phi, origin=(0, 0, 0)):
+    """Spherical -> Cartesian with the reference's conventions (functions.py:16-20): theta is the
+    azimuth measured as in `to_cartesian`, phi the polar angle from +z; the sine term takes origin[0]
+    and the cosine term origin[1] (as in the 2-D helper), and the result is ordered [x, y, z] with
+    x = the cosine term."""
+    sin_term = r * np.sin(theta) * np.sin(phi) + origin[0]
+    cos_term = r * np.cos(theta) * np.sin(phi) + origin[1]
+    height = r * np.cos(phi) + origin[2]
+    return [cos_term, sin_term, height]
+
+
+def rotation_3d(v, theta, phi):
+    """Rotate the 3-vector v by phi about the x axis, then by theta about the y axis
+    (functions.py:27-36: R = R_y(theta) @ R_x(phi))."""
+    ct, st, cp, sp = np.cos(theta), np.sin(theta), np.cos(phi), np.sin(phi)
+    about_y = np.array([[ct, 0, st], [0, 1, 0], [-st, 0, ct]])
+    about_x = np.array([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
+    return np.matmul(np.matmul(about_y, about_x), v)

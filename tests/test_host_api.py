@@ -53,6 +53,12 @@ def test_functions_helpers():
     assert np.allclose(F.rotation(np.array([1.0, 0.0]), np.pi / 2), [0.0, 1.0])
     assert np.allclose(F.normalize(np.array([3.0, 4.0])), [0.6, 0.8])
     assert np.array_equal(F.normalize(np.zeros(2)), np.zeros(2))
+    # 3-D variants (reference functions.py:16-20,27-36): [x, y, z] with x the cosine term; R_y(theta) R_x(phi)
+    assert np.allclose(F.to_cartesian_3d(2.0, 0.0, np.pi / 2), [2.0, 0.0, 0.0])
+    assert np.allclose(F.to_cartesian_3d(2.0, np.pi / 2, np.pi / 2, origin=(1, 10, 100)), [10.0, 3.0, 100.0])
+    assert np.allclose(F.to_cartesian_3d(2.0, 0.3, 0.0), [0.0, 0.0, 2.0])
+    assert np.allclose(F.rotation_3d(np.array([0.0, 1.0, 0.0]), 0.0, np.pi / 2), [0.0, 0.0, 1.0])
+    assert np.allclose(F.rotation_3d(np.array([0.0, 0.0, 1.0]), np.pi / 2, 0.0), [1.0, 0.0, 0.0])
 
 
 def test_planet_defaults_and_rng_usage():
@@ -89,6 +95,10 @@ def test_install_as_cosmosim_aliases():
         from cosmosim.util.functions import get_radius
         import cosmosim.core.planet as pl
         assert U2 is Universe and pl.Planet is Planet and get_radius is F.get_radius
+        cosmosim_b200.install_as_cosmosim(api="new")      # the 3-D batch API under the same import path
+        from cosmosim.core.universe import Object, State
+        from cosmosim_b200.core import state as S
+        assert Object is S.Object and State is S.State
     finally:
         for k in [k for k in sys.modules if k == "cosmosim" or k.startswith("cosmosim.")]:
             del sys.modules[k]
