@@ -114,12 +114,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU legs
+def host_threads():
+    """Threads the CPU arm uses: every core this process may run on, whatever OMP_NUM_THREADS says
+    (torch.distributed.run exports OMP_NUM_THREADS=1, which must not shrink the reference arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_leg(arrays, prec_n, seconds_target=12.0, steps=1, warmup=0):
     """Time the CPU oracle (port of the reference's acc_blas + integrator + collision predicate)
     on a bounded sample of target rows of the same scene, all host threads."""
     from oracle import oracle as orc
     n = arrays["radius"].shape[0]
     pos, vel, mass, rad = arrays["pos"], arrays["vel"], arrays["mass_f64"], arrays["radius"]
+    orc.set_threads(host_threads())
     cores = orc.num_threads()
 
     def sample(rows):
@@ -152,6 +162,144 @@ def cpu_oracle_leg(arrays, prec_n, seconds_target=12.0, steps=1, warmup=0):
             "ms_per_step_sample": t * 1e3, "rows": rows}
 
 
+# ------------------------------------------------------------------------------------ B200 arm helpers
+def state_digest(eng):
+    """sha1 over (ids, mass bits, position bits, merge-event count, frame) of the device state: equal
+    digests across GPU counts prove the sharded run reproduced the single-GPU one bit for bit."""
+    import hashlib
+    d = eng.download()
+    h = hashlib.sha1()
+    for k in ("id", "mass", "pos", "radius"):
+        h.update(np.ascontiguousarray(d[k]).tobytes())
+    h.update(np.array([d["status"]["n_events"], d["status"]["frame"], d["status"]["n_escaped"]], dtype=np.int64).tobytes())
+    return h.hexdigest()[:16]
+
+
+def timed_frames(eng, K, kw, flush, barrier, world, restore=None):
+    """K frames bracketed by barrier + synchronize, device-timed (max over ranks), with per-stage
+    events.  restore: a save_state() copy put back before EVERY frame (outside the per-frame events
+    but inside nothing else: its frames all start from the same full-size state)."""
+    import torch
+    import torch.distributed as dist
+    stage_events = []
+    status_log = torch.zeros(K + 1, 16, dtype=torch.int64).pin_memory()   # async snapshots, no sync
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.lib.cosmo_launch_count()
+    barrier()
+    e0.record()
+    for k in range(K):
+        if restore is not None:
+            eng.restore_state(restore)
+        status_log[k].copy_(eng.t["status"], non_blocking=True)
+        eng.step(1, DT, G, R_MAX, stage_events=stage_events, **kw)
+        flush.zero_()
+    e1.record()
+    launches = int(eng.lib.cosmo_launch_count() - launches0)     # counted inside the library
+    status_log[K].copy_(eng.t["status"], non_blocking=True)
+    barrier()
+    if restore is None:
+        ms = e0.elapsed_time(e1)
+    else:      # frames only (first to last stage event of each frame): the state restore is not part of a step
+        ms = float(sum(ev[0].elapsed_time(ev[4]) for ev in stage_events))
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    n_per_step = status_log[:K, 0].numpy().astype(np.float64)
+    return ms, n_per_step, stage_events, launches
+
+
+def stage_table(stage_events, world):
+    f = lambda a, b: float(np.mean([ev[a].elapsed_time(ev[b]) for ev in stage_events]))  # noqa: E731
+    tab = {"prep": f(0, 1), "accel_integrate" + ("+exchange" if world > 1 else ""): f(1, 2),
+           "detect" + ("+exchange" if world > 1 else ""): f(2, 3), "resolve_commit": f(3, 4)}
+    tab["sum"] = float(sum(tab.values()))
+    return tab
+
+
+def roofline_block(eng, prec, kw, peaks, stage_events, n_per_step, world, workload, ms_per_step):
+    from cosmosim_b200 import _abi
+    accel_each = np.array([ev[1].elapsed_time(ev[2]) for ev in stage_events])
+    accel_ms = float(np.mean(accel_each))
+    n_eff = math.sqrt(float(np.mean(n_per_step ** 2)))
+    # interactions/s of stage A on THIS GPU (rank 0 evaluates 1/world of the pairs; with world > 1
+    # the stage time includes the all-reduce / all-gather that follows the kernel)
+    kernel_rate = float(np.sum(n_per_step ** 2) / world / np.sum(accel_each * 1e-3))
+    opts_now = eng.params(DT, G, R_MAX, **kw).opts
+    sym = bool(opts_now & (_abi.OPT_F32_SYM | _abi.OPT_F64_SYM))
+    # the symmetric kernels evaluate each unordered pair once: 12 FMA-pipe (FP32) / 23 FP64-pipe
+    # instructions per pair = 6 / 11.5 per ordered interaction (DESIGN.md section 4); the
+    # one-sided kernels need 9 (FP32) / 20 (FP64)
+    ipi = ({"fp32": 6.0, "fp64": 11.5}[prec]) if sym else INSTR_PER_INTERACTION[prec]
+    achieved = kernel_rate * ipi * 2 / 1e12                            # FMA-equivalent TFLOP/s
+    peak = peaks.get("ffma_tflops" if prec == "fp32" else "dfma_tflops")
+    # algorithmic HBM bytes of stage A per launch: sources read once (L2-resident afterwards)
+    # + targets' state read + new state written
+    bytes_per_body = (12 + 8 + 16 + 16 + 40) if prec == "fp32" else (32 + 16 + 16 + 40)
+    hbm_gbs = n_eff * bytes_per_body / (accel_ms * 1e-3) / 1e9
+    mp = {}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = mp.get("hbm_gbs", 6650.0)
+    kname = "k_accel_%s%s" % ("f32" if prec == "fp32" else "f64", "_sym" if sym else "")
+    traffic, traffic_note = None, None
+    try:   # DRAM bytes per launch from the committed ncu capture of this kernel on this workload
+        ent = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s|%s" % (kname, workload), {})
+        if ent.get("bytes"):
+            # the capture was taken at n_capture planets; the kernel's DRAM traffic is dominated by the
+            # column-partial buffer, which scales like n^2 -> scale to this run's RMS active count
+            nc = float(ent.get("n_capture") or n_eff)
+            traffic = float(ent["bytes"]) * (n_eff / nc) ** 2 / max(1, world)
+            traffic_note = "ncu capture at n=%d (%s) scaled by (n_eff/n_capture)^2%s" % (
+                nc, ent.get("source", "profiles/"), " / ranks" if world > 1 else "")
+    except Exception:
+        pass
+    tab = stage_table(stage_events, world)
+    return {"bound": "fma_pipe_" + prec, "kernel": kname,
+            "frac_vs_one_sided_convention": (kernel_rate * INSTR_PER_INTERACTION[prec] * 2 / 1e12 / peak) if peak else None,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": (achieved / peak) if peak else None, "traffic": traffic, "traffic_note": traffic_note,
+            "algorithmic_bytes": n_eff * bytes_per_body,
+            "peak_source": "in-process %s micro-benchmark (cosmo_microbench) on this GPU; "
+                           "MEASURED_PEAKS.json holds no CUDA-core peak" % ("FFMA" if prec == "fp32" else "DFMA"),
+            "instr_per_interaction": ipi, "kernel_ms": accel_ms, "n_eff": n_eff,
+            "interactions_per_s_kernel": kernel_rate, "stage_ms": tab,
+            "outside_stage_timers_ms": ms_per_step - tab["sum"],
+            "exchange_ms": ({"after_stage_a": float(np.mean([ev[5].elapsed_time(ev[2]) for ev in stage_events])),
+                             "after_stage_b": float(np.mean([ev[6].elapsed_time(ev[3]) for ev in stage_events]))}
+                            if world > 1 else None),
+            "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in mp else "fallback"},
+            "mufu_rsq_per_s_peak": peaks.get("mufu_rsq_per_s")}
+
+
+def secondary_fp64_block(device, peaks, flush, steps=5, warmup=3):
+    """BASELINE config 3 (star+disk, N = 65,536, FP64 parity path, one GPU) measured in the same run,
+    so the parity kernel has a driver-run record of its own: value, ms per step, roofline."""
+    from cosmosim_b200.engine import Engine
+    kind, n, prec, collisions = WORKLOADS["star_disk_64k_fp64"]
+    arrays = build_arrays(kind, n)
+    eng = Engine(n, device=device)
+    eng.upload(arrays)
+    kw = dict(collisions=collisions, bounded=True, fp32=False)
+    import torch
+    for _ in range(warmup):
+        eng.step(1, DT, G, R_MAX, **kw)
+        flush.zero_()
+    torch.cuda.synchronize()
+    ms, n_per_step, stage_events, launches = timed_frames(eng, steps, kw, flush, torch.cuda.synchronize, 1)
+    st = eng.check_errors()
+    roof = roofline_block(eng, prec, kw, peaks, stage_events, n_per_step, 1, "star_disk_64k_fp64", ms / steps)
+    return {"workload": "star_disk_64k_fp64", "n_bodies": n, "precision": "fp64", "steps": steps, "warmup": warmup,
+            "value": float(np.sum(n_per_step ** 2)) / (ms * 1e-3), "unit": "interactions/s",
+            "ms_per_step": ms / steps, "steps_per_s": steps / (ms * 1e-3), "gpu_launches": launches,
+            "n_active_per_step": [int(x) for x in n_per_step], "merges": st["n_events"], "roofline": roof,
+            "parity": "FP64 path: accelerations / positions <= 1e-12 vs the reference per step, merges bit-exact "
+                      "(tests/test_gpu_parity.py)"}
+
+
 # ------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -163,7 +311,7 @@ def main():
     ap.add_argument("--bodies", dest="n", type=int, default=0, help="override the body count (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--f32-scalar", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the full-N and FP64 secondary blocks")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     a = ap.parse_args()
 
@@ -202,7 +350,6 @@ def main():
     # ---------------------------------------------------------------- B200 arm
     import torch
     import torch.distributed as dist
-    from cosmosim_b200 import _abi
     from cosmosim_b200.engine import Engine
 
     torch.cuda.set_device(local_rank)
@@ -213,7 +360,7 @@ def main():
     arrays = build_arrays(kind, n)
     eng = Engine(n, device="cuda:%d" % local_rank, group=group)
     eng.upload(arrays)
-    kw = dict(collisions=collisions, bounded=True, fp32=(prec == "fp32"), f32_scalar=a.f32_scalar)
+    kw = dict(collisions=collisions, bounded=True, fp32=(prec == "fp32"))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
 
     def barrier():
@@ -226,31 +373,13 @@ def main():
         sampler.start()              # started early: nvidia-smi needs ~0.1 s before its first sample
     # pipe peaks for the roofline denominator (tiny, before the timed region)
     peaks = measure_pipe_peaks(eng, prec) if rank == 0 else {}
+    full_state = eng.save_state() if not a.no_extras else None     # the scene at its full size, on the device
     for _ in range(W):
         eng.step(1, DT, G, R_MAX, **kw)
         flush.zero_()
     barrier()
-    n_active_start = eng.status()["n_active"]
     warm_samples = len(sampler.lines)
-    barrier()
-    stage_events = []
-    status_log = torch.zeros(K + 1, 16, dtype=torch.int64).pin_memory()   # async snapshots, no sync
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = eng.lib.cosmo_launch_count()
-    e0.record()
-    for k in range(K):
-        status_log[k].copy_(eng.t["status"], non_blocking=True)
-        eng.step(1, DT, G, R_MAX, stage_events=stage_events, **kw)
-        flush.zero_()
-    e1.record()
-    gpu_launches = int(eng.lib.cosmo_launch_count() - launches0)     # counted inside the library
-    status_log[K].copy_(eng.t["status"], non_blocking=True)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        tms = torch.tensor([ms], dtype=torch.float64, device=eng.device)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    ms, n_per_step, stage_events, gpu_launches = timed_frames(eng, K, kw, flush, barrier, world)
     clocks = None
     if rank == 0:
         timed_samples = len(sampler.lines) - warm_samples
@@ -260,66 +389,31 @@ def main():
         clocks["window"] = "timed region" if timed_samples >= 3 else "pipe micro-benchmark + warm-up + timed region (timed region shorter than 3 samples of 20 ms)"
     st = eng.check_errors()
     # interactions actually evaluated: N_active^2 per frame, and N_active shrinks as planets merge
-    n_per_step = status_log[:K, 0].numpy().astype(np.float64)
     interactions = float(np.sum(n_per_step ** 2))
     n_eff = math.sqrt(interactions / K)
     value = interactions / (ms * 1e-3)
+    config["n_eff"] = n_eff          # RMS active count over the timed frames (the scene merges ~7 % of its planets per frame)
+    roofline = roofline_block(eng, prec, kw, peaks, stage_events, n_per_step, world, a.workload, ms / K)
+    digest = state_digest(eng)
+    replicas_identical = None
+    if world > 1:
+        got = [None] * world
+        dist.all_gather_object(got, digest)
+        replicas_identical = len(set(got)) == 1
 
-    roofline = None
-    if stage_events:
-        accel_each = np.array([ev[1].elapsed_time(ev[2]) for ev in stage_events])
-        accel_ms = float(np.mean(accel_each))
-        # interactions/s of stage A on THIS GPU (rank 0 evaluates 1/world of the pairs; with world > 1
-        # the stage time includes the all-reduce / all-gather that follows the kernel)
-        kernel_rate = float(np.sum(n_per_step ** 2) / world / np.sum(accel_each * 1e-3))
-        detect_ms = float(np.mean([ev[2].elapsed_time(ev[3]) for ev in stage_events]))
-        resolve_ms = float(np.mean([ev[3].elapsed_time(ev[4]) for ev in stage_events]))
-        prep_ms = float(np.mean([ev[0].elapsed_time(ev[1]) for ev in stage_events]))
-        opts_now = eng.params(DT, G, R_MAX, **kw).opts
-        sym = bool(opts_now & (_abi.OPT_F32_SYM | _abi.OPT_F64_SYM))
-        # the symmetric kernels evaluate each unordered pair once: 12 FMA-pipe (FP32) / 23 FP64-pipe
-        # instructions per pair = 6 / 11.5 per ordered interaction; the
-        # one-sided kernels need 9 (FP32) / 20 (FP64)
-        ipi = ({"fp32": 6.0, "fp64": 11.5}[prec]) if sym else INSTR_PER_INTERACTION[prec]
-        achieved = kernel_rate * ipi * 2 / 1e12                            # FMA-equivalent TFLOP/s
-        peak_key = "ffma_tflops" if prec == "fp32" else "dfma_tflops"
-        peak = peaks.get(peak_key)
-        # algorithmic HBM bytes of stage A per launch: sources read once (L2-resident afterwards)
-        # + targets' state read + new state written
-        bytes_per_body = (12 + 8 + 16 + 16 + 40) if prec == "fp32" else (32 + 16 + 16 + 40)
-        hbm_gbs = n_eff * bytes_per_body / (accel_ms * 1e-3) / 1e9
-        mp = {}
-        try:
-            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = mp.get("hbm_gbs", 6650.0)
-        kname = "k_accel_%s%s" % ("f32" if prec == "fp32" else "f64", "_sym" if sym else "")
-        traffic = None
-        try:   # DRAM bytes per launch from the committed ncu capture of this kernel on this workload
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-                "%s|%s" % (kname, a.workload), {}).get("bytes")
-        except Exception:
-            pass
-        roofline = {"bound": "fma_pipe_" + prec,
-                    "kernel": kname,
-                    "frac_vs_one_sided_convention": (kernel_rate * INSTR_PER_INTERACTION[prec] * 2 / 1e12 / peak)
-                    if peak else None,   # SURVEY 8d counts 9 (FP32) / 20 (FP64) instr per ordered interaction
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (achieved / peak) if peak else None, "traffic": traffic,
-                    "peak_source": "in-process %s micro-benchmark (cosmo_microbench) on this GPU; "
-                                   "MEASURED_PEAKS.json holds no CUDA-core peak" % ("FFMA" if prec == "fp32" else "DFMA"),
-                    "instr_per_interaction": ipi, "kernel_ms": accel_ms,
-                    "interactions_per_s_kernel": kernel_rate,
-                    "stage_ms": {"prep": prep_ms, "accel_integrate" + ("+exchange" if world > 1 else ""): accel_ms,
-                                 "detect" + ("+exchange" if world > 1 else ""): detect_ms,
-                                 "resolve_commit": resolve_ms},
-                    "exchange_ms": ({"after_stage_a": float(np.mean([ev[5].elapsed_time(ev[2]) for ev in stage_events])),
-                                     "after_stage_b": float(np.mean([ev[6].elapsed_time(ev[3]) for ev in stage_events]))}
-                                    if world > 1 else None),
-                    "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak,
-                            "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in mp else "fallback"},
-                    "mufu_rsq_per_s_peak": peaks.get("mufu_rsq_per_s")}
+    # ---------------------------------------------------------------- full-N frames (device-timed)
+    full_n = None
+    if full_state is not None:
+        Kf = min(K, 5)
+        eng.restore_state(full_state)
+        eng.step(1, DT, G, R_MAX, **kw)          # warm this size's launch shapes
+        fms, fn, fev, _ = timed_frames(eng, Kf, kw, flush, barrier, world, restore=full_state)
+        eng.check_errors()
+        full_n = {"n_bodies": int(fn[0]), "steps": Kf, "ms_per_step": fms / Kf, "steps_per_s": Kf / (fms * 1e-3),
+                  "value": float(np.sum(fn ** 2)) / (fms * 1e-3), "unit": "interactions/s",
+                  "stage_ms": stage_table(fev, world),
+                  "what": "every frame starts from the scene's initial state (N = %d, restored device-to-device "
+                          "outside the frame's events): ms per TRUE full-size frame, device-timed" % int(fn[0])}
 
     # ---------------------------------------------------------------- e2e (host buffers)
     e2e = None
@@ -345,8 +439,15 @@ def main():
         # every e2e step re-uploads the same n-planet host state, so each evaluates n^2 pairs
         e2e = {"value": float(n) * n * K / (e_ms * 1e-3), "unit": "interactions/s",
                "h2d_bytes_per_step": int(stg["h2d_bytes"]), "d2h_bytes_per_step": int(stg["d2h_bytes"]),
-               "ms_per_step": e_ms / K, "wall_ms_per_step": wall_ms / K,
-               "path": "Engine.frame_from_host: pinned host SoA -> H2D -> cosmo_step -> D2H, stream sync per step"}
+               "ms_per_step": e_ms / K, "wall_ms_per_step": wall_ms / K, "n_bodies_per_step": n,
+               "path": stg.get("path", "Engine.frame_from_host: pinned host SoA -> H2D -> frame -> D2H, stream sync per step")}
+
+    secondary = None
+    if rank == 0 and world == 1 and not a.no_extras and a.workload == "star_disk_1m_fp32":
+        del eng
+        torch.cuda.empty_cache()
+        peaks64 = peaks if "dfma_tflops" in peaks else {}
+        secondary = secondary_fp64_block("cuda:%d" % local_rank, peaks64, flush)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -359,13 +460,13 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32" if prec == "fp32" else "f64", "data": "synthetic", "config": config,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
-                "roofline": roofline, "cpu_baseline": cpu,
+                "roofline": roofline, "cpu_baseline": cpu, "full_n": full_n, "secondary": secondary,
                 "final_state": {"n_active": st["n_active"], "merges": st["n_events"], "escaped": st["n_escaped"]},
+                "state_digest": digest, "replicas_identical": replicas_identical,
                 "n_active_per_step": [int(x) for x in n_per_step],
-                "pairs_last_frame": st["n_pairs"], "detect_mode": "grid" if eng.grid is not None else "all-pairs",
-                "jsplit": eng.params(DT, G, R_MAX, **kw).jsplit,
-                "exchange": (("nvlink peer stores + symmetric-memory barrier" if getattr(eng, "_peer", None)
-                              else "nccl (%s)" % getattr(eng, "_peer_error", "peer exchange not used")) if world > 1 else None)}
+                "pairs_last_frame": st["n_pairs"], "detect_mode": "grid (tuned on the device)" if st["n_active"] >= 8192 else "all-pairs",
+                "fp32_bound": ("per-step relative acceleration error vs the FP64 reference formula: see "
+                               "tests/test_gpu_parity.py::test_n1m_fp32_full_size_properties") if prec == "fp32" else None}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -380,6 +481,7 @@ def cpu_oracle3_leg(arrays, seconds_target=12.0, steps=1, warmup=0):
     from oracle import oracle3d as o3
     n = arrays["mass_f64"].shape[0]
     pos, vel, mass, rad = arrays["pos"], arrays["vel"], arrays["mass_f64"], arrays["radius"]
+    orc.set_threads(host_threads())
     cores = orc.num_threads()
 
     def sample(rows):

@@ -6,13 +6,13 @@ import os
 
 from . import _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 PAD = 1024
 STATUS_LEN = 16
 
 # flag / option / status constants (mirror the header)
 F_IMMOBILE, F_MASS_INT = 1, 2
-OPT_COLLISIONS, OPT_BOUNDED, OPT_FP32, OPT_STORE_ACC, OPT_F32_SCALAR, OPT_F32_SYM, OPT_DEFER_INTEGRATE, OPT_ENERGY, OPT_F64_SYM, OPT_PEER_EXCHANGE = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
+OPT_COLLISIONS, OPT_BOUNDED, OPT_FP32, OPT_STORE_ACC, OPT_F32_SYM, OPT_DEFER_INTEGRATE, OPT_ENERGY, OPT_F64_SYM, OPT_PEER_EXCHANGE = 1, 2, 4, 8, 32, 64, 128, 256, 512
 ST_N_ACTIVE, ST_STEP, ST_N_EVENTS, ST_N_PAIRS, ST_N_DEAD, ST_ERROR, ST_N_ESCAPED, ST_N_CAND, ST_N_GIANTS, ST_PMAX2, ST_N_COMPLEX, ST_SLOT_LO, ST_SLOT_HI, ST_EV_BASE, ST_N_HEAVY = range(15)
 SCAN_BLOCKS = 8192
 ERR_PAIR_OVERFLOW, ERR_EVENT_OVERFLOW, ERR_NAN, ERR_GIANT_OVERFLOW = 1, 2, 4, 8
@@ -44,7 +44,18 @@ class Scratch(C.Structure):
                 ("t_id", _vp), ("t_flags", _vp), ("t_energy", _vp),
                 ("cell_of", _vp), ("cell_count", _vp), ("cell_start", _vp), ("cell_items", _vp),
                 ("giants", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32),
-                ("peer_acc", _vp * 16), ("n_peers", C.c_int32), ("reserved_scratch", C.c_int32)]
+                ("peer_acc", _vp * 16), ("n_peers", C.c_int32), ("reserved_scratch", C.c_int32),
+                ("grid_dev", _vp), ("tune_hist", _vp)]
+
+
+class Grid(C.Structure):
+    """cosmo_grid: the device-resident broad-phase grid of the current frame."""
+    _fields_ = [("h", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("rg", C.c_double),
+                ("ncell", C.c_int64), ("c", C.c_int32), ("w", C.c_int32), ("source", C.c_int32),
+                ("reserved", C.c_int32), ("box", C.c_double), ("h_tuned", C.c_double)]
+
+
+TUNE_HIST_LEN = 2 * 65536 + 4096
 
 
 class StepParams(C.Structure):
@@ -52,7 +63,7 @@ class StepParams(C.Structure):
                 ("opts", C.c_uint32), ("n_upper", C.c_int32), ("i_begin", C.c_int32),
                 ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
                 ("jsplit", C.c_int32), ("detect_mode", C.c_int32), ("resolve_mode", C.c_int32),
-                ("small_tiles", C.c_int32), ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("sym_chunk", C.c_int32), ("reserved0", C.c_int32), ("grid_log_cells", C.c_int32), ("reserved1", C.c_int32),
+                ("small_tiles", C.c_int32), ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("sym_chunk", C.c_int32), ("near_mode", C.c_int32), ("grid_log_cells", C.c_int32), ("reserved1", C.c_int32),
                 ("cell_size", C.c_double),
                 ("grid_origin_x", C.c_double), ("grid_origin_y", C.c_double), ("cells_per_side", C.c_int32), ("jsplit_detect", C.c_int32),
                 ("giant_radius", C.c_double)]
@@ -80,7 +91,7 @@ class Scratch3(C.Structure):
                 ("t_density", _vp), ("t_radius", _vp), ("t_id", _vp), ("t_flags", _vp),
                 ("cell_of", _vp), ("cell_count", _vp), ("cell_start", _vp), ("cell_items", _vp), ("giants", _vp),
                 ("chunk_bounds", _vp), ("heavy_rows", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32),
-                ("colbuf", _vp), ("colbuf_rows", C.c_int64)]
+                ("colbuf", _vp), ("colbuf_rows", C.c_int64), ("grid_dev", _vp), ("tune_hist", _vp)]
 
 
 class StepParams3(C.Structure):
@@ -102,6 +113,7 @@ SYMBOLS = {
     "cosmo3_resolve_commit": (C.c_int, _S3),
     "cosmo3_step": (C.c_int, _S3),
     "cosmo3_integrate": (C.c_int, _S3),
+    "cosmo3_seal_pair_row": (C.c_int, [C.POINTER(State3), _vp, _vp]),
     "cosmo3_append_pair_rows": (C.c_int, [C.POINTER(State3), C.POINTER(Scratch3), _vp, C.c_int32, C.c_int64, _vp]),
     "cosmo3_suggest_jsplit": (C.c_int, [C.c_int32, C.c_int32, C.c_int, C.c_int32]),
     "cosmo3_host_truediv": (C.c_double, [C.c_uint64] * 4),
@@ -120,6 +132,7 @@ SYMBOLS = {
     "cosmo_step": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams), _vp]),
     "cosmo_append_pairs": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), _vp, _vp, C.c_int64, _vp]),
     "cosmo_append_pair_rows": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), _vp, C.c_int32, C.c_int64, _vp]),
+    "cosmo_seal_pair_row": (C.c_int, [C.POINTER(State), _vp, _vp]),
     "cosmo_accel_workspace_bytes": (C.c_int64, [C.c_int32]),
     "cosmo_accel": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "cosmo_accel_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp,

@@ -170,6 +170,14 @@ int cosmo_append_pairs(const cosmo_state *st, const cosmo_scratch *sc, const uin
     return launch_append_pairs(*st, *sc, src, count_ptr, max_count, (cudaStream_t)stream);
 }
 
+int cosmo_seal_pair_row(const cosmo_state *st, int64_t *row, void *stream) {
+    if (!st || !st->status || !row) {
+        set_error("cosmo_seal_pair_row: null argument");
+        return COSMO_E_ARG;
+    }
+    return launch_seal_pair_row(st->status, row, (cudaStream_t)stream);
+}
+
 int cosmo_append_pair_rows(const cosmo_state *st, const cosmo_scratch *sc, const int64_t *rows, int32_t n_rows,
                            int64_t max_count, void *stream) {
     if (!st || !sc || !rows || n_rows <= 0 || max_count <= 0) {

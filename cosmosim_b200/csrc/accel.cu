@@ -310,7 +310,7 @@ k_accel_f64(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
 // hot loop; the self term then contributes dx * s = 0 exactly.
 #define COSMO_F32_TINY 8.673617379884035e-19f
 
-template <int BLOCK, int IB, int TJ, bool PACKED>
+template <int BLOCK, int IB, int TJ>
 __global__ void __launch_bounds__(BLOCK)
 k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit, double G, double dt,
             double unscale, int store_acc) {
@@ -363,7 +363,7 @@ k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
         mbar_wait(&s_bar[b], (it >> 1) & 1);
         // Slots past n inside the tile hold zero mass (k_prep), so full tiles are always
         // processed: no tail bound in the hot loop.
-        if (PACKED) {
+        {
             uint64_t xi2[IB], yi2[IB], ax2[IB], ay2[IB];
             const uint64_t eps2 = pack2(COSMO_F32_TINY, COSMO_F32_TINY);
 #pragma unroll
@@ -401,25 +401,6 @@ k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
                 unpack2(ay2[k], a, c);
                 ayd[k] += (double)a + (double)c;
             }
-        } else {
-            float ax[IB], ay[IB];
-#pragma unroll
-            for (int k = 0; k < IB; ++k) { ax[k] = 0.f; ay[k] = 0.f; }
-#pragma unroll 8
-            for (int jj = 0; jj < TJ; ++jj) {
-                const float xj = s_x[b][jj], yj = s_y[b][jj], mj = s_m[b][jj];
-#pragma unroll
-                for (int k = 0; k < IB; ++k) {
-                    float dx = xj - xi[k], dy = yj - yi[k];
-                    float r2 = fmaf(dy, dy, fmaf(dx, dx, COSMO_F32_TINY));
-                    float rinv = rsqrt_approx_f32(r2);
-                    float s = (mj * rinv) * (rinv * rinv);
-                    ax[k] = fmaf(dx, s, ax[k]);
-                    ay[k] = fmaf(dy, s, ay[k]);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < IB; ++k) { axd[k] += (double)ax[k]; ayd[k] += (double)ay[k]; }
         }
         __syncthreads();
     }
@@ -436,18 +417,15 @@ constexpr int F32_BLOCK = 256, F32_IB = 4, F32_TJ = 512;
 constexpr int F64S_BLOCK = 64, F64S_IB = 1, F64S_TJ = 64;  // small-N shape: many short CTAs
 static_assert(COSMO_PAD % F64_TJ == 0 && COSMO_PAD % F32_TJ == 0, "tiles must divide the slot padding");
 
-// resident CTAs per SM of the all-pairs kernels (0: FP64, 1: FP32 packed, 2: FP32 scalar)
+// resident CTAs per SM of the all-pairs kernels (0: FP64, otherwise FP32)
 int accel_residency(int which, int *rows_per_cta, int *tile) {
     int nb = 0;
     cudaError_t e;
     if (which == 0) {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accel_f64<F64_BLOCK, F64_IB, F64_TJ>, F64_BLOCK, 0);
         *rows_per_cta = F64_BLOCK * F64_IB; *tile = F64_TJ;
-    } else if (which == 1) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accel_f32<F32_BLOCK, F32_IB, F32_TJ, true>, F32_BLOCK, 0);
-        *rows_per_cta = F32_BLOCK * F32_IB; *tile = F32_TJ;
     } else {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accel_f32<F32_BLOCK, F32_IB, F32_TJ, false>, F32_BLOCK, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accel_f32<F32_BLOCK, F32_IB, F32_TJ>, F32_BLOCK, 0);
         *rows_per_cta = F32_BLOCK * F32_IB; *tile = F32_TJ;
     }
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -479,12 +457,8 @@ int launch_accel(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_ste
         dim3 grid((rows + per - 1) / per, jsplit);
         // S = S_scaled * 2^(mass_exp - 2 pos_exp)
         const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
-        if (p.opts & COSMO_OPT_F32_SCALAR)
-            k_accel_f32<F32_BLOCK, F32_IB, F32_TJ, false><<<grid, F32_BLOCK, 0, s>>>(
-                st, sc, p.i_begin, p.i_end, jsplit, p.G, p.dt, unscale, store_acc);
-        else
-            k_accel_f32<F32_BLOCK, F32_IB, F32_TJ, true><<<grid, F32_BLOCK, 0, s>>>(
-                st, sc, p.i_begin, p.i_end, jsplit, p.G, p.dt, unscale, store_acc);
+        k_accel_f32<F32_BLOCK, F32_IB, F32_TJ><<<grid, F32_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit, p.G, p.dt,
+                                                                         unscale, store_acc);
         return COSMO_LAUNCH_CHECK("k_accel_f32");
     }
     if (p.small_tiles) {

@@ -42,20 +42,14 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src_lane) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-// PRIVATE (development variant, measured 2.5 % slower than the shared copy with 8 barriers per
-// column block: 98.3 vs 100.8 ms at N = 2^20): every warp keeps its own copy of the column sums (8 x 1024 x float2 = 64 KB of dynamic
-// shared memory); each (warp, column group) slot is written exactly once per column block, so the
-// 8 rounds need no barrier at all -- the warps drift apart and interleave their MUFU / FMA phases;
-// one barrier pair per column block for the 8-way reduction.
-template <int MINB, int SUNROLL, bool PRIVATE>
-__global__ void __launch_bounds__(SYM_THREADS, MINB)
+__global__ void __launch_bounds__(SYM_THREADS, 2)
 k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int chunk) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     float (*s_x)[SYM_BLOCK] = reinterpret_cast<float (*)[SYM_BLOCK]>(s_dyn);
     float (*s_y)[SYM_BLOCK] = s_x + 2;
     float (*s_m)[SYM_BLOCK] = s_x + 4;
-    // column accumulators of the current J: [copy][x|y][1024]; one copy unless PRIVATE
-    float (*s_c)[2][SYM_BLOCK] = reinterpret_cast<float (*)[2][SYM_BLOCK]>(s_x + 6);
+    // column accumulators of the current J: [x|y][1024]
+    float (*s_c)[SYM_BLOCK] = s_x + 6;
     __shared__ __align__(8) uint64_t s_bar[2];
 
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
@@ -104,11 +98,9 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
         const int it_j = J - J0;
         const int b = it_j & 1;
         if (tid == 0 && J + 1 < J1) issue(J + 1, b ^ 1);
-        if (!PRIVATE) {
-            for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) { s_c[0][0][q] = 0.f; s_c[0][1][q] = 0.f; }
-        }
+        for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) { s_c[0][q] = 0.f; s_c[1][q] = 0.f; }
         mbar_wait(&s_bar[b], (it_j >> 1) & 1);
-        if (!PRIVATE) __syncthreads();
+        __syncthreads();
         const bool diag = (J == I);
         uint64_t rx2[4], ry2[4];
 #pragma unroll
@@ -120,7 +112,7 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
             const float *gy = &s_y[b][g * SYM_GROUP];
             const float *gm = &s_m[b][g * SYM_GROUP];
             uint64_t tx2[2] = {0ull, 0ull}, ty2[2] = {0ull, 0ull};   // travelling column sums
-#pragma unroll SUNROLL
+#pragma unroll 2
             for (int s = 0; s < 32; ++s) {
                 const int c = (lane + s) & 31;
                 const float4 X = *reinterpret_cast<const float4 *>(gx + 4 * c);
@@ -159,19 +151,14 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
                 float a0, a1, a2, a3, b0, b1, b2, b3;
                 unpack2(tx2[0], a0, a1); unpack2(tx2[1], a2, a3);
                 unpack2(ty2[0], b0, b1); unpack2(ty2[1], b2, b3);
-                if (PRIVATE) {   // this (warp, group) slot is written once per column block
-                    *reinterpret_cast<float4 *>(&s_c[w][0][g * SYM_GROUP + 4 * lane]) = make_float4(a0, a1, a2, a3);
-                    *reinterpret_cast<float4 *>(&s_c[w][1][g * SYM_GROUP + 4 * lane]) = make_float4(b0, b1, b2, b3);
-                } else {
-                    float4 cx = *reinterpret_cast<float4 *>(&s_c[0][0][g * SYM_GROUP + 4 * lane]);
-                    float4 cy = *reinterpret_cast<float4 *>(&s_c[0][1][g * SYM_GROUP + 4 * lane]);
-                    cx.x += a0; cx.y += a1; cx.z += a2; cx.w += a3;
-                    cy.x += b0; cy.y += b1; cy.z += b2; cy.w += b3;
-                    *reinterpret_cast<float4 *>(&s_c[0][0][g * SYM_GROUP + 4 * lane]) = cx;
-                    *reinterpret_cast<float4 *>(&s_c[0][1][g * SYM_GROUP + 4 * lane]) = cy;
-                }
+                float4 cx = *reinterpret_cast<float4 *>(&s_c[0][g * SYM_GROUP + 4 * lane]);
+                float4 cy = *reinterpret_cast<float4 *>(&s_c[1][g * SYM_GROUP + 4 * lane]);
+                cx.x += a0; cx.y += a1; cx.z += a2; cx.w += a3;
+                cy.x += b0; cy.y += b1; cy.z += b2; cy.w += b3;
+                *reinterpret_cast<float4 *>(&s_c[0][g * SYM_GROUP + 4 * lane]) = cx;
+                *reinterpret_cast<float4 *>(&s_c[1][g * SYM_GROUP + 4 * lane]) = cy;
             }
-            if (!PRIVATE) __syncthreads();   // the next round moves every warp to another column group
+            __syncthreads();   // the next round moves every warp to another column group
         }
         // fold this block's FP32 row sums into the FP64 accumulators
 #pragma unroll
@@ -182,19 +169,9 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
             unpack2(ry2[k], a, c2);
             ray[k] += (double)a + (double)c2;
         }
-        if (PRIVATE) __syncthreads();   // all 8 rounds of all warps are done
         if (!diag) {
             float2 *dst = colbuf + col_row + (size_t)J * SYM_BLOCK;
-            for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) {
-                if (PRIVATE) {       // fixed order w = 0..7: deterministic
-                    float sx = 0.f, sy = 0.f;
-#pragma unroll
-                    for (int ww = 0; ww < SYM_WARPS; ++ww) { sx += s_c[ww][0][q]; sy += s_c[ww][1][q]; }
-                    dst[q] = make_float2(sx, sy);
-                } else {
-                    dst[q] = make_float2(s_c[0][0][q], s_c[0][1][q]);
-                }
-            }
+            for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) dst[q] = make_float2(s_c[0][q], s_c[1][q]);
         }
         __syncthreads();   // column accumulators and buffer b are free again
     }
@@ -289,20 +266,8 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
     if (rows_local > 0) {
         dim3 grid(rows_local, (nblk + chunk - 1) / chunk);
         constexpr size_t kTma = 6 * SYM_BLOCK * sizeof(float);                 // x, y, m double-buffered
-        constexpr size_t kShared = kTma + 2 * SYM_BLOCK * sizeof(float);       // one column copy
-        constexpr size_t kPrivate = kTma + SYM_WARPS * 2 * SYM_BLOCK * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            COSMO_TRY(check_cuda(cudaFuncSetAttribute(k_accel_f32_sym<2, 2, true>,
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrivate),
-                                 "cudaFuncSetAttribute(sym private)"));
-            attr_set = true;
-        }
-        switch (p.reserved0) {   // development variants; 0 is the shipped one
-            case 1: k_accel_f32_sym<2, 2, true><<<grid, SYM_THREADS, kPrivate, s>>>(st, sc, sh_i, sh_n, chunk); break;
-            case 2: k_accel_f32_sym<2, 1, false><<<grid, SYM_THREADS, kShared, s>>>(st, sc, sh_i, sh_n, chunk); break;
-            default: k_accel_f32_sym<2, 2, false><<<grid, SYM_THREADS, kShared, s>>>(st, sc, sh_i, sh_n, chunk); break;
-        }
+        constexpr size_t kShared = kTma + 2 * SYM_BLOCK * sizeof(float);       // + the column accumulators
+        k_accel_f32_sym<<<grid, SYM_THREADS, kShared, s>>>(st, sc, sh_i, sh_n, chunk);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_accel_f32_sym"));
     }
     const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? ((p.opts & COSMO_OPT_PEER_EXCHANGE) ? 2 : 1) : 0;

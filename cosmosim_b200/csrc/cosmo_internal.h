@@ -48,6 +48,7 @@ int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc,
 int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const uint64_t *src,
                         const int64_t *count_ptr, int64_t max_count, cudaStream_t s);
 
+int launch_seal_pair_row(int64_t *status, int64_t *row, cudaStream_t s);
 int launch_append_pair_rows(const cosmo_state &st, const cosmo_scratch &sc, const int64_t *rows, int n_rows,
                             long long max_count, cudaStream_t s);
 

@@ -99,25 +99,21 @@ k_detect_allpairs(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int 
 // ---------------------------------------------------------------------------------------
 // Uniform-grid broad phase
 // ---------------------------------------------------------------------------------------
-struct GridParams {
-    double h, cx, cy, rg;   // cell edge, centre of the linear box, giant radius
-    int c, w;               // cells per side (total), logarithmic cells on each side
-};
+// The grid of the current frame lives on the device (scratch.grid_dev, cosmo_grid): it is either
+// copied from the step parameters (detect_mode 1, k_grid_set) or TUNED ON THE DEVICE from the
+// frame's own positions and radii (detect_mode 2, k_grid_hist + k_grid_tune) -- the host never
+// reads planet data while stepping.  Only two properties matter for correctness, and both are
+// enforced here whatever the tuning says: the cell edge is at least the largest separation at which
+// two non-giants can be flagged, and every planet above the giant radius is brute-forced.
 
-// Cell edge actually used.  The reference compares the COMPUTED distance (expanded form,
+// Smallest admissible cell edge.  The reference compares the COMPUTED distance (expanded form,
 // absolute error E in d^2 of a few ulps of |p|^2) with r_i + r_j, so two non-giants (inflated
 // radius <= rg) can be flagged while truly sqrt(4 rg^2 + E) apart; the cell edge is never
 // smaller than that (plus slack for the rounding of the cell coordinate itself).
-__device__ __forceinline__ GridParams grid_params(const cosmo_state &st, double h, double ox, double oy,
-                                                  double rg, int c, int w) {
-    GridParams g;
+__device__ __forceinline__ double grid_hmin(const cosmo_state &st, double rg) {
     const double pmax2 = __longlong_as_double(st.status[COSMO_ST_PMAX2]);
     const double e = 64.0 * 1.1102230246251565e-16 * pmax2;
-    const double hmin = sqrt(4.0 * rg * rg + e) * (1.0 + 1e-6);
-    g.h = fmax(h, hmin);
-    const double half_in = 0.5 * (double)(c - 2 * w) * h;   // the centre is fixed by the host's (h, origin)
-    g.cx = ox + half_in; g.cy = oy + half_in; g.rg = rg; g.c = c; g.w = w;
-    return g;
+    return sqrt(4.0 * rg * rg + e) * (1.0 + 1e-6);
 }
 
 // Cell coordinate along one axis.  u = (x - centre) / h is mapped by a monotone function of
@@ -137,15 +133,195 @@ __device__ __forceinline__ int cell_coord(double x, double centre, double h, int
     return (int)t;
 }
 
-__global__ void __launch_bounds__(256) k_grid_max(cosmo_state st, cosmo_scratch sc) {
+template <bool D3>
+__device__ __forceinline__ double2 xy_of(const cosmo_state &st, const cosmo_scratch &sc, int k);
+
+// Tuning histograms (scratch.tune_hist, int32, all zero between frames):
+//   [0, 65536)           x coordinates of a strided sample of the planets
+//   [65536, 131072)      y coordinates
+//   [131072, 135168)     inflated radii of ALL planets
+// Coordinates are binned by the top 16 bits of an order-preserving key of their FP32 value
+// (sign, exponent, 7 mantissa bits: 0.8 % relative resolution anywhere, no range to choose);
+// radii by exponent + 4 mantissa bits (6 %).
+constexpr int TUNE_XY_BINS = 65536, TUNE_R_BINS = 4096;
+constexpr int TUNE_SAMPLE = 131072;       // coordinates sampled for the quantile box
+
+__device__ __forceinline__ uint32_t tune_key(double v) {
+    const float f = (float)fmin(fmax(v, -3.0e38), 3.0e38);
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ double tune_key_value(uint32_t key) {
+    const uint32_t u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+    return (double)__uint_as_float(u);
+}
+__device__ __forceinline__ int tune_rbin(double r) {
+    const float f = (float)fmin(fmax(r, 0.0), 3.0e38);
+    return (int)((__float_as_uint(f) >> 19) & (TUNE_R_BINS - 1));
+}
+__device__ __forceinline__ double tune_rbin_upper(int b) {
+    return (double)__uint_as_float(((uint32_t)b << 19) | 0x7ffffu);
+}
+
+// max |pos_new|^2 of the frame (-> hmin) and, with TUNE, the tuning histograms
+template <bool D3, bool TUNE>
+__global__ void __launch_bounds__(256) k_grid_hist(cosmo_state st, cosmo_scratch sc) {
+    __shared__ int s_r[TUNE ? TUNE_R_BINS : 1];
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    if (TUNE) {
+        for (int q = threadIdx.x; q < TUNE_R_BINS; q += blockDim.x) s_r[q] = 0;
+        __syncthreads();
+    }
+    const int stride = max(1, n / TUNE_SAMPLE);
     double m = 0.0;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         m = fmax(m, sc.xx_new[k]);
+        if (TUNE) {
+            atomicAdd(&s_r[tune_rbin(sc.rinf[k])], 1);
+            if (k % stride == 0) {
+                const double2 p = xy_of<D3>(st, sc, k);
+                atomicAdd(&sc.tune_hist[tune_key(p.x) >> 16], 1);
+                atomicAdd(&sc.tune_hist[TUNE_XY_BINS + (tune_key(p.y) >> 16)], 1);
+            }
+        }
+    }
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0.0)  // non-negative doubles order like their bit patterns
         atomicMax(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_PMAX2]),
                   (unsigned long long)__double_as_longlong(m));
+    if (TUNE) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < TUNE_R_BINS; q += blockDim.x)
+            if (s_r[q]) atomicAdd(&sc.tune_hist[2 * TUNE_XY_BINS + q], s_r[q]);
+    }
+}
+
+// detect_mode 1: the caller's grid (cell_size, origin of the linear box, cells per side, giant radius)
+__global__ void k_grid_set(cosmo_state st, cosmo_scratch sc, double h, double ox, double oy, double rg, int c, int w) {
+    cosmo_grid g;
+    const double half_in = 0.5 * (double)(c - 2 * w) * h;    // the centre is fixed by the caller's (h, origin)
+    g.h = fmax(h, grid_hmin(st, rg));
+    g.cx = ox + half_in; g.cy = oy + half_in; g.rg = rg;
+    g.ncell = (int64_t)c * c; g.c = c; g.w = w; g.source = 1; g.reserved = 0;
+    g.box = (double)(c - 2 * w) * h; g.h_tuned = h;
+    *sc.grid_dev = g;
+}
+
+// exclusive prefix sum over the 1024 threads of the CTA; *total = sum of all
+__device__ __forceinline__ int block_scan_1024(int v, int *s_w, int *total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int x = s_w[lane], y = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, y, o);
+            if (lane >= o) y += t;
+        }
+        s_w[32 + lane] = y - x;                 // exclusive warp offsets
+        if (lane == 31) s_w[64] = y;
+    }
+    __syncthreads();
+    *total = s_w[64];
+    return s_w[32 + w] + inc - v;
+}
+
+// detect_mode 2: one CTA turns the histograms into the frame's grid.
+//   box     robust 2 % .. 98 % quantile box of the coordinates (NOT min/max: a handful of planets
+//           flung out by a close encounter must not stretch the cells over the whole scene; they
+//           land in the logarithmic rim / border cells instead, which is exact, only slower for them)
+//   rg      giant radius from a cost model: g giants cost g*n exact tests, everybody else
+//           9 cells * (n / area) * (2 rg)^2 candidates; g in {0, 1, 2, 4, ..., 1024}
+//   h       cell edge for ~16 candidates per planet, never below 2 rg (nor below grid_hmin)
+// and returns the histograms to zero.
+__global__ void __launch_bounds__(1024) k_grid_tune(cosmo_state st, cosmo_scratch sc, int w) {
+    __shared__ int s_w[65];
+    __shared__ double s_q[4];          // x lo, x hi, y lo, y hi
+    __shared__ double s_big[12];       // (g+1)-th largest inflated radius (upper bin edge), g = 0,1,2,4,..,1024
+    const int tid = threadIdx.x;
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    if (tid < 4) s_q[tid] = 0.0;
+    if (tid < 12) s_big[tid] = -1.0;
+    // ---- coordinate quantiles: thread t owns bins [64 t, 64 t + 64) of each axis
+    for (int axis = 0; axis < 2; ++axis) {
+        int *hist = sc.tune_hist + axis * TUNE_XY_BINS;
+        int loc = 0;
+        for (int q = 0; q < 64; ++q) loc += hist[tid * 64 + q];
+        int total;
+        const int before = block_scan_1024(loc, s_w, &total);
+        const long long r_lo = (long long)(0.02 * total), r_hi = min((long long)(0.98 * total), (long long)total - 1);
+        if (total > 0) {
+            int run = before;
+            for (int q = 0; q < 64; ++q) {
+                const int cnt = hist[tid * 64 + q];
+                const uint32_t bin = (uint32_t)(tid * 64 + q);
+                if (run <= r_lo && r_lo < run + cnt) s_q[2 * axis] = tune_key_value(bin << 16);
+                if (run <= r_hi && r_hi < run + cnt) s_q[2 * axis + 1] = tune_key_value((bin << 16) | 0xffffu);
+                run += cnt;
+            }
+        }
+        __syncthreads();
+        for (int q = 0; q < 64; ++q) hist[tid * 64 + q] = 0;
+    }
+    // ---- radius order statistics from the top: thread t owns bins [4 t, 4 t + 4)
+    {
+        int *hist = sc.tune_hist + 2 * TUNE_XY_BINS;
+        int loc = 0;
+        for (int q = 0; q < 4; ++q) loc += hist[tid * 4 + q];
+        int total;
+        const int before = block_scan_1024(loc, s_w, &total);
+        int above = total - before - loc;               // planets in bins above this thread's
+        for (int q = 3; q >= 0; --q) {
+            const int cnt = hist[tid * 4 + q];
+            if (cnt) {
+#pragma unroll
+                for (int gi = 0; gi < 12; ++gi) {
+                    const int g = gi == 0 ? 0 : 1 << (gi - 1);
+                    if (above < g + 1 && g + 1 <= above + cnt) s_big[gi] = tune_rbin_upper(tid * 4 + q);
+                }
+            }
+            above += cnt;
+            hist[tid * 4 + q] = 0;
+        }
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    cosmo_grid g;
+    double box = fmax(s_q[1] - s_q[0], s_q[3] - s_q[2]);
+    const double pmax = sqrt(__longlong_as_double(st.status[COSMO_ST_PMAX2]));
+    if (!(box > 0.0) || !isfinite(box)) box = fmax(2.0 * pmax, 1e-300);
+    box *= 1.25;                                          // the bulk; tails go to the rim cells
+    g.cx = 0.5 * (s_q[0] + s_q[1]); g.cy = 0.5 * (s_q[2] + s_q[3]);
+    if (!isfinite(g.cx) || !isfinite(g.cy)) { g.cx = 0.0; g.cy = 0.0; }
+    const double dn = (double)max(n, 1), area = fmax(box * box, 1.0);
+    double best = -1.0, rg = 0.0;
+    for (int gi = 0; gi < 12; ++gi) {
+        const int gg = gi == 0 ? 0 : 1 << (gi - 1);
+        if (gg > n - 1 || s_big[gi] < 0.0) break;
+        const double cost = gg * dn + dn * 9.0 * (dn / area) * (2.0 * s_big[gi]) * (2.0 * s_big[gi]);
+        if (best < 0.0 || cost < best) { best = cost; rg = s_big[gi]; }
+    }
+    const double span = fmax(box, 4.0 * rg) * 1.1;
+    int cmax = (int)floor(sqrt((double)sc.grid_cells));
+    while ((long long)cmax * cmax > sc.grid_cells) --cmax;
+    cmax -= 2 * w;
+    if (cmax < 1) cmax = 1;
+    double h = fmax(fmax(2.0 * rg * 1.001, span / cmax), span * 4.0 / (3.0 * sqrt(dn)));   // ~16 candidates per planet
+    int c = (int)ceil(span / h);
+    c = max(1, min(cmax, c));
+    rg = fmax(rg, h / (2.0 * 1.001));     // cells wider than 2 rg: admit larger planets for free
+    g.h_tuned = h;
+    g.h = fmax(h, grid_hmin(st, rg));
+    g.rg = rg; g.c = c + 2 * w; g.w = w; g.ncell = (int64_t)g.c * g.c; g.source = 2; g.reserved = 0; g.box = box;
+    *sc.grid_dev = g;
 }
 
 // D3 = true serves the 3-D step (state3d.cu): sc.pos_new then holds three PLANES double[3][cap] and
@@ -161,9 +337,9 @@ __device__ __forceinline__ double2 xy_of(const cosmo_state &st, const cosmo_scra
 
 template <bool D3>
 __global__ void __launch_bounds__(256)
-k_grid_count(cosmo_state st, cosmo_scratch sc, double h, double ox, double oy, double rg, int c, int w) {
+k_grid_count(cosmo_state st, cosmo_scratch sc) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
-    const GridParams g = grid_params(st, h, ox, oy, rg, c, w);
+    const cosmo_grid g = *sc.grid_dev;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         if (sc.rinf[k] > g.rg) {
             unsigned long long idx =
@@ -235,8 +411,8 @@ __device__ __forceinline__ void test_and_emit(const cosmo_state &st, const cosmo
 constexpr int GRID_CHUNK = 1024;
 constexpr int GRID_HEAVY = 128;   // candidates above which a row goes to the warp-per-row pass
 
-__global__ void __launch_bounds__(128) k_grid_ranges(cosmo_state st, cosmo_scratch sc, int c) {
-    const int ncell = c * c;
+__global__ void __launch_bounds__(128) k_grid_ranges(cosmo_state st, cosmo_scratch sc) {
+    const int ncell = (int)sc.grid_dev->ncell;
     const int total = sc.cell_start[ncell];
     const int nchunk = (total + GRID_CHUNK - 1) / GRID_CHUNK;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= nchunk; k += gridDim.x * blockDim.x) {
@@ -260,7 +436,8 @@ __global__ void __launch_bounds__(128) k_grid_ranges(cosmo_state st, cosmo_scrat
 // gathers hit the same lines.  Every row is produced by exactly one rank.
 template <bool D3>
 __global__ void __launch_bounds__(128)
-k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int c) {
+k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count) {
+    const int c = sc.grid_dev->c;
     const int total = sc.cell_start[c * c];
     const int nchunk = (total + GRID_CHUNK - 1) / GRID_CHUNK;
     unsigned cand_total = 0;
@@ -312,7 +489,8 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count
 
 // Warp-per-row pass for the rows k_grid_detect set aside: the lanes stride over the candidates.
 template <bool D3>
-__global__ void __launch_bounds__(256) k_grid_detect_heavy(cosmo_state st, cosmo_scratch sc, int c) {
+__global__ void __launch_bounds__(256) k_grid_detect_heavy(cosmo_state st, cosmo_scratch sc) {
+    const int c = sc.grid_dev->c;
     const int nh = (int)st.status[COSMO_ST_N_HEAVY];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -371,35 +549,55 @@ int detect_residency(int *rows_per_cta, int *tile) {
 template <bool D3>
 static int launch_grid(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p, cudaStream_t s) {
     const int rows = p.i_end - p.i_begin;
-    const int c = p.cells_per_side;
-    if (c < 1 || (long long)c * c > sc.grid_cells || !sc.cell_count || !sc.giants) {
-        set_error("grid broad phase: cells_per_side=%d does not fit grid_cells=%d", c, sc.grid_cells);
+    if (!sc.cell_count || !sc.giants || !sc.grid_dev || sc.grid_cells < 1) {
+        set_error("grid broad phase: scratch lacks the cell arrays / grid_dev");
         return COSMO_E_ARG;
     }
     int nb = (p.n_upper + 255) / 256;
     if (nb < 1) nb = 1;
     if (nb > 148 * 8) nb = 148 * 8;
-    k_grid_max<<<nb, 256, 0, s>>>(st, sc);
-    COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_max"));
     const int w = p.grid_log_cells < 0 ? 0 : p.grid_log_cells;
-    if (c - 2 * w < 1) {
-        set_error("grid broad phase: %d logarithmic cells per side do not fit cells_per_side=%d", w, c);
-        return COSMO_E_ARG;
+    if (p.detect_mode == 2) {
+        // grid tuned on the device from this frame's positions and radii: no host round trip
+        if (!sc.tune_hist || (long long)(2 * w + 1) * (2 * w + 1) > sc.grid_cells) {
+            set_error("grid broad phase: detect_mode 2 needs scratch.tune_hist and grid_cells >= (2*%d+1)^2", w);
+            return COSMO_E_ARG;
+        }
+        k_grid_hist<D3, true><<<nb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_hist"));
+        k_grid_tune<<<1, 1024, 0, s>>>(st, sc, w);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_tune"));
+    } else {
+        const int c = p.cells_per_side;
+        if (c < 1 || (long long)c * c > sc.grid_cells) {
+            set_error("grid broad phase: cells_per_side=%d does not fit grid_cells=%d", c, sc.grid_cells);
+            return COSMO_E_ARG;
+        }
+        if (c - 2 * w < 1) {
+            set_error("grid broad phase: %d logarithmic cells per side do not fit cells_per_side=%d", w, c);
+            return COSMO_E_ARG;
+        }
+        k_grid_hist<D3, false><<<nb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_hist"));
+        k_grid_set<<<1, 1, 0, s>>>(st, sc, p.cell_size, p.grid_origin_x, p.grid_origin_y, p.giant_radius, c, w);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_set"));
     }
-    k_grid_count<D3><<<nb, 256, 0, s>>>(st, sc, p.cell_size, p.grid_origin_x, p.grid_origin_y, p.giant_radius, c, w);
+    k_grid_count<D3><<<nb, 256, 0, s>>>(st, sc);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_count"));
-    COSMO_TRY(launch_scan_exclusive(sc.cell_count, sc.cell_start, sc.scan_blk, nullptr, (long long)c * c, 0, s));
+    // the cell count c*c lives on the device (grid_dev->ncell); blocks beyond it exit at once
+    const long long scan_max = p.detect_mode == 2 ? (long long)sc.grid_cells : (long long)p.cells_per_side * p.cells_per_side;
+    COSMO_TRY(launch_scan_exclusive(sc.cell_count, sc.cell_start, sc.scan_blk, &sc.grid_dev->ncell, scan_max, 0, s));
     k_grid_fill<<<nb, 256, 0, s>>>(st, sc);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_fill"));
     const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
     const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
     const int nchunk = (p.n_upper + GRID_CHUNK - 1) / GRID_CHUNK + 1;
-    k_grid_ranges<<<(nchunk + 127) / 128, 128, 0, s>>>(st, sc, c);
+    k_grid_ranges<<<(nchunk + 127) / 128, 128, 0, s>>>(st, sc);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_ranges"));
     const int blocks = (nchunk + sh_n - 1) / sh_n;
-    k_grid_detect<D3><<<dim3(blocks > 0 ? blocks : 1, GRID_CHUNK / 128), 128, 0, s>>>(st, sc, sh_i, sh_n, c);
+    k_grid_detect<D3><<<dim3(blocks > 0 ? blocks : 1, GRID_CHUNK / 128), 128, 0, s>>>(st, sc, sh_i, sh_n);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect"));
-    k_grid_detect_heavy<D3><<<296, 256, 0, s>>>(st, sc, c);
+    k_grid_detect_heavy<D3><<<296, 256, 0, s>>>(st, sc);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect_heavy"));
     if (rows > 0) {
         k_giant_rows<D3><<<dim3(nb > 296 ? 296 : nb, 8), 256, 0, s>>>(st, sc, p.i_begin, p.i_end);
@@ -418,7 +616,7 @@ int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_st
     if (!(p.opts & COSMO_OPT_COLLISIONS)) return COSMO_OK;
     const int rows = p.i_end - p.i_begin;
     if (rows <= 0 && p.detect_mode == 0) return COSMO_OK;
-    if (p.detect_mode == 1) return launch_detect_grid(st, sc, p, s, false);
+    if (p.detect_mode != 0) return launch_detect_grid(st, sc, p, s, false);
     int jsplit = p.jsplit_detect < 1 ? 1 : p.jsplit_detect;
     if (p.small_tiles) {
         const int per = DETS_BLOCK * DETS_IB;

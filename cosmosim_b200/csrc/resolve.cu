@@ -30,6 +30,13 @@ __global__ void k_append_pairs(cosmo_state st, cosmo_scratch sc, const uint64_t 
     }
 }
 
+// sharded frame: stage B wrote this rank's pairs directly behind row[0]; publish the count there
+// and reset the counter that cosmo_append_pair_rows re-fills from all ranks' rows
+__global__ void k_seal_pair_row(int64_t *status, int64_t *row) {
+    row[0] = status[COSMO_ST_N_PAIRS];
+    status[COSMO_ST_N_PAIRS] = 0;
+}
+
 // all ranks' lists at once: row r = (count | pairs[max_count]); blockIdx.y = row
 __global__ void k_append_pair_rows(cosmo_state st, cosmo_scratch sc, const int64_t *rows, long long max_count) {
     const int64_t *row = rows + (size_t)blockIdx.y * (size_t)(max_count + 1);
@@ -731,6 +738,11 @@ int launch_append_pairs(const cosmo_state &st, const cosmo_scratch &sc, const ui
                         const int64_t *count_ptr, int64_t max_count, cudaStream_t s) {
     k_append_pairs<<<32, 256, 0, s>>>(st, sc, src, count_ptr, (long long)max_count);
     return COSMO_LAUNCH_CHECK("k_append_pairs");
+}
+
+int launch_seal_pair_row(int64_t *status, int64_t *row, cudaStream_t s) {
+    k_seal_pair_row<<<1, 1, 0, s>>>(status, row);
+    return COSMO_LAUNCH_CHECK("k_seal_pair_row");
 }
 
 int launch_append_pair_rows(const cosmo_state &st, const cosmo_scratch &sc, const int64_t *rows, int n_rows,

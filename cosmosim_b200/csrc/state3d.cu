@@ -885,7 +885,7 @@ static int launch_stage_b(const cosmo3_state &st, const cosmo3_scratch &sc, cons
                           cudaStream_t s) {
     if (!(p.opts & COSMO3_OPT_COLLISIONS)) return COSMO_OK;
     const int rows = p.i_end - p.i_begin;
-    if (p.detect_mode == 1) {
+    if (p.detect_mode != 0) {
         // the 2-D grid kernels of detect.cu on shadow structs: planes for pos_new, 3-D exact predicate
         cosmo_state s2 = {};
         cosmo_scratch c2 = {};
@@ -895,10 +895,10 @@ static int launch_stage_b(const cosmo3_state &st, const cosmo3_scratch &sc, cons
         c2.cell_of = sc.cell_of; c2.cell_count = sc.cell_count; c2.cell_start = sc.cell_start;
         c2.cell_items = sc.cell_items; c2.giants = sc.giants; c2.grid_cells = sc.grid_cells;
         c2.giant_cap = sc.giant_cap; c2.chunk_alive = sc.chunk_bounds; c2.label = sc.heavy_rows;
-        c2.scan_blk = sc.scan_blk;
+        c2.scan_blk = sc.scan_blk; c2.grid_dev = sc.grid_dev; c2.tune_hist = sc.tune_hist;
         cosmo_step_params p2 = {};
         p2.opts = COSMO_OPT_COLLISIONS; p2.n_upper = p.n_upper; p2.i_begin = p.i_begin; p2.i_end = p.i_end;
-        p2.detect_mode = 1; p2.grid_log_cells = p.grid_log_cells; p2.cells_per_side = p.cells_per_side;
+        p2.detect_mode = p.detect_mode; p2.grid_log_cells = p.grid_log_cells; p2.cells_per_side = p.cells_per_side;
         p2.cell_size = p.cell_size; p2.grid_origin_x = p.grid_origin_x; p2.grid_origin_y = p.grid_origin_y;
         p2.giant_radius = p.giant_radius;
         p2.shard_index = p.shard_count > 0 ? p.shard_index : 0;
@@ -986,6 +986,14 @@ int cosmo3_resolve_commit(const cosmo3_state *st, const cosmo3_scratch *sc, cons
 int cosmo3_integrate(const cosmo3_state *st, const cosmo3_scratch *sc, const cosmo3_step_params *p, void *stream) {
     COSMO_TRY(check_args3(st, sc, p));
     return launch_integrate3(*st, *sc, *p, (cudaStream_t)stream);
+}
+
+int cosmo3_seal_pair_row(const cosmo3_state *st, int64_t *row, void *stream) {
+    if (!st || !st->status || !row) {
+        set_error("bad argument (cosmo3_seal_pair_row)");
+        return COSMO_E_ARG;
+    }
+    return launch_seal_pair_row(st->status, row, (cudaStream_t)stream);
 }
 
 int cosmo3_append_pair_rows(const cosmo3_state *st, const cosmo3_scratch *sc, const int64_t *rows, int32_t n_rows,

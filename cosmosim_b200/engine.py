@@ -19,8 +19,8 @@ import numpy as np
 import torch
 
 from . import _abi
-from ._abi import (OPT_BOUNDED, OPT_COLLISIONS, OPT_DEFER_INTEGRATE, OPT_ENERGY, OPT_F32_SCALAR,
-                   OPT_F64_SYM,
+from ._bound import BoundTracker
+from ._abi import (OPT_BOUNDED, OPT_COLLISIONS, OPT_DEFER_INTEGRATE, OPT_ENERGY, OPT_F64_SYM,
                    OPT_F32_SYM, OPT_FP32, OPT_STORE_ACC, PAD, ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_ESCAPED, ST_N_EVENTS,
                    ST_N_PAIRS, ST_STEP, STATUS_LEN)
 
@@ -42,45 +42,7 @@ def _round_up(n, q):
     return (int(n) + q - 1) // q * q
 
 
-def tune_grid(pos, radius, grid_cells, log_cells):
-    """Broad-phase grid (cell edge, origin x, origin y, cells per side, giant radius) for planets at
-    `pos` [n,2] with radii `radius` (host side, O(N)).
-
-    giant_radius: planets with (inflated) radius above it are tested against everybody;
-    cell edge >= 2 * giant_radius so flagged non-giant pairs are always in adjacent cells
-    (the device enlarges the edge further by the rounding slack of the reference's d^2)."""
-    n = radius.shape[0]
-    r = radius * (1.0 + 2.0 ** -30)
-    # Grid box from robust quantiles of the coordinates, NOT min/max: a handful of planets flung
-    # out by a close encounter must not stretch the cells over the whole scene (they are clamped
-    # into the border cells instead, which is exact, only a little slower for them).
-    sample = pos if n <= 131072 else pos[np.random.default_rng(0).integers(0, n, 131072)]
-    lo, hi = np.quantile(sample, 0.02, axis=0), np.quantile(sample, 0.98, axis=0)
-    cx, cy = 0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1])
-    box = float(max(hi[0] - lo[0], hi[1] - lo[1], 1e-300)) * 1.25   # the bulk; tails go to the border cells
-    # cost model: g giants cost g*N exact tests, the rest 9 cells * (N / area) * h^2 each
-    top = min(n - 1, 1024)
-    biggest = np.sort(np.partition(r, n - 1 - top)[n - 1 - top:])[::-1]     # descending, top+1 values
-    area = max(box * box, 1.0)
-    best = None
-    for g in (0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
-        if g > top:
-            break
-        rg_g = float(biggest[g]) * 1.3                   # headroom: merged planets grow until the next retune
-        cost = g * n + n * 9.0 * (n / area) * (2.0 * rg_g) ** 2
-        if best is None or cost < best[0]:
-            best = (cost, rg_g)
-    rg = best[1]
-    span = max(box, 4.0 * rg) * 1.1
-    w = log_cells
-    cmax = int(math.isqrt(grid_cells)) - 2 * w
-    h = max(2.0 * rg * 1.001, span / cmax, span * 4.0 / (3.0 * math.sqrt(n)))   # ~16 candidates per planet
-    c = max(1, min(cmax, int(math.ceil(span / h))))
-    rg = max(rg, h / (2.0 * 1.001))       # cells wider than 2*rg: admit larger planets for free
-    return (h, cx - 0.5 * c * h, cy - 0.5 * c * h, c + 2 * w, rg)   # c linear + 2w logarithmic cells
-
-
-class Engine:
+class Engine(BoundTracker):
     """One GPU's replica of the world (optionally responsible for a shard of target rows)."""
 
     JSPLIT_MAX = 128
@@ -106,27 +68,20 @@ class Engine:
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
             self.cap = sharded.required_capacity(self.n_total, self.world)
         self._alloc()
-        # last completed frame's status block, refreshed by an async D2H copy after every frame:
-        # the active count only shrinks, so a slightly stale value is a safe, tight upper bound
-        self._status_host = torch.zeros(STATUS_LEN, dtype=torch.int64).pin_memory()
-        self._status_epoch = 0       # frame counter at the last upload (guards against stale reads)
-        self.n_upper = 0
+        self._init_bound()          # status snapshots / launch bound / grid control (_bound.py)
         self.pos_exp = 0
         self.mass_exp = 0
         self.frames = 0
-        self.grid = None            # (cell_size, origin_x, origin_y, cells_per_side, giant_radius)
         self.grid_log_cells = 32    # logarithmic rim of the broad-phase grid (cells per side)
         self.grid_threshold = 8192  # planets from which the grid broad phase + parallel resolver pay off
         self.small_threshold = 4096  # below: small-N kernel shape (more, shorter CTAs)
         self.sym_threshold = 32768   # FP32: from here on the symmetric kernel (each pair once) wins
         self.sym64_threshold = 16384  # FP64: same for the symmetric FP64 kernel
         self.sym_chunk = 0           # column blocks per CTA of the symmetric kernel (0 = library default)
-        self.retune_every = 16      # frames between host-side refreshes of the grid tuning
-        self._manual_n = False
         self.use_graphs = True      # small N: replay a captured CUDA graph of the frame (launch-bound regime)
         self.graph_threshold = 16384
         self._graphs = {}
-        self._since_tune = 0
+        self._params_cache = {}
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self):
@@ -175,6 +130,8 @@ class Engine:
         t["cell_of"] = z(cap, dtype=i32); t["cell_items"] = z(cap, dtype=i32)
         t["cell_count"] = z(self.grid_cells + 1, dtype=i32); t["cell_start"] = z(self.grid_cells + 1, dtype=i32)
         t["giants"] = z(self.giant_cap, dtype=i32)
+        t["grid_dev"] = z(128, dtype=u8)                       # cosmo_grid (72 bytes)
+        t["tune_hist"] = z(_abi.TUNE_HIST_LEN, dtype=i32)
         for k, dt_ in (("pos", f64), ("vel", f64)):
             t["t_" + k] = z(cap, 2, dtype=dt_)
         for k, dt_ in (("mass", f64), ("mass_hi", i64), ("mass_lo", i64), ("radius", f64), ("volume", f64),
@@ -200,7 +157,7 @@ class Engine:
                   "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_radius", "t_volume",
                   "t_eaten", "t_id", "t_flags", "t_energy", "row_count", "row_start", "pmin", "pmax", "scan_blk",
                   "pair_flag", "cplx_list", "scan_a", "ev_tmp", "label", "comp_items", "comp_root", "cell_of", "cell_items", "cell_count", "cell_start",
-                  "giants"):
+                  "giants", "grid_dev", "tune_hist"):
             setattr(sc, k, p(k))
         sc.pos_new = C.c_void_p(self._pos_new.data_ptr())
         sc.vel_new = C.c_void_p(self._vel_new.data_ptr())
@@ -249,31 +206,36 @@ class Engine:
         self.frames = int(frame)
         torch.cuda.current_stream(self.device).synchronize()
         self._status_host.copy_(status)
-        self._status_epoch = int(frame)
+        self._seed_snapshot(status)
         self._choose_scales(np.asarray(arrays["pos"], dtype=np.float64), np.asarray(arrays["mass_f64"], dtype=np.float64))
-        self._tune_grid(np.asarray(arrays["pos"], dtype=np.float64), np.asarray(arrays["radius"], dtype=np.float64))
-        self._since_tune = 0
 
-    def _tune_grid(self, pos, radius):
-        """Pick the broad-phase grid from the current positions and radii (host side, O(N))."""
-        if radius.shape[0] < self.grid_threshold:
-            self.grid = None
-            return
-        self.grid = tune_grid(pos, radius, self.grid_cells, self.grid_log_cells)
+    def _tick(self):
+        return self.frames
 
-    def retune(self):
-        """Synchronising refresh of the host-side launch parameters (active count, grid)."""
-        before = self.n_upper
-        st = self.status()
-        n = st["n_active"]
-        # crowded scenes (many merges per frame) change the radius distribution quickly
-        self.retune_every = 4 if before > 0 and (before - n) > 0.02 * before else 16
-        if n >= self.grid_threshold:
-            self._tune_grid(self.t["pos"][:n].cpu().numpy(), self.t["radius"][:n].cpu().numpy())
-        else:
-            self.grid = None
-        self._since_tune = 0
-        return st
+    STATE_KEYS = ("pos", "vel", "mass", "mass_hi", "mass_lo", "radius", "volume", "eaten", "id", "flags")
+
+    def save_state(self):
+        """Device-side copy of the active planets + status (for `restore_state`); synchronises once."""
+        n = self.status()["n_active"]
+        return {"n": n, "frames": self.frames, "status": self.t["status"].clone(),
+                "status_host": self.t["status"].cpu(), "fields": {k: self.t[k][:n].clone() for k in self.STATE_KEYS},
+                "rec_death": self.t["rec_death"].clone()}
+
+    def restore_state(self, saved):
+        """Put a `save_state` copy back (device-to-device, asynchronous, no host data involved).  The
+        merge log / death records written since are kept; the event counter is rewound with the status."""
+        n = saved["n"]
+        for k in self.STATE_KEYS:
+            self.t[k][:n].copy_(saved["fields"][k], non_blocking=True)
+        self.t["status"].copy_(saved["status"], non_blocking=True)
+        self.t["rec_death"].copy_(saved["rec_death"], non_blocking=True)
+        self.t["mod_step"].fill_(-1)
+        self.frames = saved["frames"]
+        self.n_upper = n
+        self._seed_snapshot(saved["status_host"])
+
+    def _grid_changed(self):
+        self._params_cache.clear()
 
     def _choose_scales(self, pos, mass):
         # exact power-of-two rescaling for the FP32 path: max |coord| -> [32, 64), max mass -> [2^19, 2^20)
@@ -288,7 +250,8 @@ class Engine:
         self.n_upper = int(s[ST_N_ACTIVE])
         return {"n_active": int(s[ST_N_ACTIVE]), "frame": int(s[ST_STEP]), "n_events": int(s[ST_N_EVENTS]),
                 "n_pairs": int(s[ST_N_PAIRS]), "n_dead": int(s[ST_N_DEAD]), "error": int(s[ST_ERROR]),
-                "n_escaped": int(s[ST_N_ESCAPED])}
+                "n_escaped": int(s[ST_N_ESCAPED]), "n_giants": int(s[_abi.ST_N_GIANTS]),
+                "n_candidates": int(s[_abi.ST_N_CAND])}
 
     def check_errors(self):
         st = self.status()
@@ -342,12 +305,24 @@ class Engine:
             self.sc.colbuf = C.c_void_p(self.t["colbuf"].data_ptr())
             self.sc.colbuf_rows = rows
 
-    def params(self, dt, G, r_max, collisions=True, bounded=True, fp32=False, store_acc=False,
-               f32_scalar=False, jsplit=None, f32_sym=None, energy=False, f64_sym=None):
+    def params(self, dt, G, r_max, **kw):
+        """Step parameters for the current launch bound (cached: they only depend on the arguments, the
+        bound and a few tunables)."""
+        key = (self.n_upper, dt, G, r_max, tuple(sorted(kw.items())), self.grid_threshold, self.small_threshold,
+               self.sym_threshold, self.sym64_threshold, self.sym_chunk, self.pos_exp, self.mass_exp)
+        p = self._params_cache.get(key)
+        if p is None:
+            if len(self._params_cache) > 64:
+                self._params_cache.clear()
+            p = self._params_cache[key] = self._make_params(dt, G, r_max, **kw)
+        return p
+
+    def _make_params(self, dt, G, r_max, collisions=True, bounded=True, fp32=False, store_acc=False,
+                     jsplit=None, f32_sym=None, energy=False, f64_sym=None):
         p = _abi.StepParams()
         p.G, p.dt, p.r_max = float(G), float(dt), float(r_max)
         n = self.n_upper
-        sym = bool(fp32 and not f32_scalar and (f32_sym if f32_sym is not None else n >= self.sym_threshold))
+        sym = bool(fp32 and (f32_sym if f32_sym is not None else n >= self.sym_threshold))
         sym64 = bool((not fp32) and (f64_sym if f64_sym is not None else n >= self.sym64_threshold))
         if sym:
             self._ensure_colbuf()
@@ -355,7 +330,7 @@ class Engine:
             self._ensure_colbuf(fp64=True)
         p.opts = ((OPT_COLLISIONS if collisions else 0) | (OPT_BOUNDED if bounded else 0) |
                   (OPT_FP32 if fp32 else 0) | (OPT_STORE_ACC if store_acc else 0) |
-                  (OPT_F32_SCALAR if f32_scalar else 0) | (OPT_F32_SYM if sym else 0) |
+                  (OPT_F32_SYM if sym else 0) |
                   (OPT_F64_SYM if sym64 else 0) |
                   (OPT_DEFER_INTEGRATE if ((sym or sym64) and self.world > 1) else 0) | (OPT_ENERGY if energy else 0))
         if (sym or sym64) and self.world > 1:
@@ -370,9 +345,6 @@ class Engine:
             nblk = -(-n // (512 if sym64 else 1024))
             want = (nblk * nblk) // (2 * 16 * 2 * self.sm_count * self.world) if nblk > 1 else 1
             p.sym_chunk = int(min(32, max(1, -(-nblk // self.JSPLIT_MAX), want)))
-        if os.environ.get("COSMO_SYM_CHUNK"):
-            p.sym_chunk = int(os.environ["COSMO_SYM_CHUNK"])
-        p.reserved0 = int(os.environ.get("COSMO_SYM_VARIANT", "0"))
         p.n_upper = n
         if self.world > 1:
             from . import sharded
@@ -381,27 +353,36 @@ class Engine:
             p.i_begin, p.i_end = 0, n
         p.pos_exp, p.mass_exp = self.pos_exp, self.mass_exp
         rows = max(1, p.i_end - p.i_begin)
-        kern = (2 if f32_scalar else 1) if fp32 else 0
-        with torch.cuda.device(self.device):
-            p.jsplit = int(jsplit) if jsplit else self.lib.cosmo_suggest_jsplit(rows, max(1, n), kern, self.JSPLIT_MAX)
-            p.jsplit_detect = int(jsplit) if jsplit else self.lib.cosmo_suggest_jsplit(rows, max(1, n), 3, self.JSPLIT_MAX)
-        if self.grid is not None and collisions:
-            p.detect_mode, p.resolve_mode = 1, 1
-            p.cell_size, p.grid_origin_x, p.grid_origin_y, p.cells_per_side, p.giant_radius = self.grid
+        p.small_tiles = 1 if n <= self.small_threshold else 0
+        use_grid = bool(collisions and not self._force_all_pairs and n >= self.grid_threshold)
+        if use_grid:
+            # grid tuned ON THE DEVICE from the frame's own positions and radii (detect_mode 2) unless
+            # the caller pinned one (detect_mode 1): the host never reads planet data while stepping
+            p.resolve_mode = 1
             p.grid_log_cells = self.grid_log_cells
+            if self._host_grid is not None:
+                p.detect_mode = 1
+                p.cell_size, p.grid_origin_x, p.grid_origin_y, p.cells_per_side, p.giant_radius = self._host_grid
+            else:
+                p.detect_mode = 2
         else:
             p.detect_mode, p.resolve_mode = 0, 0
-        p.small_tiles = 1 if n <= self.small_threshold else 0
-        p.shard_index, p.shard_count = self.rank, self.world
-        if p.small_tiles and not jsplit:
+        p.jsplit = p.jsplit_detect = int(jsplit) if jsplit else 1
+        if not jsplit:
             with torch.cuda.device(self.device):
-                if not fp32:
-                    p.jsplit = self.lib.cosmo_suggest_jsplit(rows, max(1, n), 4, self.JSPLIT_MAX)
-                p.jsplit_detect = self.lib.cosmo_suggest_jsplit(rows, max(1, n), 5, self.JSPLIT_MAX)
+                if not (sym or sym64):        # the one-sided kernels split the source range
+                    kern = (4 if p.small_tiles else 0) if not fp32 else 1
+                    p.jsplit = self.lib.cosmo_suggest_jsplit(rows, max(1, n), kern, self.JSPLIT_MAX)
+                if collisions and not use_grid:
+                    p.jsplit_detect = self.lib.cosmo_suggest_jsplit(rows, max(1, n), 5 if p.small_tiles else 3,
+                                                                    self.JSPLIT_MAX)
+        p.shard_index, p.shard_count = self.rank, self.world
         return p
 
     def step(self, n_frames, dt, G, r_max, stage_events=None, **kw):
-        """Enqueue n_frames frames on the current stream; never synchronises.
+        """Enqueue n_frames frames on the current stream.  The host never reads planet data here; the
+        only wait is on the status snapshot of BOUND_LAG frames ago (see __init__), which bounds the
+        queue depth and does not drain the GPU.
 
         stage_events: optional list; for every frame a tuple of four torch.cuda.Event
         (start, after stage A, after stage B, after stage C) is appended -- bench.py uses them
@@ -416,16 +397,7 @@ class Engine:
                 and self.n_upper <= self.graph_threshold):
             return self._step_graphed(int(n_frames), dt, G, r_max, kw)
         for _ in range(int(n_frames)):
-            if self._since_tune >= self.retune_every and self.n_upper >= self.grid_threshold:
-                self.retune()                      # one small D2H every retune_every frames
-                p = self.params(dt, G, r_max, **kw)
-                pp = C.byref(p)
-            self._since_tune += 1
-            # non-blocking refresh of the launch bound from the newest COMPLETED frame
-            seen_n, seen_f = int(self._status_host[ST_N_ACTIVE]), int(self._status_host[ST_STEP])
-            if (self.world == 1 and self._status_epoch <= seen_f <= self.frames and 0 < seen_n < self.n_upper
-                    and not self._manual_n):   # sharded ranks must agree on the bound: they use retune() only
-                self.n_upper = seen_n
+            if self._refresh_bound():
                 p = self.params(dt, G, r_max, **kw)
                 pp = C.byref(p)
             if self.world > 1:
@@ -447,7 +419,7 @@ class Engine:
                 ev[4].record()
                 stage_events.append(ev)
             self.frames += 1
-            self._status_host.copy_(self.t["status"], non_blocking=True)
+            self._push_snapshot()
 
     def _step_graphed(self, n_frames, dt, G, r_max, kw):
         """Launch-bound regime (N of a few thousand: a frame is ~10 kernels of a few microseconds):
@@ -518,7 +490,7 @@ class Engine:
         stg["status_in"][ST_STEP] = self.frames
         t["status"].copy_(stg["status_in"], non_blocking=True)
         self.n_upper = n
-        self._status_epoch = self.frames + 1      # ignore status snapshots of earlier frames
+        self._seed_snapshot(stg["status_in"])     # snapshots of earlier frames are void
         self.step(1, dt, G, r_max, **kw)
         for k in self.E2E_OUT:
             stg["out"][k].copy_(t[k][:n], non_blocking=True)

@@ -17,7 +17,8 @@ import torch
 from . import _abi
 from ._abi import (ERR3_INT_OVERFLOW, F3_DENS_INT, F3_MASS_INT, OPT3_COLLISIONS, OPT3_DEFER_INTEGRATE, OPT3_F32_SYM, OPT3_F64_SYM, OPT3_FP32, OPT3_STORE_ACC, PAD,
                    ST_ERROR, ST_N_ACTIVE, ST_N_DEAD, ST_N_EVENTS, ST_N_PAIRS, ST_STEP, STATUS_LEN)
-from .engine import _round_up, split_mass, tune_grid
+from ._bound import BoundTracker
+from .engine import _round_up, split_mass
 
 MAX_INT_DENSITY = 1 << 53
 
@@ -30,7 +31,7 @@ def split_density(density):
     return float(density), False
 
 
-class Engine3D:
+class Engine3D(BoundTracker):
     JSPLIT_MAX = 128
 
     def __init__(self, n_total, device=None, pair_cap=None, event_cap=None, group=None):
@@ -53,23 +54,16 @@ class Engine3D:
         self.pair_cap = int(pair_cap or max(1 << 16, 4 * self.cap))
         self.event_cap = int(event_cap or max(1 << 16, 4 * self.n_total))
         self._alloc()
-        # last completed step's status block, refreshed by an async D2H copy after every step: the
-        # object count only shrinks, so a slightly stale value is a safe, tight upper bound
-        self._status_host = torch.zeros(STATUS_LEN, dtype=torch.int64).pin_memory()
-        self._epoch = 0              # step counter at the last upload (guards against stale snapshots)
+        self._init_bound()           # status snapshots / launch bound / grid control (_bound.py)
         self.use_graphs = True       # small N: replay a captured CUDA graph of the step (launch-bound regime)
         self.graph_threshold = 16384
         self._graphs = {}
-        self.n_upper = 0
         self.pos_exp = 0
         self.mass_exp = 0
         self.steps = 0
         self._jsplit_cache = {}
-        self.grid = None             # (cell edge, origin x, origin y, cells per side, giant radius)
         self.grid_log_cells = 32
         self.grid_threshold = 16384  # objects from which the grid broad phase beats the all-pairs test
-        self.retune_every = 16       # steps between host-side refreshes of the grid tuning
-        self._since_tune = 0
         self.sym64_threshold = 16384 # FP64: from here on the symmetric kernel (each pair once) wins
         self.sym32_threshold = 32768 # FP32: same for the symmetric FP32 kernel
         self.sym_chunk = 0           # column blocks per CTA of the symmetric kernel (0 = automatic)
@@ -107,6 +101,7 @@ class Engine3D:
         t["cell_count"] = z(self.grid_cells + 1, dtype=i32); t["cell_start"] = z(self.grid_cells + 1, dtype=i32)
         t["giants"] = z(self.giant_cap, dtype=i32)
         t["chunk_bounds"] = z(cap // 1024 + 2, dtype=i32); t["heavy_rows"] = z(cap, dtype=i32)
+        t["grid_dev"] = z(128, dtype=u8); t["tune_hist"] = z(_abi.TUNE_HIST_LEN, dtype=i32)
         p = lambda k: C.c_void_p(t[k].data_ptr())  # noqa: E731
         st = _abi.State3()
         st.cap, st.n_total, st.event_cap = cap, self.n_total, self.event_cap
@@ -116,7 +111,8 @@ class Engine3D:
         for k in ("h", "pk", "acc", "pos_new", "vel_new", "xx_new", "rinf", "partial", "tile_ctr", "pairs",
                   "pairs_sorted", "exists", "cur_pos", "cur_vel", "touched", "scan_in", "scan_out", "scan_blk",
                   "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_density", "t_radius", "t_id", "t_flags",
-                  "cell_of", "cell_count", "cell_start", "cell_items", "giants", "chunk_bounds", "heavy_rows"):
+                  "cell_of", "cell_count", "cell_start", "cell_items", "giants", "chunk_bounds", "heavy_rows",
+                  "grid_dev", "tune_hist"):
             setattr(sc, k, p(k))
         sc.jsplit_max, sc.pair_cap = self.JSPLIT_MAX, self.pair_cap
         sc.grid_cells, sc.giant_cap = self.grid_cells, self.giant_cap
@@ -158,34 +154,16 @@ class Engine3D:
         self.steps = int(iteration)
         torch.cuda.current_stream(self.device).synchronize()
         self._status_host.copy_(status)
-        self._epoch = int(iteration)
+        self._seed_snapshot(status)
         pos = np.asarray(arrays["pos"], dtype=np.float64)
         mass = np.asarray(arrays["mass_f64"], dtype=np.float64)
         pmax = float(np.max(np.abs(pos))) if pos.size else 1.0
         mmax = float(np.max(np.abs(mass))) if mass.size else 1.0
         self.pos_exp = (math.frexp(pmax)[1] - 6) if pmax > 0 and math.isfinite(pmax) else 0
         self.mass_exp = (math.frexp(mmax)[1] - 20) if mmax > 0 and math.isfinite(mmax) else 0
-        self._tune(pos[:, :2], np.asarray(arrays["radius"], dtype=np.float64))
 
-    def _tune(self, pos_xy, radius):
-        """Grid of the stage-B broad phase from the (x, y) projection (host side, O(N))."""
-        self._since_tune = 0
-        if radius.shape[0] < self.grid_threshold:
-            self.grid = None
-        else:
-            self.grid = tune_grid(np.ascontiguousarray(pos_xy), radius, self.grid_cells, self.grid_log_cells)
-
-    def retune(self):
-        """Synchronising refresh of the active count and the grid tuning."""
-        st = self.status()
-        n = st["n_active"]
-        if n >= self.grid_threshold:
-            xy = self.t["pos"][:2, :n].cpu().numpy().T
-            self._tune(xy, self.t["radius"][:n].cpu().numpy())
-        else:
-            self.grid = None
-            self._since_tune = 0
-        return st
+    def _tick(self):
+        return self.steps
 
     def status(self):
         s = self.t["status"].cpu().numpy()
@@ -280,15 +258,25 @@ class Engine3D:
                   self.lib.cosmo3_suggest_jsplit(rows, n, 2, 256))
             self._jsplit_cache[key] = js
         p.jsplit, p.jsplit_detect = js
-        if collisions and self.grid is not None and n >= self.grid_threshold:
-            p.detect_mode, p.grid_log_cells = 1, self.grid_log_cells
-            p.cell_size, p.grid_origin_x, p.grid_origin_y, p.cells_per_side, p.giant_radius = self.grid
+        if collisions and not self._force_all_pairs and n >= self.grid_threshold:
+            # grid tuned on the device from the step's own positions and radii (detect_mode 2) unless
+            # the caller pinned one (detect_mode 1)
+            p.grid_log_cells = self.grid_log_cells
+            if self._host_grid is not None:
+                p.detect_mode = 1
+                p.cell_size, p.grid_origin_x, p.grid_origin_y, p.cells_per_side, p.giant_radius = self._host_grid
+            else:
+                p.detect_mode = 2
         return p
 
-    def _refresh_n_upper(self, margin=1.0):
-        """Non-blocking refresh of the launch bound from the newest COMPLETED step's snapshot."""
+    def _uses_grid(self, collisions=True):
+        return bool(collisions and not self._force_all_pairs and self.n_upper >= self.grid_threshold)
+
+    def _refresh_graph_bound(self, margin):
+        """CUDA-graph replay: non-blocking refresh of the launch bound from the newest completed
+        replay's snapshot (the graph copies the status block into _status_host)."""
         seen_n, seen_s = int(self._status_host[ST_N_ACTIVE]), int(self._status_host[ST_STEP])
-        if self._epoch <= seen_s <= self.steps and 0 < seen_n < margin * self.n_upper:
+        if self._status_epoch <= seen_s <= self.steps and 0 < seen_n < margin * self.n_upper:
             self.n_upper = seen_n
 
     def _step_graphed(self, steps, dt, G, collisions, fp32, sym):
@@ -298,7 +286,7 @@ class Engine3D:
         bound has shrunk by more than 10 %."""
         done = 0
         while done < steps:
-            self._refresh_n_upper(0.9)
+            self._refresh_graph_bound(0.9)
             p = self.params(dt, G, collisions, fp32, False, sym=sym)
             key = bytes(memoryview(p))
             g = self._graphs.get(key)
@@ -320,21 +308,18 @@ class Engine3D:
             self.steps += burst
 
     def step(self, dt, G, collisions=True, fp32=False, store_acc=False, steps=1, stage_events=None, sym=None):
-        """`steps` x State.interact on this device; asynchronous (no host sync).  stage_events: a list
+        """`steps` x State.interact on this device.  The host never reads object data here; the only
+        wait is on the status snapshot of BOUND_LAG steps ago (_bound.py).  stage_events: a list
         that receives, per step, four CUDA events bracketing stages A, B and C (bench.py)."""
         stream = torch.cuda.current_stream(self.device)
         sp = C.c_void_p(stream.cuda_stream)
         L, st, sc = self.lib, self.st, self.sc
         with torch.cuda.device(self.device):
             if (self.use_graphs and self.world == 1 and stage_events is None and not store_acc and int(steps) >= 8
-                    and self.n_upper <= self.graph_threshold and self.grid is None):
+                    and self.n_upper <= self.graph_threshold and not self._uses_grid(collisions)):
                 return self._step_graphed(int(steps), dt, G, collisions, fp32, sym)
             for _ in range(int(steps)):
-                if self.world == 1:
-                    self._refresh_n_upper()
-                if self._since_tune >= self.retune_every and ((collisions and self.grid is not None) or self.world > 1):
-                    self.retune()       # sharded: every rank refreshes n_upper at the same step (identical state)
-                self._since_tune += 1
+                self._refresh_bound()
                 p = self.params(dt, G, collisions, fp32, store_acc, sym=sym)
                 if self.world > 1:
                     from . import sharded
@@ -352,7 +337,7 @@ class Engine3D:
                     ev[3].record(stream)
                     stage_events.append(ev)
                 self.steps += 1
-                self._status_host.copy_(self.t["status"], non_blocking=True)
+                self._push_snapshot()
 
 
     # ------------------------------------------------------------------ host-buffer path (e2e)
@@ -391,7 +376,7 @@ class Engine3D:
         stg["status_in"][ST_STEP] = self.steps
         t["status"].copy_(stg["status_in"], non_blocking=True)
         self.n_upper = n
-        self._epoch = self.steps + 1      # ignore status snapshots of earlier steps
+        self._seed_snapshot(stg["status_in"])     # snapshots of earlier steps are void
         self.step(dt, G, **kw)
         for k in self.E2E_OUT:
             src = t[k][:, :n] if k in ("pos", "vel") else t[k][:n]

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 
 from . import _abi
-from ._abi import PAD, ST_N_PAIRS
+from ._abi import PAD
 
 
 def shard_rows(n: int, world: int, rank: int):
@@ -43,12 +43,41 @@ def gather_planes(planes, per: int, rank: int, world: int, group=None):
 
 def exchange_pairs(local_pairs: torch.Tensor, local_count: torch.Tensor, xchg: torch.Tensor,
                    rank: int, world: int, group=None):
-    """All-gather (count | pairs[:xcap]) rows.  xchg: int64 [world, 1 + xcap], updated in place."""
+    """All-gather (count | pairs[:xcap]) rows.  xchg: int64 [world, 1 + xcap], updated in place.
+    (Reference form of the exchange protocol for the CPU tests; the GPU frame lets stage B write its
+    pairs straight into the row and seals the count with one tiny kernel, see _detect_and_exchange.)"""
     xcap = xchg.shape[1] - 1
     xchg[rank, 0] = local_count.reshape(())
     xchg[rank, 1:] = local_pairs[:xcap]
     dist.all_gather_into_tensor(xchg.view(-1), xchg[rank], group=group)
     return xchg
+
+
+def _detect_and_exchange(eng, detect, seal, append, st, sc, pp, stream, ev_after_detect=None):
+    """Stage B on this rank's share + the exchange of the flagged pairs, without a single copy or
+    eager torch kernel: the detection kernels append straight into this rank's row of the exchange
+    buffer (scratch.pairs is pointed there for the call), one thread seals the count into row[0]
+    and resets the counter, NCCL all-gathers the rows, and one launch re-emits every rank's pairs
+    into scratch.pairs."""
+    if not hasattr(eng, "_xchg"):
+        # a rank's share of the flagged pairs is balanced by the round-robin chunking of stage B, so
+        # a fraction of pair_cap is plenty (overflow raises COSMO_ERR_PAIR_OVERFLOW, never silent)
+        xcap = max(1024, min(eng.pair_cap // eng.world, max(1 << 16, eng.cap // eng.world)))
+        eng._xchg = torch.zeros(eng.world, 1 + xcap, dtype=torch.int64, device=eng.device)
+        eng._xchg_flat, eng._xchg_row = eng._xchg.view(-1), eng._xchg[eng.rank]
+    xcap = eng._xchg.shape[1] - 1
+    row_ptr = eng._xchg_row.data_ptr()
+    keep = (eng.sc.pairs, eng.sc.pair_cap)
+    eng.sc.pairs, eng.sc.pair_cap = row_ptr + 8, xcap
+    try:
+        _abi.check(detect(st, sc, pp, stream), "detect_pairs")
+    finally:
+        eng.sc.pairs, eng.sc.pair_cap = keep
+    if ev_after_detect is not None:
+        ev_after_detect.record()          # stage B kernels done, pair exchange not yet
+    _abi.check(seal(st, C.c_void_p(row_ptr), stream), "seal_pair_row")
+    dist.all_gather_into_tensor(eng._xchg_flat, eng._xchg_row, group=eng.group)
+    _abi.check(append(st, sc, C.c_void_p(eng._xchg.data_ptr()), eng.world, xcap, stream), "append_pair_rows")
 
 
 _PEER_CACHE = {}
@@ -128,20 +157,11 @@ def frame(eng, p, stream, stage_events=None):
         ev[2].record()
     if p.opts & _abi.OPT_ENERGY:      # diagnostics: replicated over all rows (new positions are complete here)
         _abi.check(lib.cosmo_energies(st, sc, pp, stream), "cosmo_energies")
-    _abi.check(lib.cosmo_detect_pairs(st, sc, pp, stream), "cosmo_detect_pairs")
-    if ev:
-        ev[6].record()          # stage B kernels done, pair exchange not yet
-    status = eng.t["status"]
-    if not hasattr(eng, "_xchg"):
-        # every rank may contribute up to its share of the pair buffer
-        # a rank's share of the flagged pairs: balanced by the round-robin chunking of stage B, so a
-        # fraction of pair_cap is plenty (overflow raises COSMO_ERR_PAIR_OVERFLOW, never silent)
-        xcap = min(eng.pair_cap // eng.world, max(1 << 16, eng.cap // eng.world))
-        eng._xchg = torch.zeros(eng.world, 1 + max(1024, xcap), dtype=torch.int64, device=eng.device)
-    xchg = exchange_pairs(eng.t["pairs"], status[ST_N_PAIRS], eng._xchg, eng.rank, eng.world, eng.group)
-    status[ST_N_PAIRS] = 0
-    _abi.check(lib.cosmo_append_pair_rows(st, sc, C.c_void_p(xchg.data_ptr()), eng.world, xchg.shape[1] - 1, stream),
-               "cosmo_append_pair_rows")
+    if p.opts & _abi.OPT_COLLISIONS:
+        _detect_and_exchange(eng, lib.cosmo_detect_pairs, lib.cosmo_seal_pair_row, lib.cosmo_append_pair_rows,
+                             st, sc, pp, stream, ev[6] if ev else None)
+    elif ev:
+        ev[6].record()
     if ev:
         ev[3].record()
     _abi.check(lib.cosmo_resolve_commit(st, sc, pp, stream), "cosmo_resolve_commit")
@@ -172,15 +192,8 @@ def frame3d(eng, p, stream, stage_events=None):
     if ev:
         ev[1].record()
     if p.opts & _abi.OPT3_COLLISIONS:
-        _abi.check(lib.cosmo3_detect_pairs(st, sc, pp, stream), "cosmo3_detect_pairs")
-        status = eng.t["status"]
-        if not hasattr(eng, "_xchg"):
-            xcap = min(eng.pair_cap // eng.world, max(1 << 16, eng.cap // eng.world))
-            eng._xchg = torch.zeros(eng.world, 1 + max(1024, xcap), dtype=torch.int64, device=eng.device)
-        xchg = exchange_pairs(eng.t["pairs"], status[ST_N_PAIRS], eng._xchg, eng.rank, eng.world, eng.group)
-        status[ST_N_PAIRS] = 0
-        _abi.check(lib.cosmo3_append_pair_rows(st, sc, C.c_void_p(xchg.data_ptr()), eng.world, xchg.shape[1] - 1,
-                                               stream), "cosmo3_append_pair_rows")
+        _detect_and_exchange(eng, lib.cosmo3_detect_pairs, lib.cosmo3_seal_pair_row, lib.cosmo3_append_pair_rows,
+                             st, sc, pp, stream)
     if ev:
         ev[2].record()
     _abi.check(lib.cosmo3_resolve_commit(st, sc, pp, stream), "cosmo3_resolve_commit")

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define COSMO_ABI_VERSION 1
+#define COSMO_ABI_VERSION 2
 #define COSMO_PAD 1024 /* slot capacity granularity (tile size of the all-pairs kernels) */
 #define COSMO_MAX_PEERS 16   /* ranks of one NVLink domain */
 #define COSMO_SCAN_BLOCKS 8192 /* device scans handle up to COSMO_SCAN_BLOCKS * 4096 items */
@@ -60,7 +60,6 @@ extern "C" {
 #define COSMO_OPT_BOUNDED 2u     /* Universe(bounded=True), universe_old.py:349 */
 #define COSMO_OPT_FP32 4u        /* FP32 fast path for the all-pairs sum (state stays FP64) */
 #define COSMO_OPT_STORE_ACC 8u   /* also write the accelerations to scratch.acc */
-#define COSMO_OPT_F32_SCALAR 16u /* FP32 path: scalar FFMA inner loop instead of packed f32x2 */
 #define COSMO_OPT_F32_SYM 32u    /* FP32 path: symmetric kernel (each unordered pair once); needs colbuf */
 #define COSMO_OPT_PEER_EXCHANGE 512u /* with DEFER_INTEGRATE: the reduce kernel stores this rank's partial sums
                                         straight into every peer's exchange buffer over NVLink
@@ -92,6 +91,23 @@ extern "C" {
 #define COSMO_ERR_EVENT_OVERFLOW 2 /* event log full */
 #define COSMO_ERR_NAN 4            /* non-finite d^2 met in the acceleration pass */
 #define COSMO_ERR_GIANT_OVERFLOW 8 /* more brute-forced planets than giant_cap */
+
+/* Broad-phase grid of the current frame, resident on the device (scratch.grid_dev): written by the
+   first kernels of cosmo_detect_pairs -- from the step parameters (detect_mode 1) or tuned on the
+   device from the frame's own positions and radii (detect_mode 2) -- and read by the rest. */
+typedef struct cosmo_grid {
+    double h;        /* cell edge in use (>= the smallest admissible edge for giant radius rg) */
+    double cx, cy;   /* centre of the linear part of the grid */
+    double rg;       /* planets with inflated radius above this are tested against everybody */
+    int64_t ncell;   /* c * c */
+    int32_t c;       /* cells per side, including 2 * w logarithmic rim cells */
+    int32_t w;
+    int32_t source;  /* 1 = from cosmo_step_params, 2 = tuned on the device */
+    int32_t reserved;
+    double box;      /* edge of the linear part as tuned (diagnostic) */
+    double h_tuned;  /* cell edge before the admissibility clamp (diagnostic) */
+} cosmo_grid;
+#define COSMO_TUNE_HIST_LEN (2 * 65536 + 4096) /* int32 words of scratch.tune_hist */
 
 /* Persistent state.  All pointers are device pointers. */
 typedef struct cosmo_state {
@@ -184,6 +200,9 @@ typedef struct cosmo_scratch {
     double *peer_acc[COSMO_MAX_PEERS];
     int32_t n_peers;
     int32_t reserved_scratch;
+    cosmo_grid *grid_dev; /* [1] grid of the current frame (detect_mode 1 and 2) */
+    int32_t *tune_hist;   /* [COSMO_TUNE_HIST_LEN] detect_mode 2: coordinate / radius histograms, must
+                             start zeroed (self-resetting) */
 } cosmo_scratch;
 
 /* Parameters of one frame. */
@@ -198,13 +217,15 @@ typedef struct cosmo_step_params {
     int32_t pos_exp;  /* FP32 path: positions are scaled by 2^-pos_exp, masses by 2^-mass_exp */
     int32_t mass_exp;
     int32_t jsplit;   /* source-range splits of the all-pairs pass (>=1, <= jsplit_max) */
-    int32_t detect_mode; /* 0 = all-pairs predicate, 1 = uniform-grid broad phase */
+    int32_t detect_mode; /* 0 = all-pairs predicate, 1 = uniform-grid broad phase with the grid given
+                            below, 2 = uniform grid tuned on the device every frame (cell_size, origin,
+                            cells_per_side and giant_radius are ignored; grid_log_cells is used) */
     int32_t resolve_mode; /* 0 = rank sort + sequential replay (few pairs), 1 = CSR + parallel */
     int32_t small_tiles;  /* 1 = small-N kernel shape for stage A/B (more, shorter CTAs) */
     int32_t shard_index;  /* this rank / number of ranks sharing the frame (0 / 1 if single): the */
     int32_t shard_count;  /* grid broad phase splits its cell-sorted planet order evenly by these */
     int32_t sym_chunk;    /* symmetric kernel: column blocks per CTA (0 = default) */
-    int32_t reserved0;
+    int32_t near_mode;    /* FP32 path: 1 = re-evaluate the near field in FP64 (see cosmo_step_params docs) */
     int32_t grid_log_cells; /* detect_mode 1: logarithmic cells on each side of the linear box (>= 0) */
     int32_t reserved1;
     double cell_size;    /* detect_mode 1 */
@@ -286,6 +307,11 @@ int cosmo_step(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_
    a count above max_count raises COSMO_ERR_PAIR_OVERFLOW in the status block. */
 int cosmo_append_pairs(const cosmo_state *st, const cosmo_scratch *sc, const uint64_t *src,
                        const int64_t *count_ptr, int64_t max_count, void *stream);
+/* Multi-GPU frame, before the all-gather of the pair lists: stage B wrote this rank's pairs
+   straight into its row of the exchange buffer (scratch.pairs pointing at row + 1); this stores
+   their count in row[0] and resets status[COSMO_ST_N_PAIRS] for cosmo_append_pair_rows.  One
+   thread, no copy. */
+int cosmo_seal_pair_row(const cosmo_state *st, int64_t *row, void *stream);
 /* Same for `n_rows` lists laid out as rows of (count | pairs[max_count]) int64 words, i.e. the
    all-gathered exchange buffer of the multi-GPU frame, in one launch. */
 int cosmo_append_pair_rows(const cosmo_state *st, const cosmo_scratch *sc, const int64_t *rows,

@@ -107,6 +107,8 @@ typedef struct cosmo3_scratch {
     /* column partial sums of the symmetric kernel: [colbuf_rows][3][cap], one row per 512-object row block */
     double *colbuf;
     int64_t colbuf_rows;   /* FP64: >= ceil(ceil(n / 512) / ranks); FP32 (1024-object blocks, float planes): a quarter of that */
+    cosmo_grid *grid_dev;  /* [1] broad-phase grid of the current step (detect_mode 1 and 2) */
+    int32_t *tune_hist;    /* [COSMO_TUNE_HIST_LEN] detect_mode 2, must start zeroed (self-resetting) */
 } cosmo3_scratch;
 
 typedef struct cosmo3_step_params {
@@ -122,7 +124,8 @@ typedef struct cosmo3_step_params {
     int32_t jsplit_detect; /* source-range splits of the detection pass */
     /* stage B mode: 0 = all-pairs predicate; 1 = uniform-grid broad phase on the (x, y) projection
        (objects close in 3-D are at least as close in projection, so the candidates stay a superset;
-       every candidate goes through the exact 3-D predicate).  Fields as in cosmo_step_params. */
+       every candidate goes through the exact 3-D predicate); 2 = the same grid tuned on the device
+       every step.  Fields as in cosmo_step_params. */
     int32_t detect_mode;
     int32_t grid_log_cells;
     int32_t cells_per_side;
@@ -154,6 +157,8 @@ int cosmo3_resolve_commit(const cosmo3_state *st, const cosmo3_scratch *sc, cons
 int cosmo3_integrate(const cosmo3_state *st, const cosmo3_scratch *sc, const cosmo3_step_params *p, void *stream);
 /* Appends `n_rows` pair lists laid out as rows of (count | pairs[max_count]) int64 words -- the
    all-gathered exchange buffer of the multi-GPU step -- to scratch.pairs in one launch. */
+/* cosmo_seal_pair_row for the 3-D step (count of this rank's pairs -> row[0], N_PAIRS reset). */
+int cosmo3_seal_pair_row(const cosmo3_state *st, int64_t *row, void *stream);
 int cosmo3_append_pair_rows(const cosmo3_state *st, const cosmo3_scratch *sc, const int64_t *rows, int32_t n_rows,
                             int64_t max_count, void *stream);
 /* A + B + C on one device. */

@@ -32,20 +32,18 @@ def test_reference_arm_prints_the_contract_line(workload):
     assert d["vs_baseline"] is None
 
 
-def test_grid_tuning_invariants():
-    from cosmosim_b200.engine import tune_grid
-    rng = np.random.default_rng(0)
-    for n, spread, big in ((20000, 1.5e11, 7e8), (300000, 7e12, 0.0), (50000, 1.0, 0.0)):
-        pos = rng.normal(size=(n, 2)) * spread
-        pos[:5] *= 1e4                                    # a few planets flung far out must not stretch the box
-        radius = rng.uniform(1e6, 3e7, n) * (spread / 1.5e11)
-        if big:
-            radius[0] = big
-        grid_cells, w = 1 << 22, 32
-        h, ox, oy, c, rg = tune_grid(pos, radius, grid_cells, w)
-        assert c * c <= grid_cells and c - 2 * w >= 1
-        assert h >= 2.0 * rg > 0 and math.isfinite(ox) and math.isfinite(oy)
-        lin = (c - 2 * w) * h
-        assert lin < 50 * spread                          # the box follows the bulk, not the outliers
-        giants = int((radius * (1 + 2.0 ** -30) > rg).sum())
-        assert giants <= 1024                             # the cost model never brute-forces more than that
+@pytest.mark.timeout(300)
+def test_reference_arm_uses_all_cores_under_torchrun_env():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the reference arm must not shrink to one core
+    there (round-1 SCALE ratios at N >= 2 were inflated ~10x by exactly that)."""
+    cores = []
+    for extra in ({}, {"OMP_NUM_THREADS": "1", "WORLD_SIZE": "2", "RANK": "0", "LOCAL_RANK": "0"}):
+        env = dict(os.environ, **extra)
+        if not extra:
+            env.pop("OMP_NUM_THREADS", None)
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--bodies", "2000",
+                              "--steps", "1", "--warmup", "0", "--cpu-seconds", "0.2"],
+                             capture_output=True, text=True, timeout=280, cwd=ROOT, env=env)
+        assert out.returncode == 0, out.stderr[-2000:]
+        cores.append(json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]["cores"])
+    assert cores[0] == cores[1] == len(os.sched_getaffinity(0))

@@ -263,9 +263,9 @@ def test_fp32_fast_path_error_bound():
     for arr in (scenes.star_disk_arrays(20000, seed=1), scenes.cloud_arrays(20000, seed=2)):
         n = arr["radius"].shape[0]
         ref = orc.accel(arr["pos"], arr["mass_f64"], G)
-        for scalar, sym in ((False, False), (True, False), (False, True)):
+        for sym in (False, True):
             eng = make_engine(arr)
-            eng.step(1, DT, G, 100 * AU, collisions=False, store_acc=True, fp32=True, f32_scalar=scalar, f32_sym=sym)
+            eng.step(1, DT, G, 100 * AU, collisions=False, store_acc=True, fp32=True, f32_sym=sym)
             acc = eng.last_frame_tensors()["acc"][:n].cpu().numpy()
             eng.check_errors()
             rel = relerr_rows(acc, ref)
@@ -765,3 +765,53 @@ def test_disk6001_three_frames_of_the_reference(grid):
     assert np.array_equal(d["eaten"], ref["eaten"][ids])
     assert np.abs(d["radius"] - ref["radius"][ids]).max() <= np.spacing(ref["radius"][ids]).max()
     assert np.abs(d["pos"] - ref["pos"][ids]).max() <= 1e-11 * np.abs(ref["pos"][ids]).max()
+
+
+def test_device_grid_tuning_invariants():
+    """The broad-phase grid is tuned ON THE DEVICE every frame (detect_mode 2: coordinate / radius
+    histograms + one CTA).  Whatever it picks must keep the candidate set a superset: cell edge >=
+    2 x giant radius, the box follows the bulk of the planets and not a few far outliers, the cost
+    model never brute-forces more than 1024 planets, the histograms return to zero -- and the
+    flagged pairs equal the all-pairs predicate's."""
+    import ctypes as C
+    from cosmosim_b200 import _abi
+    rng = np.random.default_rng(0)
+    for n, spread, big in ((20000, 1.5e11, 7e8), (120000, 7e12, 0.0), (50000, 1.0, 0.0)):
+        pos = rng.normal(size=(n, 2)) * spread
+        pos[:5] *= 1e4                                    # a few planets flung far out must not stretch the box
+        radius = rng.uniform(1e6, 3e7, n) * (spread / 1.5e11)
+        if big:
+            radius[0] = big
+        arr = {"pos": pos, "vel": np.zeros((n, 2)), "mass_f64": rng.uniform(1e22, 1e25, n),
+               "mass_hi": np.zeros(n, np.uint64), "mass_lo": np.zeros(n, np.uint64), "flags": np.zeros(n, np.uint8),
+               "radius": radius, "volume": (4 / 3) * np.pi * radius ** 3, "eaten": np.zeros(n, np.int64),
+               "id": np.arange(n, dtype=np.int32)}
+        eng = make_engine(arr)
+        p = eng.params(0.0, 0.0, 1e300, fp32=True)
+        assert p.detect_mode == 2
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        st, sc = C.byref(eng.st), C.byref(eng.sc)
+        for fn in (eng.lib.cosmo_begin_frame, eng.lib.cosmo_accel_integrate, eng.lib.cosmo_detect_pairs):
+            _abi.check(fn(st, sc, C.byref(p), stream))
+        h, cx, cy, c, rg = eng.grid
+        w = eng.grid_log_cells
+        assert c * c <= eng.grid_cells and c - 2 * w >= 1
+        assert h >= 2.0 * rg > 0 and np.isfinite(cx) and np.isfinite(cy)
+        assert (c - 2 * w) * h < 50 * spread              # the box follows the bulk, not the outliers
+        assert abs(cx) < 0.2 * spread and abs(cy) < 0.2 * spread
+        giants = int((radius * (1 + 2.0 ** -30) > rg).sum())
+        assert giants <= 1024 and giants == eng.status()["n_giants"]
+        assert int(eng.t["tune_hist"].abs().sum()) == 0   # self-resetting
+        got = np.sort(eng.t["pairs"][: eng.status()["n_pairs"]].cpu().numpy().view(np.uint64))
+        pn = eng.last_frame_tensors()["pos_new"][:n].cpu().numpy()
+        want = orc.flags(pn, radius)
+        want = np.sort((want[:, 0].astype(np.uint64) << np.uint64(32)) | want[:, 1].astype(np.uint64))
+        assert np.array_equal(got, want)
+        # a pinned grid (detect_mode 1) flags the same pairs
+        eng.grid = (h, cx - 0.5 * (c - 2 * w) * h, cy - 0.5 * (c - 2 * w) * h, c, rg)
+        p1 = eng.params(0.0, 0.0, 1e300, fp32=True)
+        assert p1.detect_mode == 1
+        for fn in (eng.lib.cosmo_begin_frame, eng.lib.cosmo_accel_integrate, eng.lib.cosmo_detect_pairs):
+            _abi.check(fn(st, sc, C.byref(p1), stream))
+        got1 = np.sort(eng.t["pairs"][: eng.status()["n_pairs"]].cpu().numpy().view(np.uint64))
+        assert np.array_equal(got1, want)
