@@ -52,10 +52,11 @@ class Grid(C.Structure):
     """cosmo_grid: the device-resident broad-phase grid of the current frame."""
     _fields_ = [("h", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("rg", C.c_double),
                 ("ncell", C.c_int64), ("c", C.c_int32), ("w", C.c_int32), ("source", C.c_int32),
-                ("reserved", C.c_int32), ("box", C.c_double), ("h_tuned", C.c_double)]
+                ("reserved", C.c_int32), ("box", C.c_double), ("h_tuned", C.c_double),
+                ("far2", C.c_double), ("rho", C.c_double), ("cand_total", C.c_int64), ("n_counted", C.c_int64)]
 
 
-TUNE_HIST_LEN = 2 * 65536 + 4096
+TUNE_HIST_LEN = 2 * 65536 + 4096 + 64
 
 
 class StepParams(C.Structure):
@@ -63,7 +64,7 @@ class StepParams(C.Structure):
                 ("opts", C.c_uint32), ("n_upper", C.c_int32), ("i_begin", C.c_int32),
                 ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
                 ("jsplit", C.c_int32), ("detect_mode", C.c_int32), ("resolve_mode", C.c_int32),
-                ("small_tiles", C.c_int32), ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("sym_chunk", C.c_int32), ("near_mode", C.c_int32), ("grid_log_cells", C.c_int32), ("reserved1", C.c_int32),
+                ("small_tiles", C.c_int32), ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("sym_chunk", C.c_int32), ("near_mode", C.c_int32), ("reserved2", C.c_int32), ("reserved1", C.c_int32),
                 ("cell_size", C.c_double),
                 ("grid_origin_x", C.c_double), ("grid_origin_y", C.c_double), ("cells_per_side", C.c_int32), ("jsplit_detect", C.c_int32),
                 ("giant_radius", C.c_double)]
@@ -98,7 +99,7 @@ class StepParams3(C.Structure):
     _fields_ = [("G", C.c_double), ("dt", C.c_double), ("opts", C.c_uint32), ("n_upper", C.c_int32),
                 ("i_begin", C.c_int32), ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
                 ("jsplit", C.c_int32), ("jsplit_detect", C.c_int32),
-                ("detect_mode", C.c_int32), ("grid_log_cells", C.c_int32), ("cells_per_side", C.c_int32),
+                ("detect_mode", C.c_int32), ("reserved1", C.c_int32), ("cells_per_side", C.c_int32),
                 ("sym_chunk", C.c_int32), ("cell_size", C.c_double), ("grid_origin_x", C.c_double),
                 ("grid_origin_y", C.c_double), ("giant_radius", C.c_double),
                 ("shard_index", C.c_int32), ("shard_count", C.c_int32)]

@@ -80,9 +80,14 @@ class BoundTracker:
         the all-pairs predicate; `del eng.grid` returns to the device-side tuning (detect_mode 2)."""
         if self._force_all_pairs or self.n_upper < self.grid_threshold:
             return None
+        g = self.grid_info()
+        return (g["h"], g["cx"], g["cy"], g["c"], g["rg"]) if g["source"] else ()
+
+    def grid_info(self):
+        """All fields of the device-resident cosmo_grid (synchronising read; diagnostics)."""
         raw = self.t["grid_dev"].cpu().numpy().tobytes()[:C.sizeof(_abi.Grid)]
         g = _abi.Grid.from_buffer_copy(raw)
-        return (g.h, g.cx, g.cy, g.c, g.rg) if g.source else ()
+        return {name: getattr(g, name) for name, _ in _abi.Grid._fields_}
 
     @grid.setter
     def grid(self, value):
@@ -94,6 +99,12 @@ class BoundTracker:
     def grid(self):
         self._force_all_pairs, self._host_grid = False, None
         self._grid_changed()
+
+    def pin_grid(self):
+        """Pin the grid the device tuned for the last step (it otherwise adapts every step, using the
+        candidate density the previous step measured)."""
+        h, cx, cy, c, rg = self.grid
+        self.grid = (h, cx - 0.5 * c * h, cy - 0.5 * c * h, c, rg)
 
     def _grid_changed(self):
         pass

@@ -106,45 +106,59 @@ k_detect_allpairs(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int 
 // enforced here whatever the tuning says: the cell edge is at least the largest separation at which
 // two non-giants can be flagged, and every planet above the giant radius is brute-forced.
 
-// Smallest admissible cell edge.  The reference compares the COMPUTED distance (expanded form,
-// absolute error E in d^2 of a few ulps of |p|^2) with r_i + r_j, so two non-giants (inflated
-// radius <= rg) can be flagged while truly sqrt(4 rg^2 + E) apart; the cell edge is never
-// smaller than that (plus slack for the rounding of the cell coordinate itself).
-__device__ __forceinline__ double grid_hmin(const cosmo_state &st, double rg) {
-    const double pmax2 = __longlong_as_double(st.status[COSMO_ST_PMAX2]);
-    const double e = 64.0 * 1.1102230246251565e-16 * pmax2;
-    return sqrt(4.0 * rg * rg + e) * (1.0 + 1e-6);
+// Cell coordinate along one axis of the PERIODIC grid: the plane is tiled with square cells of edge
+// h and the cell (ix, iy) is stored in slot (iy mod c, ix mod c).  Planets within one cell edge of
+// each other lie in the same or in adjacent cells, hence in the same or in adjacent slots (mod c):
+// all the broad phase needs.  Cells a multiple of c apart share a slot -- that only adds candidates,
+// and every candidate goes through the exact predicate -- so the grid has no border: planets flung
+// far out of the scene (a violent disk loses a quarter of its planets to a halo within 25 frames)
+// land wherever they alias to, a few per slot, instead of piling up in border cells.  The period
+// c * h is tuned to hold the bulk of the scene, so bulk cells do not alias each other.
+__device__ __forceinline__ int cell_coord(double x, double centre, double h, int c) {
+    double t = floor((x - centre) / h + 0.5 * (double)c);
+    if (!(fabs(t) < 4.0e15)) t = 0.0;            // NaN / beyond exact integers: such planets are brute-forced (far2)
+    long long q = (long long)t % c;
+    return (int)(q < 0 ? q + c : q);
 }
 
-// Cell coordinate along one axis.  u = (x - centre) / h is mapped by a monotone function of
-// slope <= 1: identity inside the linear box |u| <= U0, U0 + log(1 + (|u| - U0)) outside, clamped
-// at the last cell.  Slope <= 1 means planets within one cell edge of each other land in the same
-// or in adjacent cells, which is all the broad phase needs; the logarithmic rim spreads planets
-// flung far out of the scene over many cells instead of piling them into the corners.
-__device__ __forceinline__ int cell_coord(double x, double centre, double h, int c, int w) {
-    const double u0 = 0.5 * (double)(c - 2 * w);
-    const double u = (x - centre) / h;
-    double t;
-    if (u > u0) t = u0 + fmin(log1p(u - u0), (double)w - 0.5);
-    else if (u < -u0) t = -u0 - fmin(log1p(-u - u0), (double)w - 0.5);
-    else t = u;
-    t = floor(t + u0 + (double)w);
-    t = fmin(fmax(t, 0.0), (double)(c - 1));   // NaN / overflow: clamp
-    return (int)t;
+// Candidate ranges of the cell-sorted item array for a planet in `cell`: its 3 x 3 slot
+// neighbourhood (mod c).  The three slots of a grid row are contiguous except across the seam,
+// where they split in two: six ranges, the odd ones mostly empty.  Needs c >= 3.
+__device__ __forceinline__ long long cand_ranges(const cosmo_scratch &sc, int cell, int c, int (&s0)[6], int (&s1)[6]) {
+    const int cx = cell % c, cy = cell / c;
+    long long cand = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        int yy = cy + d - 1;
+        yy = yy < 0 ? yy + c : (yy >= c ? yy - c : yy);
+        const int *row = sc.cell_start + (size_t)yy * c;
+        int a0 = cx - 1, a1 = cx + 1, b0 = 0, b1 = -1;          // [a0, a1] and, across the seam, [b0, b1]
+        if (cx == 0) { a0 = 0; b0 = c - 1; b1 = c - 1; }
+        else if (cx == c - 1) { a1 = c - 1; b0 = 0; b1 = 0; }
+        s0[2 * d] = row[a0]; s1[2 * d] = row[a1 + 1];
+        s0[2 * d + 1] = b1 >= b0 ? row[b0] : 0; s1[2 * d + 1] = b1 >= b0 ? row[b1 + 1] : 0;
+        cand += (s1[2 * d] - s0[2 * d]) + (s1[2 * d + 1] - s0[2 * d + 1]);
+    }
+    return cand;
 }
 
 template <bool D3>
 __device__ __forceinline__ double2 xy_of(const cosmo_state &st, const cosmo_scratch &sc, int k);
 
-// Tuning histograms (scratch.tune_hist, int32, all zero between frames):
-//   [0, 65536)           x coordinates of a strided sample of the planets
-//   [65536, 131072)      y coordinates
-//   [131072, 135168)     inflated radii of ALL planets
+// Tuning scratch (scratch.tune_hist, int32 words, all zero between frames):
+//   [0, 65536)           pass 1: x coordinates of a strided sample of the planets
+//                        pass 2: 128 x 128 occupancy of the bulk box (all planets)
+//   [65536, 131072)      pass 1: y coordinates
+//   [131072, 135168)     pass 1: inflated radii of ALL planets
+//   [135168, 135232)     32 doubles handed from k_grid_tune_box to k_grid_tune
 // Coordinates are binned by the top 16 bits of an order-preserving key of their FP32 value
 // (sign, exponent, 7 mantissa bits: 0.8 % relative resolution anywhere, no range to choose);
 // radii by exponent + 4 mantissa bits (6 %).
-constexpr int TUNE_XY_BINS = 65536, TUNE_R_BINS = 4096;
+constexpr int TUNE_XY_BINS = 65536, TUNE_R_BINS = 4096, TUNE_OCC = 128;
 constexpr int TUNE_SAMPLE = 131072;       // coordinates sampled for the quantile box
+constexpr int TUNE_AUX = 2 * TUNE_XY_BINS + TUNE_R_BINS;   // word offset of the doubles
+static_assert(TUNE_AUX + 64 == COSMO_TUNE_HIST_LEN, "header and kernels disagree on tune_hist");
+static_assert(TUNE_OCC * TUNE_OCC <= TUNE_XY_BINS, "occupancy map must fit the x histogram");
 
 __device__ __forceinline__ uint32_t tune_key(double v) {
     const float f = (float)fmin(fmax(v, -3.0e38), 3.0e38);
@@ -163,7 +177,7 @@ __device__ __forceinline__ double tune_rbin_upper(int b) {
     return (double)__uint_as_float(((uint32_t)b << 19) | 0x7ffffu);
 }
 
-// max |pos_new|^2 of the frame (-> hmin) and, with TUNE, the tuning histograms
+// pass 1: max |pos_new|^2 of the frame and, with TUNE, the 1-D tuning histograms
 template <bool D3, bool TUNE>
 __global__ void __launch_bounds__(256) k_grid_hist(cosmo_state st, cosmo_scratch sc) {
     __shared__ int s_r[TUNE ? TUNE_R_BINS : 1];
@@ -196,14 +210,32 @@ __global__ void __launch_bounds__(256) k_grid_hist(cosmo_state st, cosmo_scratch
     }
 }
 
+// Planets farther from the origin than 2^24 giant radii are brute-forced like giants: the rounding
+// slack of the reference's expanded d^2 grows with |p|^2, and one planet flung out to 10^4 AU must
+// not inflate every cell of the grid (grid_hmin then uses this bound instead of the true maximum).
+__device__ __forceinline__ double grid_far2(double rg) {
+    const double f = 16777216.0 * rg;
+    return f * f;
+}
+
+// Smallest admissible cell edge.  The reference compares the COMPUTED distance (expanded form,
+// absolute error E in d^2 of a few ulps of |p|^2) with r_i + r_j, so two non-giants (inflated
+// radius <= rg, |p|^2 <= far2) can be flagged while truly sqrt(4 rg^2 + E) apart; the cell edge is
+// never smaller than that (plus slack for the rounding of the cell coordinate itself).
+__device__ __forceinline__ double grid_hmin(const cosmo_state &st, double rg) {
+    const double pmax2 = fmin(__longlong_as_double(st.status[COSMO_ST_PMAX2]), grid_far2(rg));
+    const double e = 64.0 * 1.1102230246251565e-16 * pmax2;
+    return sqrt(4.0 * rg * rg + e) * (1.0 + 1e-6);
+}
+
 // detect_mode 1: the caller's grid (cell_size, origin of the linear box, cells per side, giant radius)
-__global__ void k_grid_set(cosmo_state st, cosmo_scratch sc, double h, double ox, double oy, double rg, int c, int w) {
+__global__ void k_grid_set(cosmo_state st, cosmo_scratch sc, double h, double ox, double oy, double rg, int c) {
     cosmo_grid g;
-    const double half_in = 0.5 * (double)(c - 2 * w) * h;    // the centre is fixed by the caller's (h, origin)
+    const double half_in = 0.5 * (double)c * h;    // the centre is fixed by the caller's (h, origin)
     g.h = fmax(h, grid_hmin(st, rg));
-    g.cx = ox + half_in; g.cy = oy + half_in; g.rg = rg;
-    g.ncell = (int64_t)c * c; g.c = c; g.w = w; g.source = 1; g.reserved = 0;
-    g.box = (double)(c - 2 * w) * h; g.h_tuned = h;
+    g.cx = ox + half_in; g.cy = oy + half_in; g.rg = rg; g.far2 = grid_far2(rg);
+    g.ncell = (int64_t)c * c; g.c = c; g.w = 0; g.source = 1; g.reserved = 0;
+    g.box = (double)c * h; g.h_tuned = h; g.rho = 0.0; g.cand_total = 0; g.n_counted = 0;
     *sc.grid_dev = g;
 }
 
@@ -234,20 +266,17 @@ __device__ __forceinline__ int block_scan_1024(int v, int *s_w, int *total) {
     return s_w[32 + w] + inc - v;
 }
 
-// detect_mode 2: one CTA turns the histograms into the frame's grid.
-//   box     robust 2 % .. 98 % quantile box of the coordinates (NOT min/max: a handful of planets
-//           flung out by a close encounter must not stretch the cells over the whole scene; they
-//           land in the logarithmic rim / border cells instead, which is exact, only slower for them)
-//   rg      giant radius from a cost model: g giants cost g*n exact tests, everybody else
-//           9 cells * (n / area) * (2 rg)^2 candidates; g in {0, 1, 2, 4, ..., 1024}
-//   h       cell edge for ~16 candidates per planet, never below 2 rg (nor below grid_hmin)
-// and returns the histograms to zero.
-__global__ void __launch_bounds__(1024) k_grid_tune(cosmo_state st, cosmo_scratch sc, int w) {
+// detect_mode 2, step 1 (one CTA): the BULK box and the radius order statistics.
+//   box   1.5 x the 10 % .. 90 % quantile range of the coordinates (NOT min/max, not even 2 % .. 98 %:
+//         in a violent scene a few per cent of the planets are flung far out within a few frames;
+//         the periodic grid has no border, they alias into the bulk's slots a few at a time)
+//   big   (g+1)-th largest inflated radius (upper bin edge) for g = 0, 1, 2, 4, ..., 1024
+// Results go to the aux doubles; the 1-D histograms return to zero.
+__global__ void __launch_bounds__(1024) k_grid_tune_box(cosmo_state st, cosmo_scratch sc) {
     __shared__ int s_w[65];
     __shared__ double s_q[4];          // x lo, x hi, y lo, y hi
-    __shared__ double s_big[12];       // (g+1)-th largest inflated radius (upper bin edge), g = 0,1,2,4,..,1024
+    __shared__ double s_big[12];
     const int tid = threadIdx.x;
-    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     if (tid < 4) s_q[tid] = 0.0;
     if (tid < 12) s_big[tid] = -1.0;
     // ---- coordinate quantiles: thread t owns bins [64 t, 64 t + 64) of each axis
@@ -257,7 +286,7 @@ __global__ void __launch_bounds__(1024) k_grid_tune(cosmo_state st, cosmo_scratc
         for (int q = 0; q < 64; ++q) loc += hist[tid * 64 + q];
         int total;
         const int before = block_scan_1024(loc, s_w, &total);
-        const long long r_lo = (long long)(0.02 * total), r_hi = min((long long)(0.98 * total), (long long)total - 1);
+        const long long r_lo = (long long)(0.10 * total), r_hi = min((long long)(0.90 * total), (long long)total - 1);
         if (total > 0) {
             int run = before;
             for (int q = 0; q < 64; ++q) {
@@ -293,34 +322,93 @@ __global__ void __launch_bounds__(1024) k_grid_tune(cosmo_state st, cosmo_scratc
         }
     }
     __syncthreads();
+    double *aux = reinterpret_cast<double *>(sc.tune_hist + TUNE_AUX);
+    if (tid < 12) aux[4 + tid] = s_big[tid];
     if (tid != 0) return;
-    cosmo_grid g;
-    double box = fmax(s_q[1] - s_q[0], s_q[3] - s_q[2]);
+    double box = fmax(s_q[1] - s_q[0], s_q[3] - s_q[2]) * 1.5;
     const double pmax = sqrt(__longlong_as_double(st.status[COSMO_ST_PMAX2]));
     if (!(box > 0.0) || !isfinite(box)) box = fmax(2.0 * pmax, 1e-300);
-    box *= 1.25;                                          // the bulk; tails go to the rim cells
-    g.cx = 0.5 * (s_q[0] + s_q[1]); g.cy = 0.5 * (s_q[2] + s_q[3]);
-    if (!isfinite(g.cx) || !isfinite(g.cy)) { g.cx = 0.0; g.cy = 0.0; }
-    const double dn = (double)max(n, 1), area = fmax(box * box, 1.0);
+    double cx = 0.5 * (s_q[0] + s_q[1]), cy = 0.5 * (s_q[2] + s_q[3]);
+    if (!isfinite(cx) || !isfinite(cy)) { cx = 0.0; cy = 0.0; }
+    aux[0] = cx; aux[1] = cy; aux[2] = box;
+}
+
+// detect_mode 2, step 2: 128 x 128 occupancy of the bulk box
+template <bool D3>
+__global__ void __launch_bounds__(256) k_grid_occupancy(cosmo_state st, cosmo_scratch sc) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const double *aux = reinterpret_cast<const double *>(sc.tune_hist + TUNE_AUX);
+    const double cx = aux[0], cy = aux[1], inv = (double)TUNE_OCC / aux[2];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const double2 p = xy_of<D3>(st, sc, k);
+        const double u = (p.x - cx) * inv + 0.5 * TUNE_OCC, v = (p.y - cy) * inv + 0.5 * TUNE_OCC;
+        if (u >= 0.0 && u < (double)TUNE_OCC && v >= 0.0 && v < (double)TUNE_OCC)
+            atomicAdd(&sc.tune_hist[(int)v * TUNE_OCC + (int)u], 1);
+    }
+}
+
+// detect_mode 2, step 3 (one CTA): the frame's grid.
+//   rho   density a planet sees on average (a plain n / area is wrong by orders of magnitude for a
+//         disk, a ring or a cluster): sum c (c - 1) / (sum c * cell area) over the occupancy map, or --
+//         finer than that map can resolve -- the density MEASURED by the previous frame's grid,
+//         candidates / (9 h^2) per planet (k_grid_density; integer sums, identical on every rank)
+//   rg    giant radius from a cost model: g giants cost g*n exact tests, everybody else
+//         9 cells * rho * (2 rg)^2 candidates; g in {0, 1, 2, 4, ..., 1024}
+//   h     cell edge for ~16 candidates per planet, never below 2 rg (nor below grid_hmin), never so
+//         small that the linear part of the grid could not cover the bulk box
+// and returns the occupancy map to zero.
+__global__ void __launch_bounds__(1024) k_grid_tune(cosmo_state st, cosmo_scratch sc) {
+    __shared__ double s_a[32], s_b[32];
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    double a = 0.0, b = 0.0;
+    for (int q = tid; q < TUNE_OCC * TUNE_OCC; q += 1024) {
+        const double c = (double)sc.tune_hist[q];
+        a += c * (c - 1.0);
+        b += c;
+        sc.tune_hist[q] = 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { s_a[wp] = a; s_b[wp] = b; }
+    __syncthreads();
+    if (tid != 0) return;
+    a = 0.0; b = 0.0;
+    for (int q = 0; q < 32; ++q) { a += s_a[q]; b += s_b[q]; }
+    double *aux = reinterpret_cast<double *>(sc.tune_hist + TUNE_AUX);
+    cosmo_grid g;
+    g.cx = aux[0]; g.cy = aux[1];
+    const double box = aux[2];
+    const double dn = (double)max(n, 1);
+    const double cell_area = (box / TUNE_OCC) * (box / TUNE_OCC);
+    double rho = b > 0.0 ? a / (b * cell_area) : 0.0;
+    rho = fmax(rho, dn / (box * box) * 1e-3);              // nearly empty map: fall back towards the mean density
+    const cosmo_grid prev = *sc.grid_dev;
+    if (prev.source == 2 && prev.n_counted > 0 && prev.cand_total > 0 && prev.h > 0.0 && isfinite(prev.h))
+        rho = fmax(rho, (double)prev.cand_total / ((double)prev.n_counted * 9.0 * prev.h * prev.h));
     double best = -1.0, rg = 0.0;
     for (int gi = 0; gi < 12; ++gi) {
         const int gg = gi == 0 ? 0 : 1 << (gi - 1);
-        if (gg > n - 1 || s_big[gi] < 0.0) break;
-        const double cost = gg * dn + dn * 9.0 * (dn / area) * (2.0 * s_big[gi]) * (2.0 * s_big[gi]);
-        if (best < 0.0 || cost < best) { best = cost; rg = s_big[gi]; }
+        const double big = aux[4 + gi];
+        if (gg > n - 1 || big < 0.0) break;
+        const double cost = gg * dn + dn * 9.0 * rho * (2.0 * big) * (2.0 * big);
+        if (best < 0.0 || cost < best) { best = cost; rg = big; }
     }
-    const double span = fmax(box, 4.0 * rg) * 1.1;
     int cmax = (int)floor(sqrt((double)sc.grid_cells));
     while ((long long)cmax * cmax > sc.grid_cells) --cmax;
-    cmax -= 2 * w;
-    if (cmax < 1) cmax = 1;
-    double h = fmax(fmax(2.0 * rg * 1.001, span / cmax), span * 4.0 / (3.0 * sqrt(dn)));   // ~16 candidates per planet
+    if (cmax < 3) cmax = 3;
+    const double span = fmax(box, 4.0 * rg) * 1.1;    // one period holds the bulk: bulk cells do not alias each other
+    double h = fmax(fmax(2.0 * rg * 1.001, span / cmax), sqrt(16.0 / (9.0 * rho)));   // ~16 candidates per planet
     int c = (int)ceil(span / h);
-    c = max(1, min(cmax, c));
+    c = max(3, min(cmax, c));
     rg = fmax(rg, h / (2.0 * 1.001));     // cells wider than 2 rg: admit larger planets for free
     g.h_tuned = h;
     g.h = fmax(h, grid_hmin(st, rg));
-    g.rg = rg; g.c = c + 2 * w; g.w = w; g.ncell = (int64_t)g.c * g.c; g.source = 2; g.reserved = 0; g.box = box;
+    g.rg = rg; g.far2 = grid_far2(rg); g.rho = rho;
+    g.c = c; g.w = 0; g.ncell = (int64_t)g.c * g.c; g.source = 2; g.reserved = 0; g.box = box;
+    g.cand_total = 0; g.n_counted = 0;
     *sc.grid_dev = g;
 }
 
@@ -341,7 +429,7 @@ k_grid_count(cosmo_state st, cosmo_scratch sc) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const cosmo_grid g = *sc.grid_dev;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        if (sc.rinf[k] > g.rg) {
+        if (sc.rinf[k] > g.rg || sc.xx_new[k] > g.far2) {
             unsigned long long idx =
                 atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_GIANTS]), 1ull);
             if ((long long)idx < sc.giant_cap)
@@ -352,7 +440,7 @@ k_grid_count(cosmo_state st, cosmo_scratch sc) {
             sc.cell_of[k] = -1;
         } else {
             const double2 p = xy_of<D3>(st, sc, k);
-            const int cell = cell_coord(p.y, g.cy, g.h, g.c, g.w) * g.c + cell_coord(p.x, g.cx, g.h, g.c, g.w);
+            const int cell = cell_coord(p.y, g.cy, g.h, g.c) * g.c + cell_coord(p.x, g.cx, g.h, g.c);
             sc.cell_of[k] = cell;
             atomicAdd(&sc.cell_count[cell], 1);
         }
@@ -368,6 +456,29 @@ __global__ void __launch_bounds__(256) k_grid_fill(cosmo_state st, cosmo_scratch
             const int slot = sc.cell_start[cell] + atomicSub(&sc.cell_count[cell], 1) - 1;
             sc.cell_items[slot] = k;
         }
+    }
+}
+
+// Candidates the grid produces, summed over ALL non-giant planets (every rank runs this over all
+// rows, so the sums -- integers -- are identical everywhere): feedback for the next frame's tuner.
+__global__ void __launch_bounds__(256) k_grid_density(cosmo_state st, cosmo_scratch sc) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int c = sc.grid_dev->c;
+    unsigned long long cand = 0, cnt = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int cell = sc.cell_of[k];
+        if (cell < 0) continue;
+        int s0[6], s1[6];
+        cand += (unsigned long long)cand_ranges(sc, cell, c, s0, s1);
+        ++cnt;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        cand += __shfl_xor_sync(0xffffffffu, cand, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(&sc.grid_dev->cand_total), cand);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&sc.grid_dev->n_counted), cnt);
     }
 }
 
@@ -444,28 +555,18 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count
   for (int chunk = shard_index + blockIdx.x * shard_count; chunk < nchunk; chunk += gridDim.x * shard_count) {
    const int s_lo = sc.chunk_alive[chunk], s_hi = sc.chunk_alive[chunk + 1];
    // blockIdx.y splits the chunk's slots: a normal chunk is one slot per thread, an oversized one
-   // (a crowded or border cell is never split across chunks) is still shared by gridDim.y blocks
+   // (a crowded cell is never split across chunks) is still shared by gridDim.y blocks
    for (int slot = s_lo + blockIdx.y * blockDim.x + threadIdx.x; slot < s_hi; slot += gridDim.y * blockDim.x) {
     const int i = sc.cell_items[slot];
     const int cell = sc.cell_of[i];
     const GridRow row = load_row<D3>(st, sc, i);
-    const int cx = cell % c, cy = cell / c;
     // candidate ranges: the three cells of a grid row are contiguous in the sorted item array
-    int s0[3], s1[3];
-    long long cand = 0;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = cy + dy;
-        const bool in = yy >= 0 && yy < c;
-        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, c - 1);
-        s0[dy + 1] = in ? sc.cell_start[yy * c + x0] : 0;
-        s1[dy + 1] = in ? sc.cell_start[yy * c + x1 + 1] : 0;
-        cand += s1[dy + 1] - s0[dy + 1];
-    }
+    int s0[6], s1[6];
+    const long long cand = cand_ranges(sc, cell, c, s0, s1);
     const int ng = (int)min((long long)st.status[COSMO_ST_N_GIANTS], (long long)sc.giant_cap);
     cand_total += (unsigned)cand;
     if (cand + ng > GRID_HEAVY) {
-        // a crowded neighbourhood (dense inner disk, logarithmic rim): one thread walking thousands
+        // a crowded neighbourhood (dense inner disk, a tight cluster): one thread walking thousands
         // of candidates would be the critical path of the whole frame -> warp-per-row pass
         const unsigned long long h =
             atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_HEAVY]), 1ull);
@@ -473,7 +574,7 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count
         continue;
     }
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
+    for (int d = 0; d < 6; ++d)
         for (int s = s0[d]; s < s1[d]; ++s) {
             const int j = sc.cell_items[s];
             if (j != i) test_and_emit<D3>(st, sc, i, row, j);
@@ -499,17 +600,13 @@ __global__ void __launch_bounds__(256) k_grid_detect_heavy(cosmo_state st, cosmo
         const int i = sc.label[h];
         const int cell = sc.cell_of[i];
         const GridRow row = load_row<D3>(st, sc, i);
-        const int cx = cell % c, cy = cell / c;
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = cy + dy;
-            if (yy < 0 || yy >= c) continue;
-            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, c - 1);
-            const int s0 = sc.cell_start[yy * c + x0], s1 = sc.cell_start[yy * c + x1 + 1];
-            for (int s = s0 + lane; s < s1; s += 32) {
+        int s0[6], s1[6];
+        cand_ranges(sc, cell, c, s0, s1);
+        for (int d = 0; d < 6; ++d)
+            for (int s = s0[d] + lane; s < s1[d]; s += 32) {
                 const int j = sc.cell_items[s];
                 if (j != i) test_and_emit<D3>(st, sc, i, row, j);
             }
-        }
         for (int g = lane; g < ng; g += 32) test_and_emit<D3>(st, sc, i, row, sc.giants[g]);
     }
 }
@@ -556,30 +653,29 @@ static int launch_grid(const cosmo_state &st, const cosmo_scratch &sc, const cos
     int nb = (p.n_upper + 255) / 256;
     if (nb < 1) nb = 1;
     if (nb > 148 * 8) nb = 148 * 8;
-    const int w = p.grid_log_cells < 0 ? 0 : p.grid_log_cells;
     if (p.detect_mode == 2) {
         // grid tuned on the device from this frame's positions and radii: no host round trip
-        if (!sc.tune_hist || (long long)(2 * w + 1) * (2 * w + 1) > sc.grid_cells) {
-            set_error("grid broad phase: detect_mode 2 needs scratch.tune_hist and grid_cells >= (2*%d+1)^2", w);
+        if (!sc.tune_hist || sc.grid_cells < 9) {
+            set_error("grid broad phase: detect_mode 2 needs scratch.tune_hist and grid_cells >= 9");
             return COSMO_E_ARG;
         }
         k_grid_hist<D3, true><<<nb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_hist"));
-        k_grid_tune<<<1, 1024, 0, s>>>(st, sc, w);
+        k_grid_tune_box<<<1, 1024, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_tune_box"));
+        k_grid_occupancy<D3><<<nb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_occupancy"));
+        k_grid_tune<<<1, 1024, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_tune"));
     } else {
         const int c = p.cells_per_side;
-        if (c < 1 || (long long)c * c > sc.grid_cells) {
-            set_error("grid broad phase: cells_per_side=%d does not fit grid_cells=%d", c, sc.grid_cells);
-            return COSMO_E_ARG;
-        }
-        if (c - 2 * w < 1) {
-            set_error("grid broad phase: %d logarithmic cells per side do not fit cells_per_side=%d", w, c);
+        if (c < 3 || (long long)c * c > sc.grid_cells) {
+            set_error("grid broad phase: cells_per_side=%d must be >= 3 and fit grid_cells=%d", c, sc.grid_cells);
             return COSMO_E_ARG;
         }
         k_grid_hist<D3, false><<<nb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_hist"));
-        k_grid_set<<<1, 1, 0, s>>>(st, sc, p.cell_size, p.grid_origin_x, p.grid_origin_y, p.giant_radius, c, w);
+        k_grid_set<<<1, 1, 0, s>>>(st, sc, p.cell_size, p.grid_origin_x, p.grid_origin_y, p.giant_radius, c);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_set"));
     }
     k_grid_count<D3><<<nb, 256, 0, s>>>(st, sc);
@@ -589,6 +685,10 @@ static int launch_grid(const cosmo_state &st, const cosmo_scratch &sc, const cos
     COSMO_TRY(launch_scan_exclusive(sc.cell_count, sc.cell_start, sc.scan_blk, &sc.grid_dev->ncell, scan_max, 0, s));
     k_grid_fill<<<nb, 256, 0, s>>>(st, sc);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_fill"));
+    if (p.detect_mode == 2) {
+        k_grid_density<<<nb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_density"));
+    }
     const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
     const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
     const int nchunk = (p.n_upper + GRID_CHUNK - 1) / GRID_CHUNK + 1;

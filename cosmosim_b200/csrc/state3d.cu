@@ -898,7 +898,7 @@ static int launch_stage_b(const cosmo3_state &st, const cosmo3_scratch &sc, cons
         c2.scan_blk = sc.scan_blk; c2.grid_dev = sc.grid_dev; c2.tune_hist = sc.tune_hist;
         cosmo_step_params p2 = {};
         p2.opts = COSMO_OPT_COLLISIONS; p2.n_upper = p.n_upper; p2.i_begin = p.i_begin; p2.i_end = p.i_end;
-        p2.detect_mode = p.detect_mode; p2.grid_log_cells = p.grid_log_cells; p2.cells_per_side = p.cells_per_side;
+        p2.detect_mode = p.detect_mode; p2.cells_per_side = p.cells_per_side;
         p2.cell_size = p.cell_size; p2.grid_origin_x = p.grid_origin_x; p2.grid_origin_y = p.grid_origin_y;
         p2.giant_radius = p.giant_radius;
         p2.shard_index = p.shard_count > 0 ? p.shard_index : 0;

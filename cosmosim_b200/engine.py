@@ -72,7 +72,6 @@ class Engine(BoundTracker):
         self.pos_exp = 0
         self.mass_exp = 0
         self.frames = 0
-        self.grid_log_cells = 32    # logarithmic rim of the broad-phase grid (cells per side)
         self.grid_threshold = 8192  # planets from which the grid broad phase + parallel resolver pay off
         self.small_threshold = 4096  # below: small-N kernel shape (more, shorter CTAs)
         self.sym_threshold = 32768   # FP32: from here on the symmetric kernel (each pair once) wins
@@ -306,8 +305,12 @@ class Engine(BoundTracker):
             self.sc.colbuf_rows = rows
 
     def params(self, dt, G, r_max, **kw):
-        """Step parameters for the current launch bound (cached: they only depend on the arguments, the
-        bound and a few tunables)."""
+        """Step parameters for the current launch bound (a private copy the caller may edit)."""
+        return _abi.StepParams.from_buffer_copy(self._params(dt, G, r_max, **kw))
+
+    def _params(self, dt, G, r_max, **kw):
+        """Cached step parameters (shared object: do not modify): they only depend on the arguments,
+        the launch bound and a few tunables."""
         key = (self.n_upper, dt, G, r_max, tuple(sorted(kw.items())), self.grid_threshold, self.small_threshold,
                self.sym_threshold, self.sym64_threshold, self.sym_chunk, self.pos_exp, self.mass_exp)
         p = self._params_cache.get(key)
@@ -359,7 +362,6 @@ class Engine(BoundTracker):
             # grid tuned ON THE DEVICE from the frame's own positions and radii (detect_mode 2) unless
             # the caller pinned one (detect_mode 1): the host never reads planet data while stepping
             p.resolve_mode = 1
-            p.grid_log_cells = self.grid_log_cells
             if self._host_grid is not None:
                 p.detect_mode = 1
                 p.cell_size, p.grid_origin_x, p.grid_origin_y, p.cells_per_side, p.giant_radius = self._host_grid
@@ -389,7 +391,7 @@ class Engine(BoundTracker):
         to time the all-pairs kernel on the launching stream."""
         if self.n_upper <= 0 or n_frames <= 0:
             return
-        p = self.params(dt, G, r_max, **kw)
+        p = self._params(dt, G, r_max, **kw)
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         st, sc, pp = C.byref(self.st), C.byref(self.sc), C.byref(p)
         lib = self.lib
@@ -398,7 +400,7 @@ class Engine(BoundTracker):
             return self._step_graphed(int(n_frames), dt, G, r_max, kw)
         for _ in range(int(n_frames)):
             if self._refresh_bound():
-                p = self.params(dt, G, r_max, **kw)
+                p = self._params(dt, G, r_max, **kw)
                 pp = C.byref(p)
             if self.world > 1:
                 self._step_sharded(p, stream, stage_events)

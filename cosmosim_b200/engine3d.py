@@ -62,7 +62,6 @@ class Engine3D(BoundTracker):
         self.mass_exp = 0
         self.steps = 0
         self._jsplit_cache = {}
-        self.grid_log_cells = 32
         self.grid_threshold = 16384  # objects from which the grid broad phase beats the all-pairs test
         self.sym64_threshold = 16384 # FP64: from here on the symmetric kernel (each pair once) wins
         self.sym32_threshold = 32768 # FP32: same for the symmetric FP32 kernel
@@ -261,7 +260,6 @@ class Engine3D(BoundTracker):
         if collisions and not self._force_all_pairs and n >= self.grid_threshold:
             # grid tuned on the device from the step's own positions and radii (detect_mode 2) unless
             # the caller pinned one (detect_mode 1)
-            p.grid_log_cells = self.grid_log_cells
             if self._host_grid is not None:
                 p.detect_mode = 1
                 p.cell_size, p.grid_origin_x, p.grid_origin_y, p.cells_per_side, p.giant_radius = self._host_grid

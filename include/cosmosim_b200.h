@@ -97,17 +97,22 @@ extern "C" {
    device from the frame's own positions and radii (detect_mode 2) -- and read by the rest. */
 typedef struct cosmo_grid {
     double h;        /* cell edge in use (>= the smallest admissible edge for giant radius rg) */
-    double cx, cy;   /* centre of the linear part of the grid */
+    double cx, cy;   /* centre of period 0 of the grid */
     double rg;       /* planets with inflated radius above this are tested against everybody */
     int64_t ncell;   /* c * c */
-    int32_t c;       /* cells per side, including 2 * w logarithmic rim cells */
-    int32_t w;
+    int32_t c;       /* slots per side of the periodic grid (>= 3) */
+    int32_t w;       /* 0 (reserved) */
     int32_t source;  /* 1 = from cosmo_step_params, 2 = tuned on the device */
     int32_t reserved;
-    double box;      /* edge of the linear part as tuned (diagnostic) */
+    double box;      /* edge of the bulk box the grid was tuned for (diagnostic) */
     double h_tuned;  /* cell edge before the admissibility clamp (diagnostic) */
+    double far2;     /* planets with |pos_new|^2 above this are brute-forced like giants */
+    double rho;      /* planets per unit area a planet sees on average, as used by the tuner (detect_mode 2) */
+    int64_t cand_total; /* broad-phase candidates summed over ALL non-giant planets of this frame (the same
+                           on every rank): next frame's tuner derives the density from it */
+    int64_t n_counted;  /* planets that sum runs over */
 } cosmo_grid;
-#define COSMO_TUNE_HIST_LEN (2 * 65536 + 4096) /* int32 words of scratch.tune_hist */
+#define COSMO_TUNE_HIST_LEN (2 * 65536 + 4096 + 64) /* int32 words of scratch.tune_hist */
 
 /* Persistent state.  All pointers are device pointers. */
 typedef struct cosmo_state {
@@ -219,20 +224,18 @@ typedef struct cosmo_step_params {
     int32_t jsplit;   /* source-range splits of the all-pairs pass (>=1, <= jsplit_max) */
     int32_t detect_mode; /* 0 = all-pairs predicate, 1 = uniform-grid broad phase with the grid given
                             below, 2 = uniform grid tuned on the device every frame (cell_size, origin,
-                            cells_per_side and giant_radius are ignored; grid_log_cells is used) */
+                            cells_per_side and giant_radius are ignored) */
     int32_t resolve_mode; /* 0 = rank sort + sequential replay (few pairs), 1 = CSR + parallel */
     int32_t small_tiles;  /* 1 = small-N kernel shape for stage A/B (more, shorter CTAs) */
     int32_t shard_index;  /* this rank / number of ranks sharing the frame (0 / 1 if single): the */
     int32_t shard_count;  /* grid broad phase splits its cell-sorted planet order evenly by these */
     int32_t sym_chunk;    /* symmetric kernel: column blocks per CTA (0 = default) */
     int32_t near_mode;    /* FP32 path: 1 = re-evaluate the near field in FP64 (see cosmo_step_params docs) */
-    int32_t grid_log_cells; /* detect_mode 1: logarithmic cells on each side of the linear box (>= 0) */
+    int32_t reserved2;
     int32_t reserved1;
-    double cell_size;    /* detect_mode 1 */
-    double grid_origin_x; /* detect_mode 1: lower corner of the LINEAR part of the grid, which has      */
-    double grid_origin_y; /* cells_per_side - 2*grid_log_cells cells per axis; beyond it the cell index */
-                          /* grows like log(1 + distance/cell) (non-expansive, so flagged pairs stay in */
-                          /* adjacent cells) and is finally clamped                                      */
+    double cell_size;     /* detect_mode 1: edge of the square cells of the PERIODIC grid: cell (ix, iy) of  */
+    double grid_origin_x; /* the tiling anchored at the origin is stored in slot (iy mod c, ix mod c), c =   */
+    double grid_origin_y; /* cells_per_side >= 3 (cells a multiple of c apart share a slot: a superset)      */
     int32_t cells_per_side;
     int32_t jsplit_detect; /* source-range splits of the stage-B all-pairs pass */
     double giant_radius; /* detect_mode 1: planets with radius above this are brute-forced */

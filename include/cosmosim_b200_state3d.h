@@ -127,7 +127,7 @@ typedef struct cosmo3_step_params {
        every candidate goes through the exact 3-D predicate); 2 = the same grid tuned on the device
        every step.  Fields as in cosmo_step_params. */
     int32_t detect_mode;
-    int32_t grid_log_cells;
+    int32_t reserved1;
     int32_t cells_per_side;
     int32_t sym_chunk;     /* symmetric kernel: column blocks per CTA (0 = default) */
     double cell_size;
