@@ -164,15 +164,23 @@ def cpu_oracle_leg(arrays, prec_n, seconds_target=12.0, steps=1, warmup=0):
 
 # ------------------------------------------------------------------------------------ B200 arm helpers
 def state_digest(eng):
-    """sha1 over (ids, mass bits, position bits, merge-event count, frame) of the device state: equal
-    digests across GPU counts prove the sharded run reproduced the single-GPU one bit for bit."""
+    """(discrete, full) sha1 digests of the device state.  discrete = ids, mass / radius / volume bits,
+    eaten counts and the whole merge stream: equal across GPU counts when the sharded run reproduced the
+    single-GPU one (the driver's 1/2/4/8 sweep can compare them).  full adds position / velocity bits,
+    which agree only to rounding across GPU counts (the cross-rank sum is another summation order)
+    but must be identical on all replicas of one run."""
     import hashlib
     d = eng.download()
+    ev = eng.events()
     h = hashlib.sha1()
-    for k in ("id", "mass", "pos", "radius"):
+    for k in ("id", "mass", "radius", "volume", "eaten"):
         h.update(np.ascontiguousarray(d[k]).tobytes())
+    h.update(np.ascontiguousarray(ev).tobytes())      # the whole merge stream (frame, absorber, absorbed)
     h.update(np.array([d["status"]["n_events"], d["status"]["frame"], d["status"]["n_escaped"]], dtype=np.int64).tobytes())
-    return h.hexdigest()[:16]
+    discrete = h.hexdigest()[:16]
+    for k in ("pos", "vel"):
+        h.update(np.ascontiguousarray(d[k]).tobytes())
+    return discrete, h.hexdigest()[:16]
 
 
 def timed_frames(eng, K, kw, flush, barrier, world, restore=None):
@@ -394,11 +402,11 @@ def main():
     value = interactions / (ms * 1e-3)
     config["n_eff"] = n_eff          # RMS active count over the timed frames (the scene merges ~7 % of its planets per frame)
     roofline = roofline_block(eng, prec, kw, peaks, stage_events, n_per_step, world, a.workload, ms / K)
-    digest = state_digest(eng)
+    digest, digest_full = state_digest(eng)
     replicas_identical = None
     if world > 1:
         got = [None] * world
-        dist.all_gather_object(got, digest)
+        dist.all_gather_object(got, digest_full)
         replicas_identical = len(set(got)) == 1
 
     # ---------------------------------------------------------------- full-N frames (device-timed)
@@ -462,7 +470,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
                 "roofline": roofline, "cpu_baseline": cpu, "full_n": full_n, "secondary": secondary,
                 "final_state": {"n_active": st["n_active"], "merges": st["n_events"], "escaped": st["n_escaped"]},
-                "state_digest": digest, "replicas_identical": replicas_identical,
+                "state_digest": digest, "state_digest_full": digest_full, "replicas_identical": replicas_identical,
                 "n_active_per_step": [int(x) for x in n_per_step],
                 "pairs_last_frame": st["n_pairs"], "detect_mode": "grid (tuned on the device)" if st["n_active"] >= 8192 else "all-pairs",
                 "fp32_bound": ("per-step relative acceleration error vs the FP64 reference formula: see "

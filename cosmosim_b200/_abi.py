@@ -45,7 +45,7 @@ class Scratch(C.Structure):
                 ("cell_of", _vp), ("cell_count", _vp), ("cell_start", _vp), ("cell_items", _vp),
                 ("giants", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32),
                 ("peer_acc", _vp * 16), ("n_peers", C.c_int32), ("reserved_scratch", C.c_int32),
-                ("grid_dev", _vp), ("tune_hist", _vp)]
+                ("grid_dev", _vp), ("tune_hist", _vp), ("corr", _vp)]
 
 
 class Grid(C.Structure):
@@ -56,7 +56,7 @@ class Grid(C.Structure):
                 ("far2", C.c_double), ("rho", C.c_double), ("cand_total", C.c_int64), ("n_counted", C.c_int64)]
 
 
-TUNE_HIST_LEN = 2 * 65536 + 4096 + 64
+TUNE_HIST_LEN = 2 * 16384 + 4096 + 64
 
 
 class StepParams(C.Structure):

@@ -313,7 +313,7 @@ k_accel_f64(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
 template <int BLOCK, int IB, int TJ>
 __global__ void __launch_bounds__(BLOCK)
 k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit, double G, double dt,
-            double unscale, int store_acc) {
+            double unscale, int store_acc, int near) {
     __shared__ __align__(16) float s_x[2][TJ];
     __shared__ __align__(16) float s_y[2][TJ];
     __shared__ __align__(16) float s_m[2][TJ];
@@ -388,7 +388,8 @@ k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
                     float ia = rsqrt_approx_f32(r2a);
                     float ib = rsqrt_approx_f32(r2b);
                     uint64_t rinv = pack2(ia, ib);
-                    uint64_t s = mul2(mul2(mj2, rinv), mul2(rinv, rinv));
+                    // same order as the symmetric kernel; nearfield.cu replays it to the bit
+                    uint64_t s = mul2(mj2, mul2(mul2(rinv, rinv), rinv));
                     ax2[k] = fma2(dx, s, ax2[k]);
                     ay2[k] = fma2(dy, s, ay2[k]);
                 }
@@ -406,6 +407,16 @@ k_accel_f32(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int jsplit
     }
 #pragma unroll
     for (int k = 0; k < IB; ++k) { axd[k] *= unscale; ayd[k] *= unscale; }
+    if (near && blockIdx.y == 0) {   // FP64 near-field corrections (nearfield.cu), once per row
+#pragma unroll
+        for (int k = 0; k < IB; ++k) {
+            const int i = base + k * BLOCK + tid;
+            if (i < i_hi) {
+                const double2 c = reinterpret_cast<const double2 *>(sc.corr)[i];
+                axd[k] += c.x; ayd[k] += c.y;
+            }
+        }
+    }
     reduce_and_integrate<BLOCK, IB>(st, sc, base, i_hi, axd, ayd, jsplit, G, dt, store_acc != 0);
 }
 
@@ -445,6 +456,7 @@ int launch_prep(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step
 
 int launch_accel(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                  cudaStream_t s) {
+    if ((p.opts & COSMO_OPT_FP32) && p.near_mode != 0) COSMO_TRY(launch_nearfield(st, sc, p, s));
     if ((p.opts & COSMO_OPT_FP32) && (p.opts & COSMO_OPT_F32_SYM)) return launch_accel_sym(st, sc, p, s);
     if (!(p.opts & COSMO_OPT_FP32) && (p.opts & COSMO_OPT_F64_SYM)) return launch_accel_sym64(st, sc, p, s);
     const int rows = p.i_end - p.i_begin;
@@ -458,7 +470,7 @@ int launch_accel(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_ste
         // S = S_scaled * 2^(mass_exp - 2 pos_exp)
         const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
         k_accel_f32<F32_BLOCK, F32_IB, F32_TJ><<<grid, F32_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit, p.G, p.dt,
-                                                                         unscale, store_acc);
+                                                                         unscale, store_acc, p.near_mode != 0);
         return COSMO_LAUNCH_CHECK("k_accel_f32");
     }
     if (p.small_tiles) {

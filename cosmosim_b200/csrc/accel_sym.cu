@@ -188,7 +188,7 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
 // (multi-GPU: all-reduced by the caller, then k_sym_integrate).
 __global__ void __launch_bounds__(256)
 k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int chunk, double unscale,
-             double G, double dt, int store_acc, int defer) {
+             double G, double dt, int store_acc, int defer, int near) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -214,6 +214,11 @@ k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count,
     }
     ax *= unscale;
     ay *= unscale;
+    if (near) {   // FP64 near-field corrections of the rows this rank evaluated (nearfield.cu; zero elsewhere)
+        const double2 c = reinterpret_cast<const double2 *>(sc.corr)[k];
+        ax += c.x;
+        ay += c.y;
+    }
     if (defer == 2) {
         // peer exchange: this rank's partial sums go straight into slot `shard_index` of every
         // rank's exchange buffer (NVLink peer stores, coalesced 16 B per lane)
@@ -272,7 +277,7 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
     }
     const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? ((p.opts & COSMO_OPT_PEER_EXCHANGE) ? 2 : 1) : 0;
     k_sym_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, unscale, p.G, p.dt,
-                                                 (p.opts & COSMO_OPT_STORE_ACC) ? 1 : 0, defer);
+                                                 (p.opts & COSMO_OPT_STORE_ACC) ? 1 : 0, defer, p.near_mode != 0);
     return COSMO_LAUNCH_CHECK("k_sym_reduce");
 }
 

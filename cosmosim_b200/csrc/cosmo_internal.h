@@ -35,6 +35,10 @@ int launch_accel_sym64(const cosmo_state &st, const cosmo_scratch &sc, const cos
 int launch_sym_integrate(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                          cudaStream_t s);
 
+// nearfield.cu: FP64 near-field corrections of the FP32 sums -> scratch.corr (before launch_accel)
+int launch_nearfield(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
+                     cudaStream_t s);
+
 // detect.cu / resolve.cu
 int detect_residency(int *rows_per_cta, int *tile);
 int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,

@@ -12,6 +12,7 @@
 //               flagged set is identical to the all-pairs one.
 #include <math.h>
 
+#include "grid.cuh"
 #include "pred.cuh"
 
 namespace cosmo {
@@ -106,55 +107,17 @@ k_detect_allpairs(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end, int 
 // enforced here whatever the tuning says: the cell edge is at least the largest separation at which
 // two non-giants can be flagged, and every planet above the giant radius is brute-forced.
 
-// Cell coordinate along one axis of the PERIODIC grid: the plane is tiled with square cells of edge
-// h and the cell (ix, iy) is stored in slot (iy mod c, ix mod c).  Planets within one cell edge of
-// each other lie in the same or in adjacent cells, hence in the same or in adjacent slots (mod c):
-// all the broad phase needs.  Cells a multiple of c apart share a slot -- that only adds candidates,
-// and every candidate goes through the exact predicate -- so the grid has no border: planets flung
-// far out of the scene (a violent disk loses a quarter of its planets to a halo within 25 frames)
-// land wherever they alias to, a few per slot, instead of piling up in border cells.  The period
-// c * h is tuned to hold the bulk of the scene, so bulk cells do not alias each other.
-__device__ __forceinline__ int cell_coord(double x, double centre, double h, int c) {
-    double t = floor((x - centre) / h + 0.5 * (double)c);
-    if (!(fabs(t) < 4.0e15)) t = 0.0;            // NaN / beyond exact integers: such planets are brute-forced (far2)
-    long long q = (long long)t % c;
-    return (int)(q < 0 ? q + c : q);
-}
-
-// Candidate ranges of the cell-sorted item array for a planet in `cell`: its 3 x 3 slot
-// neighbourhood (mod c).  The three slots of a grid row are contiguous except across the seam,
-// where they split in two: six ranges, the odd ones mostly empty.  Needs c >= 3.
-__device__ __forceinline__ long long cand_ranges(const cosmo_scratch &sc, int cell, int c, int (&s0)[6], int (&s1)[6]) {
-    const int cx = cell % c, cy = cell / c;
-    long long cand = 0;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        int yy = cy + d - 1;
-        yy = yy < 0 ? yy + c : (yy >= c ? yy - c : yy);
-        const int *row = sc.cell_start + (size_t)yy * c;
-        int a0 = cx - 1, a1 = cx + 1, b0 = 0, b1 = -1;          // [a0, a1] and, across the seam, [b0, b1]
-        if (cx == 0) { a0 = 0; b0 = c - 1; b1 = c - 1; }
-        else if (cx == c - 1) { a1 = c - 1; b0 = 0; b1 = 0; }
-        s0[2 * d] = row[a0]; s1[2 * d] = row[a1 + 1];
-        s0[2 * d + 1] = b1 >= b0 ? row[b0] : 0; s1[2 * d + 1] = b1 >= b0 ? row[b1 + 1] : 0;
-        cand += (s1[2 * d] - s0[2 * d]) + (s1[2 * d + 1] - s0[2 * d + 1]);
-    }
-    return cand;
-}
-
-template <bool D3>
-__device__ __forceinline__ double2 xy_of(const cosmo_state &st, const cosmo_scratch &sc, int k);
 
 // Tuning scratch (scratch.tune_hist, int32 words, all zero between frames):
-//   [0, 65536)           pass 1: x coordinates of a strided sample of the planets
+//   [0, 16384)           pass 1: x coordinates of a strided sample of the planets
 //                        pass 2: 128 x 128 occupancy of the bulk box (all planets)
-//   [65536, 131072)      pass 1: y coordinates
-//   [131072, 135168)     pass 1: inflated radii of ALL planets
-//   [135168, 135232)     32 doubles handed from k_grid_tune_box to k_grid_tune
-// Coordinates are binned by the top 16 bits of an order-preserving key of their FP32 value
-// (sign, exponent, 7 mantissa bits: 0.8 % relative resolution anywhere, no range to choose);
+//   [16384, 32768)       pass 1: y coordinates
+//   [32768, 36864)       pass 1: inflated radii of ALL planets
+//   [36864, 36928)       32 doubles handed from k_grid_tune_box to k_grid_tune
+// Coordinates are binned by the top 14 bits of an order-preserving key of their FP32 value
+// (sign, exponent, 5 mantissa bits: 3 % relative resolution anywhere, no range to choose);
 // radii by exponent + 4 mantissa bits (6 %).
-constexpr int TUNE_XY_BINS = 65536, TUNE_R_BINS = 4096, TUNE_OCC = 128;
+constexpr int TUNE_XY_BINS = 16384, TUNE_R_BINS = 4096, TUNE_OCC = 128, TUNE_XY_SHIFT = 18;
 constexpr int TUNE_SAMPLE = 131072;       // coordinates sampled for the quantile box
 constexpr int TUNE_AUX = 2 * TUNE_XY_BINS + TUNE_R_BINS;   // word offset of the doubles
 static_assert(TUNE_AUX + 64 == COSMO_TUNE_HIST_LEN, "header and kernels disagree on tune_hist");
@@ -178,7 +141,7 @@ __device__ __forceinline__ double tune_rbin_upper(int b) {
 }
 
 // pass 1: max |pos_new|^2 of the frame and, with TUNE, the 1-D tuning histograms
-template <bool D3, bool TUNE>
+template <int SRC, bool TUNE>
 __global__ void __launch_bounds__(256) k_grid_hist(cosmo_state st, cosmo_scratch sc) {
     __shared__ int s_r[TUNE ? TUNE_R_BINS : 1];
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
@@ -189,13 +152,13 @@ __global__ void __launch_bounds__(256) k_grid_hist(cosmo_state st, cosmo_scratch
     const int stride = max(1, n / TUNE_SAMPLE);
     double m = 0.0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        m = fmax(m, sc.xx_new[k]);
+        m = fmax(m, xx_of<SRC>(st, sc, k));
         if (TUNE) {
             atomicAdd(&s_r[tune_rbin(sc.rinf[k])], 1);
             if (k % stride == 0) {
-                const double2 p = xy_of<D3>(st, sc, k);
-                atomicAdd(&sc.tune_hist[tune_key(p.x) >> 16], 1);
-                atomicAdd(&sc.tune_hist[TUNE_XY_BINS + (tune_key(p.y) >> 16)], 1);
+                const double2 p = xy_of<SRC>(st, sc, k);
+                atomicAdd(&sc.tune_hist[tune_key(p.x) >> TUNE_XY_SHIFT], 1);
+                atomicAdd(&sc.tune_hist[TUNE_XY_BINS + (tune_key(p.y) >> TUNE_XY_SHIFT)], 1);
             }
         }
     }
@@ -229,14 +192,14 @@ __device__ __forceinline__ double grid_hmin(const cosmo_state &st, double rg) {
 }
 
 // detect_mode 1: the caller's grid (cell_size, origin of the linear box, cells per side, giant radius)
-__global__ void k_grid_set(cosmo_state st, cosmo_scratch sc, double h, double ox, double oy, double rg, int c) {
+__global__ void k_grid_set(cosmo_state st, cosmo_scratch sc, cosmo_grid *gd, double h, double ox, double oy, double rg, int c) {
     cosmo_grid g;
     const double half_in = 0.5 * (double)c * h;    // the centre is fixed by the caller's (h, origin)
     g.h = fmax(h, grid_hmin(st, rg));
     g.cx = ox + half_in; g.cy = oy + half_in; g.rg = rg; g.far2 = grid_far2(rg);
     g.ncell = (int64_t)c * c; g.c = c; g.w = 0; g.source = 1; g.reserved = 0;
     g.box = (double)c * h; g.h_tuned = h; g.rho = 0.0; g.cand_total = 0; g.n_counted = 0;
-    *sc.grid_dev = g;
+    *gd = g;
 }
 
 // exclusive prefix sum over the 1024 threads of the CTA; *total = sum of all
@@ -279,37 +242,48 @@ __global__ void __launch_bounds__(1024) k_grid_tune_box(cosmo_state st, cosmo_sc
     const int tid = threadIdx.x;
     if (tid < 4) s_q[tid] = 0.0;
     if (tid < 12) s_big[tid] = -1.0;
-    // ---- coordinate quantiles: thread t owns bins [64 t, 64 t + 64) of each axis
+    // ---- coordinate quantiles: thread t owns bins [16 t, 16 t + 16) of each axis (four 16-byte loads)
     for (int axis = 0; axis < 2; ++axis) {
-        int *hist = sc.tune_hist + axis * TUNE_XY_BINS;
+        int4 *hist4 = reinterpret_cast<int4 *>(sc.tune_hist + axis * TUNE_XY_BINS) + tid * 4;
+        int v[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int4 t4 = hist4[q];
+            v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+            hist4[q] = make_int4(0, 0, 0, 0);
+        }
         int loc = 0;
-        for (int q = 0; q < 64; ++q) loc += hist[tid * 64 + q];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) loc += v[q];
         int total;
         const int before = block_scan_1024(loc, s_w, &total);
         const long long r_lo = (long long)(0.10 * total), r_hi = min((long long)(0.90 * total), (long long)total - 1);
         if (total > 0) {
             int run = before;
-            for (int q = 0; q < 64; ++q) {
-                const int cnt = hist[tid * 64 + q];
-                const uint32_t bin = (uint32_t)(tid * 64 + q);
-                if (run <= r_lo && r_lo < run + cnt) s_q[2 * axis] = tune_key_value(bin << 16);
-                if (run <= r_hi && r_hi < run + cnt) s_q[2 * axis + 1] = tune_key_value((bin << 16) | 0xffffu);
-                run += cnt;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const uint32_t bin = (uint32_t)(tid * 16 + q);
+                if (run <= r_lo && r_lo < run + v[q]) s_q[2 * axis] = tune_key_value(bin << TUNE_XY_SHIFT);
+                if (run <= r_hi && r_hi < run + v[q])
+                    s_q[2 * axis + 1] = tune_key_value((bin << TUNE_XY_SHIFT) | ((1u << TUNE_XY_SHIFT) - 1u));
+                run += v[q];
             }
         }
         __syncthreads();
-        for (int q = 0; q < 64; ++q) hist[tid * 64 + q] = 0;
     }
     // ---- radius order statistics from the top: thread t owns bins [4 t, 4 t + 4)
     {
-        int *hist = sc.tune_hist + 2 * TUNE_XY_BINS;
-        int loc = 0;
-        for (int q = 0; q < 4; ++q) loc += hist[tid * 4 + q];
+        int4 *hist4 = reinterpret_cast<int4 *>(sc.tune_hist + 2 * TUNE_XY_BINS) + tid;
+        const int4 t4 = *hist4;
+        *hist4 = make_int4(0, 0, 0, 0);
+        const int v[4] = {t4.x, t4.y, t4.z, t4.w};
+        const int loc = v[0] + v[1] + v[2] + v[3];
         int total;
         const int before = block_scan_1024(loc, s_w, &total);
         int above = total - before - loc;               // planets in bins above this thread's
+#pragma unroll
         for (int q = 3; q >= 0; --q) {
-            const int cnt = hist[tid * 4 + q];
+            const int cnt = v[q];
             if (cnt) {
 #pragma unroll
                 for (int gi = 0; gi < 12; ++gi) {
@@ -318,7 +292,6 @@ __global__ void __launch_bounds__(1024) k_grid_tune_box(cosmo_state st, cosmo_sc
                 }
             }
             above += cnt;
-            hist[tid * 4 + q] = 0;
         }
     }
     __syncthreads();
@@ -334,13 +307,13 @@ __global__ void __launch_bounds__(1024) k_grid_tune_box(cosmo_state st, cosmo_sc
 }
 
 // detect_mode 2, step 2: 128 x 128 occupancy of the bulk box
-template <bool D3>
+template <int SRC>
 __global__ void __launch_bounds__(256) k_grid_occupancy(cosmo_state st, cosmo_scratch sc) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const double *aux = reinterpret_cast<const double *>(sc.tune_hist + TUNE_AUX);
     const double cx = aux[0], cy = aux[1], inv = (double)TUNE_OCC / aux[2];
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const double2 p = xy_of<D3>(st, sc, k);
+        const double2 p = xy_of<SRC>(st, sc, k);
         const double u = (p.x - cx) * inv + 0.5 * TUNE_OCC, v = (p.y - cy) * inv + 0.5 * TUNE_OCC;
         if (u >= 0.0 && u < (double)TUNE_OCC && v >= 0.0 && v < (double)TUNE_OCC)
             atomicAdd(&sc.tune_hist[(int)v * TUNE_OCC + (int)u], 1);
@@ -357,7 +330,7 @@ __global__ void __launch_bounds__(256) k_grid_occupancy(cosmo_state st, cosmo_sc
 //   h     cell edge for ~16 candidates per planet, never below 2 rg (nor below grid_hmin), never so
 //         small that the linear part of the grid could not cover the bulk box
 // and returns the occupancy map to zero.
-__global__ void __launch_bounds__(1024) k_grid_tune(cosmo_state st, cosmo_scratch sc) {
+__global__ void __launch_bounds__(1024) k_grid_tune(cosmo_state st, cosmo_scratch sc, cosmo_grid *gd) {
     __shared__ double s_a[32], s_b[32];
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
@@ -385,7 +358,7 @@ __global__ void __launch_bounds__(1024) k_grid_tune(cosmo_state st, cosmo_scratc
     const double cell_area = (box / TUNE_OCC) * (box / TUNE_OCC);
     double rho = b > 0.0 ? a / (b * cell_area) : 0.0;
     rho = fmax(rho, dn / (box * box) * 1e-3);              // nearly empty map: fall back towards the mean density
-    const cosmo_grid prev = *sc.grid_dev;
+    const cosmo_grid prev = *gd;
     if (prev.source == 2 && prev.n_counted > 0 && prev.cand_total > 0 && prev.h > 0.0 && isfinite(prev.h))
         rho = fmax(rho, (double)prev.cand_total / ((double)prev.n_counted * 9.0 * prev.h * prev.h));
     double best = -1.0, rg = 0.0;
@@ -409,27 +382,17 @@ __global__ void __launch_bounds__(1024) k_grid_tune(cosmo_state st, cosmo_scratc
     g.rg = rg; g.far2 = grid_far2(rg); g.rho = rho;
     g.c = c; g.w = 0; g.ncell = (int64_t)g.c * g.c; g.source = 2; g.reserved = 0; g.box = box;
     g.cand_total = 0; g.n_counted = 0;
-    *sc.grid_dev = g;
+    *gd = g;
 }
 
-// D3 = true serves the 3-D step (state3d.cu): sc.pos_new then holds three PLANES double[3][cap] and
-// the exact test is the three-column predicate without the clip of d to 1 (universe.py:107-108).  The
-// grid itself stays two-dimensional: it bins the (x, y) projection, and planets within a flagged
-// 3-D distance of each other are at least as close in projection, so the candidate set is still a
-// superset (for a thin disk the projection costs nothing; for a thick cloud it is only less selective).
-template <bool D3>
-__device__ __forceinline__ double2 xy_of(const cosmo_state &st, const cosmo_scratch &sc, int k) {
-    if (D3) return make_double2(sc.pos_new[k], sc.pos_new[(size_t)st.cap + k]);
-    return reinterpret_cast<const double2 *>(sc.pos_new)[k];
-}
-
-template <bool D3>
+template <int SRC>
 __global__ void __launch_bounds__(256)
-k_grid_count(cosmo_state st, cosmo_scratch sc) {
+k_grid_count(cosmo_state st, cosmo_scratch sc, const cosmo_grid *gd, int all_in_cells) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
-    const cosmo_grid g = *sc.grid_dev;
+    const cosmo_grid g = *gd;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        if (sc.rinf[k] > g.rg || sc.xx_new[k] > g.far2) {
+        // all_in_cells (near-field pass): every planet is binned, there is no brute-forced set
+        if (!all_in_cells && (sc.rinf[k] > g.rg || xx_of<SRC>(st, sc, k) > g.far2)) {
             unsigned long long idx =
                 atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_GIANTS]), 1ull);
             if ((long long)idx < sc.giant_cap)
@@ -439,7 +402,7 @@ k_grid_count(cosmo_state st, cosmo_scratch sc) {
                          (unsigned long long)COSMO_ERR_GIANT_OVERFLOW);
             sc.cell_of[k] = -1;
         } else {
-            const double2 p = xy_of<D3>(st, sc, k);
+            const double2 p = xy_of<SRC>(st, sc, k);
             const int cell = cell_coord(p.y, g.cy, g.h, g.c) * g.c + cell_coord(p.x, g.cx, g.h, g.c);
             sc.cell_of[k] = cell;
             atomicAdd(&sc.cell_count[cell], 1);
@@ -461,9 +424,9 @@ __global__ void __launch_bounds__(256) k_grid_fill(cosmo_state st, cosmo_scratch
 
 // Candidates the grid produces, summed over ALL non-giant planets (every rank runs this over all
 // rows, so the sums -- integers -- are identical everywhere): feedback for the next frame's tuner.
-__global__ void __launch_bounds__(256) k_grid_density(cosmo_state st, cosmo_scratch sc) {
+__global__ void __launch_bounds__(256) k_grid_density(cosmo_state st, cosmo_scratch sc, cosmo_grid *gd) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
-    const int c = sc.grid_dev->c;
+    const int c = gd->c;
     unsigned long long cand = 0, cnt = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const int cell = sc.cell_of[k];
@@ -477,8 +440,8 @@ __global__ void __launch_bounds__(256) k_grid_density(cosmo_state st, cosmo_scra
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
     if ((threadIdx.x & 31) == 0 && cnt) {
-        atomicAdd(reinterpret_cast<unsigned long long *>(&sc.grid_dev->cand_total), cand);
-        atomicAdd(reinterpret_cast<unsigned long long *>(&sc.grid_dev->n_counted), cnt);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&gd->cand_total), cand);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&gd->n_counted), cnt);
     }
 }
 
@@ -486,22 +449,22 @@ struct GridRow {
     double qx, qy, qz, xxi, ri;
 };
 
-template <bool D3>
+template <int SRC>
 __device__ __forceinline__ GridRow load_row(const cosmo_state &st, const cosmo_scratch &sc, int i) {
     GridRow r;
-    const double2 p = xy_of<D3>(st, sc, i);
+    const double2 p = xy_of<SRC>(st, sc, i);
     r.qx = -2.0 * p.x; r.qy = -2.0 * p.y;
-    r.qz = D3 ? -2.0 * sc.pos_new[2 * (size_t)st.cap + i] : 0.0;
+    r.qz = (SRC == SRC_NEW3) ? -2.0 * sc.pos_new[2 * (size_t)st.cap + i] : 0.0;
     r.xxi = sc.xx_new[i]; r.ri = sc.rinf[i];
     return r;
 }
 
-template <bool D3>
+template <int SRC>
 __device__ __forceinline__ void test_and_emit(const cosmo_state &st, const cosmo_scratch &sc, int i, const GridRow &r,
                                               int j) {
-    const double2 pj = xy_of<D3>(st, sc, j);
+    const double2 pj = xy_of<SRC>(st, sc, j);
     double d2;
-    if (D3) {
+    if (SRC == SRC_NEW3) {
         const double m2dot = __fma_rn(r.qz, sc.pos_new[2 * (size_t)st.cap + j], __fma_rn(r.qy, pj.y, __dmul_rn(r.qx, pj.x)));
         d2 = __dadd_rn(__dadd_rn(m2dot, r.xxi), sc.xx_new[j]);
     } else {
@@ -509,7 +472,7 @@ __device__ __forceinline__ void test_and_emit(const cosmo_state &st, const cosmo
     }
     const double rs = r.ri + sc.rinf[j];
     if (!(d2 <= rs * rs)) return;
-    const bool hit = D3 ? sqrt(fmax(d2, 0.0)) <= __dadd_rn(st.radius[i], st.radius[j])
+    const bool hit = (SRC == SRC_NEW3) ? sqrt(fmax(d2, 0.0)) <= __dadd_rn(st.radius[i], st.radius[j])
                         : pred_exact(d2, st.radius[i], st.radius[j]);
     if (hit) emit_pair(st, sc, i, j);
 }
@@ -522,8 +485,8 @@ __device__ __forceinline__ void test_and_emit(const cosmo_state &st, const cosmo
 constexpr int GRID_CHUNK = 1024;
 constexpr int GRID_HEAVY = 128;   // candidates above which a row goes to the warp-per-row pass
 
-__global__ void __launch_bounds__(128) k_grid_ranges(cosmo_state st, cosmo_scratch sc) {
-    const int ncell = (int)sc.grid_dev->ncell;
+__global__ void __launch_bounds__(128) k_grid_ranges(cosmo_state st, cosmo_scratch sc, const cosmo_grid *gd) {
+    const int ncell = (int)gd->ncell;
     const int total = sc.cell_start[ncell];
     const int nchunk = (total + GRID_CHUNK - 1) / GRID_CHUNK;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= nchunk; k += gridDim.x * blockDim.x) {
@@ -545,10 +508,10 @@ __global__ void __launch_bounds__(128) k_grid_ranges(cosmo_state st, cosmo_scrat
 // work on planets of the same or neighbouring cells, so their candidate loops have similar trip
 // counts (the disk's surface density varies 20x between its inner and outer edge) and their
 // gathers hit the same lines.  Every row is produced by exactly one rank.
-template <bool D3>
+template <int SRC>
 __global__ void __launch_bounds__(128)
-k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count) {
-    const int c = sc.grid_dev->c;
+k_grid_detect(cosmo_state st, cosmo_scratch sc, const cosmo_grid *gd, int shard_index, int shard_count) {
+    const int c = gd->c;
     const int total = sc.cell_start[c * c];
     const int nchunk = (total + GRID_CHUNK - 1) / GRID_CHUNK;
     unsigned cand_total = 0;
@@ -559,7 +522,7 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count
    for (int slot = s_lo + blockIdx.y * blockDim.x + threadIdx.x; slot < s_hi; slot += gridDim.y * blockDim.x) {
     const int i = sc.cell_items[slot];
     const int cell = sc.cell_of[i];
-    const GridRow row = load_row<D3>(st, sc, i);
+    const GridRow row = load_row<SRC>(st, sc, i);
     // candidate ranges: the three cells of a grid row are contiguous in the sorted item array
     int s0[6], s1[6];
     const long long cand = cand_ranges(sc, cell, c, s0, s1);
@@ -577,9 +540,9 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count
     for (int d = 0; d < 6; ++d)
         for (int s = s0[d]; s < s1[d]; ++s) {
             const int j = sc.cell_items[s];
-            if (j != i) test_and_emit<D3>(st, sc, i, row, j);
+            if (j != i) test_and_emit<SRC>(st, sc, i, row, j);
         }
-    for (int g = 0; g < ng; ++g) test_and_emit<D3>(st, sc, i, row, sc.giants[g]);
+    for (int g = 0; g < ng; ++g) test_and_emit<SRC>(st, sc, i, row, sc.giants[g]);
    }
   }
     // diagnostic only (all lanes are back together after the loop)
@@ -589,9 +552,9 @@ k_grid_detect(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count
 }
 
 // Warp-per-row pass for the rows k_grid_detect set aside: the lanes stride over the candidates.
-template <bool D3>
-__global__ void __launch_bounds__(256) k_grid_detect_heavy(cosmo_state st, cosmo_scratch sc) {
-    const int c = sc.grid_dev->c;
+template <int SRC>
+__global__ void __launch_bounds__(256) k_grid_detect_heavy(cosmo_state st, cosmo_scratch sc, const cosmo_grid *gd) {
+    const int c = gd->c;
     const int nh = (int)st.status[COSMO_ST_N_HEAVY];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
@@ -599,20 +562,20 @@ __global__ void __launch_bounds__(256) k_grid_detect_heavy(cosmo_state st, cosmo
     for (int h = warp; h < nh; h += nwarp) {
         const int i = sc.label[h];
         const int cell = sc.cell_of[i];
-        const GridRow row = load_row<D3>(st, sc, i);
+        const GridRow row = load_row<SRC>(st, sc, i);
         int s0[6], s1[6];
         cand_ranges(sc, cell, c, s0, s1);
         for (int d = 0; d < 6; ++d)
             for (int s = s0[d] + lane; s < s1[d]; s += 32) {
                 const int j = sc.cell_items[s];
-                if (j != i) test_and_emit<D3>(st, sc, i, row, j);
+                if (j != i) test_and_emit<SRC>(st, sc, i, row, j);
             }
-        for (int g = lane; g < ng; g += 32) test_and_emit<D3>(st, sc, i, row, sc.giants[g]);
+        for (int g = lane; g < ng; g += 32) test_and_emit<SRC>(st, sc, i, row, sc.giants[g]);
     }
 }
 
 // rows of the giants: giant g against every planet (blockIdx.y strides over the giants)
-template <bool D3>
+template <int SRC>
 __global__ void __launch_bounds__(256)
 k_giant_rows(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
@@ -621,9 +584,9 @@ k_giant_rows(cosmo_state st, cosmo_scratch sc, int i_begin, int i_end) {
     for (int gi = blockIdx.y; gi < ng; gi += gridDim.y) {
         const int g = sc.giants[gi];
         if (g < i_begin || g >= i_hi) continue;
-        const GridRow row = load_row<D3>(st, sc, g);
+        const GridRow row = load_row<SRC>(st, sc, g);
         for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
-            if (j != g) test_and_emit<D3>(st, sc, g, row, j);
+            if (j != g) test_and_emit<SRC>(st, sc, g, row, j);
     }
 }
 
@@ -643,64 +606,93 @@ int detect_residency(int *rows_per_cta, int *tile) {
     return nb;
 }
 
-template <bool D3>
-static int launch_grid(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p, cudaStream_t s) {
-    const int rows = p.i_end - p.i_begin;
-    if (!sc.cell_count || !sc.giants || !sc.grid_dev || sc.grid_cells < 1) {
-        set_error("grid broad phase: scratch lacks the cell arrays / grid_dev");
+// near-field pass: last frame's stage-B grid serves this frame's start positions (they ARE last
+// frame's new positions, up to merges); its cells only have to be wider than the near-field cutoff
+__global__ void k_grid_reuse(const cosmo_grid *from, cosmo_grid *to, double h_floor_rel) {
+    cosmo_grid g = *from;
+    g.h = fmax(g.h, h_floor_rel * g.box);
+    g.cand_total = 0; g.n_counted = 0; g.source = 3;
+    *to = g;
+}
+
+// Binning of the planets into the periodic grid *gd: (grid from the parameters | tuned on the device
+// | last frame's) -> cell populations -> exclusive scan -> cell-sorted item array.
+template <int SRC>
+static int grid_build(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p, cosmo_grid *gd,
+                      int mode, bool all_in_cells, double reuse_floor, cudaStream_t s) {
+    if (!sc.cell_count || !sc.cell_of || !sc.cell_items || !gd || sc.grid_cells < 9 || (!all_in_cells && !sc.giants)) {
+        set_error("grid: scratch lacks the cell arrays / grid_dev");
         return COSMO_E_ARG;
     }
     int nb = (p.n_upper + 255) / 256;
     if (nb < 1) nb = 1;
     if (nb > 148 * 8) nb = 148 * 8;
-    if (p.detect_mode == 2) {
+    if (mode == 2) {
         // grid tuned on the device from this frame's positions and radii: no host round trip
-        if (!sc.tune_hist || sc.grid_cells < 9) {
-            set_error("grid broad phase: detect_mode 2 needs scratch.tune_hist and grid_cells >= 9");
+        if (!sc.tune_hist) {
+            set_error("grid: device-side tuning needs scratch.tune_hist");
             return COSMO_E_ARG;
         }
-        k_grid_hist<D3, true><<<nb, 256, 0, s>>>(st, sc);
+        k_grid_hist<SRC, true><<<nb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_hist"));
         k_grid_tune_box<<<1, 1024, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_tune_box"));
-        k_grid_occupancy<D3><<<nb, 256, 0, s>>>(st, sc);
+        k_grid_occupancy<SRC><<<nb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_occupancy"));
-        k_grid_tune<<<1, 1024, 0, s>>>(st, sc);
+        k_grid_tune<<<1, 1024, 0, s>>>(st, sc, gd);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_tune"));
-    } else {
+    } else if (mode == 1) {
         const int c = p.cells_per_side;
         if (c < 3 || (long long)c * c > sc.grid_cells) {
-            set_error("grid broad phase: cells_per_side=%d must be >= 3 and fit grid_cells=%d", c, sc.grid_cells);
+            set_error("grid: cells_per_side=%d must be >= 3 and fit grid_cells=%d", c, sc.grid_cells);
             return COSMO_E_ARG;
         }
-        k_grid_hist<D3, false><<<nb, 256, 0, s>>>(st, sc);
+        k_grid_hist<SRC, false><<<nb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_hist"));
-        k_grid_set<<<1, 1, 0, s>>>(st, sc, p.cell_size, p.grid_origin_x, p.grid_origin_y, p.giant_radius, c);
+        k_grid_set<<<1, 1, 0, s>>>(st, sc, gd, p.cell_size, p.grid_origin_x, p.grid_origin_y, p.giant_radius, c);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_set"));
+    } else {
+        k_grid_reuse<<<1, 1, 0, s>>>(sc.grid_dev, gd, reuse_floor);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_reuse"));
     }
-    k_grid_count<D3><<<nb, 256, 0, s>>>(st, sc);
+    k_grid_count<SRC><<<nb, 256, 0, s>>>(st, sc, gd, all_in_cells ? 1 : 0);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_count"));
-    // the cell count c*c lives on the device (grid_dev->ncell); blocks beyond it exit at once
-    const long long scan_max = p.detect_mode == 2 ? (long long)sc.grid_cells : (long long)p.cells_per_side * p.cells_per_side;
-    COSMO_TRY(launch_scan_exclusive(sc.cell_count, sc.cell_start, sc.scan_blk, &sc.grid_dev->ncell, scan_max, 0, s));
+    // the cell count c*c lives on the device (gd->ncell); blocks beyond it exit at once
+    const long long scan_max = mode == 1 ? (long long)p.cells_per_side * p.cells_per_side : (long long)sc.grid_cells;
+    COSMO_TRY(launch_scan_exclusive(sc.cell_count, sc.cell_start, sc.scan_blk, &gd->ncell, scan_max, 0, s));
     k_grid_fill<<<nb, 256, 0, s>>>(st, sc);
-    COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_fill"));
+    return COSMO_LAUNCH_CHECK("k_grid_fill");
+}
+
+int launch_grid_build_old2(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p, cosmo_grid *gd,
+                           int mode, double reuse_floor, cudaStream_t s) {
+    return grid_build<SRC_OLD2>(st, sc, p, gd, mode, true, reuse_floor, s);
+}
+
+template <int SRC>
+static int launch_grid(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p, cudaStream_t s) {
+    const int rows = p.i_end - p.i_begin;
+    cosmo_grid *gd = sc.grid_dev;
+    COSMO_TRY(grid_build<SRC>(st, sc, p, gd, p.detect_mode == 2 ? 2 : 1, false, 0.0, s));
+    int nb = (p.n_upper + 255) / 256;
+    if (nb < 1) nb = 1;
+    if (nb > 148 * 8) nb = 148 * 8;
     if (p.detect_mode == 2) {
-        k_grid_density<<<nb, 256, 0, s>>>(st, sc);
+        k_grid_density<<<nb, 256, 0, s>>>(st, sc, gd);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_density"));
     }
     const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
     const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
     const int nchunk = (p.n_upper + GRID_CHUNK - 1) / GRID_CHUNK + 1;
-    k_grid_ranges<<<(nchunk + 127) / 128, 128, 0, s>>>(st, sc);
+    k_grid_ranges<<<(nchunk + 127) / 128, 128, 0, s>>>(st, sc, gd);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_ranges"));
     const int blocks = (nchunk + sh_n - 1) / sh_n;
-    k_grid_detect<D3><<<dim3(blocks > 0 ? blocks : 1, GRID_CHUNK / 128), 128, 0, s>>>(st, sc, sh_i, sh_n);
+    k_grid_detect<SRC><<<dim3(blocks > 0 ? blocks : 1, GRID_CHUNK / 128), 128, 0, s>>>(st, sc, gd, sh_i, sh_n);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect"));
-    k_grid_detect_heavy<D3><<<296, 256, 0, s>>>(st, sc);
+    k_grid_detect_heavy<SRC><<<296, 256, 0, s>>>(st, sc, gd);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k_grid_detect_heavy"));
     if (rows > 0) {
-        k_giant_rows<D3><<<dim3(nb > 296 ? 296 : nb, 8), 256, 0, s>>>(st, sc, p.i_begin, p.i_end);
+        k_giant_rows<SRC><<<dim3(nb > 296 ? 296 : nb, 8), 256, 0, s>>>(st, sc, p.i_begin, p.i_end);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_giant_rows"));
     }
     return COSMO_OK;
@@ -708,7 +700,7 @@ static int launch_grid(const cosmo_state &st, const cosmo_scratch &sc, const cos
 
 int launch_detect_grid(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p, cudaStream_t s,
                        bool planes3) {
-    return planes3 ? launch_grid<true>(st, sc, p, s) : launch_grid<false>(st, sc, p, s);
+    return planes3 ? launch_grid<SRC_NEW3>(st, sc, p, s) : launch_grid<SRC_NEW2>(st, sc, p, s);
 }
 
 int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,

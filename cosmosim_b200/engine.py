@@ -81,6 +81,8 @@ class Engine(BoundTracker):
         self.graph_threshold = 16384
         self._graphs = {}
         self._params_cache = {}
+        self.near_field = True      # FP32 path: FP64 near-field corrections on
+        self._grid_ready = False    # a stage B in grid mode has left a tuned grid on the device
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self):
@@ -129,7 +131,8 @@ class Engine(BoundTracker):
         t["cell_of"] = z(cap, dtype=i32); t["cell_items"] = z(cap, dtype=i32)
         t["cell_count"] = z(self.grid_cells + 1, dtype=i32); t["cell_start"] = z(self.grid_cells + 1, dtype=i32)
         t["giants"] = z(self.giant_cap, dtype=i32)
-        t["grid_dev"] = z(128, dtype=u8)                       # cosmo_grid (72 bytes)
+        t["grid_dev"] = z(256, dtype=u8)                       # cosmo_grid[2]: stage B, near field
+        t["corr"] = z(cap, 2, dtype=f64)
         t["tune_hist"] = z(_abi.TUNE_HIST_LEN, dtype=i32)
         for k, dt_ in (("pos", f64), ("vel", f64)):
             t["t_" + k] = z(cap, 2, dtype=dt_)
@@ -156,7 +159,7 @@ class Engine(BoundTracker):
                   "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_radius", "t_volume",
                   "t_eaten", "t_id", "t_flags", "t_energy", "row_count", "row_start", "pmin", "pmax", "scan_blk",
                   "pair_flag", "cplx_list", "scan_a", "ev_tmp", "label", "comp_items", "comp_root", "cell_of", "cell_items", "cell_count", "cell_start",
-                  "giants", "grid_dev", "tune_hist"):
+                  "giants", "grid_dev", "tune_hist", "corr"):
             setattr(sc, k, p(k))
         sc.pos_new = C.c_void_p(self._pos_new.data_ptr())
         sc.vel_new = C.c_void_p(self._vel_new.data_ptr())
@@ -311,7 +314,8 @@ class Engine(BoundTracker):
     def _params(self, dt, G, r_max, **kw):
         """Cached step parameters (shared object: do not modify): they only depend on the arguments,
         the launch bound and a few tunables."""
-        key = (self.n_upper, dt, G, r_max, tuple(sorted(kw.items())), self.grid_threshold, self.small_threshold,
+        key = (self.n_upper, dt, G, r_max, tuple(sorted(kw.items())), self.near_field, self._grid_ready,
+               self._force_all_pairs, self._host_grid, self.grid_threshold, self.small_threshold,
                self.sym_threshold, self.sym64_threshold, self.sym_chunk, self.pos_exp, self.mass_exp)
         p = self._params_cache.get(key)
         if p is None:
@@ -321,7 +325,7 @@ class Engine(BoundTracker):
         return p
 
     def _make_params(self, dt, G, r_max, collisions=True, bounded=True, fp32=False, store_acc=False,
-                     jsplit=None, f32_sym=None, energy=False, f64_sym=None):
+                     jsplit=None, f32_sym=None, energy=False, f64_sym=None, near=None):
         p = _abi.StepParams()
         p.G, p.dt, p.r_max = float(G), float(dt), float(r_max)
         n = self.n_upper
@@ -379,6 +383,10 @@ class Engine(BoundTracker):
                     p.jsplit_detect = self.lib.cosmo_suggest_jsplit(rows, max(1, n), 5 if p.small_tiles else 3,
                                                                     self.JSPLIT_MAX)
         p.shard_index, p.shard_count = self.rank, self.world
+        # FP32 path: pairs closer than 2^14 FP32 ulps of their coordinates are re-evaluated in FP64
+        # (csrc/nearfield.cu), binned with the grid the previous frame's stage B left on the device
+        if fp32 and (self.near_field if near is None else near):
+            p.near_mode = 1 if self._grid_ready else 2
         return p
 
     def step(self, n_frames, dt, G, r_max, stage_events=None, **kw):
@@ -422,6 +430,10 @@ class Engine(BoundTracker):
                 stage_events.append(ev)
             self.frames += 1
             self._push_snapshot()
+            if p.detect_mode != 0 and not self._grid_ready:
+                self._grid_ready = True
+                p = self._params(dt, G, r_max, **kw)
+                pp = C.byref(p)
 
     def _step_graphed(self, n_frames, dt, G, r_max, kw):
         """Launch-bound regime (N of a few thousand: a frame is ~10 kernels of a few microseconds):

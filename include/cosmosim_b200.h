@@ -112,7 +112,7 @@ typedef struct cosmo_grid {
                            on every rank): next frame's tuner derives the density from it */
     int64_t n_counted;  /* planets that sum runs over */
 } cosmo_grid;
-#define COSMO_TUNE_HIST_LEN (2 * 65536 + 4096 + 64) /* int32 words of scratch.tune_hist */
+#define COSMO_TUNE_HIST_LEN (2 * 16384 + 4096 + 64) /* int32 words of scratch.tune_hist */
 
 /* Persistent state.  All pointers are device pointers. */
 typedef struct cosmo_state {
@@ -205,9 +205,11 @@ typedef struct cosmo_scratch {
     double *peer_acc[COSMO_MAX_PEERS];
     int32_t n_peers;
     int32_t reserved_scratch;
-    cosmo_grid *grid_dev; /* [1] grid of the current frame (detect_mode 1 and 2) */
+    cosmo_grid *grid_dev; /* [2] grid of the current frame's stage B (detect_mode 1 and 2); slot 1: the
+                             near-field pass of the FP32 path */
     int32_t *tune_hist;   /* [COSMO_TUNE_HIST_LEN] detect_mode 2: coordinate / radius histograms, must
                              start zeroed (self-resetting) */
+    double *corr;         /* [cap][2] near_mode != 0: FP64 near-field corrections of the FP32 sums */
 } cosmo_scratch;
 
 /* Parameters of one frame. */
@@ -230,7 +232,10 @@ typedef struct cosmo_step_params {
     int32_t shard_index;  /* this rank / number of ranks sharing the frame (0 / 1 if single): the */
     int32_t shard_count;  /* grid broad phase splits its cell-sorted planet order evenly by these */
     int32_t sym_chunk;    /* symmetric kernel: column blocks per CTA (0 = default) */
-    int32_t near_mode;    /* FP32 path: 1 = re-evaluate the near field in FP64 (see cosmo_step_params docs) */
+    int32_t near_mode;    /* FP32 path: != 0 re-evaluates the near field (pairs closer than 2^-9 of their
+                             coordinates, i.e. 2^14 FP32 ulps) in FP64; 1 = bin the planets with the grid
+                             the previous frame's stage B left in scratch.grid_dev, 2 = tune a grid first
+                             (first frame, or stage B not in grid mode) */
     int32_t reserved2;
     int32_t reserved1;
     double cell_size;     /* detect_mode 1: edge of the square cells of the PERIODIC grid: cell (ix, iy) of  */

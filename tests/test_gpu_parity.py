@@ -256,9 +256,10 @@ def test_n65536_fp64_parity_and_properties():
 
 def test_fp32_fast_path_error_bound():
     """Stated FP32 bound (single step, vs the FP64 oracle), relative error of the acceleration
-    per planet: median <= 1e-5, 99th percentile <= 1e-4, max <= 1e-2 (the worst rows are
-    overlapping pairs about to merge, whose separation is a few hundred FP32 ulps of the
-    coordinates); the integrator stays FP64 and is checked exactly."""
+    per planet: median <= 1e-5, 99th percentile <= 1e-4, max <= 1e-3.  Pairs closer than 2^14 FP32
+    ulps of their coordinates -- touching planets, whose separation FP32 knows to 3 digits -- are
+    re-evaluated in FP64 (csrc/nearfield.cu); without that pass the maximum is 2e-3 here and 1e-1 in
+    the crowded 2^20-planet disk.  The integrator stays FP64 and is checked exactly."""
     from cosmosim_b200 import scenes
     for arr in (scenes.star_disk_arrays(20000, seed=1), scenes.cloud_arrays(20000, seed=2)):
         n = arr["radius"].shape[0]
@@ -269,8 +270,13 @@ def test_fp32_fast_path_error_bound():
             acc = eng.last_frame_tensors()["acc"][:n].cpu().numpy()
             eng.check_errors()
             rel = relerr_rows(acc, ref)
-            assert np.median(rel) < 1e-5 and np.quantile(rel, 0.99) < 1e-4 and rel.max() < 1e-2, \
+            assert np.median(rel) < 1e-5 and np.quantile(rel, 0.99) < 1e-4 and rel.max() < 1e-3, \
                 (np.median(rel), np.quantile(rel, 0.99), rel.max())
+            if sym:     # the near-field pass is what buys the last factor: switched off, the tail is worse
+                eng0 = make_engine(arr)
+                eng0.step(1, DT, G, 100 * AU, collisions=False, store_acc=True, fp32=True, f32_sym=sym, near=False)
+                rel0 = relerr_rows(eng0.last_frame_tensors()["acc"][:n].cpu().numpy(), ref)
+                assert np.quantile(rel0, 0.999) > np.quantile(rel, 0.999)
             # the integrator itself stays FP64: p_new is exactly integrate(p0, v0, a_gpu)
             p_chk, v_chk = orc.integrate(arr["pos"], arr["vel"], acc, DT)
             lf = eng.last_frame_tensors()
@@ -555,9 +561,12 @@ def test_bulk_universe_fp32_symmetric_path_through_the_api():
     got = u.merge_events
     a = u.arrays()
     assert u._engine.params(DT, G, 100 * AU, fp32=True).opts & 32          # OPT_F32_SYM in use
-    # FP32 accelerations move positions by ~1e-7 relative: flags at the threshold may differ, the bulk must not
+    # FP32 accelerations move positions by ~1e-11 relative: a flag sitting exactly at the threshold
+    # d == r_i + r_j may differ, nothing else
     common = len(set(got) & set(ref_events))
-    assert common >= 0.98 * len(ref_events) and len(got) <= 1.02 * len(ref_events) and len(ref_events) > 300
+    print("fp32 merge stream: %d events, %d reference, %d in common" % (len(got), len(ref_events), common))
+    assert got[:100] == ref_events[:100]
+    assert common >= 0.995 * len(ref_events) and len(got) <= 1.005 * len(ref_events) and len(ref_events) > 300
     post = ou.snapshot()
     ids = np.intersect1d(a["id"], np.nonzero(post["alive"])[0])
     sel = np.searchsorted(a["id"], ids)
@@ -645,13 +654,17 @@ def test_n1m_fp32_full_size_properties():
     acc = lf["acc"][:n].cpu().numpy()
     pn = lf["pos_new"][:n].cpu().numpy()
     rows = [(0, 96), (500000, 500096), (n - 96, n)]
-    for b, e in rows:
-        ref = orc.accel(arr["pos"], arr["mass_f64"], G, b, e)
-        rel = relerr_rows(acc[b:e], ref)
-        # the FP32 error is set by (FP32 ulp of a coordinate) / (distance to the nearest neighbours):
-        # 1.8e4 m against a mean spacing of 2.6e8 m in this crowded disk (2.8 % of it is covered by
-        # planets), hence a looser bound than for the 20 000-planet scenes
-        assert np.median(rel) < 1e-4 and rel.max() < 1e-1, (b, np.median(rel), rel.max())
+    # 64 blocks of 64 rows spread over the scene: 4096 rows against the FP64 oracle.  Stated FP32 bound
+    # at full size: median <= 1e-5, 99.9 % <= 5e-4, max <= 1e-3 (measured 5e-6 / 2e-4 / 4e-4; the FP32
+    # coordinate ulp is 9 km at 1 AU against a mean spacing of 2.6e8 m, and 2.8 % of this disk is
+    # covered by planets: the touching pairs are re-evaluated in FP64 by the near-field pass)
+    rel = []
+    for b in np.linspace(0, n - 64, 64).astype(np.int64) // 64 * 64:
+        ref = orc.accel(arr["pos"], arr["mass_f64"], G, int(b), int(b) + 64)
+        rel.append(relerr_rows(acc[b:b + 64], ref))
+    rel = np.concatenate(rel)
+    assert np.median(rel) < 1e-5 and np.quantile(rel, 0.999) < 5e-4 and rel.max() < 1e-3, \
+        (np.median(rel), np.quantile(rel, 0.999), rel.max())
     mom = (arr["mass_f64"][:, None] * acc).sum(axis=0)
     assert np.abs(mom).max() <= 1e-6 * np.abs(arr["mass_f64"][:, None] * acc).sum()
     # flagged pairs of the sampled rows (the frame's pair list is still in scratch, unsorted)
@@ -809,7 +822,7 @@ def test_device_grid_tuning_invariants():
         far = (pn ** 2).sum(axis=1) > info["far2"]      # flung-out planets are brute-forced like giants
         giants = int(((radius * (1 + 2.0 ** -30) > rg) | far).sum())
         assert giants <= 1024 + 5 and giants == eng.status()["n_giants"]
-        assert int(eng.t["tune_hist"][: 2 * 65536 + 4096].abs().sum()) == 0   # the histograms reset themselves
+        assert int(eng.t["tune_hist"][: 2 * 16384 + 4096].abs().sum()) == 0   # the histograms reset themselves
         got = np.sort(eng.t["pairs"][: eng.status()["n_pairs"]].cpu().numpy().view(np.uint64))
         want = orc.flags(pn, radius)
         want = np.sort((want[:, 0].astype(np.uint64) << np.uint64(32)) | want[:, 1].astype(np.uint64))
