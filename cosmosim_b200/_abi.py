@@ -59,6 +59,16 @@ class Grid(C.Structure):
 TUNE_HIST_LEN = 2 * 16384 + 4096 + 64
 
 
+class HostFrame(C.Structure):
+    """cosmo_host_frame: one frame's host buffers for cosmo_step_host."""
+    _fields_ = [("n", C.c_int32), ("reserved", C.c_int32), ("frame", C.c_int64),
+                ("pos", _vp), ("vel", _vp), ("mass", _vp), ("mass_hi", _vp), ("mass_lo", _vp), ("radius", _vp),
+                ("volume", _vp), ("eaten", _vp), ("id", _vp), ("flags", _vp),
+                ("pos_out", _vp), ("vel_out", _vp), ("mass_out", _vp), ("mass_hi_out", _vp), ("mass_lo_out", _vp),
+                ("radius_out", _vp), ("volume_out", _vp), ("eaten_out", _vp), ("id_out", _vp), ("flags_out", _vp),
+                ("status_out", _vp), ("events_out", _vp), ("events_cap", C.c_int64)]
+
+
 class StepParams(C.Structure):
     _fields_ = [("G", C.c_double), ("dt", C.c_double), ("r_max", C.c_double),
                 ("opts", C.c_uint32), ("n_upper", C.c_int32), ("i_begin", C.c_int32),
@@ -134,6 +144,12 @@ SYMBOLS = {
     "cosmo_append_pairs": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), _vp, _vp, C.c_int64, _vp]),
     "cosmo_append_pair_rows": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), _vp, C.c_int32, C.c_int64, _vp]),
     "cosmo_seal_pair_row": (C.c_int, [C.POINTER(State), _vp, _vp]),
+    "cosmo_workspace_bytes": (C.c_int64, [C.c_int32, C.c_uint32]),
+    "cosmo_workspace_init": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_uint32, C.POINTER(State), C.POINTER(Scratch), _vp]),
+    "cosmo_params_default": (C.c_int, [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_double,
+                                       C.c_double, C.POINTER(Scratch), C.POINTER(StepParams)]),
+    "cosmo_step_host": (C.c_int, [C.POINTER(State), C.POINTER(Scratch), C.POINTER(StepParams),
+                                  C.POINTER(HostFrame), _vp]),
     "cosmo_accel_workspace_bytes": (C.c_int64, [C.c_int32]),
     "cosmo_accel": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "cosmo_accel_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp,

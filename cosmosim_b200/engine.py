@@ -474,7 +474,8 @@ class Engine(BoundTracker):
     E2E_OUT = ("pos", "vel", "mass", "radius", "id")
 
     def make_host_staging(self, arrays):
-        """Pinned host mirrors of the state (what a host-resident caller hands over per frame)."""
+        """Pinned host mirrors of the state (what a host-resident caller hands over per frame) and the
+        cosmo_host_frame that points at them."""
         n = int(arrays["radius"].shape[0])
         src = {"pos": arrays["pos"], "vel": arrays["vel"], "mass": arrays["mass_f64"],
                "mass_hi": np.asarray(arrays["mass_hi"]).view(np.int64), "mass_lo": np.asarray(arrays["mass_lo"]).view(np.int64),
@@ -482,21 +483,53 @@ class Engine(BoundTracker):
                "id": arrays["id"], "flags": arrays["flags"]}
         stg = {"n": n, "in": {}, "out": {}}
         for k in self.E2E_IN:
-            h = torch.from_numpy(np.ascontiguousarray(src[k])).pin_memory()
-            stg["in"][k] = h
+            stg["in"][k] = torch.from_numpy(np.ascontiguousarray(src[k])).pin_memory()
         for k in self.E2E_OUT:
             stg["out"][k] = torch.empty_like(self.t[k][:n], device="cpu").pin_memory()
         stg["status_in"] = torch.zeros(STATUS_LEN, dtype=torch.int64).pin_memory()
         stg["status_out"] = torch.zeros(STATUS_LEN, dtype=torch.int64).pin_memory()
+        stg["events_out"] = torch.zeros(max(1, n), 3, dtype=torch.int64).pin_memory()
+        f = _abi.HostFrame()
+        f.n = n
+        for k in self.E2E_IN:
+            setattr(f, k, C.c_void_p(stg["in"][k].data_ptr()))
+        for k in self.E2E_OUT:
+            setattr(f, k + "_out", C.c_void_p(stg["out"][k].data_ptr()))
+        f.status_out = C.c_void_p(stg["status_out"].data_ptr())
+        f.events_out = C.c_void_p(stg["events_out"].data_ptr())
+        f.events_cap = max(1, n)
+        stg["frame"] = f
+        self._e2e_row_bytes_out = sum(self.t[k][:1].numel() * self.t[k].element_size() for k in self.E2E_OUT)
         stg["h2d_bytes"] = sum(v.numel() * v.element_size() for v in stg["in"].values()) + STATUS_LEN * 8
-        stg["d2h_bytes"] = sum(v.numel() * v.element_size() for v in stg["out"].values()) + STATUS_LEN * 8
+        stg["d2h_bytes"] = STATUS_LEN * 8          # updated by every frame_from_host: survivors + events + status
+        stg["path"] = ("cosmo_step_host (C ABI): pinned host SoA -> H2D -> frame -> status D2H -> survivors + merge "
+                       "events D2H, stream synchronised")
         return stg
 
     def frame_from_host(self, stg, dt, G, r_max, **kw):
-        """One frame the way a host-resident caller sees it: state H2D from pinned memory, the
-        frame, results D2H, stream synchronised.  Returns the device status block."""
+        """One frame the way a host-resident caller sees it.  One GPU: a single call of the C ABI's
+        cosmo_step_host (state H2D from pinned memory, the frame, survivors and merge events D2H,
+        stream synchronised).  Sharded: the same steps sequenced here, because the exchanges between
+        the stages are torch.distributed collectives.  Returns the device status block."""
         n = stg["n"]
         t = self.t
+        if self.world == 1:
+            self.n_upper = n
+            p = self._params(dt, G, r_max, **kw)
+            f = stg["frame"]
+            f.frame = self.frames
+            stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            with torch.cuda.device(self.device):
+                _abi.check(self.lib.cosmo_step_host(C.byref(self.st), C.byref(self.sc), C.byref(p), C.byref(f), stream),
+                           "cosmo_step_host")
+            self.frames += 1
+            if p.detect_mode != 0:
+                self._grid_ready = True
+            so = stg["status_out"]
+            self._seed_snapshot(so)
+            stg["d2h_bytes"] = (int(so[ST_N_ACTIVE]) * self._e2e_row_bytes_out + min(int(so[ST_N_EVENTS]), n) * 24
+                                + STATUS_LEN * 8)
+            return so
         for k in self.E2E_IN:
             t[k][:n].copy_(stg["in"][k].view(t[k][:n].shape), non_blocking=True)
         stg["status_in"].zero_()
@@ -510,4 +543,6 @@ class Engine(BoundTracker):
             stg["out"][k].copy_(t[k][:n], non_blocking=True)
         stg["status_out"].copy_(t["status"], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        stg["d2h_bytes"] = sum(v.numel() * v.element_size() for v in stg["out"].values()) + STATUS_LEN * 8
+        stg["path"] = "Engine.frame_from_host (sharded): pinned host SoA -> H2D -> frame with NCCL exchanges -> D2H, stream sync per step"
         return stg["status_out"]

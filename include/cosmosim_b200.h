@@ -336,6 +336,61 @@ int cosmo_accel(const double *pos, const double *mass, int32_t n, double G, int 
                 int32_t pos_exp, int32_t mass_exp, double *acc_out, void *workspace,
                 void *stream);
 
+/*
+ * Whole frames from host memory -- what `self.interact()` (universe_old.py:347) binds to when the
+ * planets live on the host.
+ *
+ * cosmo_workspace_bytes / cosmo_workspace_init: ONE device allocation (256-byte aligned) carved into
+ * every array of cosmo_state and cosmo_scratch for up to n_total planets and initialised (zero, and
+ * the idle values of rec_death / mod_step / pmin / pmax).  opts: pass COSMO_OPT_F32_SYM and/or
+ * COSMO_OPT_F64_SYM to include the column-partial buffer of the symmetric kernels (8 B x cap^2 / 1024
+ * for FP32, 16 B x cap^2 / 512 for FP64).
+ * cosmo_params_default: launch parameters for n active planets on one device, the defaults the Python
+ * host uses (kernel flavours and grid mode by size, source splits from the occupancy of this
+ * device, power-of-two FP32 scales from pos_max = max |coordinate| and mass_max).  opts carries the
+ * caller's COSMO_OPT_COLLISIONS / BOUNDED / FP32 / STORE_ACC / ENERGY; the symmetric-kernel bits are
+ * decided here.
+ */
+int64_t cosmo_workspace_bytes(int32_t n_total, uint32_t opts);
+int cosmo_workspace_init(void *dev_base, int64_t dev_bytes, int32_t n_total, uint32_t opts, cosmo_state *st,
+                         cosmo_scratch *sc, void *stream);
+int cosmo_params_default(int32_t n, double G, double dt, double r_max, uint32_t opts, double pos_max,
+                         double mass_max, const cosmo_scratch *sc, cosmo_step_params *p);
+
+/* One frame's host buffers (pinned memory for full-speed asynchronous copies). */
+typedef struct cosmo_host_frame {
+    int32_t n;       /* active planets handed over (== params.n_upper) */
+    int32_t reserved;
+    int64_t frame;   /* Universe.iterations before this frame (stamps the merge events) */
+    /* in: SoA of the n active planets in insertion order.  mass_hi/mass_lo/eaten may be NULL (zeros) */
+    const double *pos, *vel, *mass;
+    const uint64_t *mass_hi, *mass_lo;
+    const double *radius, *volume;
+    const int64_t *eaten;
+    const int32_t *id;
+    const uint8_t *flags;
+    /* out: the survivors, compacted, in insertion order; any pointer may be NULL (not wanted) except
+       status_out.  Arrays must hold n elements; status_out[COSMO_ST_N_ACTIVE] says how many were written */
+    double *pos_out, *vel_out, *mass_out;
+    uint64_t *mass_hi_out, *mass_lo_out;
+    double *radius_out, *volume_out;
+    int64_t *eaten_out;
+    int32_t *id_out;
+    uint8_t *flags_out;
+    int64_t *status_out;  /* [COSMO_STATUS_LEN] the device status block after the frame */
+    int64_t *events_out;  /* [events_cap][3] this frame's merges (frame, absorber id, absorbed id), in the
+                             reference's visitation order; status_out[COSMO_ST_N_EVENTS] of them */
+    int64_t events_cap;
+} cosmo_host_frame;
+
+/*
+ * The whole frame in one call: state H2D -> cosmo_step (stages A, B, C) -> status D2H -> the
+ * survivors and the frame's merge events D2H -> stream synchronised.  One device; returns 0 or a
+ * COSMO_E_* code (device-side COSMO_ERR_* bits are in status_out[COSMO_ST_ERROR]).
+ */
+int cosmo_step_host(const cosmo_state *st, const cosmo_scratch *sc, const cosmo_step_params *p,
+                    const cosmo_host_frame *f, void *stream);
+
 /* Host-buffer variant (the e2e call): copies pos/mass in, runs cosmo_accel, copies acc out
    and synchronises the stream.  *_host pointers are host memory (pinned for full speed). */
 int cosmo_accel_host(const double *pos_host, const double *mass_host, int32_t n, double G,

@@ -1,10 +1,12 @@
 """The C-ABI library loads and exports every symbol the headers under include/ declare; the
 host-callable exact-arithmetic helpers agree with Python's own numeric semantics.  No GPU."""
+import ctypes as C
 import math
 import os
 import random
 import re
 
+import pytest
 
 from cosmosim_b200 import _abi, _build
 
@@ -99,3 +101,31 @@ def test_pow_third_matches_libm_pow():
             diff += 1
             assert abs(want - got) <= math.ulp(want)
     assert diff < 0.002 * n
+
+
+def test_ctypes_structs_match_the_c_compilers_layout(tmp_path):
+    """sizeof / offsetof of every struct of both headers as gcc sees them == the ctypes mirrors."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    pairs = [("cosmo_state", _abi.State), ("cosmo_scratch", _abi.Scratch), ("cosmo_step_params", _abi.StepParams),
+             ("cosmo_grid", _abi.Grid), ("cosmo_host_frame", _abi.HostFrame), ("cosmo3_state", _abi.State3),
+             ("cosmo3_scratch", _abi.Scratch3), ("cosmo3_step_params", _abi.StepParams3)]
+    lines = []
+    for cname, ct in pairs:
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "cosmosim_b200.h"\n#include "cosmosim_b200_state3d.h"\n'
+                   'int main(void) {\n' + "\n".join(lines) + '\nreturn 0;\n}\n')
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    proc = subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in pairs:
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
