@@ -265,6 +265,17 @@ class Universe:
             self._engine.check_errors()
         return {k: d[k] for k in ("id", "pos", "vel", "mass", "radius", "volume", "eaten", "flags", "energy")}
 
+    def view(self):
+        """(n, id, pos, radius[, energy ...]) of the active planets straight from the device, for a
+        front-end: neither the Planet objects nor the death records are touched."""
+        if self._engine is None or self._host_dirty:
+            self._push()
+        return self._engine.view(energy=self.track_energy)
+
+    def peek(self, slot):
+        """One active planet by its slot in `view()` (position, velocity, mass, radius, eaten, energy)."""
+        return self._engine.peek(slot)
+
     # ------------------------------------------------------------------ stepping
     def step(self, n=1, dt=None, collisions=None):
         """Headless stepping: n frames of update_planet_lists -> interact -> destroy_escaped

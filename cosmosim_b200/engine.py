@@ -284,6 +284,27 @@ class Engine(BoundTracker):
         out["status"] = st
         return out
 
+    def view(self, energy=False):
+        """(n, id, pos, radius[, energy, totals]) of the active planets: the one small device->host copy
+        a front-end needs per displayed frame (no death records, no masses, no Planet objects)."""
+        n = self.status()["n_active"]
+        t = self.t
+        out = {"n": n, "id": t["id"][:n].cpu().numpy(), "pos": t["pos"][:n].cpu().numpy(),
+               "radius": t["radius"][:n].cpu().numpy()}
+        if energy:
+            out["energy"] = t["energy"][:n].cpu().numpy()
+            tot = t["totals"].cpu().numpy()
+            out["total_energy"], out["angular_momentum"] = float(tot[0]), float(tot[1])
+        return out
+
+    def peek(self, slot):
+        """One active planet (by slot) as Python numbers: a few words device->host."""
+        t, k = self.t, int(slot)
+        fl = int(t["flags"][k])
+        mass = ((int(t["mass_hi"][k]) & _MASK64) << 64 | (int(t["mass_lo"][k]) & _MASK64)) if fl & 2 else float(t["mass"][k])
+        return {"id": int(t["id"][k]), "pos": t["pos"][k].cpu().numpy(), "vel": t["vel"][k].cpu().numpy(), "mass": mass,
+                "radius": float(t["radius"][k]), "eaten": int(t["eaten"][k]), "energy": float(t["energy"][k])}
+
     def events(self, start=0):
         """Merge stream rows (frame, absorber id, absorbed id) from `start` on."""
         n = min(self.status()["n_events"], self.event_cap)
