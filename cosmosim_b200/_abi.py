@@ -102,14 +102,16 @@ class Scratch3(C.Structure):
                 ("t_density", _vp), ("t_radius", _vp), ("t_id", _vp), ("t_flags", _vp),
                 ("cell_of", _vp), ("cell_count", _vp), ("cell_start", _vp), ("cell_items", _vp), ("giants", _vp),
                 ("chunk_bounds", _vp), ("heavy_rows", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32),
-                ("colbuf", _vp), ("colbuf_rows", C.c_int64), ("grid_dev", _vp), ("tune_hist", _vp)]
+                ("colbuf", _vp), ("colbuf_rows", C.c_int64), ("grid_dev", _vp), ("tune_hist", _vp),
+                ("row_count", _vp), ("row_start", _vp), ("label", _vp), ("comp_root", _vp), ("comp_items", _vp),
+                ("pair_flag", _vp), ("scan_a", _vp)]
 
 
 class StepParams3(C.Structure):
     _fields_ = [("G", C.c_double), ("dt", C.c_double), ("opts", C.c_uint32), ("n_upper", C.c_int32),
                 ("i_begin", C.c_int32), ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
                 ("jsplit", C.c_int32), ("jsplit_detect", C.c_int32),
-                ("detect_mode", C.c_int32), ("reserved1", C.c_int32), ("cells_per_side", C.c_int32),
+                ("detect_mode", C.c_int32), ("resolve_mode", C.c_int32), ("cells_per_side", C.c_int32),
                 ("sym_chunk", C.c_int32), ("cell_size", C.c_double), ("grid_origin_x", C.c_double),
                 ("grid_origin_y", C.c_double), ("giant_radius", C.c_double),
                 ("shard_index", C.c_int32), ("shard_count", C.c_int32)]

@@ -32,6 +32,7 @@ class BoundTracker:
         self._host_grid = None       # caller-supplied grid (cell edge, origin x, origin y, cells per side, giant radius)
         self._force_all_pairs = False
         self.n_upper = 0
+        self.pairs_lag = 0           # flagged pairs of the step BOUND_LAG back (sizes stage C)
 
     # the engines count their steps under different names (Universe.iterations / State.iteration)
     def _tick(self) -> int:
@@ -65,6 +66,8 @@ class BoundTracker:
             self._snap_ev[k].synchronize()
             self._snap_async[k] = False
         seen_n, seen_f = int(self._snap[k][ST_N_ACTIVE]), int(self._snap[k][ST_STEP])
+        if seen_f == want:
+            self.pairs_lag = int(self._snap[k][_abi.ST_N_PAIRS])
         if seen_f == want and 0 < seen_n < self.n_upper:
             self.n_upper = seen_n
             return True

@@ -18,8 +18,8 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libcosmosim_b200.so")
 OBJ_DIR = os.path.join(_HERE, "build")
 SOURCES = ("accel.cu", "accel_sym.cu", "accel_sym64.cu", "nearfield.cu", "detect.cu", "resolve.cu", "energy.cu",
-           "scan.cu", "microbench.cu", "abi.cu", "host_step.cu", "state3d.cu", "state3d_sym.cu", "state3d_resolve.cu")
-HEADERS = ("cosmo_device.cuh", "cosmo_internal.h", "pred.cuh", "integrate.cuh", "state3d.cuh")
+           "scan.cu", "microbench.cu", "abi.cu", "host_step.cu", "state3d.cu", "state3d_sym.cu")
+HEADERS = ("cosmo_device.cuh", "cosmo_internal.h", "pred.cuh", "integrate.cuh", "grid.cuh", "state3d.cuh")
 PUBLIC_HEADERS = ("cosmosim_b200.h", "cosmosim_b200_state3d.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -33,7 +33,7 @@ def _nvcc() -> str:
 
 
 def _sources():
-    return [f for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
+    return list(SOURCES)
 
 
 def _header_mtime() -> float:

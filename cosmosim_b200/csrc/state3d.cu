@@ -572,74 +572,82 @@ __global__ void __launch_bounds__(256) k3_sort_pairs(cosmo3_state st, cosmo3_scr
 // absorbed something); an object j > i not yet visited still holds its OLD position; a destroyed
 // object holds mass 0.0 and zero vectors -- and is absorbed again by any row that still flags it,
 // because the reference tests only `obj.mass >= other.mass`.
+// One flagged ordered pair (i, j) of the loop: 0 = nothing happens (row object gone, or lighter than
+// the other), 1 = obj.absorb(other) of an object that still existed, 2 = of one destroyed earlier.
+__device__ int absorb_pair(const cosmo3_state &st, const cosmo3_scratch &sc, int i, int j, int stamp, bool *ovf) {
+    if (!sc.exists[i]) return 0;
+    const size_t cap = (size_t)st.cap;
+    const PyNum mi = load_mass(st, i), mj = load_mass(st, j);
+    if (!mass_ge(mi.is_int, mi.i, mi.f, mj.is_int, mj.i, mj.f)) return 0;
+    const bool existed = sc.exists[j] != 0;
+    const bool ti = sc.touched[i] == stamp;
+    const bool tj = sc.touched[j] == stamp;
+    const PyNum mt = pn_add(mi, mj, ovf);
+    const double fmi = pn_f(mi), fmj = pn_f(mj), fmt = pn_f(mt);
+    for (int d = 0; d < 3; ++d) {
+        const size_t oi = d * cap + i, oj = d * cap + j;
+        const double pi = ti ? sc.cur_pos[oi] : sc.pos_new[oi];
+        const double vi = ti ? sc.cur_vel[oi] : sc.vel_new[oi];
+        double pj = 0.0, vj = 0.0;
+        if (existed) {
+            if (j < i) {
+                pj = tj ? sc.cur_pos[oj] : sc.pos_new[oj];
+                vj = tj ? sc.cur_vel[oj] : sc.vel_new[oj];
+            } else {
+                pj = st.pos[oj];
+                vj = st.vel[oj];
+            }
+        }
+        sc.cur_pos[oi] = __ddiv_rn(__dadd_rn(__dmul_rn(fmi, pi), __dmul_rn(fmj, pj)), fmt);
+        sc.cur_vel[oi] = __ddiv_rn(__dadd_rn(__dmul_rn(fmi, vi), __dmul_rn(fmj, vj)), fmt);
+    }
+    sc.touched[i] = stamp;
+    const PyNum nd = pn_truediv(pn_add(pn_mul(mi, load_dens(st, i), ovf), pn_mul(mj, load_dens(st, j), ovf), ovf), mt);
+    st.density[i] = nd.f;
+    uint8_t fl = st.flags[i] & ~(COSMO3_F_MASS_INT | COSMO3_F_DENS_INT);
+    if (mt.is_int) {
+        fl |= COSMO3_F_MASS_INT;
+        st.mass_hi[i] = (uint64_t)(mt.i >> 64);
+        st.mass_lo[i] = (uint64_t)mt.i;
+    } else {
+        st.mass_hi[i] = 0;
+        st.mass_lo[i] = 0;
+    }
+    st.mass[i] = fmt;
+    st.flags[i] = fl;
+    st.radius[i] = radius_of(mt, nd);
+    // other.destroy() (universe.py:48-54)
+    sc.exists[j] = 0;
+    st.mass[j] = 0.0;
+    st.mass_hi[j] = 0;
+    st.mass_lo[j] = 0;
+    st.flags[j] &= ~COSMO3_F_MASS_INT;
+    return existed ? 1 : 2;
+}
+
 __device__ void resolve_loop(const cosmo3_state &st, const cosmo3_scratch &sc) {
     long long M = st.status[COSMO_ST_N_PAIRS];
     if (M > sc.pair_cap) M = sc.pair_cap;
     if (M == 0) return;
     const int stamp = (int)st.status[COSMO_ST_STEP];
-    const size_t cap = (size_t)st.cap;
     long long nev = st.status[COSMO_ST_N_EVENTS];
     long long dead = 0;
     bool ovf = false;
     for (long long q = 0; q < M; ++q) {
         const uint64_t key = sc.pairs_sorted[q];
         const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
-        if (!sc.exists[i]) continue;
-        const PyNum mi = load_mass(st, i), mj = load_mass(st, j);
-        if (!mass_ge(mi.is_int, mi.i, mi.f, mj.is_int, mj.i, mj.f)) continue;
-        const bool existed = sc.exists[j] != 0;
+        const int what = absorb_pair(st, sc, i, j, stamp, &ovf);
+        if (!what) continue;
         if (nev < st.event_cap) {
             st.events[4 * nev + 0] = stamp;
             st.events[4 * nev + 1] = st.id[i];
             st.events[4 * nev + 2] = st.id[j];
-            st.events[4 * nev + 3] = existed ? 1 : 0;
+            st.events[4 * nev + 3] = what == 1 ? 1 : 0;
         } else {
             st.status[COSMO_ST_ERROR] |= COSMO_ERR_EVENT_OVERFLOW;
         }
         ++nev;
-        const bool ti = sc.touched[i] == stamp;
-        const bool tj = sc.touched[j] == stamp;
-        const PyNum mt = pn_add(mi, mj, &ovf);
-        const double fmi = pn_f(mi), fmj = pn_f(mj), fmt = pn_f(mt);
-        for (int d = 0; d < 3; ++d) {
-            const size_t oi = d * cap + i, oj = d * cap + j;
-            const double pi = ti ? sc.cur_pos[oi] : sc.pos_new[oi];
-            const double vi = ti ? sc.cur_vel[oi] : sc.vel_new[oi];
-            double pj = 0.0, vj = 0.0;
-            if (existed) {
-                if (j < i) {
-                    pj = tj ? sc.cur_pos[oj] : sc.pos_new[oj];
-                    vj = tj ? sc.cur_vel[oj] : sc.vel_new[oj];
-                } else {
-                    pj = st.pos[oj];
-                    vj = st.vel[oj];
-                }
-            }
-            sc.cur_pos[oi] = __ddiv_rn(__dadd_rn(__dmul_rn(fmi, pi), __dmul_rn(fmj, pj)), fmt);
-            sc.cur_vel[oi] = __ddiv_rn(__dadd_rn(__dmul_rn(fmi, vi), __dmul_rn(fmj, vj)), fmt);
-        }
-        sc.touched[i] = stamp;
-        const PyNum nd = pn_truediv(pn_add(pn_mul(mi, load_dens(st, i), &ovf), pn_mul(mj, load_dens(st, j), &ovf), &ovf), mt);
-        st.density[i] = nd.f;
-        uint8_t fl = st.flags[i] & ~(COSMO3_F_MASS_INT | COSMO3_F_DENS_INT);
-        if (mt.is_int) {
-            fl |= COSMO3_F_MASS_INT;
-            st.mass_hi[i] = (uint64_t)(mt.i >> 64);
-            st.mass_lo[i] = (uint64_t)mt.i;
-        } else {
-            st.mass_hi[i] = 0;
-            st.mass_lo[i] = 0;
-        }
-        st.mass[i] = fmt;
-        st.flags[i] = fl;
-        st.radius[i] = radius_of(mt, nd);
-        // other.destroy() (universe.py:48-54)
-        if (existed) ++dead;
-        sc.exists[j] = 0;
-        st.mass[j] = 0.0;
-        st.mass_hi[j] = 0;
-        st.mass_lo[j] = 0;
-        st.flags[j] &= ~COSMO3_F_MASS_INT;
+        if (what == 1) ++dead;
     }
     st.status[COSMO_ST_N_EVENTS] = nev;
     st.status[COSMO_ST_N_DEAD] = dead;
@@ -649,6 +657,231 @@ __device__ void resolve_loop(const cosmo3_state &st, const cosmo3_scratch &sc) {
 __global__ void k3_resolve(cosmo3_state st, cosmo3_scratch sc) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     resolve_loop(st, sc);
+}
+
+// ---------------------------------------------------------------------------------------
+// Parallel stage C (resolve_mode 1; crowded scenes with 10^3..10^6 flagged pairs per step).
+// The absorb loop only ever touches the two objects of a flagged pair, so the connected components
+// of the flagged-pair graph are independent of each other; inside a component the reference's
+// visitation order decides everything.  Hence:
+//   counting sort of the pairs by row + per-row sort by partner  -> row-major order (= the double loop)
+//   lock-free union-find over the pair edges                      -> component root of every pair
+//   counting sort of the pair indices by root + rank sort         -> every component's pairs in order
+//   one thread per component replays its pairs (absorb_pair)      -> a result code per pair
+//   ordered compaction of the result codes                        -> the absorb-call log, in loop order
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ long long pair_count3(const cosmo3_state &st, const cosmo3_scratch &sc) {
+    const long long M = st.status[COSMO_ST_N_PAIRS];
+    return M > sc.pair_cap ? sc.pair_cap : M;
+}
+
+__device__ __forceinline__ int uf_find3(int *parent, int v) {
+    int p = *(volatile int *)&parent[v];
+    while (p != v) {
+        const int gp = *(volatile int *)&parent[p];
+        if (gp != p) parent[v] = gp;     // path halving (benign race: only ever moves towards the root)
+        v = p;
+        p = gp;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k3p_count(cosmo3_state st, cosmo3_scratch sc) {
+    const long long M = pair_count3(st, sc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st.status[COSMO_ST_N_DEAD] = 0;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const uint64_t key = sc.pairs[q];
+        const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
+        atomicAdd(&sc.row_count[i], 1);
+        sc.label[i] = i;
+        sc.label[j] = j;
+    }
+}
+
+__global__ void __launch_bounds__(256) k3p_fill(cosmo3_state st, cosmo3_scratch sc) {
+    const long long M = pair_count3(st, sc);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const uint64_t key = sc.pairs[q];
+        const int i = (int)(key >> 32);
+        const int slot = sc.row_start[i] + atomicSub(&sc.row_count[i], 1) - 1;   // counts return to zero
+        sc.pairs_sorted[slot] = key;
+    }
+}
+
+// order every row by partner: short rows by the owner of the row's first slot (insertion sort), long
+// rows (a giant flagged with thousands of objects) by a rank sort spread over a whole CTA
+constexpr int ROW_LONG = 48;
+
+__global__ void __launch_bounds__(256) k3p_sort_rows(cosmo3_state st, cosmo3_scratch sc) {
+    const long long M = pair_count3(st, sc);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(sc.pairs_sorted[q] >> 32);
+        const int s0 = sc.row_start[i], s1 = sc.row_start[i + 1];
+        sc.pair_flag[q] = 0;
+        if (q != s0 || s1 - s0 < 2 || s1 - s0 > ROW_LONG) continue;
+        for (int a = s0 + 1; a < s1; ++a) {
+            const uint64_t key = sc.pairs_sorted[a];
+            int b = a - 1;
+            while (b >= s0 && sc.pairs_sorted[b] > key) {
+                sc.pairs_sorted[b + 1] = sc.pairs_sorted[b];
+                --b;
+            }
+            sc.pairs_sorted[b + 1] = key;
+        }
+    }
+}
+
+// long rows: CTA b takes the rows i = b, b + gridDim.x, ...; ranks are counted against the row itself
+// and the sorted row is staged in `pairs` (free after k3p_fill) before it is copied back
+__global__ void __launch_bounds__(256) k3p_sort_long_rows(cosmo3_state st, cosmo3_scratch sc) {
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    if (pair_count3(st, sc) <= ROW_LONG) return;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int s0 = sc.row_start[i], s1 = sc.row_start[i + 1];
+        if (s1 - s0 <= ROW_LONG) continue;
+        for (int a = s0 + threadIdx.x; a < s1; a += blockDim.x) {
+            const uint64_t key = sc.pairs_sorted[a];
+            int rank = 0;
+            for (int b = s0; b < s1; ++b) rank += sc.pairs_sorted[b] < key;
+            sc.pairs[s0 + rank] = key;
+        }
+        __syncthreads();
+        for (int a = s0 + threadIdx.x; a < s1; a += blockDim.x) sc.pairs_sorted[a] = sc.pairs[a];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k3p_union(cosmo3_state st, cosmo3_scratch sc) {
+    const long long M = pair_count3(st, sc);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const uint64_t key = sc.pairs_sorted[q];
+        int a = uf_find3(sc.label, (int)(key >> 32)), b = uf_find3(sc.label, (int)(key & 0xffffffffu));
+        while (a != b) {
+            const int hi = max(a, b), lo = min(a, b);
+            const int old = atomicCAS(&sc.label[hi], hi, lo);    // hook root `hi` under `lo`
+            if (old == hi) break;
+            a = uf_find3(sc.label, old);                          // someone else moved it: retry from the new roots
+            b = uf_find3(sc.label, lo);
+        }
+    }
+}
+
+// flatten (root = smallest object index of the component) and count the pairs per component
+__global__ void __launch_bounds__(256) k3p_comp_count(cosmo3_state st, cosmo3_scratch sc) {
+    const long long M = pair_count3(st, sc);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const int root = uf_find3(sc.label, (int)(sc.pairs_sorted[q] >> 32));
+        sc.comp_root[q] = root;
+        atomicAdd(&sc.row_count[root], 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k3p_comp_fill(cosmo3_state st, cosmo3_scratch sc) {
+    const long long M = pair_count3(st, sc);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const int root = sc.comp_root[q];
+        const int slot = sc.row_start[root] + atomicSub(&sc.row_count[root], 1) - 1;
+        sc.comp_items[slot] = (int)q;
+    }
+}
+
+// order every component's pairs by sorted-pair index: rank = number of smaller indices in the component
+__global__ void __launch_bounds__(256) k3p_comp_rank(cosmo3_state st, cosmo3_scratch sc) {
+    const long long M = pair_count3(st, sc);
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const int root = sc.comp_root[q];
+        const int s0 = sc.row_start[root], s1 = sc.row_start[root + 1];
+        int rank = 0;
+        for (int s = s0; s < s1; ++s) rank += sc.comp_items[s] < (int)q;
+        sc.scan_a[s0 + rank] = (int)q;           // scan_a is free until the event compaction
+    }
+}
+
+// one thread per component root: the component's pairs in the loop's order
+__global__ void __launch_bounds__(128) k3p_comp_resolve(cosmo3_state st, cosmo3_scratch sc) {
+    if (pair_count3(st, sc) == 0) return;
+    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int s0 = sc.row_start[v], s1 = sc.row_start[v + 1];
+    if (s1 <= s0) return;
+    const int stamp = (int)st.status[COSMO_ST_STEP];
+    bool ovf = false;
+    unsigned long long dead = 0;
+    for (int a = s0; a < s1; ++a) {
+        const int q = sc.scan_a[a];
+        const uint64_t key = sc.pairs_sorted[q];
+        const int what = absorb_pair(st, sc, (int)(key >> 32), (int)(key & 0xffffffffu), stamp, &ovf);
+        sc.pair_flag[q] = what;
+        dead += what == 1;
+    }
+    if (dead) atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_DEAD]), dead);
+    if (ovf) atomicOr(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_ERROR]),
+                      (unsigned long long)COSMO3_ERR_INT_OVERFLOW);
+}
+
+__global__ void __launch_bounds__(256) k3p_mark(cosmo3_state st, cosmo3_scratch sc) {
+    const long long M = pair_count3(st, sc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st.status[COSMO_ST_EV_BASE] = st.status[COSMO_ST_N_EVENTS];
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x)
+        sc.scan_a[q] = sc.pair_flag[q] ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) k3p_scatter(cosmo3_state st, cosmo3_scratch sc) {
+    const long long M = pair_count3(st, sc);
+    const int stamp = (int)st.status[COSMO_ST_STEP];
+    const long long base = st.status[COSMO_ST_EV_BASE];
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
+        const int what = sc.pair_flag[q];
+        if (!what) continue;
+        const long long e = base + sc.scan_a[q];
+        if (e < st.event_cap) {
+            const uint64_t key = sc.pairs_sorted[q];
+            st.events[4 * e + 0] = stamp;
+            st.events[4 * e + 1] = st.id[(int)(key >> 32)];
+            st.events[4 * e + 2] = st.id[(int)(key & 0xffffffffu)];
+            st.events[4 * e + 3] = what == 1 ? 1 : 0;
+        } else {
+            atomicOr(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_ERROR]),
+                     (unsigned long long)COSMO_ERR_EVENT_OVERFLOW);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) st.status[COSMO_ST_N_EVENTS] = base + (M > 0 ? sc.scan_a[M] : 0);
+}
+
+static int launch_resolve_parallel(const cosmo3_state &st, const cosmo3_scratch &sc, const cosmo3_step_params &p,
+                                   cudaStream_t s) {
+    if (!sc.row_count || !sc.row_start || !sc.label || !sc.comp_root || !sc.comp_items || !sc.pair_flag || !sc.scan_a) {
+        set_error("3-D stage C: resolve_mode 1 needs the row / component arrays of cosmo3_scratch");
+        return COSMO_E_ARG;
+    }
+    const int pb = 296;
+    const int64_t *n_ptr = &st.status[COSMO_ST_N_ACTIVE];
+    k3p_count<<<pb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k3p_count"));
+    COSMO_TRY(launch_scan_exclusive(sc.row_count, sc.row_start, sc.scan_blk, n_ptr, p.n_upper, 0, s));
+    k3p_fill<<<pb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k3p_fill"));
+    k3p_sort_rows<<<pb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k3p_sort_rows"));
+    k3p_sort_long_rows<<<pb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k3p_sort_long_rows"));
+    k3p_union<<<pb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k3p_union"));
+    k3p_comp_count<<<pb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k3p_comp_count"));
+    COSMO_TRY(launch_scan_exclusive(sc.row_count, sc.row_start, sc.scan_blk, n_ptr, p.n_upper, 0, s));
+    k3p_comp_fill<<<pb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k3p_comp_fill"));
+    k3p_comp_rank<<<pb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k3p_comp_rank"));
+    k3p_comp_resolve<<<(p.n_upper + 127) / 128, 128, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k3p_comp_resolve"));
+    k3p_mark<<<pb, 256, 0, s>>>(st, sc);
+    COSMO_TRY(COSMO_LAUNCH_CHECK("k3p_mark"));
+    COSMO_TRY(launch_scan_exclusive(sc.scan_a, sc.scan_a, sc.scan_blk, &st.status[COSMO_ST_N_PAIRS], sc.pair_cap, 0, s));
+    k3p_scatter<<<pb, 256, 0, s>>>(st, sc);
+    return COSMO_LAUNCH_CHECK("k3p_scatter");
 }
 
 // obj.velocity = v[i]; obj.position = p[i] (universe.py:113-114) for every object that still exists,
@@ -927,7 +1160,9 @@ static int launch_stage_c(const cosmo3_state &st, const cosmo3_scratch &sc, cons
     }
     int blocks = (p.n_upper + 255) / 256;
     blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
-    if (p.opts & COSMO3_OPT_COLLISIONS) {
+    if ((p.opts & COSMO3_OPT_COLLISIONS) && p.resolve_mode == 1) {
+        COSMO_TRY(launch_resolve_parallel(st, sc, p, s));
+    } else if (p.opts & COSMO3_OPT_COLLISIONS) {
         k3_sort_pairs<<<64, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k3_sort_pairs"));
         k3_resolve<<<1, 32, 0, s>>>(st, sc);

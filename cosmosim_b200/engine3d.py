@@ -66,6 +66,8 @@ class Engine3D(BoundTracker):
         self.sym64_threshold = 16384 # FP64: from here on the symmetric kernel (each pair once) wins
         self.sym32_threshold = 32768 # FP32: same for the symmetric FP32 kernel
         self.sym_chunk = 0           # column blocks per CTA of the symmetric kernel (0 = automatic)
+        self.resolve_mode = None     # stage C: None = automatic, 0 = sequential loop, 1 = parallel components
+        self.resolve_parallel_from = 512   # flagged pairs per step from which the parallel stage C pays off
         self._colbuf = None
 
     def _alloc(self):
@@ -100,7 +102,11 @@ class Engine3D(BoundTracker):
         t["cell_count"] = z(self.grid_cells + 1, dtype=i32); t["cell_start"] = z(self.grid_cells + 1, dtype=i32)
         t["giants"] = z(self.giant_cap, dtype=i32)
         t["chunk_bounds"] = z(cap // 1024 + 2, dtype=i32); t["heavy_rows"] = z(cap, dtype=i32)
-        t["grid_dev"] = z(128, dtype=u8); t["tune_hist"] = z(_abi.TUNE_HIST_LEN, dtype=i32)
+        t["grid_dev"] = z(256, dtype=u8); t["tune_hist"] = z(_abi.TUNE_HIST_LEN, dtype=i32)
+        # parallel stage C (crowded steps)
+        t["row_count"] = z(cap + 1, dtype=i32); t["row_start"] = z(cap + 1, dtype=i32); t["label"] = z(cap, dtype=i32)
+        t["comp_root"] = z(self.pair_cap, dtype=i32); t["comp_items"] = z(self.pair_cap, dtype=i32)
+        t["pair_flag"] = z(self.pair_cap, dtype=i32); t["scan_a"] = z(self.pair_cap + 1, dtype=i32)
         p = lambda k: C.c_void_p(t[k].data_ptr())  # noqa: E731
         st = _abi.State3()
         st.cap, st.n_total, st.event_cap = cap, self.n_total, self.event_cap
@@ -111,7 +117,8 @@ class Engine3D(BoundTracker):
                   "pairs_sorted", "exists", "cur_pos", "cur_vel", "touched", "scan_in", "scan_out", "scan_blk",
                   "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_density", "t_radius", "t_id", "t_flags",
                   "cell_of", "cell_count", "cell_start", "cell_items", "giants", "chunk_bounds", "heavy_rows",
-                  "grid_dev", "tune_hist"):
+                  "grid_dev", "tune_hist", "row_count", "row_start", "label", "comp_root", "comp_items", "pair_flag",
+                  "scan_a"):
             setattr(sc, k, p(k))
         sc.jsplit_max, sc.pair_cap = self.JSPLIT_MAX, self.pair_cap
         sc.grid_cells, sc.giant_cap = self.grid_cells, self.giant_cap
@@ -265,6 +272,10 @@ class Engine3D(BoundTracker):
                 p.cell_size, p.grid_origin_x, p.grid_origin_y, p.cells_per_side, p.giant_radius = self._host_grid
             else:
                 p.detect_mode = 2
+        # stage C: the sequential loop is the cheaper one for a handful of flagged pairs; crowded steps
+        # (judged by the pair count of the status snapshot BOUND_LAG steps back) take the parallel one
+        mode = self.resolve_mode
+        p.resolve_mode = int(mode if mode is not None else self.pairs_lag > self.resolve_parallel_from)
         return p
 
     def _uses_grid(self, collisions=True):

@@ -109,6 +109,14 @@ typedef struct cosmo3_scratch {
     int64_t colbuf_rows;   /* FP64: >= ceil(ceil(n / 512) / ranks); FP32 (1024-object blocks, float planes): a quarter of that */
     cosmo_grid *grid_dev;  /* [1] broad-phase grid of the current step (detect_mode 1 and 2) */
     int32_t *tune_hist;    /* [COSMO_TUNE_HIST_LEN] detect_mode 2, must start zeroed (self-resetting) */
+    /* parallel stage C (resolve_mode 1): row-major form of the flagged pairs and their connected components */
+    int32_t *row_count;    /* [cap + 1] must start zeroed (self-resetting) */
+    int32_t *row_start;    /* [cap + 1] */
+    int32_t *label;        /* [cap] union-find parent / component root */
+    int32_t *comp_root;    /* [pair_cap] component root of every sorted pair */
+    int32_t *comp_items;   /* [pair_cap] sorted-pair indices grouped by component */
+    int32_t *pair_flag;    /* [pair_cap] result of the absorb call of every sorted pair */
+    int32_t *scan_a;       /* [pair_cap + 1] */
 } cosmo3_scratch;
 
 typedef struct cosmo3_step_params {
@@ -127,7 +135,8 @@ typedef struct cosmo3_step_params {
        every candidate goes through the exact 3-D predicate); 2 = the same grid tuned on the device
        every step.  Fields as in cosmo_step_params. */
     int32_t detect_mode;
-    int32_t reserved1;
+    int32_t resolve_mode;  /* stage C: 0 = rank sort + one thread (few flagged pairs), 1 = row-major counting
+                              sort + connected components replayed in parallel (crowded steps) */
     int32_t cells_per_side;
     int32_t sym_chunk;     /* symmetric kernel: column blocks per CTA (0 = default) */
     double cell_size;

@@ -44,12 +44,13 @@ def synthetic_cloud(n, seed, thick=0.2):
     return snap
 
 
-def step_once(engine3d, snap, dt, G, collisions=True, fp32=False, sym=None):
+def step_once(engine3d, snap, dt, G, collisions=True, fp32=False, sym=None, resolve_mode=None, stage_events=None):
     arr = engine3d_arrays_from_snapshot(snap)
     n = len(arr["mass_f64"])
     eng = engine3d.Engine3D(n)
+    eng.resolve_mode = resolve_mode
     eng.upload(arr)
-    eng.step(dt, G, collisions=collisions, fp32=fp32, store_acc=True, sym=sym)
+    eng.step(dt, G, collisions=collisions, fp32=fp32, store_acc=True, sym=sym, stage_events=stage_events)
     eng.check_errors()
     return eng, eng.last_step_tensors(n)
 
@@ -185,13 +186,15 @@ def test_micro_scenes(mods):
         assert np.array_equal(np.array(ev, dtype=np.int64).reshape(-1, 4), g["%s_events" % name]), name
 
 
-def test_crowded_step_against_oracle(mods):
-    """A crowded 3-D cloud (hundreds of flagged pairs, chains, destroyed-object re-absorbs) for one
-    step: pairs and the absorb stream must equal the oracle's exactly."""
+@pytest.mark.parametrize("n,squeeze,resolve_mode,min_calls", [(6000, 0.02, 0, 100), (6000, 0.02, 1, 100),
+                                                              (60000, 0.06, 1, 10000)])
+def test_crowded_step_against_oracle(mods, n, squeeze, resolve_mode, min_calls):
+    """A crowded 3-D cloud (hundreds to tens of thousands of flagged pairs, chains, destroyed-object
+    re-absorbs) for one step: pairs and the absorb stream must equal the oracle's exactly, with the
+    sequential stage C and with the parallel one (row-major counting sort + connected components)."""
     engine3d, o3, _ = mods
-    n = 6000
     snap = synthetic_cloud(n, 77, thick=0.5)
-    snap["pos"] *= 0.02                      # squeeze: radii ~ 1e7 m in a ~3e9 m cloud
+    snap["pos"] *= squeeze                   # 0.02: radii ~ 1e7 m in a ~3e9 m cloud
     rnd = random.Random(5)
     ints = [rnd.randint(int(0.1 * 5.972e24), int(100 * 5.972e24)) for _ in range(n)]
     snap["mass_is_int"][:] = True
@@ -201,9 +204,13 @@ def test_crowded_step_against_oracle(mods):
     snap["dens_f64"][:] = 30.0
     snap["dens_is_int"][:] = True
     orc = o3.OracleState(snap, dt=60.0)
-    want = orc.interact(True, record=True, cap=1 << 18)
-    assert len(want["events"]) > 100 and (want["events"][:, 2] == 0).sum() > 0
-    eng, out = step_once(engine3d, snap, 60.0, 6.674e-11)
+    want = orc.interact(True, record=True, cap=1 << 22)
+    assert len(want["events"]) > min_calls and (want["events"][:, 2] == 0).sum() > 0
+    evs = []
+    eng, out = step_once(engine3d, snap, 60.0, 6.674e-11, resolve_mode=resolve_mode, stage_events=evs)
+    assert eng.params(60.0, 6.674e-11).resolve_mode == resolve_mode
+    print("3-D stage C, n=%d, %d flagged pairs, %d absorb calls, resolve_mode %d: %.3f ms" % (
+        n, len(want["flag_pairs"]), len(want["events"]), resolve_mode, evs[0][2].elapsed_time(evs[0][3])))
     assert np.array_equal(out["flag_pairs"], want["flag_pairs"])
     assert np.array_equal(eng.events()[:, 1:], want["events"])
     d, post = eng.download(), orc.snapshot()
