@@ -182,6 +182,7 @@ class State:
 
     @iteration.setter
     def iteration(self, value):
+        self._pull()                 # otherwise the next pull would overwrite it with the device's counter
         self._iteration = value
         self._host_dirty = True
 
@@ -243,7 +244,9 @@ class State:
         for k, o in enumerate(src):
             if k not in alive and o.exists:
                 o.destroy()
-        self._objects = out
+        # in place: the reference removes absorbed objects from the very list the caller handed over
+        # (universe.py:126-128), so a second State / Universe built on that list starts from the survivors
+        self._objects[:] = out
         self._iteration = d["status"]["iteration"]
         self._device_ahead = False      # device ids keep indexing `src`, so no re-upload is needed
 
@@ -349,35 +352,49 @@ class Universe:
         self.filesize = filesize
         self.precision = precision
 
-    def run(self):
+    def run(self, save_every=1):
+        """universe.py:141-167: `iterations` steps; every state goes to `outpath` as a stream of pickles
+        (`filesize` states per file) or, without an outpath, into the returned list.
+
+        The steps between two saves run as ONE burst on the GPU (State.step) and the objects are only
+        pulled back to the host when a state is written or kept.  save_every=1 is the reference's
+        behaviour (every step is saved); a larger value keeps every save_every-th state and lets the
+        device run ahead in between."""
         try:
             from tqdm import tqdm
         except ImportError:  # pragma: no cover
             def tqdm(it, **kw):
                 return it
+        save_every = max(1, int(save_every))
         state = State(self.objects, dt=self.dt, precision=self.precision)
-        nfiles = math.ceil(self.iterations / self.filesize)
-        elapsed = 0
-        if self.outpath:
-            if not os.path.isdir(self.outpath):
-                os.mkdir(self.outpath)
-            # the reference empties the directory (universe.py:147-149); only its own data files here
-            for f in os.listdir(self.outpath):
-                if f.endswith(".dat") and f[:-4].isdigit():
-                    os.remove(os.path.join(self.outpath, f))
-            print(f"A total of {nfiles} data files will be created.")
-            for n in range(nfiles):
-                path = os.path.join(self.outpath, f"{n}.dat")
-                for _ in tqdm(range(min(self.filesize, self.iterations)), desc=f"Writing file {n}"):
-                    state.interact(self.dt)      # sic: the reference passes dt as `collisions` (universe.py:155)
-                    with open(path, "ab+") as f:
-                        state.save(f)
-                    elapsed += 1
-                    if elapsed >= self.iterations:
-                        break
-            return None
-        states = []
-        for _ in tqdm(range(self.iterations), desc="Running simulation"):
-            state.interact()
-            states.append(copy.deepcopy(state))
-        return states
+        total = int(self.iterations)
+        # the save points: every save_every-th step, and the last one
+        points = list(range(save_every, total + 1, save_every))
+        if total > 0 and (not points or points[-1] != total):
+            points.append(total)
+        if not self.outpath:
+            states, done = [], 0
+            for upto in tqdm(points, desc="Running simulation"):
+                state.step(upto - done)
+                done = upto
+                states.append(copy.deepcopy(state))
+            return states
+        if not os.path.isdir(self.outpath):
+            os.mkdir(self.outpath)
+        # the reference empties the directory (universe.py:147-149); only its own data files here
+        for f in os.listdir(self.outpath):
+            if f.endswith(".dat") and f[:-4].isdigit():
+                os.remove(os.path.join(self.outpath, f))
+        nfiles = math.ceil(len(points) / self.filesize)
+        print(f"A total of {nfiles} data files will be created.")
+        # the reference calls state.interact(self.dt) here (universe.py:155): dt lands in the
+        # `collisions` argument, so a zero dt would switch collisions off
+        collisions = bool(self.dt)
+        done = 0
+        for n in range(nfiles):
+            with open(os.path.join(self.outpath, f"{n}.dat"), "ab+") as f:
+                for upto in tqdm(points[n * self.filesize:(n + 1) * self.filesize], desc=f"Writing file {n}"):
+                    state.step(upto - done, collisions)
+                    done = upto
+                    state.save(f)
+        return None

@@ -296,6 +296,23 @@ def test_host_api_run_and_pickles(mods, tmp_path):
     last = [s for s in states if s.iteration == 5][0]
     assert np.array_equal(last.positions(), mem[-1].positions())
     assert b"ccosmosim.core.universe\nState\n" in open(os.path.join(out, "0.dat"), "rb").read()
+    # bursts between save points: the device runs ahead, the saved states are the same ones
+    some = S.Universe(build(), float(g["dt"]), 5).run(save_every=2)
+    assert [s.iteration for s in some] == [2, 4, 5]
+    for s in some:
+        assert np.array_equal(s.positions(), mem[s.iteration - 1].positions())
+    # the caller's list is pruned in place, like the reference's State.objects (universe.py:126-128), so a
+    # second run on the same list starts from the survivors (ints stay ints, nothing sits on the star)
+    objs = build()
+    st2 = S.State(objs, dt=float(g["dt"]))
+    st2.step(int(g["steps"]))
+    assert st2.objects is objs and len(objs) == len(want["id"]) and all(o.exists for o in objs)
+    again = S.Universe(objs, float(g["dt"]), 1).run()
+    assert len(again[0].objects) <= len(want["id"]) and all(isinstance(o.mass, int) for o in again[0].objects[1:])
+    # a host-side edit of the step counter survives the next step
+    st2.iteration = 100
+    st2.step(1)
+    assert st2.iteration == 101
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 63, 64, 65, 1023, 1024, 1025, 2049])
