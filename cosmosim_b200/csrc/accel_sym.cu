@@ -35,6 +35,17 @@ constexpr int SYM_WARPS = 8;
 constexpr int SYM_THREADS = SYM_WARPS * 32;
 #define COSMO_F32_TINY_SYM 8.673617379884035e-19f /* 2^-60 softening, see accel.cu */
 
+// Row blocks are dealt to the ranks of a sharded run boustrophedon-wise (0 1 .. W-1, W-1 .. 1 0, ...):
+// the work of row block I is proportional to nblk - I (the triangle), and plain round-robin would
+// hand rank 0 the longest row of every round -- a 3 % imbalance at 8 ranks; this way it is O(1 / rows).
+__host__ __device__ __forceinline__ int sym_row_of(int l, int rank, int world) {
+    return l * world + ((l & 1) ? world - 1 - rank : rank);
+}
+__host__ __device__ __forceinline__ bool sym_owns(int I, int rank, int world) {
+    const int l = I / world, rr = I % world;
+    return ((l & 1) ? world - 1 - rr : rr) == rank;
+}
+
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src_lane) {
     uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
     lo = __shfl_sync(0xffffffffu, lo, src_lane);
@@ -54,7 +65,7 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
 
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int nblk = (n + SYM_BLOCK - 1) / SYM_BLOCK;
-    const int I = shard_index + blockIdx.x * shard_count;
+    const int I = sym_row_of(blockIdx.x, shard_index, shard_count);
     if (I >= nblk) return;
     const int J0 = I + blockIdx.y * chunk;
     if (J0 >= nblk) return;
@@ -195,7 +206,7 @@ k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count,
     const int nblk = (n + SYM_BLOCK - 1) / SYM_BLOCK;
     const int K = k / SYM_BLOCK;
     double ax = 0.0, ay = 0.0;
-    if (K % shard_count == shard_index) {
+    if (sym_owns(K, shard_index, shard_count)) {
         const double2 *partial = reinterpret_cast<const double2 *>(sc.partial);
         const int nchunk = (nblk - K + chunk - 1) / chunk;
         for (int c = 0; c < nchunk; ++c) {
@@ -205,20 +216,28 @@ k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count,
         }
     }
     const float2 *colbuf = reinterpret_cast<const float2 *>(sc.colbuf);
-    // row blocks I < K owned by this rank: I = shard_index + r * shard_count
-    int r = 0;
-    for (int I = shard_index; I < K; I += shard_count, ++r) {
+    // row blocks I < K owned by this rank, in ascending order (local row r holds block sym_row_of(r))
+    for (int r = 0; sym_row_of(r, shard_index, shard_count) < K; ++r) {
         const float2 v = __ldcs(&colbuf[(size_t)r * st.cap + k]);
         ax += (double)v.x;
         ay += (double)v.y;
     }
     ax *= unscale;
     ay *= unscale;
-    if (near) {   // FP64 near-field corrections of the rows this rank evaluated (nearfield.cu; zero elsewhere)
-        const double2 c = reinterpret_cast<const double2 *>(sc.corr)[k];
-        ax += c.x;
-        ay += c.y;
+    // FP64 near-field corrections of the rows this rank evaluated (nearfield.cu; zero elsewhere)
+    double2 c = make_double2(0.0, 0.0);
+    if (near) c = reinterpret_cast<const double2 *>(sc.corr)[k];
+    if (defer == 1 && near) {
+        // Sharded: the FP32-sourced sums and the corrections travel SEPARATELY through the all-reduce.
+        // Sums of FP32 values in FP64 are exact (no rounding) and a correction comes from exactly one
+        // rank, so both reductions are independent of the partition; k_sym_integrate then adds them
+        // once -- the same single rounding as on one GPU.  That keeps a sharded run on the very
+        // trajectory of the single-GPU run instead of 1 ulp beside it (the scene is chaotic).
+        reinterpret_cast<double4 *>(sc.acc)[k] = make_double4(ax, ay, c.x, c.y);
+        return;
     }
+    ax += c.x;
+    ay += c.y;
     if (defer == 2) {
         // peer exchange: this rank's partial sums go straight into slot `shard_index` of every
         // rank's exchange buffer (NVLink peer stores, coalesced 16 B per lane)
@@ -233,7 +252,7 @@ k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count,
 }
 
 __global__ void __launch_bounds__(256)
-k_sym_integrate(cosmo_state st, cosmo_scratch sc, double G, double dt, int peer, int self) {
+k_sym_integrate(cosmo_state st, cosmo_scratch sc, double G, double dt, int peer, int self, int near) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -246,11 +265,15 @@ k_sym_integrate(cosmo_state st, cosmo_scratch sc, double G, double dt, int peer,
             a.x += v.x;
             a.y += v.y;
         }
+    } else if (near) {
+        const double4 v = reinterpret_cast<const double4 *>(sc.acc)[k];   // (sum, near-field correction)
+        a = make_double2(v.x + v.z, v.y + v.w);
     } else {
         a = reinterpret_cast<const double2 *>(sc.acc)[k];
     }
-    // sc.acc holds the all-reduced sums S; integrate_store multiplies by G and rewrites acc = G S
-    integrate_store(st, sc, k, a.x, a.y, G, dt, true);
+    // sc.acc holds the all-reduced sums S; the planets' accelerations G S go to pos_new / vel_new.  (With
+    // `near` the four-wide rows of acc are still being read by other threads: acc is not rewritten.)
+    integrate_store(st, sc, k, a.x, a.y, G, dt, !near);
 }
 
 int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
@@ -260,7 +283,8 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
     const int nblk = (n + SYM_BLOCK - 1) / SYM_BLOCK;
     const int sh_n = p.shard_count > 0 ? p.shard_count : 1;
     const int sh_i = p.shard_count > 0 ? p.shard_index : 0;
-    const int rows_local = (nblk - sh_i + sh_n - 1) / sh_n;
+    int rows_local = nblk / sh_n;                     // full boustrophedon rounds, plus a partial one
+    if (sym_row_of(rows_local, sh_i, sh_n) < nblk) ++rows_local;
     int chunk = p.sym_chunk > 0 ? p.sym_chunk : 32;
     while ((nblk + chunk - 1) / chunk > sc.jsplit_max) ++chunk;
     if (!sc.colbuf || (long long)rows_local > sc.colbuf_rows) {
@@ -289,7 +313,8 @@ int launch_sym_integrate(const cosmo_state &st, const cosmo_scratch &sc, const c
         set_error("peer exchange: n_peers=%d, rank %d", sc.n_peers, p.shard_index);
         return COSMO_E_ARG;
     }
-    k_sym_integrate<<<(p.n_upper + 255) / 256, 256, 0, s>>>(st, sc, p.G, p.dt, peer, p.shard_index);
+    const int near = (!peer && (p.opts & COSMO_OPT_FP32) && p.near_mode != 0) ? 1 : 0;
+    k_sym_integrate<<<(p.n_upper + 255) / 256, 256, 0, s>>>(st, sc, p.G, p.dt, peer, p.shard_index, near);
     return COSMO_LAUNCH_CHECK("k_sym_integrate");
 }
 

@@ -66,7 +66,7 @@ void carve(int n_total, uint32_t opts, char *base, cosmo_state *st, cosmo_scratc
     s.rec_death = w.take<int32_t>(nt); s.rec_flags = w.take<uint8_t>(nt);
     s.events = w.take<int64_t>(3 * z.event_cap);
     c.h = w.take<double>(cap); c.pk_x = w.take<float>(cap); c.pk_y = w.take<float>(cap); c.pk_m = w.take<float>(cap);
-    c.acc = w.take<double>(2 * cap);
+    c.acc = w.take<double>(4 * cap);
     c.pos_new = w.take<double>(2 * cap); c.vel_new = w.take<double>(2 * cap); c.xx_new = w.take<double>(cap);
     c.rinf = w.take<double>(cap);
     c.partial = w.take<double>((long long)kJsplitMax * 2 * cap); c.jsplit_max = kJsplitMax;

@@ -52,6 +52,30 @@ __global__ void __launch_bounds__(128) k_nf_ranges(cosmo_scratch sc, const cosmo
     }
 }
 
+// correction of the ordered pair (i <- j): exact FP64 term minus the term the FP32 kernel added,
+// replayed instruction for instruction
+__device__ __forceinline__ void near_term(const cosmo_state &st, const cosmo_scratch &sc, const double2 pi, float xis,
+                                          float yis, int j, double unscale, double &cx, double &cy) {
+    const double2 pj = reinterpret_cast<const double2 *>(st.pos)[j];
+    const double dx = pj.x - pi.x, dy = pj.y - pi.y;
+    const double r2 = dx * dx + dy * dy;
+    const float dxs = __fsub_rn(sc.pk_x[j], xis), dys = __fsub_rn(sc.pk_y[j], yis);
+    const float r2s = __fmaf_rn(dys, dys, __fmaf_rn(dxs, dxs, COSMO_F32_TINY_NF));
+    const float rinv = rsqrt_approx_f32(r2s);
+    const float sj = __fmul_rn(sc.pk_m[j], __fmul_rn(__fmul_rn(rinv, rinv), rinv));
+    const double sjd = (double)sj * unscale;
+    // d == 0 keeps the undivided (zero) difference like the reference's where= mask
+    const double w = r2 > 0.0 ? st.mass[j] / (r2 * sqrt(r2)) : 0.0;
+    cx += dx * w - (double)dxs * sjd;
+    cy += dy * w - (double)dys * sjd;
+}
+
+// The order of the planets inside a cell comes from atomics; the corrections are therefore added
+// in ascending partner index -- a fixed order, so the result is reproducible run to run and rank
+// to rank.  Near partners are few (usually none): up to NEAR_KEEP of them are kept sorted in
+// registers; a row with more falls back to repeated "next larger partner" scans.
+constexpr int NEAR_KEEP = 6;
+
 __device__ __forceinline__ void near_row(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_grid *gd, int i,
                                          double unscale) {
     const double2 *pos = reinterpret_cast<const double2 *>(st.pos);
@@ -60,28 +84,45 @@ __device__ __forceinline__ void near_row(const cosmo_state &st, const cosmo_scra
     const double ai = fmax(fabs(pi.x), fabs(pi.y));
     int s0[6], s1[6];
     cand_ranges(sc, sc.cell_of[i], gd->c, s0, s1);
-    double cx = 0.0, cy = 0.0;
+    auto is_near = [&](int j) {
+        const double2 pj = pos[j];
+        const double dx = pj.x - pi.x, dy = pj.y - pi.y;
+        const double rc = NEAR_REL * fmax(ai, fmax(fabs(pj.x), fabs(pj.y)));
+        return j != i && dx * dx + dy * dy < rc * rc;
+    };
+    int keep[NEAR_KEEP], cnt = 0;
 #pragma unroll
     for (int d = 0; d < 6; ++d)
         for (int s = s0[d]; s < s1[d]; ++s) {
             const int j = sc.cell_items[s];
-            const double2 pj = pos[j];
-            const double dx = pj.x - pi.x, dy = pj.y - pi.y;
-            const double r2 = dx * dx + dy * dy;
-            const double rc = NEAR_REL * fmax(ai, fmax(fabs(pj.x), fabs(pj.y)));
-            if (j == i || !(r2 < rc * rc)) continue;
-            // the term the FP32 kernel added for (i <- j), replayed instruction for instruction
-            const float dxs = __fsub_rn(sc.pk_x[j], xis), dys = __fsub_rn(sc.pk_y[j], yis);
-            const float r2s = __fmaf_rn(dys, dys, __fmaf_rn(dxs, dxs, COSMO_F32_TINY_NF));
-            const float rinv = rsqrt_approx_f32(r2s);
-            const float sj = __fmul_rn(sc.pk_m[j], __fmul_rn(__fmul_rn(rinv, rinv), rinv));
-            const double sjd = (double)sj * unscale;
-            // the exact term; d == 0 keeps the undivided (zero) difference like the reference's where= mask
-            const double mj = st.mass[j];
-            const double w = r2 > 0.0 ? mj / (r2 * sqrt(r2)) : 0.0;
-            cx += dx * w - (double)dxs * sjd;
-            cy += dy * w - (double)dys * sjd;
+            if (!is_near(j)) continue;
+            if (cnt < NEAR_KEEP) {          // sorted insert
+                int q = cnt;
+#pragma unroll
+                for (int t = NEAR_KEEP - 1; t > 0; --t)
+                    if (t <= q && keep[t - 1] > j) { keep[t] = keep[t - 1]; q = t - 1; }
+                keep[q] = j;
+            }
+            ++cnt;
         }
+    double cx = 0.0, cy = 0.0;
+    if (cnt <= NEAR_KEEP) {
+#pragma unroll
+        for (int t = 0; t < NEAR_KEEP; ++t)
+            if (t < cnt) near_term(st, sc, pi, xis, yis, keep[t], unscale, cx, cy);
+    } else {
+        for (int prev = -1;;) {             // a crowd: partners in ascending order, one scan each
+            int best = 0x7fffffff;
+            for (int d = 0; d < 6; ++d)
+                for (int s = s0[d]; s < s1[d]; ++s) {
+                    const int j = sc.cell_items[s];
+                    if (j > prev && j < best && is_near(j)) best = j;
+                }
+            if (best == 0x7fffffff) break;
+            near_term(st, sc, pi, xis, yis, best, unscale, cx, cy);
+            prev = best;
+        }
+    }
     reinterpret_cast<double2 *>(sc.corr)[i] = make_double2(cx, cy);
 }
 

@@ -254,6 +254,7 @@ __device__ __forceinline__ long long pair_count(const cosmo_state &st, const cos
 
 __global__ void __launch_bounds__(256) k_csr_count(cosmo_state st, cosmo_scratch sc) {
     const long long M = pair_count(st, sc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st.status[COSMO_ST_N_HEAVY] = 0;   // re-used as the long-row counter
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
         const uint64_t key = sc.pairs[q];
         const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
@@ -273,7 +274,29 @@ __global__ void __launch_bounds__(256) k_csr_fill(cosmo_state st, cosmo_scratch 
     }
 }
 
-// order every row by partner index (rows are short; the owner of the row's first slot sorts it)
+// order every row by partner index: short rows by the owner of the row's first slot (insertion
+// sort), long rows -- the star of a crowded disk is flagged with hundreds of planets -- by a rank
+// sort spread over a whole CTA (k_csr_sort_long_rows)
+constexpr int ROW_LONG = 48;
+
+__global__ void __launch_bounds__(256) k_csr_sort_long_rows(cosmo_state st, cosmo_scratch sc) {
+    const int nlong = (int)st.status[COSMO_ST_N_HEAVY];           // rows listed by k_csr_sort_rows
+    uint64_t *tmp = reinterpret_cast<uint64_t *>(sc.ev_tmp);      // free until the replay kernels
+    for (int r = blockIdx.x; r < nlong; r += gridDim.x) {
+        const int i = sc.cplx_list[r];                            // cplx_list is free until k_scatter_bit(2)
+        const int s0 = sc.row_start[i], s1 = sc.row_start[i + 1];
+        for (int a = s0 + threadIdx.x; a < s1; a += blockDim.x) {
+            const uint64_t key = sc.pairs_sorted[a];
+            int rank = 0;
+            for (int b = s0; b < s1; ++b) rank += sc.pairs_sorted[b] < key;
+            tmp[s0 + rank] = key;
+        }
+        __syncthreads();
+        for (int a = s0 + threadIdx.x; a < s1; a += blockDim.x) sc.pairs_sorted[a] = tmp[a];
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) k_csr_sort_rows(cosmo_state st, cosmo_scratch sc) {
     const long long M = pair_count(st, sc);
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
@@ -281,6 +304,12 @@ __global__ void __launch_bounds__(256) k_csr_sort_rows(cosmo_state st, cosmo_scr
         const int s0 = sc.row_start[i], s1 = sc.row_start[i + 1];
         sc.pair_flag[q] = 0;
         if (q != s0 || s1 - s0 < 2) continue;
+        if (s1 - s0 > ROW_LONG) {      // handed to k_csr_sort_long_rows (N_HEAVY is free after stage B)
+            const unsigned long long r =
+                atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_HEAVY]), 1ull);
+            sc.cplx_list[r] = i;
+            continue;
+        }
         for (int a = s0 + 1; a < s1; ++a) {
             const uint64_t key = sc.pairs_sorted[a];
             int b = a - 1;
@@ -774,6 +803,8 @@ int launch_resolve_commit(const cosmo_state &st, const cosmo_scratch &sc, const 
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_csr_fill"));
         k_csr_sort_rows<<<pb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_csr_sort_rows"));
+        k_csr_sort_long_rows<<<pb, 256, 0, s>>>(st, sc);
+        COSMO_TRY(COSMO_LAUNCH_CHECK("k_csr_sort_long_rows"));
         k_resolve_simple<<<pb, 256, 0, s>>>(st, sc);
         COSMO_TRY(COSMO_LAUNCH_CHECK("k_resolve_simple"));
         k_mark_bit<<<pb, 256, 0, s>>>(st, sc, 2);

@@ -688,7 +688,10 @@ __device__ __forceinline__ int uf_find3(int *parent, int v) {
 
 __global__ void __launch_bounds__(256) k3p_count(cosmo3_state st, cosmo3_scratch sc) {
     const long long M = pair_count3(st, sc);
-    if (blockIdx.x == 0 && threadIdx.x == 0) st.status[COSMO_ST_N_DEAD] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st.status[COSMO_ST_N_DEAD] = 0;
+        st.status[COSMO_ST_N_HEAVY] = 0;      // re-used as the long-row counter of k3p_sort_rows
+    }
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < M; q += (long long)gridDim.x * blockDim.x) {
         const uint64_t key = sc.pairs[q];
         const int i = (int)(key >> 32), j = (int)(key & 0xffffffffu);
@@ -718,7 +721,13 @@ __global__ void __launch_bounds__(256) k3p_sort_rows(cosmo3_state st, cosmo3_scr
         const int i = (int)(sc.pairs_sorted[q] >> 32);
         const int s0 = sc.row_start[i], s1 = sc.row_start[i + 1];
         sc.pair_flag[q] = 0;
-        if (q != s0 || s1 - s0 < 2 || s1 - s0 > ROW_LONG) continue;
+        if (q != s0 || s1 - s0 < 2) continue;
+        if (s1 - s0 > ROW_LONG) {      // handed to k3p_sort_long_rows (N_HEAVY is free after stage B)
+            const unsigned long long r =
+                atomicAdd(reinterpret_cast<unsigned long long *>(&st.status[COSMO_ST_N_HEAVY]), 1ull);
+            sc.comp_items[r] = i;
+            continue;
+        }
         for (int a = s0 + 1; a < s1; ++a) {
             const uint64_t key = sc.pairs_sorted[a];
             int b = a - 1;
@@ -734,11 +743,10 @@ __global__ void __launch_bounds__(256) k3p_sort_rows(cosmo3_state st, cosmo3_scr
 // long rows: CTA b takes the rows i = b, b + gridDim.x, ...; ranks are counted against the row itself
 // and the sorted row is staged in `pairs` (free after k3p_fill) before it is copied back
 __global__ void __launch_bounds__(256) k3p_sort_long_rows(cosmo3_state st, cosmo3_scratch sc) {
-    const int n = (int)st.status[COSMO_ST_N_ACTIVE];
-    if (pair_count3(st, sc) <= ROW_LONG) return;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int nlong = (int)st.status[COSMO_ST_N_HEAVY];          // rows listed by k3p_sort_rows
+    for (int r = blockIdx.x; r < nlong; r += gridDim.x) {
+        const int i = sc.comp_items[r];                          // comp_items is free until k3p_comp_fill
         const int s0 = sc.row_start[i], s1 = sc.row_start[i + 1];
-        if (s1 - s0 <= ROW_LONG) continue;
         for (int a = s0 + threadIdx.x; a < s1; a += blockDim.x) {
             const uint64_t key = sc.pairs_sorted[a];
             int rank = 0;

@@ -104,7 +104,7 @@ class Engine(BoundTracker):
         # scratch
         t["h"] = z(cap, dtype=f64)
         t["pk_x"] = z(cap, dtype=f32); t["pk_y"] = z(cap, dtype=f32); t["pk_m"] = z(cap, dtype=f32)
-        t["acc"] = z(cap, 2, dtype=f64)
+        t["acc"] = z(2 * cap, 2, dtype=f64)    # [n][2]; [n][4] while a sharded FP32 frame all-reduces (sum, correction)
         # pos_new | vel_new | xx_new live in one allocation so the sharded mode gathers once
         t["new"] = z(cap, 5, dtype=f64)
         t["rinf"] = z(cap, dtype=f64)
@@ -363,7 +363,8 @@ class Engine(BoundTracker):
                   (OPT_DEFER_INTEGRATE if ((sym or sym64) and self.world > 1) else 0) | (OPT_ENERGY if energy else 0))
         if (sym or sym64) and self.world > 1:
             from . import sharded
-            if sharded.setup_peer_exchange(self):
+            near_on = fp32 and (self.near_field if near is None else near)
+            if not near_on and sharded.setup_peer_exchange(self):   # (the experimental peer exchange carries no corrections)
                 p.opts |= _abi.OPT_PEER_EXCHANGE      # sharded.frame points scratch.peer_acc at the frame's parity
         if self.sym_chunk or not (sym or sym64):
             p.sym_chunk = int(self.sym_chunk)

@@ -152,7 +152,9 @@ typedef struct cosmo_scratch {
     float *pk_x;       /* [cap]      FP32 j-stage (scaled x, y, mass) */
     float *pk_y;       /* [cap] */
     float *pk_m;       /* [cap] */
-    double *acc;       /* [cap][2]   accelerations of the last frame (COSMO_OPT_STORE_ACC) */
+    double *acc;       /* [cap][4]   accelerations of the last frame as [n][2] (COSMO_OPT_STORE_ACC); sharded FP32
+                                     frames with near_mode != 0 pass (sum, near-field correction) rows [n][4]
+                                     through it between cosmo_accel_integrate and cosmo_integrate */
     double *pos_new;   /* [cap][2]   integrated positions of ALL active planets (A2) */
     double *vel_new;   /* [cap][2] */
     double *xx_new;    /* [cap]      squared row norms of pos_new (A3) */
