@@ -74,7 +74,7 @@ class StepParams(C.Structure):
                 ("opts", C.c_uint32), ("n_upper", C.c_int32), ("i_begin", C.c_int32),
                 ("i_end", C.c_int32), ("pos_exp", C.c_int32), ("mass_exp", C.c_int32),
                 ("jsplit", C.c_int32), ("detect_mode", C.c_int32), ("resolve_mode", C.c_int32),
-                ("small_tiles", C.c_int32), ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("sym_chunk", C.c_int32), ("near_mode", C.c_int32), ("reserved2", C.c_int32), ("reserved1", C.c_int32),
+                ("small_tiles", C.c_int32), ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("sym_chunk", C.c_int32), ("near_mode", C.c_int32), ("sym_rows", C.c_int32), ("reserved1", C.c_int32),
                 ("cell_size", C.c_double),
                 ("grid_origin_x", C.c_double), ("grid_origin_y", C.c_double), ("cells_per_side", C.c_int32), ("jsplit_detect", C.c_int32),
                 ("giant_radius", C.c_double)]

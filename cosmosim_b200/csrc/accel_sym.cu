@@ -15,12 +15,13 @@
 // planet of the group and the accumulators are back in their home lane.  Per step and lane:
 // 4 x 4 pairs = 96 FFMA2-class instructions + 16 MUFU.RSQ + 3 LDS.128 + 8 SHFL.
 //
-// The column sums of a (I, J) pair go to colbuf[I][j] (float2); the row sums to partial[chunk][i]
-// (double2).  k_sym_reduce adds, for every planet, its row partials and the column partials of
-// all I < K in ascending order -- deterministic -- and runs the integrator epilogue.  The
-// diagonal pair (J == I) runs the same schedule without the column side, which evaluates each
-// of its ordered pairs exactly once.  HBM: colbuf is written and read once per frame
-// (8 B x N^2 / 2048: 4.3 GB at N = 2^20, ~1 ms of the 180 GB part's bandwidth).
+// A CTA serves R (1, 2 or 4) row blocks against its column chunk (super tile, see the kernel): the
+// column sums of a column block J over those row blocks go to colbuf[super row][j] (float2); the row
+// sums to partial[chunk][i] (double2).  k_sym_reduce adds, for every planet, its row partials and
+// the column partials of all super rows below it in ascending order -- deterministic, no atomics --
+// and runs the integrator epilogue.  The diagonal pair (J == I) runs the same schedule without the
+// column side, which evaluates each of its ordered pairs exactly once.  HBM: colbuf is written and
+// read once per frame, 8 B x N^2 / (2048 R): 1.1 GB at N = 2^20 with R = 4.
 #include <math.h>
 
 #include "cosmo_device.cuh"
@@ -53,6 +54,12 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src_lane) {
     return ((uint64_t)hi << 32) | lo;
 }
 
+// Super-tile: a CTA serves R consecutive local row blocks (rows I_0 < I_1 < ... ) against one chunk
+// of column blocks.  A column tile is fetched ONCE for all R row blocks and its column sums are
+// accumulated over them in shared memory before they go to colbuf -- one colbuf row per SUPER row,
+// so the column-partial traffic (the only sizeable DRAM traffic of the pass) and the buffer itself
+// shrink by R.  The row sums of the R blocks live in shared memory as doubles for the CTA's lifetime.
+template <int R>
 __global__ void __launch_bounds__(SYM_THREADS, 2)
 k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int chunk) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -61,32 +68,26 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
     float (*s_m)[SYM_BLOCK] = s_x + 4;
     // column accumulators of the current J: [x|y][1024]
     float (*s_c)[SYM_BLOCK] = s_x + 6;
-    __shared__ __align__(8) uint64_t s_bar[2];
+    // staging of the NEXT row block's (x, y, m), fetched by TMA while the current block pair runs
+    float (*s_r)[SYM_BLOCK] = s_x + 8;
+    // FP64 row sums of the R row blocks: [r][1024] (x, y)
+    double2 (*s_row)[SYM_BLOCK] = reinterpret_cast<double2 (*)[SYM_BLOCK]>(s_x + 11);
+    __shared__ __align__(8) uint64_t s_bar[2], s_rbar;
 
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int nblk = (n + SYM_BLOCK - 1) / SYM_BLOCK;
-    const int I = sym_row_of(blockIdx.x, shard_index, shard_count);
-    if (I >= nblk) return;
-    const int J0 = I + blockIdx.y * chunk;
+    const int I_first = sym_row_of(blockIdx.x * R, shard_index, shard_count);
+    if (I_first >= nblk) return;
+    const int J0 = I_first + blockIdx.y * chunk;
     if (J0 >= nblk) return;
     const int J1 = min(nblk, J0 + chunk);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 
-    // row side: 4 planets per lane, strided by 32 inside the warp's group (coalesced)
-    float xi[4], yi[4], nmi[4];
-    double rax[4], ray[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int r = I * SYM_BLOCK + w * SYM_GROUP + k * 32 + lane;
-        xi[k] = sc.pk_x[r];
-        yi[k] = sc.pk_y[r];
-        nmi[k] = -sc.pk_m[r];
-        rax[k] = 0.0; ray[k] = 0.0;
-    }
-
+    for (int q = tid; q < R * SYM_BLOCK; q += SYM_THREADS) s_row[0][q] = make_double2(0.0, 0.0);
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
+        mbar_init(&s_rbar, 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -99,11 +100,20 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
         bulk_g2s(&s_y[b][0], sc.pk_y + j0, SYM_BLOCK * sizeof(float), &s_bar[b]);
         bulk_g2s(&s_m[b][0], sc.pk_m + j0, SYM_BLOCK * sizeof(float), &s_bar[b]);
     };
-    if (tid == 0) issue(J0, 0);
+    auto issue_rows = [&](int I) {
+        const size_t i0 = (size_t)I * SYM_BLOCK;
+        fence_proxy_async();
+        mbar_expect_tx(&s_rbar, kBytes);
+        bulk_g2s(&s_r[0][0], sc.pk_x + i0, SYM_BLOCK * sizeof(float), &s_rbar);
+        bulk_g2s(&s_r[1][0], sc.pk_y + i0, SYM_BLOCK * sizeof(float), &s_rbar);
+        bulk_g2s(&s_r[2][0], sc.pk_m + i0, SYM_BLOCK * sizeof(float), &s_rbar);
+    };
+    if (tid == 0) { issue(J0, 0); issue_rows(I_first); }
+    uint32_t row_loads = 0;      // row blocks consumed so far: parity of the staging barrier
 
     const uint64_t eps2 = pack2(COSMO_F32_TINY_SYM, COSMO_F32_TINY_SYM);
     float2 *colbuf = reinterpret_cast<float2 *>(sc.colbuf);
-    const size_t col_row = (size_t)blockIdx.x * (size_t)st.cap;   // local row-block index of this rank
+    const size_t col_row = (size_t)blockIdx.x * (size_t)st.cap;   // local super-row index of this rank
 
     for (int J = J0; J < J1; ++J) {
         const int it_j = J - J0;
@@ -112,85 +122,118 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
         for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) { s_c[0][q] = 0.f; s_c[1][q] = 0.f; }
         mbar_wait(&s_bar[b], (it_j >> 1) & 1);
         __syncthreads();
-        const bool diag = (J == I);
-        uint64_t rx2[4], ry2[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { rx2[k] = 0ull; ry2[k] = 0ull; }
+        bool any_col = false;
 
-        for (int it = 0; it < SYM_WARPS; ++it) {
-            const int g = (w + it) & (SYM_WARPS - 1);
-            const float *gx = &s_x[b][g * SYM_GROUP];
-            const float *gy = &s_y[b][g * SYM_GROUP];
-            const float *gm = &s_m[b][g * SYM_GROUP];
-            uint64_t tx2[2] = {0ull, 0ull}, ty2[2] = {0ull, 0ull};   // travelling column sums
+#pragma unroll 1
+        for (int r = 0; r < R; ++r) {
+            const int I = sym_row_of(blockIdx.x * R + r, shard_index, shard_count);
+            if (I >= nblk || I > J) break;         // rows are ascending: the rest lies beyond this column block
+            const bool diag = (J == I);
+            any_col = any_col || !diag;
+            // row side: 4 planets per lane, strided by 32 inside the warp's group, from the staging
+            // buffer the TMA engine filled during the previous block pair
+            float xi[4], yi[4], nmi[4];
+            mbar_wait(&s_rbar, row_loads & 1);
+            ++row_loads;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int q = w * SYM_GROUP + k * 32 + lane;
+                xi[k] = s_r[0][q];
+                yi[k] = s_r[1][q];
+                nmi[k] = -s_r[2][q];
+            }
+            uint64_t rx2[4], ry2[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { rx2[k] = 0ull; ry2[k] = 0ull; }
+
+            for (int it = 0; it < SYM_WARPS; ++it) {
+                const int g = (w + it) & (SYM_WARPS - 1);
+                const float *gx = &s_x[b][g * SYM_GROUP];
+                const float *gy = &s_y[b][g * SYM_GROUP];
+                const float *gm = &s_m[b][g * SYM_GROUP];
+                uint64_t tx2[2] = {0ull, 0ull}, ty2[2] = {0ull, 0ull};   // travelling column sums
 #pragma unroll 2
-            for (int s = 0; s < 32; ++s) {
-                const int c = (lane + s) & 31;
-                const float4 X = *reinterpret_cast<const float4 *>(gx + 4 * c);
-                const float4 Y = *reinterpret_cast<const float4 *>(gy + 4 * c);
-                const float4 M = *reinterpret_cast<const float4 *>(gm + 4 * c);
-                const uint64_t xj2[2] = {pack2(X.x, X.y), pack2(X.z, X.w)};
-                const uint64_t yj2[2] = {pack2(Y.x, Y.y), pack2(Y.z, Y.w)};
-                const uint64_t mj2[2] = {pack2(M.x, M.y), pack2(M.z, M.w)};
+                for (int s = 0; s < 32; ++s) {
+                    const int c = (lane + s) & 31;
+                    const float4 X = *reinterpret_cast<const float4 *>(gx + 4 * c);
+                    const float4 Y = *reinterpret_cast<const float4 *>(gy + 4 * c);
+                    const float4 M = *reinterpret_cast<const float4 *>(gm + 4 * c);
+                    const uint64_t xj2[2] = {pack2(X.x, X.y), pack2(X.z, X.w)};
+                    const uint64_t yj2[2] = {pack2(Y.x, Y.y), pack2(Y.z, Y.w)};
+                    const uint64_t mj2[2] = {pack2(M.x, M.y), pack2(M.z, M.w)};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t xik = pack2(xi[k], xi[k]), yik = pack2(yi[k], yi[k]);
-                    const uint64_t nmik = pack2(nmi[k], nmi[k]);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t xik = pack2(xi[k], xi[k]), yik = pack2(yi[k], yi[k]);
+                        const uint64_t nmik = pack2(nmi[k], nmi[k]);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint64_t dx = sub2(xj2[h], xik);
-                        const uint64_t dy = sub2(yj2[h], yik);
-                        const uint64_t r2 = fma2(dy, dy, fma2(dx, dx, eps2));
-                        float r2a, r2b;
-                        unpack2(r2, r2a, r2b);
-                        const uint64_t rinv = pack2(rsqrt_approx_f32(r2a), rsqrt_approx_f32(r2b));
-                        const uint64_t rinv3 = mul2(mul2(rinv, rinv), rinv);
-                        const uint64_t sj = mul2(mj2[h], rinv3);     // pull of the column planets on row k
-                        const uint64_t nsi = mul2(rinv3, nmik);      // minus the pull of row k on them
-                        rx2[k] = fma2(dx, sj, rx2[k]);
-                        ry2[k] = fma2(dy, sj, ry2[k]);
-                        tx2[h] = fma2(dx, nsi, tx2[h]);
-                        ty2[h] = fma2(dy, nsi, ty2[h]);
+                        for (int h = 0; h < 2; ++h) {
+                            const uint64_t dx = sub2(xj2[h], xik);
+                            const uint64_t dy = sub2(yj2[h], yik);
+                            const uint64_t r2 = fma2(dy, dy, fma2(dx, dx, eps2));
+                            float r2a, r2b;
+                            unpack2(r2, r2a, r2b);
+                            const uint64_t rinv = pack2(rsqrt_approx_f32(r2a), rsqrt_approx_f32(r2b));
+                            const uint64_t rinv3 = mul2(mul2(rinv, rinv), rinv);
+                            const uint64_t sj = mul2(mj2[h], rinv3);     // pull of the column planets on row k
+                            const uint64_t nsi = mul2(rinv3, nmik);      // minus the pull of row k on them
+                            rx2[k] = fma2(dx, sj, rx2[k]);
+                            ry2[k] = fma2(dy, sj, ry2[k]);
+                            tx2[h] = fma2(dx, nsi, tx2[h]);
+                            ty2[h] = fma2(dy, nsi, ty2[h]);
+                        }
                     }
+                    // hand the chunk's column sums to the lane that meets this chunk next
+                    const int src = (lane + 1) & 31;
+                    tx2[0] = shfl64(tx2[0], src); tx2[1] = shfl64(tx2[1], src);
+                    ty2[0] = shfl64(ty2[0], src); ty2[1] = shfl64(ty2[1], src);
                 }
-                // hand the chunk's column sums to the lane that meets this chunk next
-                const int src = (lane + 1) & 31;
-                tx2[0] = shfl64(tx2[0], src); tx2[1] = shfl64(tx2[1], src);
-                ty2[0] = shfl64(ty2[0], src); ty2[1] = shfl64(ty2[1], src);
+                if (!diag) {   // home again: lane l holds the sums of chunk l of group g
+                    float a0, a1, a2, a3, b0, b1, b2, b3;
+                    unpack2(tx2[0], a0, a1); unpack2(tx2[1], a2, a3);
+                    unpack2(ty2[0], b0, b1); unpack2(ty2[1], b2, b3);
+                    float4 cx = *reinterpret_cast<float4 *>(&s_c[0][g * SYM_GROUP + 4 * lane]);
+                    float4 cy = *reinterpret_cast<float4 *>(&s_c[1][g * SYM_GROUP + 4 * lane]);
+                    cx.x += a0; cx.y += a1; cx.z += a2; cx.w += a3;
+                    cy.x += b0; cy.y += b1; cy.z += b2; cy.w += b3;
+                    *reinterpret_cast<float4 *>(&s_c[0][g * SYM_GROUP + 4 * lane]) = cx;
+                    *reinterpret_cast<float4 *>(&s_c[1][g * SYM_GROUP + 4 * lane]) = cy;
+                }
+                __syncthreads();   // the next round moves every warp to another column group
+                if (it == 0 && tid == 0) {
+                    // every warp has its rows in registers: fetch the row block of the NEXT block pair
+                    const int In = r + 1 < R ? sym_row_of(blockIdx.x * R + r + 1, shard_index, shard_count) : nblk;
+                    if (In < nblk && In <= J) issue_rows(In);
+                    else if (J + 1 < J1) issue_rows(I_first);
+                }
             }
-            if (!diag) {   // home again: lane l holds the sums of chunk l of group g
-                float a0, a1, a2, a3, b0, b1, b2, b3;
-                unpack2(tx2[0], a0, a1); unpack2(tx2[1], a2, a3);
-                unpack2(ty2[0], b0, b1); unpack2(ty2[1], b2, b3);
-                float4 cx = *reinterpret_cast<float4 *>(&s_c[0][g * SYM_GROUP + 4 * lane]);
-                float4 cy = *reinterpret_cast<float4 *>(&s_c[1][g * SYM_GROUP + 4 * lane]);
-                cx.x += a0; cx.y += a1; cx.z += a2; cx.w += a3;
-                cy.x += b0; cy.y += b1; cy.z += b2; cy.w += b3;
-                *reinterpret_cast<float4 *>(&s_c[0][g * SYM_GROUP + 4 * lane]) = cx;
-                *reinterpret_cast<float4 *>(&s_c[1][g * SYM_GROUP + 4 * lane]) = cy;
-            }
-            __syncthreads();   // the next round moves every warp to another column group
-        }
-        // fold this block's FP32 row sums into the FP64 accumulators
+            // fold this block pair's FP32 row sums into the FP64 row sums (each lane owns its rows)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float a, c2;
-            unpack2(rx2[k], a, c2);
-            rax[k] += (double)a + (double)c2;
-            unpack2(ry2[k], a, c2);
-            ray[k] += (double)a + (double)c2;
+            for (int k = 0; k < 4; ++k) {
+                float ax, ax2, ay, ay2;
+                unpack2(rx2[k], ax, ax2);
+                unpack2(ry2[k], ay, ay2);
+                double2 &acc = s_row[r][w * SYM_GROUP + k * 32 + lane];
+                acc.x += (double)ax + (double)ax2;
+                acc.y += (double)ay + (double)ay2;
+            }
         }
-        if (!diag) {
+        if (any_col) {   // column sums of this block over the R row blocks: one colbuf row per super row
             float2 *dst = colbuf + col_row + (size_t)J * SYM_BLOCK;
             for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) dst[q] = make_float2(s_c[0][q], s_c[1][q]);
         }
         __syncthreads();   // column accumulators and buffer b are free again
     }
+    // row partials of every row block that met a column block of this chunk (I < J1)
     double2 *partial = reinterpret_cast<double2 *>(sc.partial);
+#pragma unroll 1
+    for (int r = 0; r < R; ++r) {
+        const int I = sym_row_of(blockIdx.x * R + r, shard_index, shard_count);
+        if (I >= nblk || I >= J1) break;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int r = I * SYM_BLOCK + w * SYM_GROUP + k * 32 + lane;
-        partial[(size_t)blockIdx.y * st.cap + r] = make_double2(rax[k], ray[k]);
+        for (int k = 0; k < 4; ++k) {
+            const int q = w * SYM_GROUP + k * 32 + lane;
+            partial[(size_t)blockIdx.y * st.cap + (size_t)I * SYM_BLOCK + q] = s_row[r][q];
+        }
     }
 }
 
@@ -198,7 +241,7 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
 // integrator epilogue (accel.cu).  With `defer` the per-rank sum goes to scratch.acc instead
 // (multi-GPU: all-reduced by the caller, then k_sym_integrate).
 __global__ void __launch_bounds__(256)
-k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int chunk, double unscale,
+k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int chunk, int R, double unscale,
              double G, double dt, int store_acc, int defer, int near) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,37 +250,32 @@ k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count,
     const int K = k / SYM_BLOCK;
     double ax = 0.0, ay = 0.0;
     if (sym_owns(K, shard_index, shard_count)) {
+        // the chunks of K's super row start at its first row block: K is met by the chunks from
+        // (K - I_first) / chunk on
         const double2 *partial = reinterpret_cast<const double2 *>(sc.partial);
-        const int nchunk = (nblk - K + chunk - 1) / chunk;
-        for (int c = 0; c < nchunk; ++c) {
+        const int I_first = sym_row_of((K / shard_count) / R * R, shard_index, shard_count);
+        const int nchunk = (nblk - I_first + chunk - 1) / chunk;
+        for (int c = (K - I_first) / chunk; c < nchunk; ++c) {
             const double2 v = partial[(size_t)c * st.cap + k];
             ax += v.x;
             ay += v.y;
         }
     }
     const float2 *colbuf = reinterpret_cast<const float2 *>(sc.colbuf);
-    // row blocks I < K owned by this rank, in ascending order (local row r holds block sym_row_of(r))
-    for (int r = 0; sym_row_of(r, shard_index, shard_count) < K; ++r) {
+    // super rows of this rank with a row block below K, in ascending order (super row r starts at
+    // block sym_row_of(r * R)); each holds the column sums of its row blocks I < K
+    for (int r = 0; sym_row_of(r * R, shard_index, shard_count) < K; ++r) {
         const float2 v = __ldcs(&colbuf[(size_t)r * st.cap + k]);
         ax += (double)v.x;
         ay += (double)v.y;
     }
     ax *= unscale;
     ay *= unscale;
-    // FP64 near-field corrections of the rows this rank evaluated (nearfield.cu; zero elsewhere)
-    double2 c = make_double2(0.0, 0.0);
-    if (near) c = reinterpret_cast<const double2 *>(sc.corr)[k];
-    if (defer == 1 && near) {
-        // Sharded: the FP32-sourced sums and the corrections travel SEPARATELY through the all-reduce.
-        // Sums of FP32 values in FP64 are exact (no rounding) and a correction comes from exactly one
-        // rank, so both reductions are independent of the partition; k_sym_integrate then adds them
-        // once -- the same single rounding as on one GPU.  That keeps a sharded run on the very
-        // trajectory of the single-GPU run instead of 1 ulp beside it (the scene is chaotic).
-        reinterpret_cast<double4 *>(sc.acc)[k] = make_double4(ax, ay, c.x, c.y);
-        return;
+    if (near) {   // FP64 near-field corrections of the rows this rank evaluated (nearfield.cu; zero elsewhere)
+        const double2 c = reinterpret_cast<const double2 *>(sc.corr)[k];
+        ax += c.x;
+        ay += c.y;
     }
-    ax += c.x;
-    ay += c.y;
     if (defer == 2) {
         // peer exchange: this rank's partial sums go straight into slot `shard_index` of every
         // rank's exchange buffer (NVLink peer stores, coalesced 16 B per lane)
@@ -252,7 +290,7 @@ k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count,
 }
 
 __global__ void __launch_bounds__(256)
-k_sym_integrate(cosmo_state st, cosmo_scratch sc, double G, double dt, int peer, int self, int near) {
+k_sym_integrate(cosmo_state st, cosmo_scratch sc, double G, double dt, int peer, int self) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -265,15 +303,28 @@ k_sym_integrate(cosmo_state st, cosmo_scratch sc, double G, double dt, int peer,
             a.x += v.x;
             a.y += v.y;
         }
-    } else if (near) {
-        const double4 v = reinterpret_cast<const double4 *>(sc.acc)[k];   // (sum, near-field correction)
-        a = make_double2(v.x + v.z, v.y + v.w);
     } else {
         a = reinterpret_cast<const double2 *>(sc.acc)[k];
     }
-    // sc.acc holds the all-reduced sums S; the planets' accelerations G S go to pos_new / vel_new.  (With
-    // `near` the four-wide rows of acc are still being read by other threads: acc is not rewritten.)
-    integrate_store(st, sc, k, a.x, a.y, G, dt, !near);
+    // sc.acc holds the all-reduced sums S; integrate_store multiplies by G and rewrites acc = G S
+    integrate_store(st, sc, k, a.x, a.y, G, dt, true);
+}
+
+template <int R>
+static int launch_sym_kernel(const cosmo_state &st, const cosmo_scratch &sc, dim3 grid, int sh_i, int sh_n, int chunk,
+                             cudaStream_t s) {
+    constexpr size_t kTma = 6 * SYM_BLOCK * sizeof(float);                 // x, y, m double-buffered
+    constexpr size_t kShared = kTma + 2 * SYM_BLOCK * sizeof(float)        // + the column accumulators
+                               + 3 * SYM_BLOCK * sizeof(float)             // + the staging of the next row block
+                               + (size_t)R * SYM_BLOCK * sizeof(double2);  // + the FP64 row sums of R row blocks
+    static bool attr_set = false;
+    if (!attr_set) {   // R = 4: 108 KB of dynamic shared memory (two CTAs per SM)
+        COSMO_TRY(check_cuda(cudaFuncSetAttribute(k_accel_f32_sym<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)kShared), "cudaFuncSetAttribute(k_accel_f32_sym)"));
+        attr_set = true;
+    }
+    k_accel_f32_sym<R><<<grid, SYM_THREADS, kShared, s>>>(st, sc, sh_i, sh_n, chunk);
+    return COSMO_LAUNCH_CHECK("k_accel_f32_sym");
 }
 
 int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
@@ -287,20 +338,24 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
     if (sym_row_of(rows_local, sh_i, sh_n) < nblk) ++rows_local;
     int chunk = p.sym_chunk > 0 ? p.sym_chunk : 32;
     while ((nblk + chunk - 1) / chunk > sc.jsplit_max) ++chunk;
-    if (!sc.colbuf || (long long)rows_local > sc.colbuf_rows) {
-        set_error("symmetric accel: colbuf has %lld rows, %d needed", (long long)sc.colbuf_rows, rows_local);
+    // row blocks per CTA: p.sym_rows, raised if the column-partial buffer is too small for it
+    int R = p.sym_rows >= 4 ? 4 : (p.sym_rows >= 2 ? 2 : 1);
+    if (sc.colbuf_rows > 0)
+        while (R < 4 && (rows_local + R - 1) / R > sc.colbuf_rows) R *= 2;
+    const int super_rows = (rows_local + R - 1) / R;
+    if (!sc.colbuf || (long long)super_rows > sc.colbuf_rows) {
+        set_error("symmetric accel: colbuf has %lld rows, %d needed", (long long)sc.colbuf_rows, super_rows);
         return COSMO_E_ARG;
     }
     const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
     if (rows_local > 0) {
-        dim3 grid(rows_local, (nblk + chunk - 1) / chunk);
-        constexpr size_t kTma = 6 * SYM_BLOCK * sizeof(float);                 // x, y, m double-buffered
-        constexpr size_t kShared = kTma + 2 * SYM_BLOCK * sizeof(float);       // + the column accumulators
-        k_accel_f32_sym<<<grid, SYM_THREADS, kShared, s>>>(st, sc, sh_i, sh_n, chunk);
-        COSMO_TRY(COSMO_LAUNCH_CHECK("k_accel_f32_sym"));
+        dim3 grid(super_rows, (nblk + chunk - 1) / chunk);
+        if (R == 4) COSMO_TRY(launch_sym_kernel<4>(st, sc, grid, sh_i, sh_n, chunk, s));
+        else if (R == 2) COSMO_TRY(launch_sym_kernel<2>(st, sc, grid, sh_i, sh_n, chunk, s));
+        else COSMO_TRY(launch_sym_kernel<1>(st, sc, grid, sh_i, sh_n, chunk, s));
     }
     const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? ((p.opts & COSMO_OPT_PEER_EXCHANGE) ? 2 : 1) : 0;
-    k_sym_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, unscale, p.G, p.dt,
+    k_sym_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, R, unscale, p.G, p.dt,
                                                  (p.opts & COSMO_OPT_STORE_ACC) ? 1 : 0, defer, p.near_mode != 0);
     return COSMO_LAUNCH_CHECK("k_sym_reduce");
 }
@@ -313,8 +368,7 @@ int launch_sym_integrate(const cosmo_state &st, const cosmo_scratch &sc, const c
         set_error("peer exchange: n_peers=%d, rank %d", sc.n_peers, p.shard_index);
         return COSMO_E_ARG;
     }
-    const int near = (!peer && (p.opts & COSMO_OPT_FP32) && p.near_mode != 0) ? 1 : 0;
-    k_sym_integrate<<<(p.n_upper + 255) / 256, 256, 0, s>>>(st, sc, p.G, p.dt, peer, p.shard_index, near);
+    k_sym_integrate<<<(p.n_upper + 255) / 256, 256, 0, s>>>(st, sc, p.G, p.dt, peer, p.shard_index);
     return COSMO_LAUNCH_CHECK("k_sym_integrate");
 }
 

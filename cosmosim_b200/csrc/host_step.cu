@@ -29,7 +29,7 @@ Sizes sizes_for(int n_total, uint32_t opts) {
     z.grid_cells = 8LL * z.cap > (1 << 16) ? 8LL * z.cap : (1 << 16);
     if (z.grid_cells > (long long)COSMO_SCAN_BLOCKS * 4096 - 1) z.grid_cells = (long long)COSMO_SCAN_BLOCKS * 4096 - 1;
     z.colbuf_rows = 0;
-    if (opts & COSMO_OPT_F32_SYM) z.colbuf_rows = z.cap / 1024;
+    if (opts & COSMO_OPT_F32_SYM) z.colbuf_rows = (z.cap / 1024 + 3) / 4 + 1;   // super rows of four row blocks
     if (opts & COSMO_OPT_F64_SYM) z.colbuf_rows = 2LL * (z.cap / 512) > z.colbuf_rows ? 2LL * (z.cap / 512) : z.colbuf_rows;
     return z;
 }
@@ -66,7 +66,7 @@ void carve(int n_total, uint32_t opts, char *base, cosmo_state *st, cosmo_scratc
     s.rec_death = w.take<int32_t>(nt); s.rec_flags = w.take<uint8_t>(nt);
     s.events = w.take<int64_t>(3 * z.event_cap);
     c.h = w.take<double>(cap); c.pk_x = w.take<float>(cap); c.pk_y = w.take<float>(cap); c.pk_m = w.take<float>(cap);
-    c.acc = w.take<double>(4 * cap);
+    c.acc = w.take<double>(2 * cap);
     c.pos_new = w.take<double>(2 * cap); c.vel_new = w.take<double>(2 * cap); c.xx_new = w.take<double>(cap);
     c.rinf = w.take<double>(cap);
     c.partial = w.take<double>((long long)kJsplitMax * 2 * cap); c.jsplit_max = kJsplitMax;
@@ -164,7 +164,7 @@ int cosmo_params_default(int32_t n, double G, double dt, double r_max, uint32_t 
     opts &= ~(COSMO_OPT_F32_SYM | COSMO_OPT_F64_SYM | COSMO_OPT_DEFER_INTEGRATE | COSMO_OPT_PEER_EXCHANGE);
     const long long nblk32 = (n + 1023) / 1024, nblk64 = (n + 511) / 512;
     bool sym = false;
-    if (fp32 && n >= 32768 && sc && sc->colbuf && sc->colbuf_rows >= nblk32) { opts |= COSMO_OPT_F32_SYM; sym = true; }
+    if (fp32 && n >= 32768 && sc && sc->colbuf && sc->colbuf_rows >= (nblk32 + 3) / 4) { opts |= COSMO_OPT_F32_SYM; sym = true; }
     if (!fp32 && n >= 16384 && sc && sc->colbuf && sc->colbuf_rows >= 2 * nblk64) { opts |= COSMO_OPT_F64_SYM; sym = true; }
     p->opts = opts;
     {   // FP32 path: exact power-of-two rescaling, max |coordinate| -> [32, 64), max mass -> [2^19, 2^20)
@@ -183,9 +183,14 @@ int cosmo_params_default(int32_t n, double G, double dt, double r_max, uint32_t 
     if (sym) {
         int sms = 148, dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        // ~16 CTAs per resident slot; FP32: as many row blocks per CTA as that allows (1, 2 or 4)
         const long long nblk = fp32 ? nblk32 : nblk64;
         long long want = nblk > 1 ? (nblk * nblk) / (2LL * 16 * 2 * sms) : 1;
-        long long lo = (nblk + jmax - 1) / jmax;
+        const long long lo = (nblk + jmax - 1) / jmax;
+        if (fp32) {
+            p->sym_rows = want >= 16 ? 4 : (want >= 4 ? 2 : 1);
+            want /= p->sym_rows;
+        }
         long long chunk = want < lo ? lo : want;
         p->sym_chunk = (int32_t)(chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk));   // the launcher raises it if partial rows run out
     } else if (n > 0) {

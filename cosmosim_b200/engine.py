@@ -76,7 +76,8 @@ class Engine(BoundTracker):
         self.small_threshold = 4096  # below: small-N kernel shape (more, shorter CTAs)
         self.sym_threshold = 32768   # FP32: from here on the symmetric kernel (each pair once) wins
         self.sym64_threshold = 16384  # FP64: same for the symmetric FP64 kernel
-        self.sym_chunk = 0           # column blocks per CTA of the symmetric kernel (0 = library default)
+        self.sym_chunk = 0           # column blocks per CTA of the symmetric kernel (0 = automatic)
+        self.sym_rows = 0            # row blocks per CTA of the symmetric FP32 kernel (0 = automatic)
         self.use_graphs = True      # small N: replay a captured CUDA graph of the frame (launch-bound regime)
         self.graph_threshold = 16384
         self._graphs = {}
@@ -104,7 +105,7 @@ class Engine(BoundTracker):
         # scratch
         t["h"] = z(cap, dtype=f64)
         t["pk_x"] = z(cap, dtype=f32); t["pk_y"] = z(cap, dtype=f32); t["pk_m"] = z(cap, dtype=f32)
-        t["acc"] = z(2 * cap, 2, dtype=f64)    # [n][2]; [n][4] while a sharded FP32 frame all-reduces (sum, correction)
+        t["acc"] = z(cap, 2, dtype=f64)
         # pos_new | vel_new | xx_new live in one allocation so the sharded mode gathers once
         t["new"] = z(cap, 5, dtype=f64)
         t["rinf"] = z(cap, dtype=f64)
@@ -316,11 +317,24 @@ class Engine(BoundTracker):
         return {"acc": self.t["acc"], "pos_new": self._pos_new.view(cap, 2), "vel_new": self._vel_new.view(cap, 2)}
 
     # ------------------------------------------------------------------ stepping
+    def _sym_tiling(self, n):
+        """(row blocks per CTA, column blocks per CTA) of the symmetric FP32 kernel: about 16 CTAs per
+        resident slot and rank keep the tail short; within that, as many row blocks per CTA as possible
+        (the column-partial traffic and buffer shrink by that factor), and no more column chunks than the
+        row-partial buffer has rows (JSPLIT_MAX)."""
+        nblk = -(-n // 1024)
+        target = (nblk * nblk) // (2 * 16 * 2 * self.sm_count * self.world) if nblk > 1 else 1
+        rows = 4 if target >= 16 else (2 if target >= 4 else 1)
+        chunk = int(min(32, max(1, -(-nblk // self.JSPLIT_MAX), target // rows)))
+        return rows, chunk
+
     def _ensure_colbuf(self, fp64=False):
-        """Column-partial buffer of the symmetric FP32 kernel: one float2 row of `cap` per local row
-        block (8 B x N^2 / 1024 / ranks: 8.6 GB at N = 2^20 on one GPU -- HBM3e capacity is what makes
-        the deterministic, atomic-free reduction affordable)."""
-        rows = -(-(self.cap // PAD) // self.world)
+        """Column-partial buffer of the symmetric kernels.  FP32: one float2 row of `cap` per SUPER row
+        (sym_rows row blocks of 1024 planets): 8 B x N^2 / (1024 sym_rows ranks), 2.1 GB at N = 2^20 on one
+        GPU with sym_rows = 4.  HBM capacity is what makes the deterministic, atomic-free reduction
+        affordable."""
+        local = -(-(-(-max(1, self.n_upper) // PAD)) // self.world) + 1      # row blocks of this rank (+1: partial round)
+        rows = -(-local // self._sym_tiling(max(1, self.n_upper))[0])
         if fp64:                                  # 512-planet row blocks, double2 = two float2 rows each
             rows = 2 * -(-(self.cap // 512) // self.world)
         if "colbuf" not in self.t or self.t["colbuf"].shape[0] < rows:
@@ -337,7 +351,7 @@ class Engine(BoundTracker):
         the launch bound and a few tunables."""
         key = (self.n_upper, dt, G, r_max, tuple(sorted(kw.items())), self.near_field, self._grid_ready,
                self._force_all_pairs, self._host_grid, self.grid_threshold, self.small_threshold,
-               self.sym_threshold, self.sym64_threshold, self.sym_chunk, self.pos_exp, self.mass_exp)
+               self.sym_threshold, self.sym64_threshold, self.sym_chunk, self.sym_rows, self.pos_exp, self.mass_exp)
         p = self._params_cache.get(key)
         if p is None:
             if len(self._params_cache) > 64:
@@ -363,15 +377,20 @@ class Engine(BoundTracker):
                   (OPT_DEFER_INTEGRATE if ((sym or sym64) and self.world > 1) else 0) | (OPT_ENERGY if energy else 0))
         if (sym or sym64) and self.world > 1:
             from . import sharded
-            near_on = fp32 and (self.near_field if near is None else near)
-            if not near_on and sharded.setup_peer_exchange(self):   # (the experimental peer exchange carries no corrections)
+            if sharded.setup_peer_exchange(self):
                 p.opts |= _abi.OPT_PEER_EXCHANGE      # sharded.frame points scratch.peer_acc at the frame's parity
-        if self.sym_chunk or not (sym or sym64):
+        if sym:
+            p.sym_rows, p.sym_chunk = self._sym_tiling(n)
+            if self.sym_chunk:
+                p.sym_chunk = int(self.sym_chunk)
+            if self.sym_rows:
+                p.sym_rows = int(self.sym_rows)
+        elif self.sym_chunk or not sym64:
             p.sym_chunk = int(self.sym_chunk)
         else:
             # column blocks per CTA: enough CTAs (~16 per resident slot and rank) to keep the tail short,
             # few enough that the row partials fit `partial` (JSPLIT_MAX rows)
-            nblk = -(-n // (512 if sym64 else 1024))
+            nblk = -(-n // 512)
             want = (nblk * nblk) // (2 * 16 * 2 * self.sm_count * self.world) if nblk > 1 else 1
             p.sym_chunk = int(min(32, max(1, -(-nblk // self.JSPLIT_MAX), want)))
         p.n_upper = n

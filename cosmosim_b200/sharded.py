@@ -149,10 +149,7 @@ def frame(eng, p, stream, stage_events=None):
     elif p.opts & _abi.OPT_DEFER_INTEGRATE:
         # symmetric kernels, NCCL: every rank holds partial sums for ALL planets (its row blocks +
         # the column sides of its pairs) -> all-reduce, then every rank integrates all rows
-        # (FP32 with the near field on: rows of four doubles, the sums and the FP64 corrections travel
-        # separately so that both reductions are exact -- see k_sym_reduce)
-        wide = 2 if ((p.opts & _abi.OPT_FP32) and p.near_mode != 0) else 1
-        dist.all_reduce(eng.t["acc"][:wide * n], op=dist.ReduceOp.SUM, group=eng.group)
+        dist.all_reduce(eng.t["acc"][:n], op=dist.ReduceOp.SUM, group=eng.group)
         _abi.check(lib.cosmo_integrate(st, sc, pp, stream), "cosmo_integrate")
     else:
         gather_planes(((eng._pos_new, 2), (eng._vel_new, 2), (eng._xx_new, 1)), per, eng.rank, eng.world, eng.group)

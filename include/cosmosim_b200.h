@@ -152,9 +152,7 @@ typedef struct cosmo_scratch {
     float *pk_x;       /* [cap]      FP32 j-stage (scaled x, y, mass) */
     float *pk_y;       /* [cap] */
     float *pk_m;       /* [cap] */
-    double *acc;       /* [cap][4]   accelerations of the last frame as [n][2] (COSMO_OPT_STORE_ACC); sharded FP32
-                                     frames with near_mode != 0 pass (sum, near-field correction) rows [n][4]
-                                     through it between cosmo_accel_integrate and cosmo_integrate */
+    double *acc;       /* [cap][2]   accelerations of the last frame (COSMO_OPT_STORE_ACC) */
     double *pos_new;   /* [cap][2]   integrated positions of ALL active planets (A2) */
     double *vel_new;   /* [cap][2] */
     double *xx_new;    /* [cap]      squared row norms of pos_new (A3) */
@@ -164,7 +162,7 @@ typedef struct cosmo_scratch {
     float *colbuf;        /* [colbuf_rows][cap][2] column partial sums of the symmetric kernels (FP32:
                              float2 per planet and 1024-planet row block; FP64: double2 = two rows
                              per 512-planet row block) */
-    int64_t colbuf_rows;  /* FP32: >= ceil(ceil(n/1024)/ranks); FP64: >= 2 * ceil(ceil(n/512)/ranks) */
+    int64_t colbuf_rows;  /* FP32: >= ceil(ceil(ceil(n/1024)/ranks) / sym_rows); FP64: >= 2 * ceil(ceil(n/512)/ranks) */
     int32_t *tile_ctr; /* [cap / 64 + 4] arrival counters, must start zeroed */
     uint8_t *alive;    /* [cap]      1 while the slot's planet is alive in this frame */
     uint8_t *escaped;  /* [cap]      start-of-frame escape flags (A6) */
@@ -238,7 +236,8 @@ typedef struct cosmo_step_params {
                              coordinates, i.e. 2^14 FP32 ulps) in FP64; 1 = bin the planets with the grid
                              the previous frame's stage B left in scratch.grid_dev, 2 = tune a grid first
                              (first frame, or stage B not in grid mode) */
-    int32_t reserved2;
+    int32_t sym_rows;     /* symmetric FP32 kernel: row blocks per CTA (1, 2 or 4; 0 = 1).  colbuf needs
+                             ceil(local row blocks / sym_rows) rows; the launcher raises sym_rows if it has fewer */
     int32_t reserved1;
     double cell_size;     /* detect_mode 1: edge of the square cells of the PERIODIC grid: cell (ix, iy) of  */
     double grid_origin_x; /* the tiling anchored at the origin is stored in slot (iy mod c, ix mod c), c =   */
