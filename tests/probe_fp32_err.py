@@ -1,7 +1,8 @@
-"""FP32 fast path: per-row relative acceleration error vs the FP64 oracle, near field on / off (development)."""
+"""FP32 fast path: per-row relative acceleration error vs the FP64 oracle, near field on / off.
+Not a test (pytest does not collect it): a measurement script, kept under tests/ because it uses the
+oracle, which only tests / smoke() / the CPU leg of bench.py may do.  python tests/probe_fp32_err.py"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 from cosmosim_b200 import scenes
 from cosmosim_b200.engine import Engine
