@@ -283,29 +283,32 @@ def roofline_block(eng, prec, kw, peaks, stage_events, n_per_step, world, worklo
             "mufu_rsq_per_s_peak": peaks.get("mufu_rsq_per_s")}
 
 
-def secondary_fp64_block(device, peaks, flush, steps=5, warmup=3):
-    """BASELINE config 3 (star+disk, N = 65,536, FP64 parity path, one GPU) measured in the same run,
-    so the parity kernel has a driver-run record of its own: value, ms per step, roofline."""
-    from cosmosim_b200.engine import Engine
-    kind, n, prec, collisions = WORKLOADS["star_disk_64k_fp64"]
-    arrays = build_arrays(kind, n)
-    eng = Engine(n, device=device)
-    eng.upload(arrays)
-    kw = dict(collisions=collisions, bounded=True, fp32=False)
+def secondary_block(workload, device, peaks, flush, barrier, group=None, world=1, steps=5, warmup=3):
+    """Another BASELINE configuration measured in the same run, so that it has a driver-run record of
+    its own (value, ms per step, roofline, stage table): config 3 (star+disk, N = 65,536, FP64 parity
+    path) on one GPU, config 4 (rotating cloud, N = 262,144, FP32, rows sharded) on N > 1 GPUs."""
     import torch
+    import torch.distributed as dist
+    from cosmosim_b200.engine import Engine
+    kind, n, prec, collisions = WORKLOADS[workload]
+    arrays = build_arrays(kind, n)
+    eng = Engine(n, device=device, group=group)
+    eng.upload(arrays)
+    kw = dict(collisions=collisions, bounded=True, fp32=(prec == "fp32"))
     for _ in range(warmup):
         eng.step(1, DT, G, R_MAX, **kw)
         flush.zero_()
-    torch.cuda.synchronize()
-    ms, n_per_step, stage_events, launches = timed_frames(eng, steps, kw, flush, torch.cuda.synchronize, 1)
+    barrier()
+    ms, n_per_step, stage_events, launches = timed_frames(eng, steps, kw, flush, barrier, world)
     st = eng.check_errors()
-    roof = roofline_block(eng, prec, kw, peaks, stage_events, n_per_step, 1, "star_disk_64k_fp64", ms / steps)
-    return {"workload": "star_disk_64k_fp64", "n_bodies": n, "precision": "fp64", "steps": steps, "warmup": warmup,
+    roof = roofline_block(eng, prec, kw, peaks, stage_events, n_per_step, world, workload, ms / steps)
+    return {"workload": workload, "n_bodies": n, "precision": prec, "n_gpus": world, "steps": steps, "warmup": warmup,
             "value": float(np.sum(n_per_step ** 2)) / (ms * 1e-3), "unit": "interactions/s",
             "ms_per_step": ms / steps, "steps_per_s": steps / (ms * 1e-3), "gpu_launches": launches,
             "n_active_per_step": [int(x) for x in n_per_step], "merges": st["n_events"], "roofline": roof,
-            "parity": "FP64 path: accelerations / positions <= 1e-12 vs the reference per step, merges bit-exact "
-                      "(tests/test_gpu_parity.py)"}
+            "parity": ("FP64 path: accelerations / positions <= 1e-12 vs the reference per step, merges bit-exact"
+                       if prec == "fp64" else "FP32 path + FP64 near field: median <= 1e-5, max <= 1e-3 per step")
+                      + " (tests/test_gpu_parity.py)"}
 
 
 # ------------------------------------------------------------------------------------ main
@@ -479,11 +482,15 @@ def main():
                "path": stg.get("path", "Engine.frame_from_host: pinned host SoA -> H2D -> frame -> D2H, stream sync per step")}
 
     secondary = None
-    if rank == 0 and world == 1 and not a.no_extras and a.workload == "star_disk_1m_fp32":
+    exchange = (("nvlink peer stores + symmetric-memory barrier" if getattr(eng, "_peer", None)
+                 else "nccl all-reduce of the partial sums + all-gather of the pair lists") if world > 1 else None)
+    if not a.no_extras and a.workload == "star_disk_1m_fp32":
         del eng
         torch.cuda.empty_cache()
-        peaks64 = peaks if "dfma_tflops" in peaks else {}
-        secondary = secondary_fp64_block("cuda:%d" % local_rank, peaks64, flush)
+        if world == 1:      # BASELINE config 3
+            secondary = secondary_block("star_disk_64k_fp64", "cuda:%d" % local_rank, peaks, flush, barrier)
+        else:               # BASELINE config 4: N = 262,144 FP32, rows sharded over the ranks
+            secondary = secondary_block("cloud_256k_fp32", "cuda:%d" % local_rank, peaks, flush, barrier, group, world)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -500,6 +507,7 @@ def main():
                 "final_state": {"n_active": st["n_active"], "merges": st["n_events"], "escaped": st["n_escaped"]},
                 "state_digest": digest, "state_digest_full": digest_full, "replicas_identical": replicas_identical,
                 "sharded_vs_single": sharded_vs_single,
+                "exchange": exchange,
                 "n_active_per_step": [int(x) for x in n_per_step],
                 "pairs_last_frame": st["n_pairs"], "detect_mode": "grid (tuned on the device)" if st["n_active"] >= 8192 else "all-pairs",
                 "fp32_bound": ("per-step relative acceleration error vs the FP64 reference formula: see "
