@@ -16,12 +16,12 @@
 // 4 x 4 pairs = 96 FFMA2-class instructions + 16 MUFU.RSQ + 3 LDS.128 + 8 SHFL.
 //
 // A CTA serves R (1, 2 or 4) row blocks against its column chunk (super tile, see the kernel): the
-// column sums of a column block J over those row blocks go to colbuf[super row][j] (float2); the row
+// column sums of a column block J over those row blocks go to colbuf[super row][j] (double2); the row
 // sums to partial[chunk][i] (double2).  k_sym_reduce adds, for every planet, its row partials and
 // the column partials of all super rows below it in ascending order -- deterministic, no atomics --
 // and runs the integrator epilogue.  The diagonal pair (J == I) runs the same schedule without the
 // column side, which evaluates each of its ordered pairs exactly once.  HBM: colbuf is written and
-// read once per frame, 8 B x N^2 / (2048 R): 1.1 GB at N = 2^20 with R = 4.
+// read once per frame, 16 B x N^2 / (2048 R): 2.1 GB at N = 2^20 with R = 4.
 #include <math.h>
 
 #include "cosmo_device.cuh"
@@ -58,7 +58,8 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src_lane) {
 // of column blocks.  A column tile is fetched ONCE for all R row blocks and its column sums are
 // accumulated over them in shared memory before they go to colbuf -- one colbuf row per SUPER row,
 // so the column-partial traffic (the only sizeable DRAM traffic of the pass) and the buffer itself
-// shrink by R.  The row sums of the R blocks live in shared memory as doubles for the CTA's lifetime.
+// shrink (by R / 2: the sums over several row blocks are kept in FP64, see s_c).  The row sums of the
+// R blocks live in shared memory as doubles for the CTA's lifetime.
 template <int R>
 __global__ void __launch_bounds__(SYM_THREADS, 2)
 k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int chunk) {
@@ -66,13 +67,13 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
     float (*s_x)[SYM_BLOCK] = reinterpret_cast<float (*)[SYM_BLOCK]>(s_dyn);
     float (*s_y)[SYM_BLOCK] = s_x + 2;
     float (*s_m)[SYM_BLOCK] = s_x + 4;
-    // column accumulators of the current J: [x|y][1024]
-    float (*s_c)[SYM_BLOCK] = s_x + 6;
-    // staging of the NEXT row block's (x, y, m), fetched by TMA while the current block pair runs
-    float (*s_r)[SYM_BLOCK] = s_x + 8;
+    // column accumulators of the current J over the R row blocks: [x|y][1024], FP64 -- the sum of the
+    // FP32 per-block sums is then exact, i.e. independent of how row blocks are grouped into super
+    // rows and dealt to ranks (a sharded run reproduces the single-GPU sums bit for bit)
+    double (*s_c)[SYM_BLOCK] = reinterpret_cast<double (*)[SYM_BLOCK]>(s_x + 6);
     // FP64 row sums of the R row blocks: [r][1024] (x, y)
-    double2 (*s_row)[SYM_BLOCK] = reinterpret_cast<double2 (*)[SYM_BLOCK]>(s_x + 11);
-    __shared__ __align__(8) uint64_t s_bar[2], s_rbar;
+    double2 (*s_row)[SYM_BLOCK] = reinterpret_cast<double2 (*)[SYM_BLOCK]>(s_x + 10);
+    __shared__ __align__(8) uint64_t s_bar[2];
 
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int nblk = (n + SYM_BLOCK - 1) / SYM_BLOCK;
@@ -87,7 +88,6 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
-        mbar_init(&s_rbar, 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -100,26 +100,17 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
         bulk_g2s(&s_y[b][0], sc.pk_y + j0, SYM_BLOCK * sizeof(float), &s_bar[b]);
         bulk_g2s(&s_m[b][0], sc.pk_m + j0, SYM_BLOCK * sizeof(float), &s_bar[b]);
     };
-    auto issue_rows = [&](int I) {
-        const size_t i0 = (size_t)I * SYM_BLOCK;
-        fence_proxy_async();
-        mbar_expect_tx(&s_rbar, kBytes);
-        bulk_g2s(&s_r[0][0], sc.pk_x + i0, SYM_BLOCK * sizeof(float), &s_rbar);
-        bulk_g2s(&s_r[1][0], sc.pk_y + i0, SYM_BLOCK * sizeof(float), &s_rbar);
-        bulk_g2s(&s_r[2][0], sc.pk_m + i0, SYM_BLOCK * sizeof(float), &s_rbar);
-    };
-    if (tid == 0) { issue(J0, 0); issue_rows(I_first); }
-    uint32_t row_loads = 0;      // row blocks consumed so far: parity of the staging barrier
+    if (tid == 0) issue(J0, 0);
 
     const uint64_t eps2 = pack2(COSMO_F32_TINY_SYM, COSMO_F32_TINY_SYM);
-    float2 *colbuf = reinterpret_cast<float2 *>(sc.colbuf);
+    double2 *colbuf = reinterpret_cast<double2 *>(sc.colbuf);
     const size_t col_row = (size_t)blockIdx.x * (size_t)st.cap;   // local super-row index of this rank
 
     for (int J = J0; J < J1; ++J) {
         const int it_j = J - J0;
         const int b = it_j & 1;
         if (tid == 0 && J + 1 < J1) issue(J + 1, b ^ 1);
-        for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) { s_c[0][q] = 0.f; s_c[1][q] = 0.f; }
+        for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) { s_c[0][q] = 0.0; s_c[1][q] = 0.0; }
         mbar_wait(&s_bar[b], (it_j >> 1) & 1);
         __syncthreads();
         bool any_col = false;
@@ -130,17 +121,14 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
             if (I >= nblk || I > J) break;         // rows are ascending: the rest lies beyond this column block
             const bool diag = (J == I);
             any_col = any_col || !diag;
-            // row side: 4 planets per lane, strided by 32 inside the warp's group, from the staging
-            // buffer the TMA engine filled during the previous block pair
+            // row side: 4 planets per lane, strided by 32 inside the warp's group (coalesced, L2-resident)
             float xi[4], yi[4], nmi[4];
-            mbar_wait(&s_rbar, row_loads & 1);
-            ++row_loads;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int q = w * SYM_GROUP + k * 32 + lane;
-                xi[k] = s_r[0][q];
-                yi[k] = s_r[1][q];
-                nmi[k] = -s_r[2][q];
+                const int row = I * SYM_BLOCK + w * SYM_GROUP + k * 32 + lane;
+                xi[k] = sc.pk_x[row];
+                yi[k] = sc.pk_y[row];
+                nmi[k] = -sc.pk_m[row];
             }
             uint64_t rx2[4], ry2[4];
 #pragma unroll
@@ -191,20 +179,15 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
                     float a0, a1, a2, a3, b0, b1, b2, b3;
                     unpack2(tx2[0], a0, a1); unpack2(tx2[1], a2, a3);
                     unpack2(ty2[0], b0, b1); unpack2(ty2[1], b2, b3);
-                    float4 cx = *reinterpret_cast<float4 *>(&s_c[0][g * SYM_GROUP + 4 * lane]);
-                    float4 cy = *reinterpret_cast<float4 *>(&s_c[1][g * SYM_GROUP + 4 * lane]);
-                    cx.x += a0; cx.y += a1; cx.z += a2; cx.w += a3;
-                    cy.x += b0; cy.y += b1; cy.z += b2; cy.w += b3;
-                    *reinterpret_cast<float4 *>(&s_c[0][g * SYM_GROUP + 4 * lane]) = cx;
-                    *reinterpret_cast<float4 *>(&s_c[1][g * SYM_GROUP + 4 * lane]) = cy;
+                    double4 *px = reinterpret_cast<double4 *>(&s_c[0][g * SYM_GROUP + 4 * lane]);
+                    double4 *py = reinterpret_cast<double4 *>(&s_c[1][g * SYM_GROUP + 4 * lane]);
+                    double4 cx = *px, cy = *py;
+                    cx.x += (double)a0; cx.y += (double)a1; cx.z += (double)a2; cx.w += (double)a3;
+                    cy.x += (double)b0; cy.y += (double)b1; cy.z += (double)b2; cy.w += (double)b3;
+                    *px = cx;
+                    *py = cy;
                 }
                 __syncthreads();   // the next round moves every warp to another column group
-                if (it == 0 && tid == 0) {
-                    // every warp has its rows in registers: fetch the row block of the NEXT block pair
-                    const int In = r + 1 < R ? sym_row_of(blockIdx.x * R + r + 1, shard_index, shard_count) : nblk;
-                    if (In < nblk && In <= J) issue_rows(In);
-                    else if (J + 1 < J1) issue_rows(I_first);
-                }
             }
             // fold this block pair's FP32 row sums into the FP64 row sums (each lane owns its rows)
 #pragma unroll
@@ -218,8 +201,8 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
             }
         }
         if (any_col) {   // column sums of this block over the R row blocks: one colbuf row per super row
-            float2 *dst = colbuf + col_row + (size_t)J * SYM_BLOCK;
-            for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) dst[q] = make_float2(s_c[0][q], s_c[1][q]);
+            double2 *dst = colbuf + col_row + (size_t)J * SYM_BLOCK;
+            for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) dst[q] = make_double2(s_c[0][q], s_c[1][q]);
         }
         __syncthreads();   // column accumulators and buffer b are free again
     }
@@ -261,13 +244,13 @@ k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count,
             ay += v.y;
         }
     }
-    const float2 *colbuf = reinterpret_cast<const float2 *>(sc.colbuf);
+    const double2 *colbuf = reinterpret_cast<const double2 *>(sc.colbuf);
     // super rows of this rank with a row block below K, in ascending order (super row r starts at
-    // block sym_row_of(r * R)); each holds the column sums of its row blocks I < K
+    // block sym_row_of(r * R)); each holds the (exact) column sums of its row blocks I < K
     for (int r = 0; sym_row_of(r * R, shard_index, shard_count) < K; ++r) {
-        const float2 v = __ldcs(&colbuf[(size_t)r * st.cap + k]);
-        ax += (double)v.x;
-        ay += (double)v.y;
+        const double2 v = __ldcs(&colbuf[(size_t)r * st.cap + k]);
+        ax += v.x;
+        ay += v.y;
     }
     ax *= unscale;
     ay *= unscale;
@@ -314,11 +297,10 @@ template <int R>
 static int launch_sym_kernel(const cosmo_state &st, const cosmo_scratch &sc, dim3 grid, int sh_i, int sh_n, int chunk,
                              cudaStream_t s) {
     constexpr size_t kTma = 6 * SYM_BLOCK * sizeof(float);                 // x, y, m double-buffered
-    constexpr size_t kShared = kTma + 2 * SYM_BLOCK * sizeof(float)        // + the column accumulators
-                               + 3 * SYM_BLOCK * sizeof(float)             // + the staging of the next row block
+    constexpr size_t kShared = kTma + 2 * SYM_BLOCK * sizeof(double)       // + the FP64 column accumulators
                                + (size_t)R * SYM_BLOCK * sizeof(double2);  // + the FP64 row sums of R row blocks
     static bool attr_set = false;
-    if (!attr_set) {   // R = 4: 108 KB of dynamic shared memory (two CTAs per SM)
+    if (!attr_set) {   // R = 4: 104 KB of dynamic shared memory (two CTAs per SM)
         COSMO_TRY(check_cuda(cudaFuncSetAttribute(k_accel_f32_sym<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)kShared), "cudaFuncSetAttribute(k_accel_f32_sym)"));
         attr_set = true;
@@ -341,10 +323,10 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
     // row blocks per CTA: p.sym_rows, raised if the column-partial buffer is too small for it
     int R = p.sym_rows >= 4 ? 4 : (p.sym_rows >= 2 ? 2 : 1);
     if (sc.colbuf_rows > 0)
-        while (R < 4 && (rows_local + R - 1) / R > sc.colbuf_rows) R *= 2;
+        while (R < 4 && 2LL * ((rows_local + R - 1) / R) > sc.colbuf_rows) R *= 2;
     const int super_rows = (rows_local + R - 1) / R;
-    if (!sc.colbuf || (long long)super_rows > sc.colbuf_rows) {
-        set_error("symmetric accel: colbuf has %lld rows, %d needed", (long long)sc.colbuf_rows, super_rows);
+    if (!sc.colbuf || 2LL * super_rows > sc.colbuf_rows) {      // a double2 row = two float2 rows
+        set_error("symmetric accel: colbuf has %lld rows, %d needed", (long long)sc.colbuf_rows, 2 * super_rows);
         return COSMO_E_ARG;
     }
     const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);

@@ -29,7 +29,7 @@ Sizes sizes_for(int n_total, uint32_t opts) {
     z.grid_cells = 8LL * z.cap > (1 << 16) ? 8LL * z.cap : (1 << 16);
     if (z.grid_cells > (long long)COSMO_SCAN_BLOCKS * 4096 - 1) z.grid_cells = (long long)COSMO_SCAN_BLOCKS * 4096 - 1;
     z.colbuf_rows = 0;
-    if (opts & COSMO_OPT_F32_SYM) z.colbuf_rows = (z.cap / 1024 + 3) / 4 + 1;   // super rows of four row blocks
+    if (opts & COSMO_OPT_F32_SYM) z.colbuf_rows = 2 * ((z.cap / 1024 + 3) / 4 + 1);   // double2 per super row of four row blocks
     if (opts & COSMO_OPT_F64_SYM) z.colbuf_rows = 2LL * (z.cap / 512) > z.colbuf_rows ? 2LL * (z.cap / 512) : z.colbuf_rows;
     return z;
 }
@@ -164,7 +164,7 @@ int cosmo_params_default(int32_t n, double G, double dt, double r_max, uint32_t 
     opts &= ~(COSMO_OPT_F32_SYM | COSMO_OPT_F64_SYM | COSMO_OPT_DEFER_INTEGRATE | COSMO_OPT_PEER_EXCHANGE);
     const long long nblk32 = (n + 1023) / 1024, nblk64 = (n + 511) / 512;
     bool sym = false;
-    if (fp32 && n >= 32768 && sc && sc->colbuf && sc->colbuf_rows >= (nblk32 + 3) / 4) { opts |= COSMO_OPT_F32_SYM; sym = true; }
+    if (fp32 && n >= 32768 && sc && sc->colbuf && sc->colbuf_rows >= 2 * ((nblk32 + 3) / 4)) { opts |= COSMO_OPT_F32_SYM; sym = true; }
     if (!fp32 && n >= 16384 && sc && sc->colbuf && sc->colbuf_rows >= 2 * nblk64) { opts |= COSMO_OPT_F64_SYM; sym = true; }
     p->opts = opts;
     {   // FP32 path: exact power-of-two rescaling, max |coordinate| -> [32, 64), max mass -> [2^19, 2^20)

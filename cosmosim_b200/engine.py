@@ -329,12 +329,12 @@ class Engine(BoundTracker):
         return rows, chunk
 
     def _ensure_colbuf(self, fp64=False):
-        """Column-partial buffer of the symmetric kernels.  FP32: one float2 row of `cap` per SUPER row
-        (sym_rows row blocks of 1024 planets): 8 B x N^2 / (1024 sym_rows ranks), 2.1 GB at N = 2^20 on one
-        GPU with sym_rows = 4.  HBM capacity is what makes the deterministic, atomic-free reduction
-        affordable."""
+        """Column-partial buffer of the symmetric kernels.  FP32: one double2 row of `cap` (= two float2
+        rows) per SUPER row (sym_rows row blocks of 1024 planets): 16 B x N^2 / (1024 sym_rows ranks),
+        4.3 GB at N = 2^20 on one GPU with sym_rows = 4.  HBM capacity is what makes the deterministic,
+        atomic-free reduction affordable."""
         local = -(-(-(-max(1, self.n_upper) // PAD)) // self.world) + 1      # row blocks of this rank (+1: partial round)
-        rows = -(-local // self._sym_tiling(max(1, self.n_upper))[0])
+        rows = 2 * -(-local // self._sym_tiling(max(1, self.n_upper))[0])
         if fp64:                                  # 512-planet row blocks, double2 = two float2 rows each
             rows = 2 * -(-(self.cap // 512) // self.world)
         if "colbuf" not in self.t or self.t["colbuf"].shape[0] < rows:
