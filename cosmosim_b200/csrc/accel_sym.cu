@@ -16,7 +16,8 @@
 // 4 x 4 pairs = 96 FFMA2-class instructions + 16 MUFU.RSQ + 3 LDS.128 + 8 SHFL.
 //
 // A CTA serves R (1, 2 or 4) row blocks against its column chunk (super tile, see the kernel): the
-// column sums of a column block J over those row blocks go to colbuf[super row][j] (double2); the row
+// column sums of a column block J over those row blocks go to colbuf[super row][j] (double2; float2
+// when R = 1: a single FP32 block sum is exact as it is); the row
 // sums to partial[chunk][i] (double2).  k_sym_reduce adds, for every planet, its row partials and
 // the column partials of all super rows below it in ascending order -- deterministic, no atomics --
 // and runs the integrator epilogue.  The diagonal pair (J == I) runs the same schedule without the
@@ -53,6 +54,15 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src_lane) {
     hi = __shfl_sync(0xffffffffu, hi, src_lane);
     return ((uint64_t)hi << 32) | lo;
 }
+
+template <int R> struct SymCol {
+    typedef double2 type;
+    static __device__ __forceinline__ double2 make(double x, double y) { return make_double2(x, y); }
+};
+template <> struct SymCol<1> {
+    typedef float2 type;
+    static __device__ __forceinline__ float2 make(double x, double y) { return make_float2((float)x, (float)y); }
+};
 
 // Super-tile: a CTA serves R consecutive local row blocks (rows I_0 < I_1 < ... ) against one chunk
 // of column blocks.  A column tile is fetched ONCE for all R row blocks and its column sums are
@@ -103,7 +113,10 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
     if (tid == 0) issue(J0, 0);
 
     const uint64_t eps2 = pack2(COSMO_F32_TINY_SYM, COSMO_F32_TINY_SYM);
-    double2 *colbuf = reinterpret_cast<double2 *>(sc.colbuf);
+    // colbuf entry: the sum over ONE row block is a pair of FP32 values (float2 is exact); the sum over
+    // several needs FP64
+    typedef typename SymCol<R>::type col_t;
+    col_t *colbuf = reinterpret_cast<col_t *>(sc.colbuf);
     const size_t col_row = (size_t)blockIdx.x * (size_t)st.cap;   // local super-row index of this rank
 
     for (int J = J0; J < J1; ++J) {
@@ -201,8 +214,8 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
             }
         }
         if (any_col) {   // column sums of this block over the R row blocks: one colbuf row per super row
-            double2 *dst = colbuf + col_row + (size_t)J * SYM_BLOCK;
-            for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) dst[q] = make_double2(s_c[0][q], s_c[1][q]);
+            col_t *dst = colbuf + col_row + (size_t)J * SYM_BLOCK;
+            for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) dst[q] = SymCol<R>::make(s_c[0][q], s_c[1][q]);
         }
         __syncthreads();   // column accumulators and buffer b are free again
     }
@@ -244,13 +257,23 @@ k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count,
             ay += v.y;
         }
     }
-    const double2 *colbuf = reinterpret_cast<const double2 *>(sc.colbuf);
     // super rows of this rank with a row block below K, in ascending order (super row r starts at
-    // block sym_row_of(r * R)); each holds the (exact) column sums of its row blocks I < K
-    for (int r = 0; sym_row_of(r * R, shard_index, shard_count) < K; ++r) {
-        const double2 v = __ldcs(&colbuf[(size_t)r * st.cap + k]);
-        ax += v.x;
-        ay += v.y;
+    // block sym_row_of(r * R)); each holds the (exact) column sums of its row blocks I < K: float2 for
+    // single row blocks, double2 for sums over several
+    if (R == 1) {
+        const float2 *colbuf = reinterpret_cast<const float2 *>(sc.colbuf);
+        for (int r = 0; sym_row_of(r, shard_index, shard_count) < K; ++r) {
+            const float2 v = __ldcs(&colbuf[(size_t)r * st.cap + k]);
+            ax += (double)v.x;
+            ay += (double)v.y;
+        }
+    } else {
+        const double2 *colbuf = reinterpret_cast<const double2 *>(sc.colbuf);
+        for (int r = 0; sym_row_of(r * R, shard_index, shard_count) < K; ++r) {
+            const double2 v = __ldcs(&colbuf[(size_t)r * st.cap + k]);
+            ax += v.x;
+            ay += v.y;
+        }
     }
     ax *= unscale;
     ay *= unscale;
@@ -322,11 +345,12 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
     while ((nblk + chunk - 1) / chunk > sc.jsplit_max) ++chunk;
     // row blocks per CTA: p.sym_rows, raised if the column-partial buffer is too small for it
     int R = p.sym_rows >= 4 ? 4 : (p.sym_rows >= 2 ? 2 : 1);
+    auto rows_needed = [&](int r) { return (r == 1 ? 1LL : 2LL) * ((rows_local + r - 1) / r); };   // in float2 rows
     if (sc.colbuf_rows > 0)
-        while (R < 4 && 2LL * ((rows_local + R - 1) / R) > sc.colbuf_rows) R *= 2;
+        while (R < 4 && rows_needed(R) > sc.colbuf_rows) R *= 2;
     const int super_rows = (rows_local + R - 1) / R;
-    if (!sc.colbuf || 2LL * super_rows > sc.colbuf_rows) {      // a double2 row = two float2 rows
-        set_error("symmetric accel: colbuf has %lld rows, %d needed", (long long)sc.colbuf_rows, 2 * super_rows);
+    if (!sc.colbuf || rows_needed(R) > sc.colbuf_rows) {
+        set_error("symmetric accel: colbuf has %lld rows, %lld needed", (long long)sc.colbuf_rows, rows_needed(R));
         return COSMO_E_ARG;
     }
     const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);

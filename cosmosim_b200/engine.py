@@ -333,8 +333,15 @@ class Engine(BoundTracker):
         rows) per SUPER row (sym_rows row blocks of 1024 planets): 16 B x N^2 / (1024 sym_rows ranks),
         4.3 GB at N = 2^20 on one GPU with sym_rows = 4.  HBM capacity is what makes the deterministic,
         atomic-free reduction affordable."""
-        local = -(-(-(-max(1, self.n_upper) // PAD)) // self.world) + 1      # row blocks of this rank (+1: partial round)
-        rows = 2 * -(-local // self._sym_tiling(max(1, self.n_upper))[0])
+        def rows_for(n):
+            local = -(-(-(-n // PAD)) // self.world) + 1        # row blocks of this rank (+1: partial round)
+            r = self.sym_rows or self._sym_tiling(n)[0]
+            return (1 if r == 1 else 2) * -(-local // r)
+        rows = rows_for(max(1, self.n_upper))
+        if not fp64 and ("colbuf" not in self.t or self.t["colbuf"].shape[0] < rows):
+            # allocate once for the whole run: as planets merge the active count shrinks and the tiling
+            # drops to fewer row blocks per CTA (more, smaller colbuf rows) -- never reallocate mid-run
+            rows = max(rows_for(n) for n in range(PAD, max(1, self.n_upper) + PAD, PAD))
         if fp64:                                  # 512-planet row blocks, double2 = two float2 rows each
             rows = 2 * -(-(self.cap // 512) // self.world)
         if "colbuf" not in self.t or self.t["colbuf"].shape[0] < rows:

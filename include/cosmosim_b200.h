@@ -159,10 +159,12 @@ typedef struct cosmo_scratch {
     double *rinf;      /* [cap]      radii inflated by 2^-30 (candidate filter of stage B) */
     double *partial;   /* [jsplit_max][cap][2] partial sums of the all-pairs pass */
     int32_t jsplit_max;
-    float *colbuf;        /* [colbuf_rows][cap][2] floats: column partial sums of the symmetric kernels, one
-                             double2 (= two float2 rows) per planet and super row (FP32: sym_rows
-                             1024-planet row blocks) / per 512-planet row block (FP64) */
-    int64_t colbuf_rows;  /* FP32: >= 2 * ceil(ceil(ceil(n/1024)/ranks) / sym_rows); FP64: >= 2 * ceil(ceil(n/512)/ranks) */
+    float *colbuf;        /* [colbuf_rows][cap][2] floats: column partial sums of the symmetric kernels.  FP32:
+                             per planet and super row (sym_rows 1024-planet row blocks) one float2 if
+                             sym_rows == 1, else one double2 (= two float2 rows); FP64: one double2 per
+                             512-planet row block */
+    int64_t colbuf_rows;  /* FP32: >= (sym_rows == 1 ? 1 : 2) * ceil(ceil(ceil(n/1024)/ranks) / sym_rows);
+                             FP64: >= 2 * ceil(ceil(n/512)/ranks) */
     int32_t *tile_ctr; /* [cap / 64 + 4] arrival counters, must start zeroed */
     uint8_t *alive;    /* [cap]      1 while the slot's planet is alive in this frame */
     uint8_t *escaped;  /* [cap]      start-of-frame escape flags (A6) */
@@ -236,8 +238,8 @@ typedef struct cosmo_step_params {
                              coordinates, i.e. 2^14 FP32 ulps) in FP64; 1 = bin the planets with the grid
                              the previous frame's stage B left in scratch.grid_dev, 2 = tune a grid first
                              (first frame, or stage B not in grid mode) */
-    int32_t sym_rows;     /* symmetric FP32 kernel: row blocks per CTA (1, 2 or 4; 0 = 1).  colbuf needs
-                             2 * ceil(local row blocks / sym_rows) rows; the launcher raises sym_rows if it has fewer */
+    int32_t sym_rows;     /* symmetric FP32 kernel: row blocks per CTA (1, 2 or 4; 0 = 1); see colbuf_rows --
+                             the launcher raises sym_rows if colbuf has fewer rows */
     int32_t reserved1;
     double cell_size;     /* detect_mode 1: edge of the square cells of the PERIODIC grid: cell (ix, iy) of  */
     double grid_origin_x; /* the tiling anchored at the origin is stored in slot (iy mod c, ix mod c), c =   */
