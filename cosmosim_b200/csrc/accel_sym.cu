@@ -16,8 +16,8 @@
 // 4 x 4 pairs = 96 FFMA2-class instructions + 16 MUFU.RSQ + 3 LDS.128 + 8 SHFL.
 //
 // A CTA serves R (1, 2 or 4) row blocks against its column chunk (super tile, see the kernel): the
-// column sums of a column block J over those row blocks go to colbuf[super row][j] (double2; float2
-// when R = 1: a single FP32 block sum is exact as it is); the row
+// column sums of a column block J over those row blocks go to colbuf[super row][j] (double2: the
+// eight rounds and the R row blocks are summed in FP64, exactly, so no tiling changes a bit); the row
 // sums to partial[chunk][i] (double2).  k_sym_reduce adds, for every planet, its row partials and
 // the column partials of all super rows below it in ascending order -- deterministic, no atomics --
 // and runs the integrator epilogue.  The diagonal pair (J == I) runs the same schedule without the
@@ -54,15 +54,6 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src_lane) {
     hi = __shfl_sync(0xffffffffu, hi, src_lane);
     return ((uint64_t)hi << 32) | lo;
 }
-
-template <int R> struct SymCol {
-    typedef double2 type;
-    static __device__ __forceinline__ double2 make(double x, double y) { return make_double2(x, y); }
-};
-template <> struct SymCol<1> {
-    typedef float2 type;
-    static __device__ __forceinline__ float2 make(double x, double y) { return make_float2((float)x, (float)y); }
-};
 
 // Super-tile: a CTA serves R consecutive local row blocks (rows I_0 < I_1 < ... ) against one chunk
 // of column blocks.  A column tile is fetched ONCE for all R row blocks and its column sums are
@@ -113,11 +104,20 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
     if (tid == 0) issue(J0, 0);
 
     const uint64_t eps2 = pack2(COSMO_F32_TINY_SYM, COSMO_F32_TINY_SYM);
-    // colbuf entry: the sum over ONE row block is a pair of FP32 values (float2 is exact); the sum over
-    // several needs FP64
-    typedef typename SymCol<R>::type col_t;
-    col_t *colbuf = reinterpret_cast<col_t *>(sc.colbuf);
+    double2 *colbuf = reinterpret_cast<double2 *>(sc.colbuf);
     const size_t col_row = (size_t)blockIdx.x * (size_t)st.cap;   // local super-row index of this rank
+
+    float xi[4], yi[4], nmi[4];     // row side: 4 planets per lane, strided by 32 inside the warp's group
+    auto load_rows = [&](int I) {   // coalesced, L2-resident
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int row = I * SYM_BLOCK + w * SYM_GROUP + k * 32 + lane;
+            xi[k] = sc.pk_x[row];
+            yi[k] = sc.pk_y[row];
+            nmi[k] = -sc.pk_m[row];
+        }
+    };
+    if (R == 1) load_rows(I_first);      // a single row block: its operands stay in registers
 
     for (int J = J0; J < J1; ++J) {
         const int it_j = J - J0;
@@ -134,15 +134,7 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
             if (I >= nblk || I > J) break;         // rows are ascending: the rest lies beyond this column block
             const bool diag = (J == I);
             any_col = any_col || !diag;
-            // row side: 4 planets per lane, strided by 32 inside the warp's group (coalesced, L2-resident)
-            float xi[4], yi[4], nmi[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int row = I * SYM_BLOCK + w * SYM_GROUP + k * 32 + lane;
-                xi[k] = sc.pk_x[row];
-                yi[k] = sc.pk_y[row];
-                nmi[k] = -sc.pk_m[row];
-            }
+            if (R > 1) load_rows(I);
             uint64_t rx2[4], ry2[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) { rx2[k] = 0ull; ry2[k] = 0ull; }
@@ -214,8 +206,8 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
             }
         }
         if (any_col) {   // column sums of this block over the R row blocks: one colbuf row per super row
-            col_t *dst = colbuf + col_row + (size_t)J * SYM_BLOCK;
-            for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) dst[q] = SymCol<R>::make(s_c[0][q], s_c[1][q]);
+            double2 *dst = colbuf + col_row + (size_t)J * SYM_BLOCK;
+            for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS) dst[q] = make_double2(s_c[0][q], s_c[1][q]);
         }
         __syncthreads();   // column accumulators and buffer b are free again
     }
@@ -258,22 +250,12 @@ k_sym_reduce(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count,
         }
     }
     // super rows of this rank with a row block below K, in ascending order (super row r starts at
-    // block sym_row_of(r * R)); each holds the (exact) column sums of its row blocks I < K: float2 for
-    // single row blocks, double2 for sums over several
-    if (R == 1) {
-        const float2 *colbuf = reinterpret_cast<const float2 *>(sc.colbuf);
-        for (int r = 0; sym_row_of(r, shard_index, shard_count) < K; ++r) {
-            const float2 v = __ldcs(&colbuf[(size_t)r * st.cap + k]);
-            ax += (double)v.x;
-            ay += (double)v.y;
-        }
-    } else {
-        const double2 *colbuf = reinterpret_cast<const double2 *>(sc.colbuf);
-        for (int r = 0; sym_row_of(r * R, shard_index, shard_count) < K; ++r) {
-            const double2 v = __ldcs(&colbuf[(size_t)r * st.cap + k]);
-            ax += v.x;
-            ay += v.y;
-        }
+    // block sym_row_of(r * R)); each holds the (exact) column sums of its row blocks I < K
+    const double2 *colbuf = reinterpret_cast<const double2 *>(sc.colbuf);
+    for (int r = 0; sym_row_of(r * R, shard_index, shard_count) < K; ++r) {
+        const double2 v = __ldcs(&colbuf[(size_t)r * st.cap + k]);
+        ax += v.x;
+        ay += v.y;
     }
     ax *= unscale;
     ay *= unscale;
@@ -345,7 +327,7 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
     while ((nblk + chunk - 1) / chunk > sc.jsplit_max) ++chunk;
     // row blocks per CTA: p.sym_rows, raised if the column-partial buffer is too small for it
     int R = p.sym_rows >= 4 ? 4 : (p.sym_rows >= 2 ? 2 : 1);
-    auto rows_needed = [&](int r) { return (r == 1 ? 1LL : 2LL) * ((rows_local + r - 1) / r); };   // in float2 rows
+    auto rows_needed = [&](int r) { return 2LL * ((rows_local + r - 1) / r); };   // in float2 rows: a double2 row is two
     if (sc.colbuf_rows > 0)
         while (R < 4 && rows_needed(R) > sc.colbuf_rows) R *= 2;
     const int super_rows = (rows_local + R - 1) / R;

@@ -336,7 +336,7 @@ class Engine(BoundTracker):
         def rows_for(n):
             local = -(-(-(-n // PAD)) // self.world) + 1        # row blocks of this rank (+1: partial round)
             r = self.sym_rows or self._sym_tiling(n)[0]
-            return (1 if r == 1 else 2) * -(-local // r)
+            return 2 * -(-local // r)
         rows = rows_for(max(1, self.n_upper))
         if not fp64 and ("colbuf" not in self.t or self.t["colbuf"].shape[0] < rows):
             # allocate once for the whole run: as planets merge the active count shrinks and the tiling

@@ -159,12 +159,10 @@ typedef struct cosmo_scratch {
     double *rinf;      /* [cap]      radii inflated by 2^-30 (candidate filter of stage B) */
     double *partial;   /* [jsplit_max][cap][2] partial sums of the all-pairs pass */
     int32_t jsplit_max;
-    float *colbuf;        /* [colbuf_rows][cap][2] floats: column partial sums of the symmetric kernels.  FP32:
-                             per planet and super row (sym_rows 1024-planet row blocks) one float2 if
-                             sym_rows == 1, else one double2 (= two float2 rows); FP64: one double2 per
-                             512-planet row block */
-    int64_t colbuf_rows;  /* FP32: >= (sym_rows == 1 ? 1 : 2) * ceil(ceil(ceil(n/1024)/ranks) / sym_rows);
-                             FP64: >= 2 * ceil(ceil(n/512)/ranks) */
+    float *colbuf;        /* [colbuf_rows][cap][2] floats: column partial sums of the symmetric kernels, one
+                             double2 (= two float2 rows) per planet and super row (FP32: sym_rows
+                             1024-planet row blocks) / per 512-planet row block (FP64) */
+    int64_t colbuf_rows;  /* FP32: >= 2 * ceil(ceil(ceil(n/1024)/ranks) / sym_rows); FP64: >= 2 * ceil(ceil(n/512)/ranks) */
     int32_t *tile_ctr; /* [cap / 64 + 4] arrival counters, must start zeroed */
     uint8_t *alive;    /* [cap]      1 while the slot's planet is alive in this frame */
     uint8_t *escaped;  /* [cap]      start-of-frame escape flags (A6) */
