@@ -104,7 +104,7 @@ class Scratch3(C.Structure):
                 ("chunk_bounds", _vp), ("heavy_rows", _vp), ("grid_cells", C.c_int32), ("giant_cap", C.c_int32),
                 ("colbuf", _vp), ("colbuf_rows", C.c_int64), ("grid_dev", _vp), ("tune_hist", _vp),
                 ("row_count", _vp), ("row_start", _vp), ("label", _vp), ("comp_root", _vp), ("comp_items", _vp),
-                ("pair_flag", _vp), ("scan_a", _vp)]
+                ("pair_flag", _vp), ("scan_a", _vp), ("corr", _vp)]
 
 
 class StepParams3(C.Structure):
@@ -114,7 +114,8 @@ class StepParams3(C.Structure):
                 ("detect_mode", C.c_int32), ("resolve_mode", C.c_int32), ("cells_per_side", C.c_int32),
                 ("sym_chunk", C.c_int32), ("cell_size", C.c_double), ("grid_origin_x", C.c_double),
                 ("grid_origin_y", C.c_double), ("giant_radius", C.c_double),
-                ("shard_index", C.c_int32), ("shard_count", C.c_int32)]
+                ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("near_mode", C.c_int32),
+                ("reserved2", C.c_int32)]
 
 
 _S3 = [C.POINTER(State3), C.POINTER(Scratch3), C.POINTER(StepParams3), _vp]

@@ -24,6 +24,7 @@
 // column side, which evaluates each of its ordered pairs exactly once.  HBM: colbuf is written and
 // read once per frame, 16 B x N^2 / (2048 R): 2.1 GB at N = 2^20 with R = 4.
 #include <math.h>
+#include <stdlib.h>
 
 #include "cosmo_device.cuh"
 #include "cosmo_internal.h"
@@ -61,9 +62,14 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src_lane) {
 // so the column-partial traffic (the only sizeable DRAM traffic of the pass) and the buffer itself
 // shrink (by R / 2: the sums over several row blocks are kept in FP64, see s_c).  The row sums of the
 // R blocks live in shared memory as doubles for the CTA's lifetime.
-template <int R>
+template <int R, int RL>
 __global__ void __launch_bounds__(SYM_THREADS, 2)
 k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int chunk) {
+    // RL row planets per lane: a row block takes WPB = 1024 / (32 RL) warps, and the CTA's 8 warps serve
+    // NH = 8 / WPB row blocks of the super tile at once (RL = 4: one, RL = 8: two "halves").  The column
+    // sums travel through the warp with 8 SHFL per rotation step whatever RL is, so RL = 8 halves the
+    // SHFL / LDS / address instructions per pair.
+    constexpr int WPB = SYM_BLOCK / (32 * RL), NH = SYM_WARPS / WPB, ROW_GROUP = 32 * RL;
     extern __shared__ __align__(16) unsigned char s_dyn[];
     float (*s_x)[SYM_BLOCK] = reinterpret_cast<float (*)[SYM_BLOCK]>(s_dyn);
     float (*s_y)[SYM_BLOCK] = s_x + 2;
@@ -83,7 +89,9 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
     const int J0 = I_first + blockIdx.y * chunk;
     if (J0 >= nblk) return;
     const int J1 = min(nblk, J0 + chunk);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler too (no BRA.DIV around the SHFLs)
+    const int half = w / WPB, wq = w % WPB;
 
     for (int q = tid; q < R * SYM_BLOCK; q += SYM_THREADS) s_row[0][q] = make_double2(0.0, 0.0);
     if (tid == 0) {
@@ -107,17 +115,17 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
     double2 *colbuf = reinterpret_cast<double2 *>(sc.colbuf);
     const size_t col_row = (size_t)blockIdx.x * (size_t)st.cap;   // local super-row index of this rank
 
-    float xi[4], yi[4], nmi[4];     // row side: 4 planets per lane, strided by 32 inside the warp's group
+    float xi[RL], yi[RL], nmi[RL];  // row side: RL planets per lane, strided by 32 inside the warp's group
     auto load_rows = [&](int I) {   // coalesced, L2-resident
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int row = I * SYM_BLOCK + w * SYM_GROUP + k * 32 + lane;
+        for (int k = 0; k < RL; ++k) {
+            const int row = I * SYM_BLOCK + wq * ROW_GROUP + k * 32 + lane;
             xi[k] = sc.pk_x[row];
             yi[k] = sc.pk_y[row];
             nmi[k] = -sc.pk_m[row];
         }
     };
-    if (R == 1) load_rows(I_first);      // a single row block: its operands stay in registers
+    if (R == 1 && half == 0) load_rows(I_first);      // a single row block: its operands stay in registers
 
     for (int J = J0; J < J1; ++J) {
         const int it_j = J - J0;
@@ -129,80 +137,96 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
         bool any_col = false;
 
 #pragma unroll 1
-        for (int r = 0; r < R; ++r) {
-            const int I = sym_row_of(blockIdx.x * R + r, shard_index, shard_count);
-            if (I >= nblk || I > J) break;         // rows are ascending: the rest lies beyond this column block
+        for (int r0 = 0; r0 < R; r0 += NH) {
+            // rows are ascending: once the first block of a pass lies beyond this column block, all do
+            const int Ia = sym_row_of(blockIdx.x * R + r0, shard_index, shard_count);
+            if (Ia >= nblk || Ia > J) break;
+            const int r = r0 + half;
+            const int I = r < R ? sym_row_of(blockIdx.x * R + r, shard_index, shard_count) : nblk;
+            const bool active = I < nblk && I <= J;   // warp-uniform
             const bool diag = (J == I);
-            any_col = any_col || !diag;
-            if (R > 1) load_rows(I);
-            uint64_t rx2[4], ry2[4];
+            if (NH == 1) {
+                any_col = any_col || !diag;
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { rx2[k] = 0ull; ry2[k] = 0ull; }
+                for (int h = 0; h < NH; ++h) {
+                    const int Ih = r0 + h < R ? sym_row_of(blockIdx.x * R + r0 + h, shard_index, shard_count) : nblk;
+                    any_col = any_col || (Ih < nblk && Ih < J);
+                }
+            }
+            if (R > 1 && active) load_rows(I);
+            uint64_t rx2[RL], ry2[RL];
+#pragma unroll
+            for (int k = 0; k < RL; ++k) { rx2[k] = 0ull; ry2[k] = 0ull; }
 
             for (int it = 0; it < SYM_WARPS; ++it) {
                 const int g = (w + it) & (SYM_WARPS - 1);
-                const float *gx = &s_x[b][g * SYM_GROUP];
-                const float *gy = &s_y[b][g * SYM_GROUP];
-                const float *gm = &s_m[b][g * SYM_GROUP];
-                uint64_t tx2[2] = {0ull, 0ull}, ty2[2] = {0ull, 0ull};   // travelling column sums
-#pragma unroll 2
-                for (int s = 0; s < 32; ++s) {
-                    const int c = (lane + s) & 31;
-                    const float4 X = *reinterpret_cast<const float4 *>(gx + 4 * c);
-                    const float4 Y = *reinterpret_cast<const float4 *>(gy + 4 * c);
-                    const float4 M = *reinterpret_cast<const float4 *>(gm + 4 * c);
-                    const uint64_t xj2[2] = {pack2(X.x, X.y), pack2(X.z, X.w)};
-                    const uint64_t yj2[2] = {pack2(Y.x, Y.y), pack2(Y.z, Y.w)};
-                    const uint64_t mj2[2] = {pack2(M.x, M.y), pack2(M.z, M.w)};
+                if (active) {
+                    const float *gx = &s_x[b][g * SYM_GROUP];
+                    const float *gy = &s_y[b][g * SYM_GROUP];
+                    const float *gm = &s_m[b][g * SYM_GROUP];
+                    uint64_t tx2[2] = {0ull, 0ull}, ty2[2] = {0ull, 0ull};   // travelling column sums
+#pragma unroll(RL == 4 ? 2 : 1)
+                    for (int s = 0; s < 32; ++s) {
+                        const int c = (lane + s) & 31;
+                        const float4 X = *reinterpret_cast<const float4 *>(gx + 4 * c);
+                        const float4 Y = *reinterpret_cast<const float4 *>(gy + 4 * c);
+                        const float4 M = *reinterpret_cast<const float4 *>(gm + 4 * c);
+                        const uint64_t xj2[2] = {pack2(X.x, X.y), pack2(X.z, X.w)};
+                        const uint64_t yj2[2] = {pack2(Y.x, Y.y), pack2(Y.z, Y.w)};
+                        const uint64_t mj2[2] = {pack2(M.x, M.y), pack2(M.z, M.w)};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t xik = pack2(xi[k], xi[k]), yik = pack2(yi[k], yi[k]);
-                        const uint64_t nmik = pack2(nmi[k], nmi[k]);
+                        for (int k = 0; k < RL; ++k) {
+                            const uint64_t xik = pack2(xi[k], xi[k]), yik = pack2(yi[k], yi[k]);
+                            const uint64_t nmik = pack2(nmi[k], nmi[k]);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const uint64_t dx = sub2(xj2[h], xik);
-                            const uint64_t dy = sub2(yj2[h], yik);
-                            const uint64_t r2 = fma2(dy, dy, fma2(dx, dx, eps2));
-                            float r2a, r2b;
-                            unpack2(r2, r2a, r2b);
-                            const uint64_t rinv = pack2(rsqrt_approx_f32(r2a), rsqrt_approx_f32(r2b));
-                            const uint64_t rinv3 = mul2(mul2(rinv, rinv), rinv);
-                            const uint64_t sj = mul2(mj2[h], rinv3);     // pull of the column planets on row k
-                            const uint64_t nsi = mul2(rinv3, nmik);      // minus the pull of row k on them
-                            rx2[k] = fma2(dx, sj, rx2[k]);
-                            ry2[k] = fma2(dy, sj, ry2[k]);
-                            tx2[h] = fma2(dx, nsi, tx2[h]);
-                            ty2[h] = fma2(dy, nsi, ty2[h]);
+                            for (int h = 0; h < 2; ++h) {
+                                const uint64_t dx = sub2(xj2[h], xik);
+                                const uint64_t dy = sub2(yj2[h], yik);
+                                const uint64_t r2 = fma2(dy, dy, fma2(dx, dx, eps2));
+                                float r2a, r2b;
+                                unpack2(r2, r2a, r2b);
+                                const uint64_t rinv = pack2(rsqrt_approx_f32(r2a), rsqrt_approx_f32(r2b));
+                                const uint64_t rinv3 = mul2(mul2(rinv, rinv), rinv);
+                                const uint64_t sj = mul2(mj2[h], rinv3);     // pull of the column planets on row k
+                                const uint64_t nsi = mul2(rinv3, nmik);      // minus the pull of row k on them
+                                rx2[k] = fma2(dx, sj, rx2[k]);
+                                ry2[k] = fma2(dy, sj, ry2[k]);
+                                tx2[h] = fma2(dx, nsi, tx2[h]);
+                                ty2[h] = fma2(dy, nsi, ty2[h]);
+                            }
                         }
+                        // hand the chunk's column sums to the lane that meets this chunk next
+                        const int src = (lane + 1) & 31;
+                        tx2[0] = shfl64(tx2[0], src); tx2[1] = shfl64(tx2[1], src);
+                        ty2[0] = shfl64(ty2[0], src); ty2[1] = shfl64(ty2[1], src);
                     }
-                    // hand the chunk's column sums to the lane that meets this chunk next
-                    const int src = (lane + 1) & 31;
-                    tx2[0] = shfl64(tx2[0], src); tx2[1] = shfl64(tx2[1], src);
-                    ty2[0] = shfl64(ty2[0], src); ty2[1] = shfl64(ty2[1], src);
-                }
-                if (!diag) {   // home again: lane l holds the sums of chunk l of group g
-                    float a0, a1, a2, a3, b0, b1, b2, b3;
-                    unpack2(tx2[0], a0, a1); unpack2(tx2[1], a2, a3);
-                    unpack2(ty2[0], b0, b1); unpack2(ty2[1], b2, b3);
-                    double4 *px = reinterpret_cast<double4 *>(&s_c[0][g * SYM_GROUP + 4 * lane]);
-                    double4 *py = reinterpret_cast<double4 *>(&s_c[1][g * SYM_GROUP + 4 * lane]);
-                    double4 cx = *px, cy = *py;
-                    cx.x += (double)a0; cx.y += (double)a1; cx.z += (double)a2; cx.w += (double)a3;
-                    cy.x += (double)b0; cy.y += (double)b1; cy.z += (double)b2; cy.w += (double)b3;
-                    *px = cx;
-                    *py = cy;
+                    if (!diag) {   // home again: lane l holds the sums of chunk l of group g
+                        float a0, a1, a2, a3, b0, b1, b2, b3;
+                        unpack2(tx2[0], a0, a1); unpack2(tx2[1], a2, a3);
+                        unpack2(ty2[0], b0, b1); unpack2(ty2[1], b2, b3);
+                        double4 *px = reinterpret_cast<double4 *>(&s_c[0][g * SYM_GROUP + 4 * lane]);
+                        double4 *py = reinterpret_cast<double4 *>(&s_c[1][g * SYM_GROUP + 4 * lane]);
+                        double4 cx = *px, cy = *py;
+                        cx.x += (double)a0; cx.y += (double)a1; cx.z += (double)a2; cx.w += (double)a3;
+                        cy.x += (double)b0; cy.y += (double)b1; cy.z += (double)b2; cy.w += (double)b3;
+                        *px = cx;
+                        *py = cy;
+                    }
                 }
                 __syncthreads();   // the next round moves every warp to another column group
             }
             // fold this block pair's FP32 row sums into the FP64 row sums (each lane owns its rows)
+            if (active) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float ax, ax2, ay, ay2;
-                unpack2(rx2[k], ax, ax2);
-                unpack2(ry2[k], ay, ay2);
-                double2 &acc = s_row[r][w * SYM_GROUP + k * 32 + lane];
-                acc.x += (double)ax + (double)ax2;
-                acc.y += (double)ay + (double)ay2;
+                for (int k = 0; k < RL; ++k) {
+                    float ax, ax2, ay, ay2;
+                    unpack2(rx2[k], ax, ax2);
+                    unpack2(ry2[k], ay, ay2);
+                    double2 &acc = s_row[r][wq * ROW_GROUP + k * 32 + lane];
+                    acc.x += (double)ax + (double)ax2;
+                    acc.y += (double)ay + (double)ay2;
+                }
             }
         }
         if (any_col) {   // column sums of this block over the R row blocks: one colbuf row per super row
@@ -213,15 +237,11 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
     }
     // row partials of every row block that met a column block of this chunk (I < J1)
     double2 *partial = reinterpret_cast<double2 *>(sc.partial);
-#pragma unroll 1
     for (int r = 0; r < R; ++r) {
         const int I = sym_row_of(blockIdx.x * R + r, shard_index, shard_count);
         if (I >= nblk || I >= J1) break;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int q = w * SYM_GROUP + k * 32 + lane;
+        for (int q = tid; q < SYM_BLOCK; q += SYM_THREADS)
             partial[(size_t)blockIdx.y * st.cap + (size_t)I * SYM_BLOCK + q] = s_row[r][q];
-        }
     }
 }
 
@@ -298,7 +318,7 @@ k_sym_integrate(cosmo_state st, cosmo_scratch sc, double G, double dt, int peer,
     integrate_store(st, sc, k, a.x, a.y, G, dt, true);
 }
 
-template <int R>
+template <int R, int RL>
 static int launch_sym_kernel(const cosmo_state &st, const cosmo_scratch &sc, dim3 grid, int sh_i, int sh_n, int chunk,
                              cudaStream_t s) {
     constexpr size_t kTma = 6 * SYM_BLOCK * sizeof(float);                 // x, y, m double-buffered
@@ -306,11 +326,11 @@ static int launch_sym_kernel(const cosmo_state &st, const cosmo_scratch &sc, dim
                                + (size_t)R * SYM_BLOCK * sizeof(double2);  // + the FP64 row sums of R row blocks
     static bool attr_set = false;
     if (!attr_set) {   // R = 4: 104 KB of dynamic shared memory (two CTAs per SM)
-        COSMO_TRY(check_cuda(cudaFuncSetAttribute(k_accel_f32_sym<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        COSMO_TRY(check_cuda(cudaFuncSetAttribute(k_accel_f32_sym<R, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)kShared), "cudaFuncSetAttribute(k_accel_f32_sym)"));
         attr_set = true;
     }
-    k_accel_f32_sym<R><<<grid, SYM_THREADS, kShared, s>>>(st, sc, sh_i, sh_n, chunk);
+    k_accel_f32_sym<R, RL><<<grid, SYM_THREADS, kShared, s>>>(st, sc, sh_i, sh_n, chunk);
     return COSMO_LAUNCH_CHECK("k_accel_f32_sym");
 }
 
@@ -338,9 +358,16 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
     const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
     if (rows_local > 0) {
         dim3 grid(super_rows, (nblk + chunk - 1) / chunk);
-        if (R == 4) COSMO_TRY(launch_sym_kernel<4>(st, sc, grid, sh_i, sh_n, chunk, s));
-        else if (R == 2) COSMO_TRY(launch_sym_kernel<2>(st, sc, grid, sh_i, sh_n, chunk, s));
-        else COSMO_TRY(launch_sym_kernel<1>(st, sc, grid, sh_i, sh_n, chunk, s));
+        static const int rl = getenv("COSMO_SYM_RL") ? atoi(getenv("COSMO_SYM_RL")) : 4;   // experiment switch
+        if (rl == 8) {
+            if (R == 4) COSMO_TRY((launch_sym_kernel<4, 8>(st, sc, grid, sh_i, sh_n, chunk, s)));
+            else if (R == 2) COSMO_TRY((launch_sym_kernel<2, 8>(st, sc, grid, sh_i, sh_n, chunk, s)));
+            else COSMO_TRY((launch_sym_kernel<1, 8>(st, sc, grid, sh_i, sh_n, chunk, s)));
+        } else {
+            if (R == 4) COSMO_TRY((launch_sym_kernel<4, 4>(st, sc, grid, sh_i, sh_n, chunk, s)));
+            else if (R == 2) COSMO_TRY((launch_sym_kernel<2, 4>(st, sc, grid, sh_i, sh_n, chunk, s)));
+            else COSMO_TRY((launch_sym_kernel<1, 4>(st, sc, grid, sh_i, sh_n, chunk, s)));
+        }
     }
     const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? ((p.opts & COSMO_OPT_PEER_EXCHANGE) ? 2 : 1) : 0;
     k_sym_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, R, unscale, p.G, p.dt,

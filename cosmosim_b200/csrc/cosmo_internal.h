@@ -39,6 +39,10 @@ int launch_sym_integrate(const cosmo_state &st, const cosmo_scratch &sc, const c
 int launch_nearfield(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,
                      cudaStream_t s);
 
+// the same for the 3-D step, on shadow structs (state3d.cu)
+int launch_nearfield3(const cosmo_state &st2, const cosmo_scratch &sc2, const cosmo_step_params &p2, const float *pk,
+                      const double *mass, double *corr3, int sym, cudaStream_t s);
+
 // detect.cu / resolve.cu
 int detect_residency(int *rows_per_cta, int *tile);
 int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,

@@ -669,6 +669,11 @@ int launch_grid_build_old2(const cosmo_state &st, const cosmo_scratch &sc, const
     return grid_build<SRC_OLD2>(st, sc, p, gd, mode, true, reuse_floor, s);
 }
 
+int launch_grid_build_old3(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p, cosmo_grid *gd,
+                           int mode, double reuse_floor, cudaStream_t s) {
+    return grid_build<SRC_OLD3>(st, sc, p, gd, mode, true, reuse_floor, s);
+}
+
 template <int SRC>
 static int launch_grid(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p, cudaStream_t s) {
     const int rows = p.i_end - p.i_begin;

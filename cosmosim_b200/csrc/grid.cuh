@@ -14,19 +14,21 @@ namespace cosmo {
 //             set is still a superset (for a thin disk the projection costs nothing; for a thick cloud
 //             it is only less selective)
 //   SRC_OLD2  state.pos, the start-of-frame positions                    (near-field pass of stage A)
-enum { SRC_NEW2 = 0, SRC_NEW3 = 1, SRC_OLD2 = 2 };
+//   SRC_OLD3  state.pos as three planes (near-field pass of the 3-D step; binned by (x, y) like SRC_NEW3)
+enum { SRC_NEW2 = 0, SRC_NEW3 = 1, SRC_OLD2 = 2, SRC_OLD3 = 3 };
 
 template <int SRC>
 __device__ __forceinline__ double2 xy_of(const cosmo_state &st, const cosmo_scratch &sc, int k) {
     if (SRC == SRC_NEW3) return make_double2(sc.pos_new[k], sc.pos_new[(size_t)st.cap + k]);
     if (SRC == SRC_OLD2) return reinterpret_cast<const double2 *>(st.pos)[k];
+    if (SRC == SRC_OLD3) return make_double2(st.pos[k], st.pos[(size_t)st.cap + k]);
     return reinterpret_cast<const double2 *>(sc.pos_new)[k];
 }
 
 template <int SRC>
 __device__ __forceinline__ double xx_of(const cosmo_state &st, const cosmo_scratch &sc, int k) {
-    if (SRC == SRC_OLD2) {
-        const double2 p = reinterpret_cast<const double2 *>(st.pos)[k];
+    if (SRC == SRC_OLD2 || SRC == SRC_OLD3) {
+        const double2 p = xy_of<SRC>(st, sc, k);
         return p.x * p.x + p.y * p.y;
     }
     return sc.xx_new[k];

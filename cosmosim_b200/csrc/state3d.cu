@@ -366,7 +366,7 @@ k3_accel_f64(cosmo3_state st, cosmo3_scratch sc, int i_begin, int i_end, int jsp
 template <int BLOCK, int IB, int TJ>
 __global__ void __launch_bounds__(BLOCK)
 k3_accel_f32(cosmo3_state st, cosmo3_scratch sc, int i_begin, int i_end, int jsplit, double G, double dt,
-             double unscale, int store_acc) {
+             double unscale, int store_acc, int near) {
     __shared__ __align__(16) float s_p[2][4][TJ];
     __shared__ __align__(8) uint64_t s_bar[2];
 
@@ -429,7 +429,8 @@ k3_accel_f32(cosmo3_state st, cosmo3_scratch sc, int i_begin, int i_end, int jsp
                 float r2a, r2b;
                 unpack2(r2, r2a, r2b);
                 uint64_t rinv = pack2(rsqrt_approx_f32(r2a), rsqrt_approx_f32(r2b));
-                uint64_t s = mul2(mul2(mj2, rinv), mul2(rinv, rinv));
+                // same order as the symmetric kernel; nearfield.cu replays it to the bit
+                uint64_t s = mul2(mj2, mul2(mul2(rinv, rinv), rinv));
                 ax2[k] = fma2(dx, s, ax2[k]);
                 ay2[k] = fma2(dy, s, ay2[k]);
                 az2[k] = fma2(dz, s, az2[k]);
@@ -446,6 +447,14 @@ k3_accel_f32(cosmo3_state st, cosmo3_scratch sc, int i_begin, int i_end, int jsp
     }
 #pragma unroll
     for (int k = 0; k < IB; ++k) { axd[k] *= unscale; ayd[k] *= unscale; azd[k] *= unscale; }
+    if (near && blockIdx.y == 0) {   // FP64 near-field corrections (nearfield.cu), once per row
+        const size_t cap = (size_t)st.cap;
+#pragma unroll
+        for (int k = 0; k < IB; ++k) {
+            const int i = base + k * BLOCK + threadIdx.x;
+            if (i < i_hi) { axd[k] += sc.corr[i]; ayd[k] += sc.corr[cap + i]; azd[k] += sc.corr[2 * cap + i]; }
+        }
+    }
     reduce_and_integrate3<BLOCK, IB>(st, sc, base, i_hi, axd, ayd, azd, jsplit, G, dt, store_acc != 0);
 }
 
@@ -1091,6 +1100,22 @@ static int launch_stage_a(const cosmo3_state &st, const cosmo3_scratch &sc, cons
     const int f32 = (p.opts & COSMO3_OPT_FP32) ? 1 : 0;
     k3_prep<<<blocks, 256, 0, s>>>(st, sc, p.pos_exp, p.mass_exp, f32);
     COSMO_TRY(COSMO_LAUNCH_CHECK("k3_prep"));
+    if (f32 && p.near_mode != 0) {
+        // FP64 near field of the FP32 flavours (nearfield.cu) on shadow structs: positions as planes, the
+        // grid arrays of stage B (free until then), corrections into scratch.corr
+        cosmo_state s2 = {};
+        cosmo_scratch c2 = {};
+        s2.cap = st.cap; s2.n_total = st.n_total; s2.status = st.status; s2.pos = st.pos; s2.radius = st.radius;
+        c2.rinf = sc.rinf; c2.cell_of = sc.cell_of; c2.cell_count = sc.cell_count; c2.cell_start = sc.cell_start;
+        c2.cell_items = sc.cell_items; c2.giants = sc.giants; c2.grid_cells = sc.grid_cells; c2.giant_cap = sc.giant_cap;
+        c2.chunk_alive = sc.chunk_bounds; c2.scan_blk = sc.scan_blk; c2.grid_dev = sc.grid_dev; c2.tune_hist = sc.tune_hist;
+        cosmo_step_params p2 = {};
+        p2.n_upper = p.n_upper; p2.i_begin = p.i_begin; p2.i_end = p.i_end; p2.near_mode = p.near_mode;
+        p2.pos_exp = p.pos_exp; p2.mass_exp = p.mass_exp;
+        p2.shard_index = p.shard_count > 0 ? p.shard_index : 0;
+        p2.shard_count = p.shard_count > 0 ? p.shard_count : 1;
+        COSMO_TRY(launch_nearfield3(s2, c2, p2, sc.pk, st.mass, sc.corr, (p.opts & COSMO3_OPT_F32_SYM) ? 1 : 0, s));
+    }
     // the symmetric kernels take their rows from shard_index / shard_count (round-robin row blocks), not
     // from [i_begin, i_end): a rank whose contiguous range is empty still owns row blocks
     if (f32 && (p.opts & COSMO3_OPT_F32_SYM)) return launch_accel3_sym32(st, sc, p, s);
@@ -1105,7 +1130,7 @@ static int launch_stage_a(const cosmo3_state &st, const cosmo3_scratch &sc, cons
         dim3 grid((rows + per - 1) / per, jsplit);
         const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
         k3_accel_f32<A32_BLOCK, A32_IB, A32_TJ><<<grid, A32_BLOCK, 0, s>>>(st, sc, p.i_begin, p.i_end, jsplit, p.G,
-                                                                           p.dt, unscale, store_acc);
+                                                                           p.dt, unscale, store_acc, p.near_mode != 0);
         return COSMO_LAUNCH_CHECK("k3_accel_f32");
     }
     if (p.n_upper <= SMALL_N) {

@@ -459,7 +459,7 @@ k3_accel_f32_sym(cosmo3_state st, cosmo3_scratch sc, int shard_index, int shard_
 
 __global__ void __launch_bounds__(256)
 k3_sym32_reduce(cosmo3_state st, cosmo3_scratch sc, int shard_index, int shard_count, int chunk, double unscale,
-                double G, double dt, int store_acc, int defer) {
+                double G, double dt, int store_acc, int defer, int near) {
     const int n = (int)st.status[COSMO_ST_N_ACTIVE];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -480,6 +480,10 @@ k3_sym32_reduce(cosmo3_state st, cosmo3_scratch sc, int shard_index, int shard_c
         for (int d = 0; d < 3; ++d) a[d] += (double)__ldcs(&colbuf[((size_t)r * 3 + d) * cap + k]);
 #pragma unroll
     for (int d = 0; d < 3; ++d) a[d] *= unscale;
+    if (near) {   // FP64 near-field corrections of the rows this rank evaluated (nearfield.cu; zero elsewhere)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a[d] += sc.corr[d * cap + k];
+    }
     if (defer) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) sc.acc[d * cap + k] = a[d];
@@ -513,7 +517,7 @@ int launch_accel3_sym32(const cosmo3_state &st, const cosmo3_scratch &sc, const 
     const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
     k3_sym32_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, unscale, p.G, p.dt,
                                                     (p.opts & COSMO3_OPT_STORE_ACC) ? 1 : 0,
-                                                    (p.opts & COSMO3_OPT_DEFER_INTEGRATE) ? 1 : 0);
+                                                    (p.opts & COSMO3_OPT_DEFER_INTEGRATE) ? 1 : 0, p.near_mode != 0);
     return COSMO_LAUNCH_CHECK("k3_sym32_reduce");
 }
 

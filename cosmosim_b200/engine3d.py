@@ -66,6 +66,8 @@ class Engine3D(BoundTracker):
         self.sym64_threshold = 16384 # FP64: from here on the symmetric kernel (each pair once) wins
         self.sym32_threshold = 32768 # FP32: same for the symmetric FP32 kernel
         self.sym_chunk = 0           # column blocks per CTA of the symmetric kernel (0 = automatic)
+        self.near_field = True       # FP32 flavours: FP64 near-field corrections on
+        self._grid_ready = False     # a stage B in grid mode has left a tuned grid on the device
         self.resolve_mode = None     # stage C: None = automatic, 0 = sequential loop, 1 = parallel components
         self.resolve_parallel_from = 512   # flagged pairs per step from which the parallel stage C pays off
         self._colbuf = None
@@ -107,6 +109,7 @@ class Engine3D(BoundTracker):
         t["row_count"] = z(cap + 1, dtype=i32); t["row_start"] = z(cap + 1, dtype=i32); t["label"] = z(cap, dtype=i32)
         t["comp_root"] = z(self.pair_cap, dtype=i32); t["comp_items"] = z(self.pair_cap, dtype=i32)
         t["pair_flag"] = z(self.pair_cap, dtype=i32); t["scan_a"] = z(self.pair_cap + 1, dtype=i32)
+        t["corr"] = z(3, cap, dtype=f64)                       # FP64 near-field corrections of the FP32 flavours
         p = lambda k: C.c_void_p(t[k].data_ptr())  # noqa: E731
         st = _abi.State3()
         st.cap, st.n_total, st.event_cap = cap, self.n_total, self.event_cap
@@ -118,7 +121,7 @@ class Engine3D(BoundTracker):
                   "t_pos", "t_vel", "t_mass", "t_mass_hi", "t_mass_lo", "t_density", "t_radius", "t_id", "t_flags",
                   "cell_of", "cell_count", "cell_start", "cell_items", "giants", "chunk_bounds", "heavy_rows",
                   "grid_dev", "tune_hist", "row_count", "row_start", "label", "comp_root", "comp_items", "pair_flag",
-                  "scan_a"):
+                  "scan_a", "corr"):
             setattr(sc, k, p(k))
         sc.jsplit_max, sc.pair_cap = self.JSPLIT_MAX, self.pair_cap
         sc.grid_cells, sc.giant_cap = self.grid_cells, self.giant_cap
@@ -230,7 +233,7 @@ class Engine3D(BoundTracker):
             self.sc.colbuf = C.c_void_p(self._colbuf.data_ptr())
             self.sc.colbuf_rows = rows
 
-    def params(self, dt, G, collisions=True, fp32=False, store_acc=False, i_begin=0, i_end=None, sym=None):
+    def params(self, dt, G, collisions=True, fp32=False, store_acc=False, i_begin=0, i_end=None, sym=None, near=None):
         n = self.n_upper
         p = _abi.StepParams3()
         p.G, p.dt = float(G), float(dt)
@@ -274,6 +277,10 @@ class Engine3D(BoundTracker):
                 p.detect_mode = 2
         # stage C: the sequential loop is the cheaper one for a handful of flagged pairs; crowded steps
         # (judged by the pair count of the status snapshot BOUND_LAG steps back) take the parallel one
+        # FP32 flavours: pairs closer than 2^14 FP32 ulps of their coordinates are re-evaluated in FP64
+        # (csrc/nearfield.cu), binned with the grid the previous step's stage B left on the device
+        if fp32 and whole and (self.near_field if near is None else near):
+            p.near_mode = 1 if self._grid_ready else 2
         mode = self.resolve_mode
         p.resolve_mode = int(mode if mode is not None else self.pairs_lag > self.resolve_parallel_from)
         return p
@@ -316,7 +323,7 @@ class Engine3D(BoundTracker):
             done += burst
             self.steps += burst
 
-    def step(self, dt, G, collisions=True, fp32=False, store_acc=False, steps=1, stage_events=None, sym=None):
+    def step(self, dt, G, collisions=True, fp32=False, store_acc=False, steps=1, stage_events=None, sym=None, near=None):
         """`steps` x State.interact on this device.  The host never reads object data here; the only
         wait is on the status snapshot of BOUND_LAG steps ago (_bound.py).  stage_events: a list
         that receives, per step, four CUDA events bracketing stages A, B and C (bench.py)."""
@@ -329,7 +336,7 @@ class Engine3D(BoundTracker):
                 return self._step_graphed(int(steps), dt, G, collisions, fp32, sym)
             for _ in range(int(steps)):
                 self._refresh_bound()
-                p = self.params(dt, G, collisions, fp32, store_acc, sym=sym)
+                p = self.params(dt, G, collisions, fp32, store_acc, sym=sym, near=near)
                 if self.world > 1:
                     from . import sharded
                     sharded.frame3d(self, p, sp, stage_events)
@@ -347,6 +354,8 @@ class Engine3D(BoundTracker):
                     stage_events.append(ev)
                 self.steps += 1
                 self._push_snapshot()
+                if p.detect_mode != 0:
+                    self._grid_ready = True
 
 
     # ------------------------------------------------------------------ host-buffer path (e2e)

@@ -117,6 +117,7 @@ typedef struct cosmo3_scratch {
     int32_t *comp_items;   /* [pair_cap] sorted-pair indices grouped by component */
     int32_t *pair_flag;    /* [pair_cap] result of the absorb call of every sorted pair */
     int32_t *scan_a;       /* [pair_cap + 1] */
+    double *corr;          /* [3][cap] near_mode != 0: FP64 near-field corrections of the FP32 sums */
 } cosmo3_scratch;
 
 typedef struct cosmo3_step_params {
@@ -145,6 +146,10 @@ typedef struct cosmo3_step_params {
     double giant_radius;
     int32_t shard_index;   /* this rank / number of ranks sharing the step (0 / 1 if single): the grid broad */
     int32_t shard_count;   /* phase and the symmetric kernel deal their chunks / row blocks round-robin      */
+    int32_t near_mode;     /* FP32 path: != 0 re-evaluates pairs closer than 2^-9 of their coordinates in FP64
+                              (cosmo_step_params.near_mode: 1 = bin with the grid of the previous step's stage B,
+                              2 = tune a grid first) */
+    int32_t reserved2;
 } cosmo3_step_params;
 
 /* Stage A: per-step preparation + all-pairs acceleration (FP64: the reference's rounding sequence

@@ -267,6 +267,52 @@ def test_fp32_flavour_accuracy(mods, sym):
     assert np.array_equal(out["vel_new"], v) and np.array_equal(out["pos_new"], snap["pos"] + v * 60.0)
 
 
+@pytest.mark.parametrize("sym", [False, True])
+def test_fp32_near_field_3d(mods, sym):
+    """FP64 near field of the 3-D FP32 flavours (csrc/nearfield.cu, k_nearfield3): a thin crowded disk
+    with planted close pairs (separations of 1e6..1e8 m at 1 AU, where an FP32 coordinate is known to
+    ~1e4 m).  With the pass on the stated bound of the 2-D path holds for every row (median <= 1e-5,
+    max <= 1e-3 of |a|); switched off, the planted rows are far outside it.  The second step takes the
+    grid the first step's stage B left on the device (near_mode 1), the first tunes its own (2)."""
+    engine3d, o3, _ = mods
+    n = 40960
+    snap = synthetic_cloud(n, 11, thick=0.001)
+    rng = np.random.default_rng(5)
+    twins = rng.choice(np.arange(1, n), size=400, replace=False)      # object k gets a close companion
+    for q, k in enumerate(twins[:200]):
+        d = rng.normal(size=3)
+        snap["pos"][twins[200 + q]] = snap["pos"][k] + d / np.linalg.norm(d) * 10.0 ** rng.uniform(6.0, 8.0)
+    G = 6.674e-11
+    want = o3.accel(snap["pos"], snap["mass_f64"], G)
+    arr = engine3d_arrays_from_snapshot(snap)
+    errs = {}
+    for near in (True, False):
+        eng = engine3d.Engine3D(n)
+        eng.upload(arr)
+        eng.step(60.0, G, collisions=False, fp32=True, store_acc=True, sym=sym, near=near)
+        eng.check_errors()
+        p = eng.params(60.0, G, False, True, sym=sym, near=near)
+        assert bool(p.opts & _abi_bits(mods).OPT3_F32_SYM) == sym and p.near_mode == (2 if near else 0)
+        errs[near] = relerr_rows(eng.last_step_tensors(n)["acc"], want)
+    on, off = errs[True], errs[False]
+    assert np.median(on) < 1e-5 and on.max() < 1e-3, (np.median(on), on.max())
+    assert off.max() > 10 * on.max(), (off.max(), on.max())
+    # collisions on (grid broad phase): the next step bins the near field with stage B's grid
+    eng = engine3d.Engine3D(n)
+    eng.grid_threshold = 1024
+    eng.upload(arr)
+    eng.step(60.0, G, collisions=True, fp32=True, store_acc=True, sym=sym)
+    assert eng.params(60.0, G, True, True, sym=sym).near_mode == 1
+    st = eng.check_errors()
+    d = eng.download()
+    m = st["n_active"]
+    want2 = o3.accel(d["pos"], d["mass"], G)
+    eng.step(60.0, G, collisions=False, fp32=True, store_acc=True, sym=sym)
+    eng.check_errors()
+    err2 = relerr_rows(eng.last_step_tensors(m)["acc"], want2)
+    assert np.median(err2) < 1e-5 and err2.max() < 1e-3, (np.median(err2), err2.max())
+
+
 def test_host_api_run_and_pickles(mods, tmp_path):
     """Object / State / Universe.run through the drop-in module: in-memory run vs the reference
     fixture, and the on-disk pickle stream (universe.py:151-158) read back."""
