@@ -271,7 +271,14 @@ def roofline_block(eng, prec, kw, peaks, stage_events, n_per_step, world, worklo
             "frac": (achieved / peak) if peak else None, "traffic": traffic, "traffic_note": traffic_note,
             "algorithmic_bytes": n_eff * bytes_per_body,
             "peak_source": "in-process %s micro-benchmark (cosmo_microbench) on this GPU; "
-                           "MEASURED_PEAKS.json holds no CUDA-core peak" % ("FFMA" if prec == "fp32" else "DFMA"),
+                           "MEASURED_PEAKS.json holds no CUDA-core peak" % ("FFMA / FFMA2 (the better of the two)" if prec == "fp32" else "DFMA"),
+            "instruction_mix_ceiling": ({"tflops": peaks.get("pair_chain_tflops"),
+                                         "frac_of_peak": peaks["pair_chain_tflops"] / peak,
+                                         "kernel_frac_of_ceiling": achieved / peaks["pair_chain_tflops"],
+                                         "what": "the kernel's pair chain (2 FADD2 + 6 FFMA2 + 4 FMUL2 + 2 MUFU per two pairs) "
+                                                 "on registers only, no shared memory / shuffles / barriers "
+                                                 "(cosmo_microbench kind 11): operand bandwidth of the register file"}
+                                        if prec == "fp32" and peak and peaks.get("pair_chain_tflops") else None),
             "instr_per_interaction": ipi, "kernel_ms": accel_ms, "n_eff": n_eff,
             "interactions_per_s_kernel": kernel_rate, "stage_ms": tab,
             "outside_stage_timers_ms": ms_per_step - tab["sum"],
@@ -706,9 +713,9 @@ def measure_pipe_peaks(eng, prec):
     out = torch.zeros(eng.sm_count * 2 * 1024, dtype=torch.float64, device=eng.device)
     stream = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
 
-    def rate(kind, iters):
+    def rate(kind, iters, shapes=((512, 2), (1024, 1), (1024, 2))):
         best = 0.0
-        for threads, bps in ((512, 2), (1024, 1), (1024, 2)):
+        for threads, bps in shapes:
             ops = C.c_int64()
             for _ in range(3):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -721,8 +728,14 @@ def measure_pipe_peaks(eng, prec):
         return best
 
     ffma, dfma, mufu = rate(0, 8000), rate(2, 3000), rate(3, 3000)
-    return {"ffma_per_s": ffma, "dfma_per_s": dfma, "mufu_rsq_per_s": mufu,
-            "ffma_tflops": 2 * ffma / 1e12, "dfma_tflops": 2 * dfma / 1e12}
+    # packed FP32: FFMA2 with operands from the reuse cache (the pipe's peak: two FMAs per lane and
+    # instruction), and the pair chain of k_accel_f32_sym on registers only (kind 11: the ceiling of the
+    # kernel's instruction mix -- an FFMA2 with three live register-pair operands takes 3 cycles, the
+    # register file delivers two pairs per two cycles; profiles/r02_kernel_experiments.md)
+    ffma2, chain = rate(1, 4000), rate(11, 2000, ((256, 2), (256, 4)))   # kinds 9-12: CTAs of 256
+    return {"ffma_per_s": ffma, "dfma_per_s": dfma, "mufu_rsq_per_s": mufu, "ffma2_per_s": ffma2,
+            "ffma_tflops": max(2 * ffma, 4 * ffma2) / 1e12, "ffma_scalar_tflops": 2 * ffma / 1e12,
+            "ffma2_tflops": 4 * ffma2 / 1e12, "pair_chain_tflops": 4 * chain / 1e12, "dfma_tflops": 2 * dfma / 1e12}
 
 
 if __name__ == "__main__":

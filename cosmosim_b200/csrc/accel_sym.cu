@@ -3,17 +3,18 @@
 // half a MUFU per ORDERED interaction instead of 9 and 1.  Same entry point / reference lines as
 // accel.cu (acc_blas, cosmosim/util/blas.py:4-41; integrator universe_old.py:177-178).
 //
-// Decomposition.  Planets are cut into blocks of 1024 (8 groups of 128).  A CTA of 8 warps owns
-// one ROW block I and walks a chunk of COLUMN blocks J >= I.  Warp w keeps group w of I in
-// registers (4 planets per lane: the "row" side, accumulated in packed FP32 registers).  For a
-// column block J, staged in shared memory by TMA bulk copies, the CTA runs 8 rounds; in round
-// `it` warp w works on column group g = (w + it) & 7, so no two warps touch the same column
-// group in the same round.  Inside a round the 128 column planets are dealt to the lanes in
-// chunks of 4 and ROTATE through the warp: at step s lane l reads chunk (l + s) & 31 from
-// shared memory and holds that chunk's partial column accumulators, which it then hands to
-// lane l-1 with 8 SHFLs -- after 32 steps every row planet of the warp has met every column
-// planet of the group and the accumulators are back in their home lane.  Per step and lane:
-// 4 x 4 pairs = 96 FFMA2-class instructions + 16 MUFU.RSQ + 3 LDS.128 + 8 SHFL.
+// Decomposition.  Planets are cut into blocks of 1024.  A CTA of 8 warps works on TWO row blocks
+// at a time ("halves": warps 0-3 and 4-7) and walks a chunk of COLUMN blocks J >= I.  A warp keeps
+// 256 planets of its row block in registers (8 per lane: the "row" side, accumulated in packed FP32
+// registers).  A column block J, staged in shared memory by TMA bulk copies, is cut into 8 groups of
+// 128; the CTA runs 8 rounds, in round `it` warp w works on column group g = (w + it) & 7, so no
+// two warps touch the same column group in the same round.  Inside a round the 128 column planets
+// are dealt to the lanes in chunks of 4 and ROTATE through the warp: at step s lane l reads chunk
+// (l + s) & 31 from shared memory and holds that chunk's partial column accumulators, which it
+// then hands to lane l-1 with 8 SHFLs -- after 32 steps every row planet of the warp has met every
+// column planet of the group and the accumulators are back in their home lane.  Per step and lane:
+// 8 x 4 pairs = 192 FFMA2-class instructions + 32 MUFU.RSQ + 3 LDS.128 + 8 SHFL (8 row planets per
+// lane instead of 4 halve the SHFL / LDS / address instructions per pair; profiles/r02_kernel_experiments.md).
 //
 // A CTA serves R (1, 2 or 4) row blocks against its column chunk (super tile, see the kernel): the
 // column sums of a column block J over those row blocks go to colbuf[super row][j] (double2: the
@@ -24,7 +25,6 @@
 // column side, which evaluates each of its ordered pairs exactly once.  HBM: colbuf is written and
 // read once per frame, 16 B x N^2 / (2048 R): 2.1 GB at N = 2^20 with R = 4.
 #include <math.h>
-#include <stdlib.h>
 
 #include "cosmo_device.cuh"
 #include "cosmo_internal.h"
@@ -33,8 +33,12 @@
 namespace cosmo {
 
 constexpr int SYM_BLOCK = 1024;   // planets per block
-constexpr int SYM_GROUP = 128;    // planets per warp (4 per lane)
+constexpr int SYM_GROUP = 128;    // column planets per warp and round (4 per lane)
 constexpr int SYM_WARPS = 8;
+constexpr int SYM_RL = 8;         // row planets per lane
+constexpr int SYM_WPB = SYM_BLOCK / (32 * SYM_RL);   // warps per row block (4)
+constexpr int SYM_NH = SYM_WARPS / SYM_WPB;          // row blocks a CTA works on at once (2)
+constexpr int SYM_ROW_GROUP = 32 * SYM_RL;           // row planets per warp (256)
 constexpr int SYM_THREADS = SYM_WARPS * 32;
 #define COSMO_F32_TINY_SYM 8.673617379884035e-19f /* 2^-60 softening, see accel.cu */
 
@@ -47,6 +51,14 @@ __host__ __device__ __forceinline__ int sym_row_of(int l, int rank, int world) {
 __host__ __device__ __forceinline__ bool sym_owns(int I, int rank, int world) {
     const int l = I / world, rr = I % world;
     return ((l & 1) ? world - 1 - rr : rr) == rank;
+}
+
+// (x, x) built where it is used: ptxas then folds it into the broadcast operand form of the packed
+// instruction (FADD2 d, a, -Rx.F32) and the row operands stay one register each
+__device__ __forceinline__ uint64_t dup2(float x) {
+    uint64_t r;
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x));
+    return r;
 }
 
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src_lane) {
@@ -62,14 +74,10 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src_lane) {
 // so the column-partial traffic (the only sizeable DRAM traffic of the pass) and the buffer itself
 // shrink (by R / 2: the sums over several row blocks are kept in FP64, see s_c).  The row sums of the
 // R blocks live in shared memory as doubles for the CTA's lifetime.
-template <int R, int RL>
+template <int R>
 __global__ void __launch_bounds__(SYM_THREADS, 2)
 k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_count, int chunk) {
-    // RL row planets per lane: a row block takes WPB = 1024 / (32 RL) warps, and the CTA's 8 warps serve
-    // NH = 8 / WPB row blocks of the super tile at once (RL = 4: one, RL = 8: two "halves").  The column
-    // sums travel through the warp with 8 SHFL per rotation step whatever RL is, so RL = 8 halves the
-    // SHFL / LDS / address instructions per pair.
-    constexpr int WPB = SYM_BLOCK / (32 * RL), NH = SYM_WARPS / WPB, ROW_GROUP = 32 * RL;
+    constexpr int RL = SYM_RL, WPB = SYM_WPB, NH = SYM_NH, ROW_GROUP = SYM_ROW_GROUP;
     extern __shared__ __align__(16) unsigned char s_dyn[];
     float (*s_x)[SYM_BLOCK] = reinterpret_cast<float (*)[SYM_BLOCK]>(s_dyn);
     float (*s_y)[SYM_BLOCK] = s_x + 2;
@@ -145,14 +153,10 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
             const int I = r < R ? sym_row_of(blockIdx.x * R + r, shard_index, shard_count) : nblk;
             const bool active = I < nblk && I <= J;   // warp-uniform
             const bool diag = (J == I);
-            if (NH == 1) {
-                any_col = any_col || !diag;
-            } else {
 #pragma unroll
-                for (int h = 0; h < NH; ++h) {
-                    const int Ih = r0 + h < R ? sym_row_of(blockIdx.x * R + r0 + h, shard_index, shard_count) : nblk;
-                    any_col = any_col || (Ih < nblk && Ih < J);
-                }
+            for (int h = 0; h < NH; ++h) {   // (CTA-uniform) does any half add column sums for this J?
+                const int Ih = r0 + h < R ? sym_row_of(blockIdx.x * R + r0 + h, shard_index, shard_count) : nblk;
+                any_col = any_col || (Ih < nblk && Ih < J);
             }
             if (R > 1 && active) load_rows(I);
             uint64_t rx2[RL], ry2[RL];
@@ -166,7 +170,7 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
                     const float *gy = &s_y[b][g * SYM_GROUP];
                     const float *gm = &s_m[b][g * SYM_GROUP];
                     uint64_t tx2[2] = {0ull, 0ull}, ty2[2] = {0ull, 0ull};   // travelling column sums
-#pragma unroll(RL == 4 ? 2 : 1)
+#pragma unroll 2
                     for (int s = 0; s < 32; ++s) {
                         const int c = (lane + s) & 31;
                         const float4 X = *reinterpret_cast<const float4 *>(gx + 4 * c);
@@ -175,12 +179,15 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
                         const uint64_t xj2[2] = {pack2(X.x, X.y), pack2(X.z, X.w)};
                         const uint64_t yj2[2] = {pack2(Y.x, Y.y), pack2(Y.z, Y.w)};
                         const uint64_t mj2[2] = {pack2(M.x, M.y), pack2(M.z, M.w)};
+                        // (column half outside, row planets inside and the products written (s, d): the
+                        // schedule ptxas derives from this order has the fewest instructions and operand
+                        // reads of the orders tried -- the results are the same bits for all of them)
 #pragma unroll
-                        for (int k = 0; k < RL; ++k) {
-                            const uint64_t xik = pack2(xi[k], xi[k]), yik = pack2(yi[k], yi[k]);
-                            const uint64_t nmik = pack2(nmi[k], nmi[k]);
+                        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
+                            for (int k = 0; k < RL; ++k) {
+                                const uint64_t xik = dup2(xi[k]), yik = dup2(yi[k]);
+                                const uint64_t nmik = dup2(nmi[k]);
                                 const uint64_t dx = sub2(xj2[h], xik);
                                 const uint64_t dy = sub2(yj2[h], yik);
                                 const uint64_t r2 = fma2(dy, dy, fma2(dx, dx, eps2));
@@ -190,10 +197,10 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
                                 const uint64_t rinv3 = mul2(mul2(rinv, rinv), rinv);
                                 const uint64_t sj = mul2(mj2[h], rinv3);     // pull of the column planets on row k
                                 const uint64_t nsi = mul2(rinv3, nmik);      // minus the pull of row k on them
-                                rx2[k] = fma2(dx, sj, rx2[k]);
-                                ry2[k] = fma2(dy, sj, ry2[k]);
-                                tx2[h] = fma2(dx, nsi, tx2[h]);
-                                ty2[h] = fma2(dy, nsi, ty2[h]);
+                                rx2[k] = fma2(sj, dx, rx2[k]);
+                                ry2[k] = fma2(sj, dy, ry2[k]);
+                                tx2[h] = fma2(nsi, dx, tx2[h]);
+                                ty2[h] = fma2(nsi, dy, ty2[h]);
                             }
                         }
                         // hand the chunk's column sums to the lane that meets this chunk next
@@ -214,19 +221,23 @@ k_accel_f32_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
                         *py = cy;
                     }
                 }
-                __syncthreads();   // the next round moves every warp to another column group
-            }
-            // fold this block pair's FP32 row sums into the FP64 row sums (each lane owns its rows)
-            if (active) {
+                // Fold the FP32 row sums into the FP64 ones after every 4 rounds: the two halves walk the
+                // column groups in orders that differ by a swap of the two 4-round segments ((w + it) & 7
+                // with w = wq and w = wq + 4), so each segment's FP32 sum -- and, the FP64 fold being exact,
+                // the total -- does not depend on which half served the row block (tilings, rank counts).
+                if ((it & 3) == 3 && active) {
 #pragma unroll
-                for (int k = 0; k < RL; ++k) {
-                    float ax, ax2, ay, ay2;
-                    unpack2(rx2[k], ax, ax2);
-                    unpack2(ry2[k], ay, ay2);
-                    double2 &acc = s_row[r][wq * ROW_GROUP + k * 32 + lane];
-                    acc.x += (double)ax + (double)ax2;
-                    acc.y += (double)ay + (double)ay2;
+                    for (int k = 0; k < RL; ++k) {
+                        float ax, ax2, ay, ay2;
+                        unpack2(rx2[k], ax, ax2);
+                        unpack2(ry2[k], ay, ay2);
+                        double2 &acc = s_row[r][wq * ROW_GROUP + k * 32 + lane];   // each lane owns its rows
+                        acc.x += (double)ax + (double)ax2;
+                        acc.y += (double)ay + (double)ay2;
+                        rx2[k] = 0ull; ry2[k] = 0ull;
+                    }
                 }
+                __syncthreads();   // the next round moves every warp to another column group
             }
         }
         if (any_col) {   // column sums of this block over the R row blocks: one colbuf row per super row
@@ -318,7 +329,7 @@ k_sym_integrate(cosmo_state st, cosmo_scratch sc, double G, double dt, int peer,
     integrate_store(st, sc, k, a.x, a.y, G, dt, true);
 }
 
-template <int R, int RL>
+template <int R>
 static int launch_sym_kernel(const cosmo_state &st, const cosmo_scratch &sc, dim3 grid, int sh_i, int sh_n, int chunk,
                              cudaStream_t s) {
     constexpr size_t kTma = 6 * SYM_BLOCK * sizeof(float);                 // x, y, m double-buffered
@@ -326,11 +337,11 @@ static int launch_sym_kernel(const cosmo_state &st, const cosmo_scratch &sc, dim
                                + (size_t)R * SYM_BLOCK * sizeof(double2);  // + the FP64 row sums of R row blocks
     static bool attr_set = false;
     if (!attr_set) {   // R = 4: 104 KB of dynamic shared memory (two CTAs per SM)
-        COSMO_TRY(check_cuda(cudaFuncSetAttribute(k_accel_f32_sym<R, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        COSMO_TRY(check_cuda(cudaFuncSetAttribute(k_accel_f32_sym<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)kShared), "cudaFuncSetAttribute(k_accel_f32_sym)"));
         attr_set = true;
     }
-    k_accel_f32_sym<R, RL><<<grid, SYM_THREADS, kShared, s>>>(st, sc, sh_i, sh_n, chunk);
+    k_accel_f32_sym<R><<<grid, SYM_THREADS, kShared, s>>>(st, sc, sh_i, sh_n, chunk);
     return COSMO_LAUNCH_CHECK("k_accel_f32_sym");
 }
 
@@ -358,16 +369,9 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
     const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
     if (rows_local > 0) {
         dim3 grid(super_rows, (nblk + chunk - 1) / chunk);
-        static const int rl = getenv("COSMO_SYM_RL") ? atoi(getenv("COSMO_SYM_RL")) : 4;   // experiment switch
-        if (rl == 8) {
-            if (R == 4) COSMO_TRY((launch_sym_kernel<4, 8>(st, sc, grid, sh_i, sh_n, chunk, s)));
-            else if (R == 2) COSMO_TRY((launch_sym_kernel<2, 8>(st, sc, grid, sh_i, sh_n, chunk, s)));
-            else COSMO_TRY((launch_sym_kernel<1, 8>(st, sc, grid, sh_i, sh_n, chunk, s)));
-        } else {
-            if (R == 4) COSMO_TRY((launch_sym_kernel<4, 4>(st, sc, grid, sh_i, sh_n, chunk, s)));
-            else if (R == 2) COSMO_TRY((launch_sym_kernel<2, 4>(st, sc, grid, sh_i, sh_n, chunk, s)));
-            else COSMO_TRY((launch_sym_kernel<1, 4>(st, sc, grid, sh_i, sh_n, chunk, s)));
-        }
+        if (R == 4) COSMO_TRY(launch_sym_kernel<4>(st, sc, grid, sh_i, sh_n, chunk, s));
+        else if (R == 2) COSMO_TRY(launch_sym_kernel<2>(st, sc, grid, sh_i, sh_n, chunk, s));
+        else COSMO_TRY(launch_sym_kernel<1>(st, sc, grid, sh_i, sh_n, chunk, s));
     }
     const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? ((p.opts & COSMO_OPT_PEER_EXCHANGE) ? 2 : 1) : 0;
     k_sym_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, R, unscale, p.G, p.dt,

@@ -17,7 +17,7 @@ from oracle import ref_harness as rh
 def test_struct_layouts_and_argument_checks():
     assert C.sizeof(_abi.State3) == 8 + 11 * 8 + 8
     assert C.sizeof(_abi.StepParams3) == 2 * 8 + 8 * 4 + 4 * 4 + 4 * 8 + 4 * 4
-    assert C.sizeof(_abi.Scratch3) == 29 * 8 + 7 * 8 + 8 + 2 * 8 + 2 * 8 + 7 * 8    # + grid_dev, tune_hist, parallel stage C
+    assert C.sizeof(_abi.Scratch3) == 29 * 8 + 7 * 8 + 8 + 2 * 8 + 2 * 8 + 7 * 8 + 8    # + grid_dev, tune_hist, parallel stage C, corr
     L = _abi.lib()
     assert L.cosmo3_step(None, None, None, None) == -1
     assert b"bad argument" in L.cosmo_last_error()
