@@ -157,6 +157,7 @@ SYMBOLS = {
     "cosmo_accel": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "cosmo_accel_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_double, C.c_int, C.c_int32, C.c_int32, _vp,
                                    _vp, C.c_int64, _vp]),
+    "cosmo_sym_tuned_available": (C.c_int, []),
     "cosmo_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_int64), _vp]),
     "cosmo_host_pow_third": (C.c_double, [C.c_double]),
     "cosmo_host_u128_to_double": (C.c_double, [C.c_uint64, C.c_uint64]),

@@ -304,6 +304,8 @@ int cosmo_microbench(int kind, int blocks, int threads, int iters, double *out, 
     return launch_microbench(kind, blocks, threads, iters, out, ops_per_thread, (cudaStream_t)stream);
 }
 
+int cosmo_sym_tuned_available(void) { return sym_tuned_available(); }
+
 // host-callable copies of the resolver's exact scalar helpers (CPU tests pin them against
 // Python's own int/float semantics and libm pow)
 double cosmo_host_pow_third(double x) { return pow_third(x); }

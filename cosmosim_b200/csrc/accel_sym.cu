@@ -335,7 +335,26 @@ static int launch_sym_kernel(const cosmo_state &st, const cosmo_scratch &sc, dim
     constexpr size_t kTma = 6 * SYM_BLOCK * sizeof(float);                 // x, y, m double-buffered
     constexpr size_t kShared = kTma + 2 * SYM_BLOCK * sizeof(double)       // + the FP64 column accumulators
                                + (size_t)R * SYM_BLOCK * sizeof(double2);  // + the FP64 row sums of R row blocks
-    static bool attr_set = false;
+    static bool attr_set = false, tuned_attr_set = false;
+    // the post-scheduled copy of this kernel (sym_tuned.cu, sass_tune.py) if the build produced one
+    const void *tuned = sym_tuned_kernel(R);
+    if (tuned) {
+        if (!tuned_attr_set) {
+            if (cudaFuncSetAttribute(tuned, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShared) != cudaSuccess) {
+                cudaGetLastError();
+                tuned = nullptr;
+            } else {
+                tuned_attr_set = true;
+            }
+        }
+    }
+    if (tuned) {
+        cosmo_state st_v = st;
+        cosmo_scratch sc_v = sc;
+        void *args[] = {&st_v, &sc_v, &sh_i, &sh_n, &chunk};
+        COSMO_TRY(check_cuda(cudaLaunchKernel(tuned, grid, dim3(SYM_THREADS), args, kShared, s), "k_accel_f32_sym (tuned)"));
+        return COSMO_OK;
+    }
     if (!attr_set) {   // R = 4: 104 KB of dynamic shared memory (two CTAs per SM)
         COSMO_TRY(check_cuda(cudaFuncSetAttribute(k_accel_f32_sym<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)kShared), "cudaFuncSetAttribute(k_accel_f32_sym)"));

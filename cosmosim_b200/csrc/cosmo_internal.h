@@ -43,6 +43,10 @@ int launch_nearfield(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
 int launch_nearfield3(const cosmo_state &st2, const cosmo_scratch &sc2, const cosmo_step_params &p2, const float *pk,
                       const double *mass, double *corr3, int sym, cudaStream_t s);
 
+// sym_tuned.cu: the post-scheduled k_accel_f32_sym<R> (nullptr: use the kernel compiled into the library)
+const void *sym_tuned_kernel(int R);
+int sym_tuned_available();
+
 // detect.cu / resolve.cu
 int detect_residency(int *rows_per_cta, int *tile);
 int launch_detect(const cosmo_state &st, const cosmo_scratch &sc, const cosmo_step_params &p,

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(1024) k_microbench(int iters, double *out) {
 //   KIND 11  the pair chain of the symmetric kernel on registers only (2 FADD2, 6 FFMA2, 4 FMUL2, 2 MUFU
 //            per two pairs; no shared memory, no shuffles, no barriers): the ceiling of the instruction mix
 //   KIND 12  the same chain with the two MUFU replaced by moves of the argument
+//   KIND 13 / 14  DFMA with three changing operands / two changing operands and a constant
 template <int KIND>
 __global__ void __launch_bounds__(256, 2) k_microbench2(int iters, double *out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +68,23 @@ __global__ void __launch_bounds__(256, 2) k_microbench2(int iters, double *out) 
         v[k] = pack2(0.5f * f, 0.25f * f);
     }
     const uint64_t ua = pack2(0.9999f, 0.9999f);
-    if (KIND == 9 || KIND == 10) {
+    if (KIND == 13 || KIND == 14) {
+        double d[8], e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { d[k] = 1.0 + 1e-3 * (double)(k + (t & 7)); e[k] = 0.5 * d[k]; }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (KIND == 13) d[k] = __fma_rn(e[(k + r) & 7], d[(k + 3) & 7], d[k]);
+                    if (KIND == 14) d[k] = __fma_rn(e[k], 0.9999, d[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) u[k] = (uint64_t)__double_as_longlong(d[k]) >> 3;
+    } else if (KIND == 9 || KIND == 10) {
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
@@ -140,12 +157,14 @@ int launch_microbench(int kind, int blocks, int threads, int iters, double *out,
         set_error("cosmo_microbench: bad launch shape");
         return COSMO_E_ARG;
     }
-    if (ops_per_thread) *ops_per_thread = (int64_t)iters * (kind >= 11 ? 96 : 16 * 8);   // packed FMA-pipe instructions
+    if (ops_per_thread) *ops_per_thread = (int64_t)iters * ((kind == 11 || kind == 12) ? 96 : 16 * 8);   // packed FMA-pipe instructions
     switch (kind) {
         case 9: k_microbench2<9><<<blocks, threads, 0, s>>>(iters, out); break;
         case 10: k_microbench2<10><<<blocks, threads, 0, s>>>(iters, out); break;
         case 11: k_microbench2<11><<<blocks, threads, 0, s>>>(iters, out); break;
         case 12: k_microbench2<12><<<blocks, threads, 0, s>>>(iters, out); break;
+        case 13: k_microbench2<13><<<blocks, threads, 0, s>>>(iters, out); break;
+        case 14: k_microbench2<14><<<blocks, threads, 0, s>>>(iters, out); break;
         case 0: k_microbench<0><<<blocks, threads, 0, s>>>(iters, out); break;
         case 1: k_microbench<1><<<blocks, threads, 0, s>>>(iters, out); break;
         case 2: k_microbench<2><<<blocks, threads, 0, s>>>(iters, out); break;

@@ -400,13 +400,22 @@ int cosmo_accel_host(const double *pos_host, const double *mass_host, int32_t n,
 
 /*
  * Pipe micro-benchmarks (the roofline denominators must be measured).
- * kind: 0 FFMA, 1 FFMA2 (fma.rn.f32x2), 2 DFMA, 3 MUFU.RSQ, 4 DADD, 5 DMUL, 6 FMUL, 7 FADD.
+ * kind: 0 FFMA, 1 FFMA2 (fma.rn.f32x2), 2 DFMA, 3 MUFU.RSQ, 4 DADD, 5 DMUL, 6 FMUL, 7 FADD, 8 MUFU.RSQ64H;
+ * operand-bandwidth probes (CTAs of at most 256 threads): 9 FFMA2 with three changing operands,
+ * 10 FFMA2 with two changing operands and a constant, 11 the pair chain of k_accel_f32_sym on registers
+ * only (the ceiling of its instruction mix), 12 the same without the MUFUs, 13 / 14 like 9 / 10 for DFMA.
  * Runs `iters` iterations of 8 independent chains per thread on `blocks` x `threads`;
  * out (device, >= blocks*threads doubles) receives a value so nothing is optimised away.
  * ops_per_thread receives the instruction count per thread.
  */
 int cosmo_microbench(int kind, int blocks, int threads, int iters, double *out,
                      int64_t *ops_per_thread, void *stream);
+
+/* 1 if the library carries (and this device loaded) the post-scheduled copy of k_accel_f32_sym -- the
+   same instructions with the accumulation FFMA2 of the inner loop regrouped for the operand-reuse cache
+   (cosmosim_b200/sass_tune.py).  The environment variable COSMO_SYM_TUNED=0 selects the kernel as ptxas
+   scheduled it; both produce the same bits. */
+int cosmo_sym_tuned_available(void);
 
 /* Host-side copies of the resolver's exact scalar helpers (no GPU needed): float(int) with
    round-half-even, Python's exact int/float `>=`, and pow(x, 1/3) as planet.py:82 rounds it. */

@@ -15,8 +15,9 @@ out = torch.zeros(sm * 8 * 1024, dtype=torch.float64, device=dev)
 stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 NAMES = {0: "FFMA scalar, constant operands", 1: "FFMA2, constant operands", 9: "FFMA2, three changing operands",
          10: "FFMA2, two changing operands + constant", 11: "pair chain of the symmetric kernel (registers only)",
-         12: "pair chain without the MUFUs"}
-for kind, iters in ((0, 4000), (1, 4000), (9, 4000), (10, 4000), (11, 4000), (12, 4000)):
+         12: "pair chain without the MUFUs", 2: "DFMA, constant operands", 13: "DFMA, three changing operands",
+         14: "DFMA, two changing operands + constant"}
+for kind, iters in ((0, 4000), (1, 4000), (9, 4000), (10, 4000), (11, 4000), (12, 4000), (2, 2000), (13, 2000), (14, 2000)):
     for bps in (2, 4):
         best = 0.0
         ops = C.c_int64()
@@ -28,5 +29,5 @@ for kind, iters in ((0, 4000), (1, 4000), (9, 4000), (10, 4000), (11, 4000), (12
             e1.record()
             torch.cuda.synchronize()
             best = max(best, ops.value * sm * bps * 256 / (e0.elapsed_time(e1) * 1e-3))
-        lanes = 1 if kind == 0 else 2
+        lanes = 1 if kind in (0, 2, 13, 14) else 2
         print("kind %2d  %d CTAs of 256 per SM: %.3e instr/s = %.2f TFLOP/s  (%s)" % (kind, bps, best, best * lanes * 2 / 1e12, NAMES[kind]))
