@@ -335,19 +335,12 @@ static int launch_sym_kernel(const cosmo_state &st, const cosmo_scratch &sc, dim
     constexpr size_t kTma = 6 * SYM_BLOCK * sizeof(float);                 // x, y, m double-buffered
     constexpr size_t kShared = kTma + 2 * SYM_BLOCK * sizeof(double)       // + the FP64 column accumulators
                                + (size_t)R * SYM_BLOCK * sizeof(double2);  // + the FP64 row sums of R row blocks
-    static bool attr_set = false, tuned_attr_set = false;
+    static bool attr_set = false;
     // the post-scheduled copy of this kernel (sym_tuned.cu, sass_tune.py) if the build produced one
-    const void *tuned = sym_tuned_kernel(R);
-    if (tuned) {
-        if (!tuned_attr_set) {
-            if (cudaFuncSetAttribute(tuned, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShared) != cudaSuccess) {
-                cudaGetLastError();
-                tuned = nullptr;
-            } else {
-                tuned_attr_set = true;
-            }
-        }
-    }
+    static const char *const kName = R == 4   ? "_ZN5cosmo15k_accel_f32_symILi4EEEv11cosmo_state13cosmo_scratchiii"
+                                     : R == 2 ? "_ZN5cosmo15k_accel_f32_symILi2EEEv11cosmo_state13cosmo_scratchiii"
+                                              : "_ZN5cosmo15k_accel_f32_symILi1EEEv11cosmo_state13cosmo_scratchiii";
+    const void *tuned = tuned_kernel(kName, (int)kShared);
     if (tuned) {
         cosmo_state st_v = st;
         cosmo_scratch sc_v = sc;

@@ -109,7 +109,8 @@ k_accel_f64_sym(cosmo_state st, cosmo_scratch sc, int shard_index, int shard_cou
     const int J0 = I + blockIdx.y * chunk;
     if (J0 >= nblk) return;
     const int J1 = min(nblk, J0 + chunk);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler too (no BRA.DIV around the SHFLs)
     const double2 *pos = reinterpret_cast<const double2 *>(st.pos);
 
     double xi[2], yi[2], qix[2], qiy[2], hi[2], nmi[2], rax[2], ray[2];
@@ -252,8 +253,18 @@ int launch_accel_sym64(const cosmo_state &st, const cosmo_scratch &sc, const cos
     }
     if (rows_local > 0) {
         dim3 grid(rows_local, (nblk + chunk - 1) / chunk);
-        k_accel_f64_sym<<<grid, S64_THREADS, 0, s>>>(st, sc, sh_i, sh_n, chunk);
-        COSMO_TRY(COSMO_LAUNCH_CHECK("k_accel_f64_sym"));
+        // the post-scheduled copy of the kernel (sym_tuned.cu, sass_tune.py) if the build produced one
+        const void *tuned = tuned_kernel("_ZN5cosmo15k_accel_f64_symE11cosmo_state13cosmo_scratchiii", 0);
+        if (tuned) {
+            cosmo_state st_v = st;
+            cosmo_scratch sc_v = sc;
+            int a_i = sh_i, a_n = sh_n, a_c = chunk;
+            void *args[] = {&st_v, &sc_v, &a_i, &a_n, &a_c};
+            COSMO_TRY(check_cuda(cudaLaunchKernel(tuned, grid, dim3(S64_THREADS), args, 0, s), "k_accel_f64_sym (tuned)"));
+        } else {
+            k_accel_f64_sym<<<grid, S64_THREADS, 0, s>>>(st, sc, sh_i, sh_n, chunk);
+            COSMO_TRY(COSMO_LAUNCH_CHECK("k_accel_f64_sym"));
+        }
     }
     const int defer = (p.opts & COSMO_OPT_DEFER_INTEGRATE) ? ((p.opts & COSMO_OPT_PEER_EXCHANGE) ? 2 : 1) : 0;
     k_sym64_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, p.G, p.dt,

@@ -43,8 +43,9 @@ int launch_nearfield(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
 int launch_nearfield3(const cosmo_state &st2, const cosmo_scratch &sc2, const cosmo_step_params &p2, const float *pk,
                       const double *mass, double *corr3, int sym, cudaStream_t s);
 
-// sym_tuned.cu: the post-scheduled k_accel_f32_sym<R> (nullptr: use the kernel compiled into the library)
-const void *sym_tuned_kernel(int R);
+// sym_tuned.cu: the post-scheduled copy of a kernel by mangled name (nullptr: use the one compiled into
+// the library); number of tuned kernels loaded
+const void *tuned_kernel(const char *mangled, int dyn_smem);
 int sym_tuned_available();
 
 // detect.cu / resolve.cu

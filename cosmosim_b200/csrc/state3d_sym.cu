@@ -25,6 +25,20 @@ constexpr size_t T_SMEM = (size_t)(2 * 5 + 3) * T_BLOCK * sizeof(double) + 2 * s
 
 int configure_sym_kernels();
 
+// mangled names of the two symmetric kernels: their post-scheduled copies (sym_tuned.cu, sass_tune.py)
+static const char *const kTuned64 = "_ZN5cosmo2s316k3_accel_f64_symE12cosmo3_state14cosmo3_scratchiii";
+static const char *const kTuned32 = "_ZN5cosmo2s316k3_accel_f32_symE12cosmo3_state14cosmo3_scratchiii";
+
+// launch the tuned copy if the build produced one, else the kernel compiled into the library
+static int launch_sym3(const char *mangled, const void *builtin, const char *what, dim3 grid, int threads, size_t smem,
+                       const cosmo3_state &st, const cosmo3_scratch &sc, int sh_i, int sh_n, int chunk, cudaStream_t s) {
+    const void *tuned = tuned_kernel(mangled, (int)smem);
+    cosmo3_state st_v = st;
+    cosmo3_scratch sc_v = sc;
+    void *args[] = {&st_v, &sc_v, &sh_i, &sh_n, &chunk};
+    return check_cuda(cudaLaunchKernel(tuned ? tuned : builtin, grid, dim3(threads), args, smem, s), what);
+}
+
 __device__ __forceinline__ double shfl_f64(double v, int src_lane) {
     int lo = __double2loint(v), hi = __double2hiint(v);
     lo = __shfl_sync(0xffffffffu, lo, src_lane);
@@ -279,8 +293,8 @@ int launch_accel3_sym64(const cosmo3_state &st, const cosmo3_scratch &sc, const 
     COSMO_TRY(configure_sym_kernels());
     if (rows_local > 0) {
         dim3 grid(rows_local, (nblk + chunk - 1) / chunk);
-        k3_accel_f64_sym<<<grid, T_THREADS, T_SMEM, s>>>(st, sc, sh_i, sh_n, chunk);
-        COSMO_TRY(COSMO_LAUNCH_CHECK("k3_accel_f64_sym"));
+        COSMO_TRY(launch_sym3(kTuned64, (const void *)k3_accel_f64_sym, "k3_accel_f64_sym", grid, T_THREADS, T_SMEM, st, sc,
+                              sh_i, sh_n, chunk, s));
     }
     k3_sym64_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, p.G, p.dt,
                                                     (p.opts & COSMO3_OPT_STORE_ACC) ? 1 : 0,
@@ -511,8 +525,8 @@ int launch_accel3_sym32(const cosmo3_state &st, const cosmo3_scratch &sc, const 
     COSMO_TRY(configure_sym_kernels());
     if (rows_local > 0) {
         dim3 grid(rows_local, (nblk + chunk - 1) / chunk);
-        k3_accel_f32_sym<<<grid, U_THREADS, U_SMEM, s>>>(st, sc, sh_i, sh_n, chunk);
-        COSMO_TRY(COSMO_LAUNCH_CHECK("k3_accel_f32_sym"));
+        COSMO_TRY(launch_sym3(kTuned32, (const void *)k3_accel_f32_sym, "k3_accel_f32_sym", grid, U_THREADS, U_SMEM, st, sc,
+                              sh_i, sh_n, chunk, s));
     }
     const double unscale = scalbn(1.0, p.mass_exp - 2 * p.pos_exp);
     k3_sym32_reduce<<<(n + 255) / 256, 256, 0, s>>>(st, sc, sh_i, sh_n, chunk, unscale, p.G, p.dt,
@@ -536,6 +550,9 @@ int configure_sym_kernels() {
                                               (int)T_SMEM), "cudaFuncSetAttribute(k3_accel_f64_sym)"));
     COSMO_TRY(check_cuda(cudaFuncSetAttribute(k3_accel_f32_sym, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)U_SMEM), "cudaFuncSetAttribute(k3_accel_f32_sym)"));
+    // the post-scheduled copies (sym_tuned.cu) are loaded and opted in here too, never inside a capture
+    tuned_kernel(kTuned64, (int)T_SMEM);
+    tuned_kernel(kTuned32, (int)U_SMEM);
     configured = true;
     return COSMO_OK;
 }

@@ -907,28 +907,32 @@ def test_symmetric_fp32_super_tiles_and_emulated_ranks(n):
 @pytest.mark.gpu
 @pytest.mark.parametrize("n", [9000, 70000])
 def test_tuned_sass_equals_ptxas_schedule(n):
-    """k_accel_f32_sym runs from a post-scheduled copy of its SASS (cosmosim_b200/sass_tune.py: the
-    accumulation FFMA2 of the inner loop regrouped for the operand-reuse cache, stall counts recomputed).
-    Same instructions, same arithmetic: for every tiling the accelerations must be the SAME BITS as those of
-    the kernel as ptxas scheduled it (COSMO_SYM_TUNED=0), on a scene with merges-in-waiting, a star and
-    ragged last blocks."""
+    """The symmetric kernels run from post-scheduled copies of their SASS (cosmosim_b200/sass_tune.py: the
+    accumulation FFMA2 / DFMA of the inner loops regrouped for the operand-reuse cache, stall counts
+    recomputed).  Same instructions, same arithmetic: the accelerations must be the SAME BITS as those of
+    the kernels as ptxas scheduled them (COSMO_SYM_TUNED=0) -- FP32 for every tiling, FP64 -- on a scene
+    with a star, touching planets and ragged last blocks."""
     import os
     from cosmosim_b200 import _abi, scenes
-    assert _abi.lib().cosmo_sym_tuned_available() == 1, "the build did not produce / load the tuned kernel"
+    assert _abi.lib().cosmo_sym_tuned_available() == 6, "the build did not produce / load the tuned kernels"
     arr = scenes.star_disk_arrays(n, seed=7)
     old = os.environ.get("COSMO_SYM_TUNED")
     try:
-        for rows in (1, 2, 4):
+        for rows, fp32 in ((1, True), (2, True), (4, True), (0, False)):
             got = {}
             for tuned in ("0", "1"):
                 os.environ["COSMO_SYM_TUNED"] = tuned
                 eng = make_engine(arr)
-                eng.sym_rows = rows
-                eng.step(1, DT, G, 100 * AU, collisions=False, store_acc=True, fp32=True, f32_sym=True, near=False)
+                if fp32:
+                    eng.sym_rows = rows
+                    eng.step(1, DT, G, 100 * AU, collisions=False, store_acc=True, fp32=True, f32_sym=True, near=False)
+                else:
+                    eng.step(1, DT, G, 100 * AU, collisions=False, store_acc=True, f64_sym=True)
                 eng.check_errors()
-                got[tuned] = eng.last_frame_tensors()["acc"][:n].cpu().numpy()
+                t = eng.last_frame_tensors()
+                got[tuned] = np.concatenate([t[k][:n].cpu().numpy().reshape(n, -1) for k in ("acc", "pos_new", "vel_new")], axis=1)
             assert np.isfinite(got["1"]).all()
-            assert np.array_equal(got["0"].view(np.uint64), got["1"].view(np.uint64)), rows
+            assert np.array_equal(got["0"].view(np.uint64), got["1"].view(np.uint64)), (rows, fp32)
     finally:
         if old is None:
             os.environ.pop("COSMO_SYM_TUNED", None)

@@ -313,6 +313,35 @@ def test_fp32_near_field_3d(mods, sym):
     assert np.median(err2) < 1e-5 and err2.max() < 1e-3, (np.median(err2), err2.max())
 
 
+@pytest.mark.parametrize("fp32", [False, True])
+def test_tuned_sass_equals_ptxas_schedule_3d(mods, fp32):
+    """The symmetric 3-D kernels run from post-scheduled copies of their SASS (cosmosim_b200/sass_tune.py);
+    same instructions, same arithmetic: accelerations and new state must be the SAME BITS as those of the
+    kernels as ptxas scheduled them (COSMO_SYM_TUNED=0)."""
+    import os
+    engine3d, o3, _ = mods
+    n = 20000 if not fp32 else 40000
+    arr = engine3d_arrays_from_snapshot(synthetic_cloud(n, 21, thick=0.05))
+    old = os.environ.get("COSMO_SYM_TUNED")
+    got = {}
+    try:
+        for tuned in ("0", "1"):
+            os.environ["COSMO_SYM_TUNED"] = tuned
+            eng = engine3d.Engine3D(n)
+            eng.upload(arr)
+            eng.step(60.0, 6.674e-11, collisions=False, fp32=fp32, store_acc=True, sym=True, near=False)
+            eng.check_errors()
+            t = eng.last_step_tensors(n)
+            got[tuned] = np.concatenate([t[k] for k in ("acc", "pos_new", "vel_new")], axis=1)
+    finally:
+        if old is None:
+            os.environ.pop("COSMO_SYM_TUNED", None)
+        else:
+            os.environ["COSMO_SYM_TUNED"] = old
+    assert np.isfinite(got["1"]).all()
+    assert np.array_equal(got["0"].view(np.uint64), got["1"].view(np.uint64))
+
+
 def test_host_api_run_and_pickles(mods, tmp_path):
     """Object / State / Universe.run through the drop-in module: in-memory run vs the reference
     fixture, and the on-disk pickle stream (universe.py:151-158) read back."""
