@@ -369,7 +369,7 @@ int launch_accel_sym(const cosmo_state &st, const cosmo_scratch &sc, const cosmo
     int chunk = p.sym_chunk > 0 ? p.sym_chunk : 32;
     while ((nblk + chunk - 1) / chunk > sc.jsplit_max) ++chunk;
     // row blocks per CTA: p.sym_rows, raised if the column-partial buffer is too small for it
-    int R = p.sym_rows >= 4 ? 4 : (p.sym_rows >= 2 ? 2 : 1);
+    int R = p.sym_rows >= 4 ? 4 : (p.sym_rows == 1 ? 1 : 2);   // unset (0): 2, the smallest tiling that fills the CTA
     auto rows_needed = [&](int r) { return 2LL * ((rows_local + r - 1) / r); };   // in float2 rows: a double2 row is two
     if (sc.colbuf_rows > 0)
         while (R < 4 && rows_needed(R) > sc.colbuf_rows) R *= 2;

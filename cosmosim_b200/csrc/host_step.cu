@@ -183,12 +183,13 @@ int cosmo_params_default(int32_t n, double G, double dt, double r_max, uint32_t 
     if (sym) {
         int sms = 148, dev = 0;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        // ~16 CTAs per resident slot; FP32: as many row blocks per CTA as that allows (1, 2 or 4)
+        // ~16 CTAs per resident slot; FP32: as many row blocks per CTA as that allows (4 or 2 -- a CTA works
+        // on two row blocks at once, so 1 would idle half of its warps)
         const long long nblk = fp32 ? nblk32 : nblk64;
         long long want = nblk > 1 ? (nblk * nblk) / (2LL * 16 * 2 * sms) : 1;
         const long long lo = (nblk + jmax - 1) / jmax;
         if (fp32) {
-            p->sym_rows = want >= 16 ? 4 : (want >= 4 ? 2 : 1);
+            p->sym_rows = want >= 16 ? 4 : 2;
             want /= p->sym_rows;
         }
         long long chunk = want < lo ? lo : want;

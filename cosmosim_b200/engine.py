@@ -324,7 +324,9 @@ class Engine(BoundTracker):
         row-partial buffer has rows (JSPLIT_MAX)."""
         nblk = -(-n // 1024)
         target = (nblk * nblk) // (2 * 16 * 2 * self.sm_count * self.world) if nblk > 1 else 1
-        rows = 4 if target >= 16 else (2 if target >= 4 else 1)
+        # (a CTA works on two row blocks at once, so 2 is the smallest tiling that keeps all its warps busy;
+        # sym_rows = 1 remains available for tests)
+        rows = 4 if target >= 16 else 2
         chunk = int(min(32, max(1, -(-nblk // self.JSPLIT_MAX), target // rows)))
         return rows, chunk
 

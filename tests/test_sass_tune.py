@@ -1,0 +1,79 @@
+"""The SASS post-scheduler of the symmetric kernels (cosmosim_b200/sass_tune.py) on the CPU: it runs at
+build time on cubins nvcc cross-compiles here; cuobjdump disassembles them without a GPU.  The bitwise
+equality of the tuned kernels with ptxas's schedule is a GPU test (test_tuned_sass_equals_ptxas_schedule*)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from cosmosim_b200 import _build, sass_tune
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None or shutil.which("nvcc") is None,
+                                reason="needs nvcc and cuobjdump")
+
+
+@pytest.fixture(scope="module")
+def cubins(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cubins")
+    out = {}
+    for src, kernels in _build.TUNED:
+        cubin = str(d / (src[:-3] + ".cubin"))
+        flags = [f for f in _build.NVCC_FLAGS if f not in ("-Xcompiler", "-fPIC", "-Xptxas", "-v")]
+        subprocess.run([_build._nvcc()] + flags + ["-I", _build.INCLUDE, "-I", _build.CSRC, "-cubin", "-o", cubin,
+                                                    os.path.join(_build.CSRC, src)], check=True, capture_output=True)
+        out[src] = (cubin, kernels, str(d / (src[:-3] + "_tuned.cubin")))
+    return out
+
+
+def test_every_registered_kernel_is_tuned_and_verified(cubins):
+    """tune_cubin re-disassembles its output and compares it instruction by instruction with the plan (same
+    opcodes, registers and immediates, only accumulations moved / their product operands swapped, nothing
+    outside the loops touched); here: it accepts every kernel the build registers and finds reuse."""
+    for src, (cubin, kernels, tuned) in cubins.items():
+        stats = sass_tune.tune_cubin(cubin, tuned, kernels)
+        assert [s["kernel"] for s in stats] == list(kernels)
+        for st in stats:
+            assert st["moved"] >= st["accumulations"] // 2, st["kernel"]
+            assert st["reuse_flags_on_moved"] >= st["moved"] // 2, st["kernel"]
+        assert os.path.getsize(tuned) == os.path.getsize(cubin)
+        # deterministic: the same input gives the same bytes
+        again = tuned + ".again"
+        sass_tune.tune_cubin(cubin, again, kernels)
+        assert open(again, "rb").read() == open(tuned, "rb").read()
+
+
+def test_new_order_respects_every_dependency_and_latency(cubins):
+    """Independent re-check on the patched SASS of the FP32 kernel: inside the tuned loop every register is
+    written and read in an order that is consistent with the original def-use chains, and every dependent
+    pair of two-cycle instructions is at least the pipeline latency apart by the stall counts."""
+    cubin, kernels, tuned = cubins["accel_sym.cu"]
+    sass_tune.tune_cubin(cubin, tuned, kernels)
+    k = kernels[-1]
+    before = sass_tune._disassemble(cubin, k)
+    after = sass_tune._disassemble(tuned, k)
+    (first, last), = sass_tune._find_loops(before)
+    assert sorted(t.replace(".reuse", "") for _, t, _, _ in before[first:last + 1] if not t.startswith("FFMA2")) == \
+        sorted(t.replace(".reuse", "") for _, t, _, _ in after[first:last + 1] if not t.startswith("FFMA2"))
+    body = [sass_tune._parse(a, t, lo, hi, i) for i, (a, t, lo, hi) in enumerate(after[first:last + 1])]
+    lat = sass_tune._latency_table(before)
+    fma_lat = min(v for (p, c), v in lat.items() if p in ("FFMA2", "FMUL2", "FADD2") and c in ("FFMA2", "FMUL2", "FADD2"))
+    t, issue, writer = 0, {}, {}
+    for i, x in enumerate(body):
+        for r in x.src:
+            w = writer.get(r)
+            if w is not None and body[w].base in ("FFMA2", "FMUL2", "FADD2") and x.base in ("FFMA2", "FMUL2", "FADD2"):
+                assert t - issue[w] >= fma_lat, (x.text, body[w].text)
+        issue[i] = t
+        for r in x.dst:
+            writer[r] = i
+        t += max(1, x.stall())
+    # reuse flags only where the next instruction really reads that register in that slot
+    for x, y in zip(body, body[1:]):
+        if ".reuse" in x.text and x.base in sass_tune.PACKED:
+            flagged = [s for s, a in enumerate(x.text.split(",")[1:]) if ".reuse" in a]
+            xs = [a.strip().replace(".reuse", "") for a in x.text.split(",")[1:]]
+            ys = [a.strip().replace(".reuse", "") for a in y.text.split(",")[1:]]
+            for s in flagged:
+                if x.base == y.base:
+                    assert s < len(ys) and xs[s].lstrip("-") == ys[s].lstrip("-"), (x.text, y.text)
