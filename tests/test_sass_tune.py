@@ -77,3 +77,46 @@ def test_new_order_respects_every_dependency_and_latency(cubins):
             for s in flagged:
                 if x.base == y.base:
                     assert s < len(ys) and xs[s].lstrip("-") == ys[s].lstrip("-"), (x.text, y.text)
+
+
+def test_dataflow_of_every_tuned_loop_is_unchanged(cubins):
+    """Independent of the tool's own dependency graph: in every tuned loop of every registered kernel each
+    source register of each instruction is produced by the SAME instruction as before (or is live-in as
+    before), and the last writer of every register at the end of the body is the same instruction -- i.e.
+    the patched body computes the same dataflow graph, whatever order it issues it in."""
+    for src, (cubin, kernels, tuned) in cubins.items():
+        stats = sass_tune.tune_cubin(cubin, tuned, kernels)
+        for st in stats:
+            before = sass_tune._disassemble(cubin, st["kernel"])
+            assert st["loops"], st["kernel"]
+            for loop in st["loops"]:
+                first, order = loop["first"], loop["order"]
+                body = [sass_tune._parse(a, t, lo, hi, i) for i, (a, t, lo, hi) in enumerate(before[first:first + len(order)])]
+
+                def flow(seq):
+                    writer, prod = {}, {}
+                    for i in seq:
+                        x = body[i]
+                        prod[i] = tuple(sorted((r, writer.get(r, -1)) for r in set(x.src)))
+                        for r in x.dst:
+                            writer[r] = i
+                    return prod, writer
+
+                p0, w0 = flow(range(len(body)))
+                p1, w1 = flow(order)
+                assert p0 == p1, (st["kernel"], hex(loop["loop"][0]))
+                assert w0 == w1, (st["kernel"], hex(loop["loop"][0]))
+
+
+def test_the_build_shipped_tuned_kernels():
+    """The in-tree build ran the tuner on every registered kernel (none declined)."""
+    import cosmosim_b200
+    cosmosim_b200.build()
+    log = open(os.path.join(_build.OBJ_DIR, "sass_tune.log")).read()
+    assert "declined" not in log, log
+    for _, kernels in _build.TUNED:
+        for k in kernels:
+            assert k in log
+    import re
+    sizes = [int(m) for m in re.findall(r"\{kTunedCubin\d+, (\d+)\}", open(_build.TUNED_INC).read())]
+    assert len(sizes) == len(_build.TUNED) and all(s > 100000 for s in sizes), sizes
