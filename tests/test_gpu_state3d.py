@@ -267,6 +267,61 @@ def test_fp32_flavour_accuracy(mods, sym):
     assert np.array_equal(out["vel_new"], v) and np.array_equal(out["pos_new"], snap["pos"] + v * 60.0)
 
 
+def crowded_thin_disk(n):
+    """Thin disk with 200 planted pairs 1e6..1e8 m apart (an FP32 coordinate at 1 AU is known to ~1e4 m)."""
+    snap = synthetic_cloud(n, 11, thick=0.001)
+    rng = np.random.default_rng(5)
+    twins = rng.choice(np.arange(1, n), size=400, replace=False)      # object k gets a close companion
+    for q, k in enumerate(twins[:200]):
+        d = rng.normal(size=3)
+        snap["pos"][twins[200 + q]] = snap["pos"][k] + d / np.linalg.norm(d) * 10.0 ** rng.uniform(6.0, 8.0)
+    return snap
+
+
+@pytest.mark.parametrize("sym", [False, True])
+def test_fp32_near_field_3d_emulated_ranks(mods, sym):
+    """The sharded protocol of the 3-D FP32 step with the near field on, emulated on one GPU: every "rank"
+    runs stage A on its share (symmetric kernel: row blocks and cell-sorted near-field chunks dealt round
+    robin, partial sums added like the all-reduce does; one-sided kernel: its own row range with its own
+    corrections) -- the result must be the single-GPU accelerations to 1e-12 (every near pair corrected
+    exactly once, whatever the rank count)."""
+    import ctypes as C
+    import torch
+    from cosmosim_b200 import sharded
+    engine3d, o3, abi = mods
+    n, G = 40960, 6.674e-11
+    arr = engine3d_arrays_from_snapshot(crowded_thin_disk(n))
+    eng = engine3d.Engine3D(n)
+    eng.upload(arr)
+    eng.step(60.0, G, collisions=False, fp32=True, store_acc=True, sym=sym)
+    eng.check_errors()
+    assert eng.params(60.0, G, False, True, sym=sym).near_mode == 2
+    base = eng.last_step_tensors(n)["acc"]
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for world in (2, 3):
+        e2 = engine3d.Engine3D(n)
+        e2.upload(arr)
+        total = np.zeros((n, 3))
+        for r in range(world):
+            p = e2.params(60.0, G, False, True, True, sym=sym)
+            assert p.near_mode == 2
+            p.shard_index, p.shard_count = r, world
+            i0, i1, _ = sharded.shard_rows(n, world, r)
+            if sym:
+                p.opts |= abi.OPT3_DEFER_INTEGRATE
+            else:
+                p.i_begin, p.i_end = i0, i1
+            abi.check(e2.lib.cosmo3_accel_integrate(C.byref(e2.st), C.byref(e2.sc), C.byref(p), stream), "cosmo3_accel_integrate")
+            acc = e2.t["acc"][:, :n].cpu().numpy().T
+            if sym:
+                total += acc
+            else:
+                total[i0:i1] = acc[i0:i1]
+        e2.check_errors()
+        got = total * G if sym else total
+        assert np.abs(got - base).max() <= 1e-12 * np.abs(base).max(), (world, sym)
+
+
 @pytest.mark.parametrize("sym", [False, True])
 def test_fp32_near_field_3d(mods, sym):
     """FP64 near field of the 3-D FP32 flavours (csrc/nearfield.cu, k_nearfield3): a thin crowded disk
@@ -276,12 +331,7 @@ def test_fp32_near_field_3d(mods, sym):
     grid the first step's stage B left on the device (near_mode 1), the first tunes its own (2)."""
     engine3d, o3, _ = mods
     n = 40960
-    snap = synthetic_cloud(n, 11, thick=0.001)
-    rng = np.random.default_rng(5)
-    twins = rng.choice(np.arange(1, n), size=400, replace=False)      # object k gets a close companion
-    for q, k in enumerate(twins[:200]):
-        d = rng.normal(size=3)
-        snap["pos"][twins[200 + q]] = snap["pos"][k] + d / np.linalg.norm(d) * 10.0 ** rng.uniform(6.0, 8.0)
+    snap = crowded_thin_disk(n)
     G = 6.674e-11
     want = o3.accel(snap["pos"], snap["mass_f64"], G)
     arr = engine3d_arrays_from_snapshot(snap)
