@@ -55,6 +55,8 @@ class Engine(BoundTracker):
         sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
         with torch.cuda.device(self.device):
             _abi.check(self.lib.cosmo_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), "cosmo_device_info")
+            # load the post-scheduled kernels now (csrc/sym_tuned.cu): never inside a CUDA-graph capture
+            self.tuned_kernels = int(self.lib.cosmo_sym_tuned_available())
         self.sm_count = sm.value
         self.n_total = int(n_total)
         self.cap = max(PAD, _round_up(self.n_total, PAD))
